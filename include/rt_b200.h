@@ -1,0 +1,219 @@
+/* rt_b200.h — C ABI of the B200-native replacement for raytracer_lib's per-pixel render loop.
+ *
+ * This is the drop-in boundary: exactly the calls a Rust `RayTracer` shim would bind to
+ * replace raytracer_lib/src/raytracer/mod.rs. Every entry point cites the reference interface it replaces
+ * (paths relative to the upstream repository Andreas-Edling/raytracer-rs).
+ *
+ * Conventions
+ *   - return value 0 (RT_OK) = success, negative = error; the message is available from rt_last_error().
+ *   - every input buffer is caller-owned and copied during the call; every output buffer is caller-allocated.
+ *   - a handle may be moved between host threads (the reference moves RayTracer into its render thread,
+ *     raytracer/src/main.rs:194-196) but must not be called concurrently. No global mutable state.
+ *   - all arithmetic on the path is IEEE binary32 with the reference's operation order; there is no CPU
+ *     fallback: every render entry point fails with RT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_OK 0
+#define RT_ERR_INVALID -1  /* bad argument */
+#define RT_ERR_LOAD -2     /* Collada / texture loading failed (message mirrors SceneLoadError's Display) */
+#define RT_ERR_CUDA -3     /* CUDA runtime error or no usable device */
+#define RT_ERR_UNSUPPORTED -4
+
+/* raytracer_lib/src/raytracer/accel_intersect/oct_tree_intersector.rs:12 (re-exported lib.rs:7) */
+#define RT_DEFAULT_TRIANGLES_PER_LEAF 70
+#define RT_DEVICE_NONE (-2)
+
+typedef struct rt_scene rt_scene;         /* flattened scene on the host  (scene/mod.rs:24-29 `Scene`) */
+typedef struct rt_raytracer rt_raytracer; /* device-resident renderer     (raytracer/mod.rs:32-47 `RayTracer`) */
+
+/* ---- flattened scene description (structure-of-arrays) ------------------------------------------------ */
+
+enum { RT_DIFFUSE_COLOR = 0, RT_DIFFUSE_TEXTURE = 1 }; /* scene/color.rs:98-101 `Diffuse` */
+
+typedef struct rt_material { /* scene/mod.rs:63-69 `Material`; only `diffuse` is used by the path */
+    int32_t kind;            /* RT_DIFFUSE_COLOR / RT_DIFFUSE_TEXTURE */
+    float rgb[3];            /* Diffuse::Color */
+    uint32_t texture_id;     /* Diffuse::TextureId */
+} rt_material;
+
+typedef struct rt_light { /* scene/mod.rs:12-22 `Light` */
+    float pos[3];
+    float color[3];
+} rt_light;
+
+typedef struct rt_texture { /* scene/texture.rs:6-10 `Texture`, texels already byte/256 (texture.rs:40-46) */
+    uint32_t width, height;
+    const float* rgb; /* width*height*3 */
+} rt_texture;
+
+typedef struct rt_scene_desc {
+    uint32_t num_triangles;
+    const float* vertices;    /* num_triangles*9: v0 v1 v2 of every triangle, geometry order then triangle
+                                 order (Geometry::transformed_vertices, scene/mod.rs:46-61) */
+    const uint32_t* tri_geom; /* num_triangles: geometry index per triangle, non-decreasing */
+    uint32_t num_geometries;
+    const rt_material* materials; /* num_geometries */
+    uint32_t num_lights;
+    const rt_light* lights;
+    uint32_t num_textures;
+    const rt_texture* textures;
+    float camera_orientation[16]; /* cameras[0]: ColladaMatrix::to_vecmath_matrix of its node (row-vector convention) */
+    float camera_fov_deg;         /* xfov */
+} rt_scene_desc;
+
+/* ---- configuration ------------------------------------------------------------------------------------ */
+
+enum { RT_ACCEL_OCTREE = 0, /* flattened reference octree, traversal bit-identical to oct_tree_intersector.rs:148-272 */
+       RT_ACCEL_BVH = 1 };  /* SAH BVH, closest hit + lowest-index tie break + root-cube acceptance */
+enum { RT_JITTER_FIXED_HALF = 0, /* xi = (0.5, 0.5): the pinned parity mode */
+       RT_JITTER_HASHED = 1 };   /* xi = hash(seed, pixel, sample, axis) * 2^-24: stands in for StdRng::from_os_rng
+                                    (raytracer/mod.rs:84, scene/camera.rs:82-84) */
+
+typedef struct rt_config {
+    uint32_t width, height;
+    uint32_t triangles_per_leaf; /* create_raytracer's `triangles_per_leaf` (lib.rs:15); 0 = default 70 */
+    uint32_t rows_per_call;      /* rows traced by rt_trace_frame_additive; 0 = 50 (raytracer/mod.rs:87) */
+    int32_t recursions;          /* RECURSIONS (mod.rs:81): reference value 2; 0 = primary + shadow only */
+    uint32_t sub_spread;         /* SUB_SPREAD (mod.rs:82): reference value 1 */
+    int32_t jitter_mode;         /* RT_JITTER_* */
+    uint32_t seed;
+    int32_t accel;               /* RT_ACCEL_* */
+    int32_t device;              /* CUDA device ordinal; -1 = current device; RT_DEVICE_NONE = host-side handle
+                                    (construction, camera, acceleration-structure introspection; render calls
+                                    fail with RT_ERR_CUDA — used by CPU-only tests of the host logic) */
+    /* image sharding for one-process-per-GPU rendering: this instance owns the bands b (of `band_rows` rows)
+       with b % shard_count == shard_index. shard_count = 0 or 1 = whole image. */
+    uint32_t shard_index, shard_count, band_rows;
+} rt_config;
+
+/* Fills *cfg with the reference's defaults (recursions 2, spread 1, hashed jitter, 50 rows, 70 triangles/leaf). */
+void rt_config_default(rt_config* cfg, uint32_t width, uint32_t height);
+
+/* ---- scene loading: replaces scene/loaders (ColladaLoader::from_file / from_str, loaders/colladaloader.rs:22-46) -- */
+
+int rt_scene_load_file(const char* collada_filename, rt_scene** out, char* err, size_t err_len);
+int rt_scene_load_str(const char* collada_doc, const char* data_dir /* may be NULL */, rt_scene** out, char* err,
+                      size_t err_len);
+/* Pointers inside *desc stay valid until rt_scene_free. */
+int rt_scene_get_desc(const rt_scene* scene, rt_scene_desc* desc);
+void rt_scene_free(rt_scene* scene);
+
+/* ---- construction: replaces lib.rs:15-44 ------------------------------------------------------------- */
+
+/* create_raytracer(collada_doc, triangles_per_leaf, width, height) -> Result<RayTracer, String>   (lib.rs:15-20) */
+int rt_create_raytracer(const char* collada_doc, size_t triangles_per_leaf, size_t width, size_t height,
+                        rt_raytracer** out, char* err, size_t err_len);
+/* create_raytracer_from_file(collada_filename, triangles_per_leaf, width, height)                  (lib.rs:22-27) */
+int rt_create_raytracer_from_file(const char* collada_filename, size_t triangles_per_leaf, size_t width, size_t height,
+                                  rt_raytracer** out, char* err, size_t err_len);
+/* build_raytracer(scene, ...) (lib.rs:29-44) on an already flattened scene: the FFI entry a Rust host that keeps
+   its own Collada loader calls. */
+int rt_create(const rt_scene_desc* scene, const rt_config* cfg, rt_raytracer** out, char* err, size_t err_len);
+void rt_destroy(rt_raytracer* rt);
+const char* rt_last_error(const rt_raytracer* rt);
+
+/* Change pinned-mode switches after construction (rebuilds nothing except when `accel` changes). */
+int rt_configure(rt_raytracer* rt, int32_t recursions, uint32_t sub_spread, int32_t jitter_mode, uint32_t seed,
+                 int32_t accel);
+int rt_set_rows_per_call(rt_raytracer* rt, uint32_t rows);
+
+/* ---- the render loop: replaces raytracer/mod.rs:80-128 ------------------------------------------------ */
+
+/* RayTracer::trace_frame_additive(&mut self) -> u32   (mod.rs:80-117): traces `rows_per_call` rows starting at the
+   internal current row (wrapping modulo height), accumulates into the device film, returns rows*width. */
+int rt_trace_frame_additive(rt_raytracer* rt, uint32_t* num_primary_rays);
+/* Same loop over an explicit row range, `spp` passes: the whole-frame / multi-sample launch used by the benchmark.
+   n_primary / n_shadow (may be NULL) receive the rays issued by this call (shadow: one per (hit, light) with
+   n.l >= 0, mod.rs:218-226). */
+int rt_trace_rows(rt_raytracer* rt, uint32_t first_row, uint32_t n_rows, uint32_t spp, uint64_t* n_primary,
+                  uint64_t* n_shadow);
+/* RayTracer::get_tonemapped_pixels(&self) -> Vec<u32>   (mod.rs:120-128): width*height 0xAARRGGBB, caller-allocated. */
+int rt_get_tonemapped_pixels(rt_raytracer* rt, uint32_t* out);
+/* Film::clear (film.rs:37-41) through the pub field `film` (raytracer/src/main.rs:126). */
+int rt_film_clear(rt_raytracer* rt);
+/* Film contents: width*height*7 floats per pixel: sum rgb, sum of squares rgb, num_samples (film.rs:3-7). */
+int rt_get_film(rt_raytracer* rt, float* out);
+/* Parity hook: global triangle index (geometry order, then triangle order) of the last primary hit per pixel,
+   0xFFFFFFFF for a miss. */
+int rt_get_primary_ids(rt_raytracer* rt, uint32_t* out);
+
+/* ---- camera: the pub field `camera` (scene/camera.rs:63-78, used raytracer/src/main.rs:125-161) -------- */
+
+int rt_camera_move_rel(rt_raytracer* rt, float x, float y, float z);
+int rt_camera_add_x_angle(rt_raytracer* rt, float radians);
+int rt_camera_add_y_angle(rt_raytracer* rt, float radians);
+/* out34: rotation_matrix[16], orientation_matrix[16], max_x, max_y */
+int rt_camera_get(const rt_raytracer* rt, float* out34);
+/* Direct state injection for hosts that keep Camera in their own language: angles + position, then
+   update_matrices() (camera.rs:92-98). Uploads 128 bytes to the device on the next trace call. */
+int rt_camera_set_state(rt_raytracer* rt, float x_angle, float y_angle, const float pos[3]);
+
+/* ---- device-side access for multi-GPU gather and for timing on a caller-owned stream ------------------- */
+
+/* All later launches / copies of this handle are issued on `cuda_stream` (a cudaStream_t; NULL = default stream). */
+int rt_set_stream(rt_raytracer* rt, void* cuda_stream);
+/* Device pointer to the width*height packed LDR frame kept current by the trace kernel's epilogue. */
+int rt_get_ldr_device_ptr(rt_raytracer* rt, void** dev_ptr);
+/* Redirect the LDR stores of the rows this instance owns into `dev_ptr` (e.g. a peer-mapped framebuffer of
+   rank 0, or a torch tensor): the fused trace+gather path. NULL restores the internal buffer. */
+int rt_set_ldr_target(rt_raytracer* rt, void* dev_ptr);
+/* Copies only the rows owned by this shard, compacted (owned rows in ascending order), into dev_out. */
+int rt_get_owned_ldr_rows_device(rt_raytracer* rt, void* dev_out, uint32_t* n_rows);
+/* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
+typedef struct rt_launch_stats {
+    uint32_t kernels_launched; /* CUDA kernels launched by the call */
+    float trace_kernel_ms;     /* device time of the trace kernel(s), CUDA events on the launching stream */
+    uint64_t n_primary, n_shadow, n_bounce;
+} rt_launch_stats;
+int rt_get_launch_stats(const rt_raytracer* rt, rt_launch_stats* out);
+/* Total kernels launched by this handle since creation. */
+uint64_t rt_kernels_launched(const rt_raytracer* rt);
+
+/* ---- acceleration-structure introspection (parity of the build, oct_tree_intersector.rs:66-146) -------- */
+
+/* out[6]: nodes, inner nodes, leaves, empty leaves, triangle references, depth */
+int rt_octree_stats(const rt_raytracer* rt, uint64_t* out);
+/* cubes: nodes*6 (min xyz, max xyz); first_child: nodes (-1 = leaf); leaf_offset: nodes+1; leaf_tris: references.
+   Any pointer may be NULL. Returns the number of triangle references through *n_refs. */
+int rt_octree_export(const rt_raytracer* rt, float* cubes, int32_t* first_child, uint32_t* leaf_offset,
+                     uint32_t* leaf_tris, uint64_t* n_refs);
+/* out[4]: bvh nodes, leaves, max leaf size, depth */
+int rt_bvh_stats(const rt_raytracer* rt, uint64_t* out);
+/* boxes: nodes*12 (child0 lo xyz, hi xyz, child1 lo xyz, hi xyz); children: nodes*2 (>= 0 inner node, < 0 leaf with
+   ~child = first triangle slot); counts: nodes*2 (triangles of a leaf child); tri_order: slot -> global triangle. */
+int rt_bvh_export(const rt_raytracer* rt, float* boxes, int32_t* children, int32_t* counts, uint32_t* tri_order);
+
+/* ---- stats.rs / timing crate stand-ins ---------------------------------------------------------------- */
+
+typedef struct rt_stats rt_stats;             /* raytracer_lib/src/stats.rs:1-40 `Stats` */
+rt_stats* rt_stats_new(void);                 /* Stats::new */
+void rt_stats_free(rt_stats* s);
+/* Stats::stats(num_primary_rays) -> "fps: {}  primary rays/s: {}" */
+int rt_stats_stats(rt_stats* s, uint32_t num_primary_rays, char* out, size_t out_len);
+/* Stats::mean_stats() -> "mean fps: {}  mean primary rays/s: {}" */
+int rt_stats_mean_stats(const rt_stats* s, char* out, size_t out_len);
+
+typedef struct rt_benchmark rt_benchmark;     /* timing/src/lib.rs:6-59 `BenchMark` */
+rt_benchmark* rt_benchmark_new(void);
+void rt_benchmark_free(rt_benchmark* b);
+int rt_benchmark_start(rt_benchmark* b, const char* name);
+int rt_benchmark_stop(rt_benchmark* b, const char* name); /* RT_ERR_INVALID for an unknown name (the reference panics) */
+/* Display impl (timing/src/lib.rs:95-109): "{name} total: {}ms, mean: {}ms, samples: {}\n", sorted by total, descending */
+int rt_benchmark_report(const rt_benchmark* b, char* out, size_t out_len);
+
+/* Library identification: "rt_b200 <version> sm_100a". */
+const char* rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

@@ -1,0 +1,61 @@
+// device_types.h — layouts shared by the host upload code and the sm_100a kernels.
+//
+// Everything a ray touches is packed for 16-byte (LDG.128) loads:
+//   octree node   2 x float4 : (min.xyz | first_child or first triangle slot) (max.xyz | meta)
+//   bvh node      4 x float4 : both child boxes + child references
+//   triangle      3 x float4 : v0.xyz e1.x | e1.yz e2.xy | e2.z, global id, -, -        (e1 = v1-v0, e2 = v2-v0)
+//   shade record  1 x float4 : unit normal xyz | geometry index
+// e1/e2/normal are computed on the host with the same f32 operations the reference performs per ray
+// (intersect.rs:66-67, mod.rs:198-205), so precomputing them is bit-identical.
+#pragma once
+#include <cstdint>
+
+namespace rtb {
+
+struct DevCamera {
+    float rot[16];  // Camera::rotation_matrix
+    float pos[3];   // orientation_matrix * (0,0,0,1)
+    float max_x, max_y;
+    uint32_t width, height;
+};
+
+struct DevTexture {
+    const float* rgb;  // width*height*3
+    uint32_t width, height;
+};
+
+constexpr uint32_t kOctLeafFlag = 0x80000000u;
+constexpr uint32_t kNoHit = 0xFFFFFFFFu;
+constexpr int kOctStack = 64;  // >= 7 * depth + 1 with depth <= 9 (oct_tree_intersector.rs:108)
+constexpr int kBvhStack = 48;
+
+enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3, CNT_SLOTS = 4 };
+
+struct TraceParams {
+    DevCamera cam;
+    // acceleration structures (either may be null when not built)
+    const float4* oct_nodes;
+    const float4* oct_tris;
+    const float4* bvh_nodes;
+    const float4* bvh_tris;
+    // shading data
+    const float4* tri_shade;  // per global triangle
+    const float4* materials;  // per geometry: rgb | texture id or -1
+    const float4* lights;     // 2 per light: pos | color
+    const DevTexture* textures;
+    uint32_t num_lights;
+    // film
+    float4* film_sum;  // sum rgb | num_samples (uint bits)
+    float4* film_sq;   // sum of squares rgb
+    uint32_t* ldr;     // packed 0xAARRGGBB, kept current by the epilogue
+    uint32_t* ldr_remote;  // optional second target (peer-mapped framebuffer of rank 0), may be null
+    uint32_t* primary_ids;
+    unsigned long long* counters;
+    // work: compact rows [0, n_rows) -> image row (first_row + c) % height, or row_list[c] when non-null
+    const uint32_t* row_list;
+    uint32_t first_row, n_rows;
+    uint32_t jitter_mode, seed;
+    float root_lo[3], root_hi[3];  // scene AABB = octree root cube (acceptance rule of the BVH path)
+};
+
+}  // namespace rtb

@@ -1,0 +1,486 @@
+// kernels.cu — hand-written sm_100a kernels for the per-pixel render loop.
+//
+// One fused kernel per launch: camera ray (camera.rs:80-90) -> closest hit (octree: oct_tree_intersector.rs:148-272,
+// or BVH) -> normal -> per light: facing test, shadow closest hit, Phong + texture (mod.rs:207-261) -> film add
+// (film.rs:20-24) -> mean, tonemap, pack (film.rs:43-48, tonemap.rs:4-10, color.rs:89-95) stored to the LDR frame.
+//
+// Numerics: every operation whose result can change a pixel uses the explicit round-to-nearest intrinsics
+// (__fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn/__fsqrt_rn). They are never contracted into FMAs, so the results are
+// bit-identical to the reference's Rust f32 arithmetic (and to oracle/rt_oracle.cpp) regardless of compiler flags.
+// BVH box tests are allowed to use FMAs because the boxes are padded and only decide which triangles get tested.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+
+#include "device_types.h"
+#include "kernels.h"
+
+namespace rtb {
+
+// ------------------------------------------------------------------------------------------------------
+// exact f32 helpers
+// ------------------------------------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return {fsub(a.x, b.x), fsub(a.y, b.y), fsub(a.z, b.z)}; }
+__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return {fadd(a.x, b.x), fadd(a.y, b.y), fadd(a.z, b.z)}; }
+__device__ __forceinline__ V3 vscale(V3 a, float s) { return {fmul(a.x, s), fmul(a.y, s), fmul(a.z, s)}; }
+__device__ __forceinline__ float vdot(V3 a, V3 b) {  // vecmath.rs:74-76, left to right
+    return fadd(fadd(fmul(a.x, b.x), fmul(a.y, b.y)), fmul(a.z, b.z));
+}
+__device__ __forceinline__ V3 vcross(V3 a, V3 b) {  // vecmath.rs:79-85
+    return {fsub(fmul(a.y, b.z), fmul(a.z, b.y)), fsub(fmul(a.z, b.x), fmul(a.x, b.z)), fsub(fmul(a.x, b.y), fmul(a.y, b.x))};
+}
+__device__ __forceinline__ V3 vunit(V3 v) {  // Vec3::normalized, vecmath.rs:23-26
+    const float len = __fsqrt_rn(fadd(fadd(fmul(v.x, v.x), fmul(v.y, v.y)), fmul(v.z, v.z)));
+    return {fdiv(v.x, len), fdiv(v.y, len), fdiv(v.z, len)};
+}
+
+struct HitRec {
+    float t, u, v;
+    uint32_t tri;  // global triangle index
+};
+
+// counter-based generator shared with the oracle (rt_oracle.cpp: mix32/hash4/u01)
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x7feb352dU;
+    h ^= h >> 15;
+    h *= 0x846ca68bU;
+    h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ uint32_t hash4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t h = mix32(a + 0x9e3779b9U);
+    h = mix32(h ^ (b + 0x85ebca6bU));
+    h = mix32(h ^ (c + 0xc2b2ae35U));
+    h = mix32(h ^ (d + 0x27d4eb2fU));
+    return h;
+}
+__device__ __forceinline__ float u01(uint32_t h) { return fmul((float)(h >> 8), 1.0f / 16777216.0f); }
+
+// ------------------------------------------------------------------------------------------------------
+// Moller-Trumbore, "late out" variant (intersect.rs:62-98) on a packed triangle record
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool moller_trumbore(const V3& o, const V3& d, const float4 t0, const float4 t1, const float4 t2, float* t,
+                                                float* u, float* v) {
+    const V3 v0 = {t0.x, t0.y, t0.z};
+    const V3 e1 = {t0.w, t1.x, t1.y};
+    const V3 e2 = {t1.z, t1.w, t2.x};
+    const V3 pvec = vcross(d, e2);
+    const float det = vdot(e1, pvec);
+    if (fabsf(det) < FLT_EPSILON) return false;
+    const float inv_det = fdiv(1.0f, det);
+    const V3 tvec = vsub(o, v0);
+    const float uu = fmul(vdot(tvec, pvec), inv_det);
+    const V3 qvec = vcross(tvec, e1);
+    const float vv = fmul(vdot(d, qvec), inv_det);
+    const float tt = fmul(vdot(e2, qvec), inv_det);
+    if (uu < 0.0f || uu > 1.0f) return false;
+    if (vv < 0.0f || fadd(uu, vv) > 1.0f) return false;
+    if (tt < 0.0f) return false;
+    *t = tt;
+    *u = uu;
+    *v = vv;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// exact octree traversal (oct_tree_intersector.rs:148-196, 240-272, 348-372)
+//
+// The recursion becomes an explicit stack: an inner node slab-tests its 8 children, and pushes the hit ones in
+// DESCENDING (t, child) order so they pop in the stable ascending order of the reference's sort_by. The 8 child
+// cubes are not loaded: they are (min | mid | max) selections of the parent's cube, with
+// mid = 0.5*(max+min) evaluated exactly as generate_child_cubes (:275) did when the stored cubes were built, so
+// the 48 subtractions/multiplications of the reference collapse to 9 with identical values.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool octree_closest_hit(const TraceParams& P, const V3& o, const V3& d, HitRec* out) {
+    const V3 inv = {fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z)};  // :241-244
+    int stack[kOctStack];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const int node = stack[--sp];
+        const float4 A = __ldg(&P.oct_nodes[2 * node]);
+        const float4 B = __ldg(&P.oct_nodes[2 * node + 1]);
+        const uint32_t meta = __float_as_uint(B.w);
+        if (meta & kOctLeafFlag) {
+            // ---- leaf: closest triangle of the list (strict <, first wins ties), then the in-cube test ----
+            const uint32_t count = meta & ~kOctLeafFlag;
+            const float4* tri = P.oct_tris + 3 * (size_t)__float_as_uint(A.w);
+            bool have = false;
+            HitRec best;
+            best.t = 0.f;
+            best.u = 0.f;
+            best.v = 0.f;
+            best.tri = kNoHit;
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4 t0 = __ldg(tri + 3 * i), t1 = __ldg(tri + 3 * i + 1), t2 = __ldg(tri + 3 * i + 2);
+                float t, u, v;
+                if (!moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) continue;
+                if (!have || t < best.t) {
+                    have = true;
+                    best.t = t;
+                    best.u = u;
+                    best.v = v;
+                    best.tri = __float_as_uint(t2.y);
+                }
+            }
+            if (have) {
+                const V3 hp = vadd(o, vscale(d, best.t));  // ray.pos + ray.dir * t  (:164)
+                const bool outside = hp.x < A.x || hp.x > B.x || hp.y < A.y || hp.y > B.y || hp.z < A.z || hp.z > B.z;
+                if (!outside) {
+                    *out = best;
+                    return true;
+                }
+            }
+            continue;
+        }
+        // ---- inner node ----
+        const int first_child = (int)__float_as_uint(A.w);
+        uint32_t live = meta & 0xffu;  // children that hold at least one triangle (empty leaves return None at once)
+        const float midx = fmul(0.5f, fadd(B.x, A.x)), midy = fmul(0.5f, fadd(B.y, A.y)), midz = fmul(0.5f, fadd(B.z, A.z));
+        const float xl = fmul(fsub(A.x, o.x), inv.x), xm = fmul(fsub(midx, o.x), inv.x), xh = fmul(fsub(B.x, o.x), inv.x);
+        const float yl = fmul(fsub(A.y, o.y), inv.y), ym = fmul(fsub(midy, o.y), inv.y), yh = fmul(fsub(B.y, o.y), inv.y);
+        const float zl = fmul(fsub(A.z, o.z), inv.z), zm = fmul(fsub(midz, o.z), inv.z), zh = fmul(fsub(B.z, o.z), inv.z);
+        const float nx[2] = {fminf(xl, xm), fminf(xm, xh)}, fx[2] = {fmaxf(xl, xm), fmaxf(xm, xh)};
+        const float ny[2] = {fminf(yl, ym), fminf(ym, yh)}, fy[2] = {fmaxf(yl, ym), fmaxf(ym, yh)};
+        const float nz[2] = {fminf(zl, zm), fminf(zm, zh)}, fz[2] = {fmaxf(zl, zm), fmaxf(zm, zh)};
+        float tc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float tmin = fmaxf(fmaxf(nx[c & 1], ny[(c >> 1) & 1]), nz[c >> 2]);
+            const float tmax = fminf(fminf(fx[c & 1], fy[(c >> 1) & 1]), fz[c >> 2]);
+            tc[c] = tmin;
+            if (!(tmax >= tmin && tmax > 0.0f)) live &= ~(1u << c);
+        }
+        while (live) {
+            int pick = -1;
+            float pt = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if ((live >> c) & 1u) {
+                    if (pick < 0 || tc[c] >= pt) {
+                        pick = c;
+                        pt = tc[c];
+                    }
+                }
+            }
+            live &= ~(1u << pick);
+            stack[sp++] = first_child + pick;
+        }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// BVH traversal: true closest hit with the reference's tie rule (lowest global triangle index wins equal t,
+// oct_tree_intersector.rs:258-268 + :332-342) followed by the root-cube acceptance rule (:164-169 applied to
+// the scene AABB). `t_limit` (exclusive) clips the search; `early_t`: any hit with t <= early_t ends
+// the search at once (shadow rays: such a hit makes the point lit whatever lies beyond, mod.rs:226-230).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool bvh_closest_hit(const TraceParams& P, const V3& o, const V3& d, float t_limit, float early_t, HitRec* out) {
+    const float ix = fdiv(1.0f, d.x), iy = fdiv(1.0f, d.y), iz = fdiv(1.0f, d.z);
+    const float ox = -o.x * ix, oy = -o.y * iy, oz = -o.z * iz;
+    int stack_node[kBvhStack];
+    float stack_t[kBvhStack];
+    int sp = 0;
+    HitRec best;
+    best.t = t_limit;
+    best.u = 0.f;
+    best.v = 0.f;
+    best.tri = kNoHit;
+    int cur = 0;
+    for (;;) {
+        if (cur >= 0) {
+            const float4* n = P.bvh_nodes + 4 * (size_t)cur;
+            const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+            // child 0: lo = (q0.x q0.y q0.z) hi = (q0.w q1.x q1.y); child 1: lo = (q1.z q1.w q2.x) hi = (q2.y q2.z q2.w)
+            const float a0x = fmaf(q0.x, ix, ox), b0x = fmaf(q0.w, ix, ox);
+            const float a0y = fmaf(q0.y, iy, oy), b0y = fmaf(q1.x, iy, oy);
+            const float a0z = fmaf(q0.z, iz, oz), b0z = fmaf(q1.y, iz, oz);
+            const float a1x = fmaf(q1.z, ix, ox), b1x = fmaf(q2.y, ix, ox);
+            const float a1y = fmaf(q1.w, iy, oy), b1y = fmaf(q2.z, iy, oy);
+            const float a1z = fmaf(q2.x, iz, oz), b1z = fmaf(q2.w, iz, oz);
+            const float n0 = fmaxf(fmaxf(fminf(a0x, b0x), fminf(a0y, b0y)), fmaxf(fminf(a0z, b0z), 0.0f));
+            const float f0 = fminf(fminf(fmaxf(a0x, b0x), fmaxf(a0y, b0y)), fminf(fmaxf(a0z, b0z), best.t));
+            const float n1 = fmaxf(fmaxf(fminf(a1x, b1x), fminf(a1y, b1y)), fmaxf(fminf(a1z, b1z), 0.0f));
+            const float f1 = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), best.t));
+            const bool h0 = n0 <= f0, h1 = n1 <= f1;
+            const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+            if (h0 && h1) {
+                const bool first0 = n0 <= n1;
+                stack_node[sp] = first0 ? c1 : c0;
+                stack_t[sp] = first0 ? n1 : n0;
+                ++sp;
+                cur = first0 ? c0 : c1;
+                continue;
+            }
+            if (h0) {
+                cur = c0;
+                continue;
+            }
+            if (h1) {
+                cur = c1;
+                continue;
+            }
+        } else {
+            const uint32_t ref = (uint32_t)~cur;
+            const uint32_t count = ref & 15u;
+            const float4* tri = P.bvh_tris + 3 * (size_t)(ref >> 4);
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4 t0 = __ldg(tri + 3 * i), t1 = __ldg(tri + 3 * i + 1), t2 = __ldg(tri + 3 * i + 2);
+                float t, u, v;
+                if (!moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) continue;
+                const uint32_t id = __float_as_uint(t2.y);
+                if (t < best.t || (t == best.t && id < best.tri)) {
+                    best.t = t;
+                    best.u = u;
+                    best.v = v;
+                    best.tri = id;
+                    if (t <= early_t) {
+                        *out = best;
+                        return true;
+                    }
+                }
+            }
+        }
+        // pop, skipping subtrees that start beyond the current closest hit
+        for (;;) {
+            if (sp == 0) goto done;
+            --sp;
+            if (stack_t[sp] <= best.t) {
+                cur = stack_node[sp];
+                break;
+            }
+        }
+    }
+done:
+    if (best.tri == kNoHit) return false;
+    const V3 hp = vadd(o, vscale(d, best.t));
+    const bool outside = hp.x < P.root_lo[0] || hp.x > P.root_hi[0] || hp.y < P.root_lo[1] || hp.y > P.root_hi[1] || hp.z < P.root_lo[2] ||
+                         hp.z > P.root_hi[2];
+    if (outside) return false;
+    *out = best;
+    return true;
+}
+
+template <int ACCEL>
+__device__ __forceinline__ bool closest_hit(const TraceParams& P, const V3& o, const V3& d, HitRec* out) {
+    if (ACCEL == 0) return octree_closest_hit(P, o, d, out);
+    return bvh_closest_hit(P, o, d, FLT_MAX, -1.0f, out);
+}
+// blocked <=> the closest hit has 0.01 < t < 1.0 (mod.rs:226-230)
+template <int ACCEL>
+__device__ __forceinline__ bool shadow_blocked(const TraceParams& P, const V3& o, const V3& d) {
+    HitRec h;
+    if (ACCEL == 0) {
+        if (!octree_closest_hit(P, o, d, &h)) return false;
+        return h.t > 0.01f && h.t < 1.0f;
+    }
+    // BVH: hits with t >= 1 can never block, a hit with t <= 0.01 decides "lit" immediately
+    if (!bvh_closest_hit(P, o, d, 1.0f, 0.01f, &h)) return false;
+    return h.t > 0.01f && h.t < 1.0f;
+}
+
+// x^32 by five squarings in binary64, rounded once to binary32: the correctly rounded value of powf(x, 32)
+// (glibc's powf, which the reference reaches through f32::powf, is within 1 ulp of it; mod.rs:255)
+__device__ __forceinline__ float pow32(float x) {
+    double p = (double)x;
+    p *= p;
+    p *= p;
+    p *= p;
+    p *= p;
+    p *= p;
+    return (float)p;
+}
+
+__device__ __forceinline__ uint32_t to_u8(float x) {  // color.rs:89-93: (x.min(1).max(0) * 255) as u8
+    return __float2uint_rz(fmul(fmaxf(fminf(x, 1.0f), 0.0f), 255.0f));
+}
+__device__ __forceinline__ uint32_t tonemap_pack(float sr, float sg, float sb, uint32_t n) {
+    const float inv = fdiv(1.0f, (float)n);  // film.rs:46: pixel_sum * (1.0 / num_samples as f32)
+    const float r = fmul(sr, inv), g = fmul(sg, inv), b = fmul(sb, inv);
+    const float mr = fdiv(r, fadd(1.0f, r)), mg = fdiv(g, fadd(1.0f, g)), mb = fdiv(b, fadd(1.0f, b));  // tonemap.rs:4-10
+    return to_u8(mb) | (to_u8(mg) << 8) | (to_u8(mr) << 16) | (255u << 24);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// the fused trace + shade + film kernel.  Block = 8 warps, each warp an 8x4 pixel tile, block = 32x8 pixels.
+// ------------------------------------------------------------------------------------------------------
+template <int ACCEL>
+__global__ void __launch_bounds__(256) trace_shade_kernel(const __grid_constant__ TraceParams P) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t col = blockIdx.x * 32u + (warp & 3u) * 8u + (lane & 7u);
+    const uint32_t crow = blockIdx.y * 8u + (warp >> 2) * 4u + (lane >> 3);
+    const uint32_t W = P.cam.width, H = P.cam.height;
+    const bool active = col < W && crow < P.n_rows;
+    uint32_t shadow_rays = 0, prim_hit = 0, blocked_cnt = 0;
+    if (active) {
+        const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % H;
+        const uint32_t idx = row * W + col;
+        float4 fs_ = P.film_sum[idx];
+        const uint32_t nsamp = __float_as_uint(fs_.w);
+        float xi1 = 0.5f, xi2 = 0.5f;
+        if (P.jitter_mode == 1) {
+            xi1 = u01(hash4(P.seed, idx, nsamp, 0));
+            xi2 = u01(hash4(P.seed, idx, nsamp, 1));
+        }
+        // camera.rs:80-90 with (u, v) = (idx % width, idx / height)  [sic, mod.rs:96]
+        const uint32_t pu = idx % W, pv = idx / H;
+        const float dir_x = fadd(-P.cam.max_x, fmul(fmul(2.0f, P.cam.max_x), fdiv(fadd((float)pu, xi1), (float)W)));
+        const float dir_y = fadd(-P.cam.max_y, fmul(fmul(2.0f, P.cam.max_y), fdiv(fadd((float)pv, xi2), (float)H)));
+        const float ndy = -dir_y;
+        const float* R = P.cam.rot;
+        V3 d;
+        d.x = fadd(fadd(fadd(fmul(dir_x, R[0]), fmul(ndy, R[4])), fmul(1.0f, R[8])), fmul(1.0f, R[12]));
+        d.y = fadd(fadd(fadd(fmul(dir_x, R[1]), fmul(ndy, R[5])), fmul(1.0f, R[9])), fmul(1.0f, R[13]));
+        d.z = fadd(fadd(fadd(fmul(dir_x, R[2]), fmul(ndy, R[6])), fmul(1.0f, R[10])), fmul(1.0f, R[14]));
+        const V3 o = {P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]};
+
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        HitRec hit;
+        uint32_t id = kNoHit;
+        if (closest_hit<ACCEL>(P, o, d, &hit)) {
+            prim_hit = 1;
+            id = hit.tri;
+            const float4 sh = __ldg(&P.tri_shade[hit.tri]);
+            const V3 nrm = {sh.x, sh.y, sh.z};
+            const uint32_t geom = __float_as_uint(sh.w);
+            const V3 hp = vadd(o, vscale(d, hit.t));  // ray.pos + t * ray.dir  (mod.rs:212)
+            for (uint32_t li = 0; li < P.num_lights; ++li) {
+                const float4 lp = __ldg(&P.lights[2 * li]), lc = __ldg(&P.lights[2 * li + 1]);
+                const V3 L = vsub(V3{lp.x, lp.y, lp.z}, hp);
+                const V3 Ln = vunit(L);
+                const float ndl = vdot(nrm, Ln);
+                if (ndl < 0.0f) continue;
+                ++shadow_rays;
+                const V3 so = vadd(hp, vscale(L, 0.01f));
+                if (shadow_blocked<ACCEL>(P, so, L)) {
+                    ++blocked_cnt;
+                    continue;
+                }
+                const float4 mat = __ldg(&P.materials[geom]);
+                float dr = mat.x, dg = mat.y, db = mat.z;
+                const int tex = __float_as_int(mat.w);
+                if (tex >= 0) {  // Texture::get_texel(hit.u, hit.v), texture.rs:21-27 (index clamped instead of panicking)
+                    const DevTexture T = P.textures[tex];
+                    const float fx = fmul(hit.u, (float)T.width), fy = fmul(hit.v, (float)T.height);
+                    const size_t x = fx > 0.0f ? (size_t)__float2ull_rz(fx) : 0, y = fy > 0.0f ? (size_t)__float2ull_rz(fy) : 0;
+                    size_t ti = y * T.width + x;
+                    const size_t last = (size_t)T.width * T.height - 1;
+                    if (ti > last) ti = last;
+                    dr = T.rgb[3 * ti];
+                    dg = T.rgb[3 * ti + 1];
+                    db = T.rgb[3 * ti + 2];
+                }
+                const V3 view = vunit(d);
+                const V3 refl = vsub(vscale(nrm, fmul(2.0f, ndl)), Ln);  // 2.0 * ndl * normal - normalize(L)
+                const float spec = pow32(vdot(view, refl));
+                cr = fadd(cr, fmul(fadd(fmul(dr, ndl), spec), lc.x));
+                cg = fadd(cg, fmul(fadd(fmul(dg, ndl), spec), lc.y));
+                cb = fadd(cb, fmul(fadd(fmul(db, ndl), spec), lc.z));
+            }
+        }
+        // add_sample (film.rs:20-24)
+        float4 sq = P.film_sq[idx];
+        fs_.x = fadd(fs_.x, cr);
+        fs_.y = fadd(fs_.y, cg);
+        fs_.z = fadd(fs_.z, cb);
+        sq.x = fadd(sq.x, fmul(cr, cr));
+        sq.y = fadd(sq.y, fmul(cg, cg));
+        sq.z = fadd(sq.z, fmul(cb, cb));
+        const uint32_t n_new = nsamp + 1u;
+        fs_.w = __uint_as_float(n_new);
+        P.film_sum[idx] = fs_;
+        P.film_sq[idx] = sq;
+        P.primary_ids[idx] = id;
+        const uint32_t px = tonemap_pack(fs_.x, fs_.y, fs_.z, n_new);
+        P.ldr[idx] = px;
+        if (P.ldr_remote) P.ldr_remote[idx] = px;
+    }
+    // ray counters: warp reduce, one atomic per warp and counter
+    shadow_rays = __reduce_add_sync(0xffffffffu, shadow_rays);
+    prim_hit = __reduce_add_sync(0xffffffffu, prim_hit);
+    blocked_cnt = __reduce_add_sync(0xffffffffu, blocked_cnt);
+    if (lane == 0) {
+        if (shadow_rays) atomicAdd(&P.counters[CNT_SHADOW], (unsigned long long)shadow_rays);
+        if (prim_hit) atomicAdd(&P.counters[CNT_PRIMARY_HITS], (unsigned long long)prim_hit);
+        if (blocked_cnt) atomicAdd(&P.counters[CNT_BLOCKED], (unsigned long long)blocked_cnt);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// film clear / full-frame tonemap / owned-row compaction
+// ------------------------------------------------------------------------------------------------------
+__global__ void film_clear_kernel(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sum[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+    sq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ldr[i] = 0xFFFFFFFFu;  // mean of zero samples is NaN -> every channel 255
+    ids[i] = kNoHit;
+}
+
+// RayTracer::get_tonemapped_pixels over the whole film (mod.rs:120-128); 4 pixels per thread, 16-byte stores
+__global__ void tonemap_pack_kernel(const float4* __restrict__ sum, uint32_t* __restrict__ ldr, uint32_t n) {
+    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i4 >= n) return;
+    uint32_t px[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (i4 + k < n) {
+            const float4 s = sum[i4 + k];
+            px[k] = tonemap_pack(s.x, s.y, s.z, __float_as_uint(s.w));
+        } else
+            px[k] = 0;
+    }
+    if (i4 + 3 < n && (n % 4u) == 0u) {
+        *reinterpret_cast<uint4*>(ldr + i4) = make_uint4(px[0], px[1], px[2], px[3]);
+    } else {
+        for (int k = 0; k < 4 && i4 + k < n; ++k) ldr[i4 + k] = px[k];
+    }
+}
+
+__global__ void gather_rows_kernel(const uint32_t* __restrict__ ldr, const uint32_t* __restrict__ row_list, uint32_t n_rows, uint32_t width,
+                                   uint32_t* __restrict__ out) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = blockIdx.y;
+    if (x < width && r < n_rows) out[(size_t)r * width + x] = ldr[(size_t)row_list[r] * width + x];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------------
+cudaError_t launch_trace(const TraceParams& p, int accel, cudaStream_t stream) {
+    if (p.n_rows == 0) return cudaSuccess;
+    dim3 grid((p.cam.width + 31u) / 32u, (p.n_rows + 7u) / 8u);
+    if (accel == 0)
+        trace_shade_kernel<0><<<grid, 256, 0, stream>>>(p);
+    else
+        trace_shade_kernel<1><<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream) {
+    film_clear_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(sum, sq, ldr, ids, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_tonemap(const float4* sum, uint32_t* ldr, uint32_t n, cudaStream_t stream) {
+    const uint32_t threads = (n + 3u) / 4u;
+    tonemap_pack_kernel<<<(threads + 255u) / 256u, 256, 0, stream>>>(sum, ldr, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_gather_rows(const uint32_t* ldr, const uint32_t* row_list, uint32_t n_rows, uint32_t width, uint32_t* out, cudaStream_t stream) {
+    if (n_rows == 0) return cudaSuccess;
+    dim3 grid((width + 255u) / 256u, n_rows);
+    gather_rows_kernel<<<grid, 256, 0, stream>>>(ldr, row_list, n_rows, width, out);
+    return cudaGetLastError();
+}
+
+}  // namespace rtb

@@ -1,0 +1,16 @@
+// kernels.h — launchers of the sm_100a kernels (defined in kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+
+namespace rtb {
+
+// fused primary ray -> closest hit -> shadow rays -> Phong/texture -> film -> tonemap/pack
+cudaError_t launch_trace(const TraceParams& p, int accel, cudaStream_t stream);
+cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream);
+cudaError_t launch_tonemap(const float4* sum, uint32_t* ldr, uint32_t n, cudaStream_t stream);
+cudaError_t launch_gather_rows(const uint32_t* ldr, const uint32_t* row_list, uint32_t n_rows, uint32_t width, uint32_t* out,
+                               cudaStream_t stream);
+
+}  // namespace rtb

@@ -1,0 +1,776 @@
+// raytracer.cu — device-resident RayTracer and the C ABI declared in include/rt_b200.h.
+//
+// Host-side mirror of raytracer_lib's public surface (lib.rs:15-44, raytracer/mod.rs:32-128): construction wires
+// loader -> acceleration structure -> renderer, the render calls launch the fused kernel of kernels.cu on the
+// handle's stream. There is deliberately no CPU rendering path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "accel_build.h"
+#include "device_types.h"
+#include "host_scene.h"
+#include "kernels.h"
+
+using namespace rtb;
+
+struct rt_scene {
+    HostScene scene;
+};
+
+namespace {
+
+struct CudaFail {
+    std::string what;
+};
+#define RT_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) throw CudaFail{std::string(#expr) + ": " + cudaGetErrorString(e__)};     \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        RT_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+        n = count;
+    }
+    void upload(const std::vector<T>& h, cudaStream_t s) {
+        alloc(h.size());
+        if (!h.empty()) RT_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+};
+
+void copy_err(const std::string& msg, char* err, size_t err_len) {
+    if (err && err_len) {
+        std::snprintf(err, err_len, "%s", msg.c_str());
+    }
+}
+
+}  // namespace
+
+struct rt_raytracer {
+    rt_config cfg{};
+    HostScene scene;
+    HostCamera camera;
+    FlatOctree octree;
+    bool octree_built = false;
+    FlatBvh bvh;
+    bool bvh_built = false;
+    std::string last_error;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+
+    // device data
+    DevBuf<float4> d_oct_nodes, d_oct_tris, d_bvh_nodes, d_bvh_tris, d_tri_shade, d_materials, d_lights;
+    std::vector<std::unique_ptr<DevBuf<float>>> d_tex_data;
+    DevBuf<DevTexture> d_textures;
+    DevBuf<float4> d_film_sum, d_film_sq;
+    DevBuf<uint32_t> d_ldr, d_ids, d_row_list, d_owned_rows;
+    DevBuf<unsigned long long> d_counters;
+    unsigned long long* h_counters = nullptr;  // pinned
+    uint32_t* ldr_remote = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+
+    // host state
+    uint32_t current_row = 0;
+    std::vector<uint32_t> owned_rows;       // all rows of this shard, ascending
+    std::vector<uint32_t> row_list_cache;   // rows of the last sharded / wrapped launch
+    uint32_t cached_first = ~0u, cached_n = ~0u;
+    uint64_t total_kernels = 0;
+    rt_launch_stats last{};
+    bool stats_pending = false;
+
+    ~rt_raytracer() {
+        if (h_counters) cudaFreeHost(h_counters);
+        if (ev_start) cudaEventDestroy(ev_start);
+        if (ev_stop) cudaEventDestroy(ev_stop);
+    }
+
+    bool host_only = false;  // cfg.device == RT_DEVICE_NONE: construction, camera and accel introspection only
+    void bind_device() {
+        if (host_only) throw CudaFail{"this handle was created with RT_DEVICE_NONE (host-side introspection only); rendering needs a B200"};
+        RT_CUDA(cudaSetDevice(device));
+    }
+    uint32_t npix() const { return cfg.width * cfg.height; }
+    bool sharded() const { return cfg.shard_count > 1; }
+    bool owns_row(uint32_t r) const {
+        if (!sharded()) return true;
+        return ((r / cfg.band_rows) % cfg.shard_count) == cfg.shard_index;
+    }
+
+    void init(const HostScene& sc, const rt_config& c) {
+        cfg = c;
+        if (cfg.width == 0 || cfg.height == 0) throw CudaFail{"width and height must be positive"};
+        if (cfg.triangles_per_leaf == 0) cfg.triangles_per_leaf = RT_DEFAULT_TRIANGLES_PER_LEAF;
+        if (cfg.rows_per_call == 0) cfg.rows_per_call = 50;
+        if (cfg.band_rows == 0) cfg.band_rows = 8;
+        if (cfg.shard_count == 0) cfg.shard_count = 1;
+        if (cfg.shard_index >= cfg.shard_count) throw CudaFail{"shard_index out of range"};
+        scene = sc;
+        camera.init(cfg.width, cfg.height, scene.camera_orientation, scene.camera_fov_deg);
+        for (uint32_t r = 0; r < cfg.height; ++r)
+            if (owns_row(r)) owned_rows.push_back(r);
+        if (cfg.device == RT_DEVICE_NONE) {
+            host_only = true;
+            return;
+        }
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw CudaFail{std::string("no CUDA device available (") + cudaGetErrorString(e) + "); rt_b200 has no CPU fallback"};
+        if (cfg.device >= 0) {
+            device = cfg.device;
+        } else {
+            RT_CUDA(cudaGetDevice(&device));
+        }
+        bind_device();
+        cudaDeviceProp prop;
+        RT_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) throw CudaFail{std::string("device '") + prop.name + "' is not sm_100 (Blackwell B200); rt_b200 ships sm_100a code only"};
+        RT_CUDA(cudaEventCreate(&ev_start));
+        RT_CUDA(cudaEventCreate(&ev_stop));
+        RT_CUDA(cudaHostAlloc((void**)&h_counters, CNT_SLOTS * sizeof(unsigned long long), cudaHostAllocDefault));
+        d_counters.alloc(CNT_SLOTS);
+        upload_scene();
+        ensure_accel(cfg.accel);
+        d_film_sum.alloc(npix());
+        d_film_sq.alloc(npix());
+        d_ldr.alloc(npix());
+        d_ids.alloc(npix());
+        d_owned_rows.upload(owned_rows, stream);
+        film_clear();
+        RT_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void upload_scene() {
+        const uint32_t nt = scene.num_triangles();
+        std::vector<float4> shade(nt);
+        for (uint32_t t = 0; t < nt; ++t) {
+            const float* v = &scene.vertices[9 * (size_t)t];
+            const f3 v0{v[0], v[1], v[2]}, v1{v[3], v[4], v[5]}, v2{v[6], v[7], v[8]};
+            const f3 n = unit3(cross3(v1 - v0, v2 - v0));  // calc_normal, mod.rs:198-205
+            uint32_t g = scene.tri_geom[t];
+            float gw;
+            std::memcpy(&gw, &g, 4);
+            shade[t] = make_float4(n.x, n.y, n.z, gw);
+        }
+        d_tri_shade.upload(shade, stream);
+        std::vector<float4> mats(scene.materials.size());
+        for (size_t g = 0; g < mats.size(); ++g) {
+            const rt_material& m = scene.materials[g];
+            int32_t tex = m.kind == RT_DIFFUSE_TEXTURE ? (int32_t)m.texture_id : -1;
+            if (tex >= (int32_t)scene.textures.size()) throw CudaFail{"material references a texture that does not exist"};
+            float tw;
+            std::memcpy(&tw, &tex, 4);
+            mats[g] = make_float4(m.rgb[0], m.rgb[1], m.rgb[2], tw);
+        }
+        d_materials.upload(mats, stream);
+        std::vector<float4> lights;
+        for (const rt_light& l : scene.lights) {
+            lights.push_back(make_float4(l.pos[0], l.pos[1], l.pos[2], 0.f));
+            lights.push_back(make_float4(l.color[0], l.color[1], l.color[2], 0.f));
+        }
+        d_lights.upload(lights, stream);
+        std::vector<DevTexture> tex;
+        for (const HostTexture& t : scene.textures) {
+            auto buf = std::make_unique<DevBuf<float>>();
+            buf->upload(t.rgb, stream);
+            tex.push_back(DevTexture{buf->p, t.width, t.height});
+            d_tex_data.push_back(std::move(buf));
+        }
+        d_textures.upload(tex, stream);
+    }
+
+    static float4 tri_word0(const float* v) { return make_float4(v[0], v[1], v[2], v[3] - v[0]); }
+    static void pack_triangle(const float* v, uint32_t id, float4* out) {
+        // e1 = v1 - v0, e2 = v2 - v0: the subtractions intersect.rs:66-67 performs per ray
+        const float e1x = v[3] - v[0], e1y = v[4] - v[1], e1z = v[5] - v[2];
+        const float e2x = v[6] - v[0], e2y = v[7] - v[1], e2z = v[8] - v[2];
+        float idw;
+        std::memcpy(&idw, &id, 4);
+        out[0] = make_float4(v[0], v[1], v[2], e1x);
+        out[1] = make_float4(e1y, e1z, e2x, e2y);
+        out[2] = make_float4(e2z, idw, 0.f, 0.f);
+    }
+
+    void ensure_octree_host() {
+        if (octree_built) return;
+        octree = build_octree(scene, cfg.triangles_per_leaf);
+        octree_built = true;
+    }
+
+    void ensure_bvh_host() {
+        if (bvh_built) return;
+        bvh = build_bvh(scene, 4);
+        bvh_built = true;
+    }
+
+    void ensure_accel(int accel) {
+        if (accel == RT_ACCEL_OCTREE) {
+            ensure_octree_host();
+            if (d_oct_nodes.p) return;
+            if (octree.max_stack > (uint32_t)kOctStack) throw CudaFail{"octree deeper than the traversal stack"};
+            const size_t nn = octree.num_nodes();
+            std::vector<float4> nodes(2 * nn);
+            for (size_t i = 0; i < nn; ++i) {
+                const float* c = &octree.cubes[6 * i];
+                uint32_t a_w, b_w;
+                if (octree.first_child[i] < 0) {
+                    a_w = octree.leaf_offset[i];
+                    b_w = kOctLeafFlag | (octree.leaf_offset[i + 1] - octree.leaf_offset[i]);
+                } else {
+                    a_w = (uint32_t)octree.first_child[i];
+                    b_w = 0;
+                    for (int k = 0; k < 8; ++k) {
+                        const size_t ch = (size_t)octree.first_child[i] + k;
+                        const bool empty_leaf = octree.first_child[ch] < 0 && octree.leaf_offset[ch + 1] == octree.leaf_offset[ch];
+                        if (!empty_leaf) b_w |= 1u << k;
+                    }
+                }
+                float aw, bw;
+                std::memcpy(&aw, &a_w, 4);
+                std::memcpy(&bw, &b_w, 4);
+                nodes[2 * i] = make_float4(c[0], c[1], c[2], aw);
+                nodes[2 * i + 1] = make_float4(c[3], c[4], c[5], bw);
+            }
+            std::vector<float4> tris(3 * octree.leaf_tris.size());
+            for (size_t r = 0; r < octree.leaf_tris.size(); ++r) {
+                const uint32_t t = octree.leaf_tris[r];
+                pack_triangle(&scene.vertices[9 * (size_t)t], t, &tris[3 * r]);
+            }
+            d_oct_nodes.upload(nodes, stream);
+            d_oct_tris.upload(tris, stream);
+        } else if (accel == RT_ACCEL_BVH) {
+            if (d_bvh_nodes.p) return;
+            ensure_bvh_host();
+            if (bvh.depth + 2 > (uint32_t)kBvhStack) throw CudaFail{"BVH deeper than the traversal stack"};
+            std::vector<float4> nodes(4 * bvh.nodes.size());
+            for (size_t i = 0; i < bvh.nodes.size(); ++i) {
+                const FlatBvh::Node& n = bvh.nodes[i];
+                int32_t ref[2];
+                for (int k = 0; k < 2; ++k) {
+                    if (n.child[k] >= 0)
+                        ref[k] = n.child[k];
+                    else
+                        ref[k] = ~(int32_t)(((uint32_t)(~n.child[k]) << 4) | (uint32_t)n.count[k]);
+                }
+                float r0, r1;
+                std::memcpy(&r0, &ref[0], 4);
+                std::memcpy(&r1, &ref[1], 4);
+                nodes[4 * i + 0] = make_float4(n.lo[0][0], n.lo[0][1], n.lo[0][2], n.hi[0][0]);
+                nodes[4 * i + 1] = make_float4(n.hi[0][1], n.hi[0][2], n.lo[1][0], n.lo[1][1]);
+                nodes[4 * i + 2] = make_float4(n.lo[1][2], n.hi[1][0], n.hi[1][1], n.hi[1][2]);
+                nodes[4 * i + 3] = make_float4(r0, r1, 0.f, 0.f);
+            }
+            std::vector<float4> tris(3 * bvh.tri_order.size());
+            for (size_t s = 0; s < bvh.tri_order.size(); ++s) {
+                const uint32_t t = bvh.tri_order[s];
+                pack_triangle(&scene.vertices[9 * (size_t)t], t, &tris[3 * s]);
+            }
+            d_bvh_nodes.upload(nodes, stream);
+            d_bvh_tris.upload(tris, stream);
+        } else {
+            throw CudaFail{"unknown accel"};
+        }
+    }
+
+    void film_clear() {
+        RT_CUDA(launch_film_clear(d_film_sum.p, d_film_sq.p, d_ldr.p, d_ids.p, npix(), stream));
+        ++total_kernels;
+    }
+
+    void fill_params(TraceParams* p) {
+        std::memset(p, 0, sizeof(*p));
+        std::memcpy(p->cam.rot, camera.rotation.data(), 64);
+        const f3 o = camera.ray_origin();
+        p->cam.pos[0] = o.x;
+        p->cam.pos[1] = o.y;
+        p->cam.pos[2] = o.z;
+        p->cam.max_x = camera.max_x;
+        p->cam.max_y = camera.max_y;
+        p->cam.width = cfg.width;
+        p->cam.height = cfg.height;
+        p->oct_nodes = d_oct_nodes.p;
+        p->oct_tris = d_oct_tris.p;
+        p->bvh_nodes = d_bvh_nodes.p;
+        p->bvh_tris = d_bvh_tris.p;
+        p->tri_shade = d_tri_shade.p;
+        p->materials = d_materials.p;
+        p->lights = d_lights.p;
+        p->textures = d_textures.p;
+        p->num_lights = (uint32_t)scene.lights.size();
+        p->film_sum = d_film_sum.p;
+        p->film_sq = d_film_sq.p;
+        p->ldr = d_ldr.p;
+        p->ldr_remote = ldr_remote;
+        p->primary_ids = d_ids.p;
+        p->counters = d_counters.p;
+        p->jitter_mode = (uint32_t)cfg.jitter_mode;
+        p->seed = cfg.seed;
+        // scene AABB (= octree root cube, calc_extents :315-330)
+        float lo[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, hi[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+        for (size_t k = 0; k < scene.vertices.size(); ++k) {
+            lo[k % 3] = std::fmin(lo[k % 3], scene.vertices[k]);
+            hi[k % 3] = std::fmax(hi[k % 3], scene.vertices[k]);
+        }
+        std::memcpy(p->root_lo, lo, 12);
+        std::memcpy(p->root_hi, hi, 12);
+    }
+
+    // rows [first_row, first_row + n_rows) modulo height, `spp` passes
+    void trace_rows(uint32_t first_row, uint32_t n_rows, uint32_t spp) {
+        if (cfg.recursions != 0) throw CudaFail{"recursions > 0 (bounce rays) is not available in this build; call rt_configure(recursions = 0)"};
+        ensure_accel(cfg.accel);
+        TraceParams p;
+        fill_params(&p);
+        uint32_t launch_rows = n_rows;
+        first_row %= cfg.height;
+        const bool wraps_twice = n_rows > cfg.height;
+        if (sharded() || wraps_twice) {
+            if (cached_first != first_row || cached_n != n_rows) {
+                row_list_cache.clear();
+                for (uint32_t k = 0; k < n_rows; ++k) {
+                    const uint32_t r = (first_row + k) % cfg.height;
+                    if (owns_row(r)) row_list_cache.push_back(r);
+                }
+                d_row_list.upload(row_list_cache, stream);
+                cached_first = first_row;
+                cached_n = n_rows;
+            }
+            p.row_list = d_row_list.p;
+            launch_rows = (uint32_t)row_list_cache.size();
+        }
+        p.first_row = first_row;
+        RT_CUDA(cudaMemsetAsync(d_counters.p, 0, CNT_SLOTS * sizeof(unsigned long long), stream));
+        RT_CUDA(cudaEventRecord(ev_start, stream));
+        uint32_t launches = 0;
+        if (wraps_twice && !sharded()) {
+            // the same pixel appears more than once: keep the reference's sequential order, one launch per lap
+            for (uint32_t s = 0; s < spp; ++s)
+                for (uint32_t off = 0; off < launch_rows; off += cfg.height) {
+                    TraceParams q = p;
+                    q.row_list = d_row_list.p + off;
+                    q.n_rows = std::min(cfg.height, launch_rows - off);
+                    RT_CUDA(launch_trace(q, cfg.accel, stream));
+                    ++launches;
+                }
+        } else {
+            p.n_rows = launch_rows;
+            for (uint32_t s = 0; s < spp; ++s) {
+                RT_CUDA(launch_trace(p, cfg.accel, stream));
+                ++launches;
+            }
+        }
+        RT_CUDA(cudaEventRecord(ev_stop, stream));
+        RT_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, CNT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        total_kernels += launches;
+        last = rt_launch_stats{};
+        last.kernels_launched = launches;
+        last.n_primary = (uint64_t)launch_rows * cfg.width * spp;
+        stats_pending = true;
+    }
+
+    void finish_stats() {
+        if (!stats_pending) return;
+        RT_CUDA(cudaStreamSynchronize(stream));
+        float ms = 0.f;
+        RT_CUDA(cudaEventElapsedTime(&ms, ev_start, ev_stop));
+        last.trace_kernel_ms = ms;
+        last.n_shadow = h_counters[CNT_SHADOW];
+        last.n_bounce = h_counters[CNT_BOUNCE];
+        stats_pending = false;
+    }
+};
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+#define RT_GUARD(rt, ...)                      \
+    if (!(rt)) return RT_ERR_INVALID;          \
+    try {                                      \
+        (rt)->bind_device();                   \
+        __VA_ARGS__;                           \
+        return RT_OK;                          \
+    } catch (CudaFail & f) {                   \
+        (rt)->last_error = f.what;             \
+        return RT_ERR_CUDA;                    \
+    } catch (std::exception & e) {             \
+        (rt)->last_error = e.what();           \
+        return RT_ERR_INVALID;                 \
+    }
+
+#define RT_GUARD_HOST(rt, ...)                 \
+    if (!(rt)) return RT_ERR_INVALID;          \
+    try {                                      \
+        __VA_ARGS__;                           \
+        return RT_OK;                          \
+    } catch (CudaFail & f) {                   \
+        (rt)->last_error = f.what;             \
+        return RT_ERR_CUDA;                    \
+    } catch (std::exception & e) {             \
+        (rt)->last_error = e.what();           \
+        return RT_ERR_INVALID;                 \
+    }
+
+extern "C" {
+
+const char* rt_version(void) { return "rt_b200 0.1.0 sm_100a"; }
+
+void rt_config_default(rt_config* cfg, uint32_t width, uint32_t height) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->width = width;
+    cfg->height = height;
+    cfg->triangles_per_leaf = RT_DEFAULT_TRIANGLES_PER_LEAF;
+    cfg->rows_per_call = 50;
+    cfg->recursions = 2;
+    cfg->sub_spread = 1;
+    cfg->jitter_mode = RT_JITTER_HASHED;
+    cfg->seed = 0;
+    cfg->accel = RT_ACCEL_BVH;
+    cfg->device = -1;
+    cfg->shard_index = 0;
+    cfg->shard_count = 1;
+    cfg->band_rows = 8;
+}
+
+int rt_scene_load_file(const char* collada_filename, rt_scene** out, char* err, size_t err_len) {
+    if (!collada_filename || !out) return RT_ERR_INVALID;
+    auto s = std::make_unique<rt_scene>();
+    std::string e;
+    if (!load_collada_file(collada_filename, &s->scene, &e)) {
+        copy_err(e, err, err_len);
+        return RT_ERR_LOAD;
+    }
+    *out = s.release();
+    return RT_OK;
+}
+
+int rt_scene_load_str(const char* collada_doc, const char* data_dir, rt_scene** out, char* err, size_t err_len) {
+    if (!collada_doc || !out) return RT_ERR_INVALID;
+    auto s = std::make_unique<rt_scene>();
+    std::string e;
+    if (!load_collada_str(collada_doc, data_dir, &s->scene, &e)) {
+        copy_err(e, err, err_len);
+        return RT_ERR_LOAD;
+    }
+    *out = s.release();
+    return RT_OK;
+}
+
+int rt_scene_get_desc(const rt_scene* scene, rt_scene_desc* desc) {
+    if (!scene || !desc) return RT_ERR_INVALID;
+    const_cast<rt_scene*>(scene)->scene.make_desc(desc);
+    return RT_OK;
+}
+
+void rt_scene_free(rt_scene* scene) { delete scene; }
+
+static int create_from_host_scene(const HostScene& sc, const rt_config& cfg, rt_raytracer** out, char* err, size_t err_len) {
+    if (!sc.has_camera) {
+        copy_err("scene has no camera (the reference indexes scene.cameras[0], lib.rs:39)", err, err_len);
+        return RT_ERR_LOAD;
+    }
+    auto rt = std::make_unique<rt_raytracer>();
+    try {
+        rt->init(sc, cfg);
+    } catch (CudaFail& f) {
+        copy_err(f.what, err, err_len);
+        return RT_ERR_CUDA;
+    } catch (std::exception& e) {
+        copy_err(e.what(), err, err_len);
+        return RT_ERR_INVALID;
+    }
+    *out = rt.release();
+    return RT_OK;
+}
+
+int rt_create(const rt_scene_desc* scene, const rt_config* cfg, rt_raytracer** out, char* err, size_t err_len) {
+    if (!scene || !cfg || !out) return RT_ERR_INVALID;
+    for (uint32_t t = 0; t < scene->num_triangles; ++t)
+        if (scene->tri_geom[t] >= scene->num_geometries) {
+            copy_err("tri_geom entry out of range", err, err_len);
+            return RT_ERR_INVALID;
+        }
+    return create_from_host_scene(HostScene::from_desc(*scene), *cfg, out, err, err_len);
+}
+
+int rt_create_raytracer(const char* collada_doc, size_t triangles_per_leaf, size_t width, size_t height, rt_raytracer** out, char* err,
+                        size_t err_len) {
+    if (!collada_doc || !out) return RT_ERR_INVALID;
+    HostScene sc;
+    std::string e;
+    if (!load_collada_str(collada_doc, nullptr, &sc, &e)) {
+        copy_err(e, err, err_len);
+        return RT_ERR_LOAD;
+    }
+    rt_config cfg;
+    rt_config_default(&cfg, (uint32_t)width, (uint32_t)height);
+    cfg.triangles_per_leaf = (uint32_t)triangles_per_leaf;
+    return create_from_host_scene(sc, cfg, out, err, err_len);
+}
+
+int rt_create_raytracer_from_file(const char* collada_filename, size_t triangles_per_leaf, size_t width, size_t height, rt_raytracer** out,
+                                  char* err, size_t err_len) {
+    if (!collada_filename || !out) return RT_ERR_INVALID;
+    HostScene sc;
+    std::string e;
+    if (!load_collada_file(collada_filename, &sc, &e)) {
+        copy_err(e, err, err_len);
+        return RT_ERR_LOAD;
+    }
+    rt_config cfg;
+    rt_config_default(&cfg, (uint32_t)width, (uint32_t)height);
+    cfg.triangles_per_leaf = (uint32_t)triangles_per_leaf;
+    return create_from_host_scene(sc, cfg, out, err, err_len);
+}
+
+void rt_destroy(rt_raytracer* rt) {
+    if (!rt) return;
+    if (!rt->host_only) {
+        cudaSetDevice(rt->device);
+        cudaStreamSynchronize(rt->stream);
+    }
+    delete rt;
+}
+
+const char* rt_last_error(const rt_raytracer* rt) { return rt ? rt->last_error.c_str() : "null handle"; }
+
+int rt_configure(rt_raytracer* rt, int32_t recursions, uint32_t sub_spread, int32_t jitter_mode, uint32_t seed, int32_t accel) {
+    RT_GUARD_HOST(rt, {
+        if (accel != RT_ACCEL_OCTREE && accel != RT_ACCEL_BVH) throw std::invalid_argument("unknown accel");
+        if (jitter_mode != RT_JITTER_FIXED_HALF && jitter_mode != RT_JITTER_HASHED) throw std::invalid_argument("unknown jitter mode");
+        if (recursions < 0) throw std::invalid_argument("negative recursions");
+        rt->cfg.recursions = recursions;
+        rt->cfg.sub_spread = sub_spread;
+        rt->cfg.jitter_mode = jitter_mode;
+        rt->cfg.seed = seed;
+        rt->cfg.accel = accel;
+        if (!rt->host_only) {
+            rt->bind_device();
+            rt->ensure_accel(accel);
+        }
+    });
+}
+
+int rt_set_rows_per_call(rt_raytracer* rt, uint32_t rows) {
+    RT_GUARD_HOST(rt, {
+        if (rows == 0) throw std::invalid_argument("rows_per_call must be positive");
+        rt->cfg.rows_per_call = rows;
+    });
+}
+
+int rt_trace_frame_additive(rt_raytracer* rt, uint32_t* num_primary_rays) {
+    RT_GUARD(rt, {
+        const uint32_t rows = rt->cfg.rows_per_call;
+        rt->trace_rows(rt->current_row, rows, 1);
+        rt->current_row = (rt->current_row + rows) % rt->cfg.height;
+        if (num_primary_rays) *num_primary_rays = rows * rt->cfg.width;  // mod.rs:113-116
+    });
+}
+
+int rt_trace_rows(rt_raytracer* rt, uint32_t first_row, uint32_t n_rows, uint32_t spp, uint64_t* n_primary, uint64_t* n_shadow) {
+    RT_GUARD(rt, {
+        rt->trace_rows(first_row, n_rows, spp);
+        if (n_primary) *n_primary = rt->last.n_primary;
+        if (n_shadow) {
+            rt->finish_stats();
+            *n_shadow = rt->last.n_shadow;
+        }
+    });
+}
+
+int rt_get_tonemapped_pixels(rt_raytracer* rt, uint32_t* out) {
+    RT_GUARD(rt, {
+        if (!out) throw std::invalid_argument("null output");
+        RT_CUDA(cudaMemcpyAsync(out, rt->d_ldr.p, (size_t)rt->npix() * 4, cudaMemcpyDeviceToHost, rt->stream));
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+    });
+}
+
+int rt_film_clear(rt_raytracer* rt) { RT_GUARD(rt, { rt->film_clear(); }); }
+
+int rt_get_film(rt_raytracer* rt, float* out) {
+    RT_GUARD(rt, {
+        if (!out) throw std::invalid_argument("null output");
+        const size_t n = rt->npix();
+        std::vector<float4> sum(n), sq(n);
+        RT_CUDA(cudaMemcpyAsync(sum.data(), rt->d_film_sum.p, n * sizeof(float4), cudaMemcpyDeviceToHost, rt->stream));
+        RT_CUDA(cudaMemcpyAsync(sq.data(), rt->d_film_sq.p, n * sizeof(float4), cudaMemcpyDeviceToHost, rt->stream));
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+        for (size_t i = 0; i < n; ++i) {
+            uint32_t cnt;
+            std::memcpy(&cnt, &sum[i].w, 4);
+            float* o = out + 7 * i;
+            o[0] = sum[i].x;
+            o[1] = sum[i].y;
+            o[2] = sum[i].z;
+            o[3] = sq[i].x;
+            o[4] = sq[i].y;
+            o[5] = sq[i].z;
+            o[6] = (float)cnt;
+        }
+    });
+}
+
+int rt_get_primary_ids(rt_raytracer* rt, uint32_t* out) {
+    RT_GUARD(rt, {
+        if (!out) throw std::invalid_argument("null output");
+        RT_CUDA(cudaMemcpyAsync(out, rt->d_ids.p, (size_t)rt->npix() * 4, cudaMemcpyDeviceToHost, rt->stream));
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+    });
+}
+
+int rt_camera_move_rel(rt_raytracer* rt, float x, float y, float z) {
+    if (!rt) return RT_ERR_INVALID;
+    rt->camera.move_rel(x, y, z);
+    return RT_OK;
+}
+int rt_camera_add_x_angle(rt_raytracer* rt, float radians) {
+    if (!rt) return RT_ERR_INVALID;
+    rt->camera.add_x_angle(radians);
+    return RT_OK;
+}
+int rt_camera_add_y_angle(rt_raytracer* rt, float radians) {
+    if (!rt) return RT_ERR_INVALID;
+    rt->camera.add_y_angle(radians);
+    return RT_OK;
+}
+int rt_camera_get(const rt_raytracer* rt, float* out34) {
+    if (!rt || !out34) return RT_ERR_INVALID;
+    std::memcpy(out34, rt->camera.rotation.data(), 64);
+    std::memcpy(out34 + 16, rt->camera.orientation.data(), 64);
+    out34[32] = rt->camera.max_x;
+    out34[33] = rt->camera.max_y;
+    return RT_OK;
+}
+int rt_camera_set_state(rt_raytracer* rt, float x_angle, float y_angle, const float pos[3]) {
+    if (!rt || !pos) return RT_ERR_INVALID;
+    rt->camera.x_angle = x_angle;
+    rt->camera.y_angle = y_angle;
+    rt->camera.pos = f3{pos[0], pos[1], pos[2]};
+    rt->camera.update_matrices();
+    return RT_OK;
+}
+
+int rt_set_stream(rt_raytracer* rt, void* cuda_stream) {
+    RT_GUARD(rt, {
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+        rt->stream = (cudaStream_t)cuda_stream;
+    });
+}
+int rt_get_ldr_device_ptr(rt_raytracer* rt, void** dev_ptr) {
+    if (!rt || !dev_ptr) return RT_ERR_INVALID;
+    *dev_ptr = rt->d_ldr.p;
+    return RT_OK;
+}
+int rt_set_ldr_target(rt_raytracer* rt, void* dev_ptr) {
+    if (!rt) return RT_ERR_INVALID;
+    rt->ldr_remote = (uint32_t*)dev_ptr;
+    return RT_OK;
+}
+int rt_get_owned_ldr_rows_device(rt_raytracer* rt, void* dev_out, uint32_t* n_rows) {
+    RT_GUARD(rt, {
+        if (n_rows) *n_rows = (uint32_t)rt->owned_rows.size();
+        if (dev_out) {
+            RT_CUDA(launch_gather_rows(rt->d_ldr.p, rt->d_owned_rows.p, (uint32_t)rt->owned_rows.size(), rt->cfg.width, (uint32_t*)dev_out,
+                                       rt->stream));
+            ++rt->total_kernels;
+        }
+    });
+}
+int rt_get_launch_stats(const rt_raytracer* rt_c, rt_launch_stats* out) {
+    rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
+    RT_GUARD(rt, {
+        if (!out) throw std::invalid_argument("null output");
+        rt->finish_stats();
+        *out = rt->last;
+    });
+}
+uint64_t rt_kernels_launched(const rt_raytracer* rt) { return rt ? rt->total_kernels : 0; }
+
+int rt_octree_stats(const rt_raytracer* rt_c, uint64_t* out) {
+    rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
+    if (!rt || !out) return RT_ERR_INVALID;
+    rt->ensure_octree_host();
+    const FlatOctree& o = rt->octree;
+    uint64_t inner = 0, leaves = 0, empty = 0;
+    for (size_t i = 0; i < o.num_nodes(); ++i) {
+        if (o.first_child[i] < 0) {
+            ++leaves;
+            if (o.leaf_offset[i + 1] == o.leaf_offset[i]) ++empty;
+        } else
+            ++inner;
+    }
+    out[0] = o.num_nodes();
+    out[1] = inner;
+    out[2] = leaves;
+    out[3] = empty;
+    out[4] = o.leaf_tris.size();
+    out[5] = o.depth;
+    return RT_OK;
+}
+int rt_octree_export(const rt_raytracer* rt_c, float* cubes, int32_t* first_child, uint32_t* leaf_offset, uint32_t* leaf_tris,
+                     uint64_t* n_refs) {
+    rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
+    if (!rt) return RT_ERR_INVALID;
+    rt->ensure_octree_host();
+    const FlatOctree& o = rt->octree;
+    if (cubes) std::memcpy(cubes, o.cubes.data(), o.cubes.size() * 4);
+    if (first_child) std::memcpy(first_child, o.first_child.data(), o.first_child.size() * 4);
+    if (leaf_offset) std::memcpy(leaf_offset, o.leaf_offset.data(), o.leaf_offset.size() * 4);
+    if (leaf_tris) std::memcpy(leaf_tris, o.leaf_tris.data(), o.leaf_tris.size() * 4);
+    if (n_refs) *n_refs = o.leaf_tris.size();
+    return RT_OK;
+}
+int rt_bvh_stats(const rt_raytracer* rt_c, uint64_t* out) {
+    rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
+    if (!rt || !out) return RT_ERR_INVALID;
+    rt->ensure_bvh_host();
+    out[0] = rt->bvh.nodes.size();
+    out[1] = rt->bvh.num_leaves;
+    out[2] = rt->bvh.max_leaf;
+    out[3] = rt->bvh.depth;
+    return RT_OK;
+}
+int rt_bvh_export(const rt_raytracer* rt_c, float* boxes, int32_t* children, int32_t* counts, uint32_t* tri_order) {
+    rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
+    if (!rt) return RT_ERR_INVALID;
+    rt->ensure_bvh_host();
+    for (size_t i = 0; i < rt->bvh.nodes.size(); ++i) {
+        const FlatBvh::Node& n = rt->bvh.nodes[i];
+        for (int k = 0; k < 2; ++k) {
+            if (boxes) {
+                std::memcpy(boxes + 12 * i + 6 * k, n.lo[k], 12);
+                std::memcpy(boxes + 12 * i + 6 * k + 3, n.hi[k], 12);
+            }
+            if (children) children[2 * i + k] = n.child[k];
+            if (counts) counts[2 * i + k] = n.count[k];
+        }
+    }
+    if (tri_order && !rt->bvh.tri_order.empty()) std::memcpy(tri_order, rt->bvh.tri_order.data(), rt->bvh.tri_order.size() * 4);
+    return RT_OK;
+}
+
+}  // extern "C"
