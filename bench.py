@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the per-pixel render loop on B200 (BASELINE.json metric).
+
+A step = one full frame (1 sample per pixel over all H rows) of data/thai2.dae at 1920x1080, primary + shadow
+rays (recursions = 0, fixed sub-pixel offset 0.5: the pinned parity mode), accumulated into the device film.
+  value    : Mrays/s (primary + shadow), scene/film resident in HBM, timed with CUDA events on the launching stream
+  e2e      : same metric through the public API with HOST buffers: camera state in, 8.3 MB LDR frame out (pinned),
+             every step, wall clock
+  roofline : algorithmic bytes of the reference algorithm (24 B per cube test + 36 B per triangle test + 4 B per
+             pixel) / measured duration of the trace kernel, against the measured HBM copy peak
+  cpu_baseline / --impl reference : the CPU oracle (C++ restatement of the reference, oracle/) on the host cores
+
+N > 1 (torchrun, one process per GPU): the frame is sharded by interleaved 8-row bands, the scene is replicated,
+rank 0 receives the packed frame over NVLink (see --gather). scaling = "strong": total work per step is fixed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s (primary+shadow) on thai2.dae 1920x1080"
+UNIT = "Mrays/s"
+WORKLOADS = {
+    # name: (file, width, height, spp)
+    "thai2_1080p": ("thai2.dae", 1920, 1080, 1),
+    "ico2_1024x768": ("ico2.dae", 1024, 768, 1),
+    "4boxes_1080p": ("4boxes.dae", 1920, 1080, 1),
+    "ico3_tex_1080p": ("ico3_tex.dae", 1920, 1080, 1),
+    "thai2_4k_16spp": ("thai2.dae", 3840, 2160, 16),
+}
+# Exact work of the REFERENCE algorithm (octree, triangles_per_leaf = 70) for one pinned-mode frame, counted by
+# the oracle (tools/count_work.py; checked again against the live oracle in the cpu_baseline leg):
+# (primary rays, shadow rays, cube tests, triangle tests)
+REFERENCE_WORK = {
+    "thai2_1080p": (2073600, 525594, 64718736 + 21902544, 83666141 + 36577192),
+    "ico2_1024x768": (786432, 313374, 17397368 + 6640944, 28736151 + 16316966),
+    "4boxes_1080p": (2073600, 311140, 0, 99532800 + 14934720),
+    "ico3_tex_1080p": (2073600, 619720, 38552600 + 13133280, 56826791 + 32284213),
+}
+
+
+def algorithmic_bytes(workload: str):
+    if workload not in REFERENCE_WORK:
+        return None
+    prim, _sh, cubes, tris = REFERENCE_WORK[workload]
+    return 24 * cubes + 36 * tris + 4 * prim
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.max_mhz = [], None  # (time, sm MHz, reason names)
+        self._halt = threading.Event()
+        self.ready = threading.Event()
+        self.err = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+                nv.nvmlClocksThrottleReasonSyncBoost: "sync_boost",
+                nv.nvmlClocksThrottleReasonApplicationsClocksSetting: "applications_clocks_setting",
+            }
+            while not self._halt.is_set():
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((time.perf_counter(), mhz, tuple(name for bit, name in names.items() if r & bit)))
+                self.ready.set()
+                time.sleep(0.002)
+        except Exception as e:  # NVML missing: report it, never fake numbers
+            self.err = repr(e)
+            self.ready.set()
+
+    def window(self, t0, t1):
+        """median SM clock and the union of throttle reasons of the samples taken inside [t0, t1]"""
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        mhz = sorted(x[1] for x in inside)
+        reasons = sorted({r for x in inside for r in x[2]})
+        return {"sm_mhz": (mhz[len(mhz) // 2] if mhz else None), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(inside), **({"error": self.err} if self.err else {})}
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port; the Rust original cannot be
+    built here) on all host threads. Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import raytracer_rs_b200 as rt  # product loader only flattens the scene file; the render below is the oracle's
+    from oracle_lib import JITTER_FIXED, Oracle, lib as orc_lib
+
+    fname, w, h, spp = WORKLOADS[args.workload]
+    scene = rt.load_scene(os.path.join(ROOT, "data", fname))
+    orc = Oracle(scene, w, h, rt.DEFAULT_TRIANGLES_PER_LEAF)
+    orc.configure(recursions=0, jitter=JITTER_FIXED)
+    threads = orc_lib().orc_max_threads()
+    for _ in range(args.warmup):
+        orc.trace_rows(0, h, spp, threads=threads)
+        orc.get_tonemapped_pixels()
+    orc.counters(reset=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.trace_rows(0, h, spp, threads=threads)
+        orc.get_tonemapped_pixels()
+    dt = time.perf_counter() - t0
+    c = orc.counters()
+    rays = c["rays"]["primary"] + c["rays"]["shadow"]
+    value = rays / dt / 1e6
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "reference scene fixture data/%s (the upstream repository's own scene), pinned camera" % fname,
+        "config": {"workload": args.workload, "width": w, "height": h, "spp": spp, "recursions": 0, "jitter": "fixed 0.5",
+                   "accel": "reference octree, triangles_per_leaf 70", "step": "one full frame + get_tonemapped_pixels"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d full frames (%d rays) of the same workload, OpenMP over rows" % (args.steps, rays)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(workload, rt, scene):
+    """Oracle timed on the GPU box's host cores: all threads (value) and one thread (what the reference ships)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import JITTER_FIXED, Oracle, lib as orc_lib
+
+    _f, w, h, spp = WORKLOADS[workload]
+    spp = min(spp, 1)  # bounded sample: one sample per pixel
+    orc = Oracle(scene, w, h, rt.DEFAULT_TRIANGLES_PER_LEAF)
+    orc.configure(recursions=0, jitter=JITTER_FIXED)
+    threads = orc_lib().orc_max_threads()
+    orc.trace_rows(0, h, 1, threads=threads)  # warm
+    orc.counters(reset=True)
+    frames = 0
+    t0 = time.perf_counter()
+    while True:
+        orc.trace_rows(0, h, 1, threads=threads)
+        orc.get_tonemapped_pixels()
+        frames += 1
+        if time.perf_counter() - t0 > 4.0 or frames >= 20:
+            break
+    dt = time.perf_counter() - t0
+    c = orc.counters(reset=True)
+    rays = c["rays"]["primary"] + c["rays"]["shadow"]
+    work_ok = None
+    if workload in REFERENCE_WORK:
+        p, s, cu, tr = REFERENCE_WORK[workload]
+        got = (c["rays"]["primary"] // frames, c["rays"]["shadow"] // frames,
+               (c["cube_tests"]["primary"] + c["cube_tests"]["shadow"]) // frames,
+               (c["tri_tests"]["primary"] + c["tri_tests"]["shadow"]) // frames)
+        work_ok = got == (p, s, cu, tr)
+    # single thread on a quarter of the rows (bounded), scaled by its own ray count
+    rows = max(1, h // 4)
+    t1 = time.perf_counter()
+    orc.trace_rows(0, rows, 1, threads=1)
+    dt1 = time.perf_counter() - t1
+    c1 = orc.counters(reset=True)
+    rays1 = c1["rays"]["primary"] + c1["rays"]["shadow"]
+    return {
+        "value": rays / dt / 1e6,
+        "unit": UNIT,
+        "cores": threads,
+        "kind": "port",
+        "sample": "%d full frames (%d rays) all threads; single-thread leg: rows 0..%d (%d rays)" % (frames, rays, rows, rays1),
+        "single_thread_value": rays1 / dt1 / 1e6,
+        "reference_work_matches_constants": work_ok,
+    }
+
+
+class _DevPtr:
+    """Wraps a raw device pointer for torch.as_tensor (zero copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="thai2_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--accel", default="bvh", choices=["bvh", "octree"])
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N>1: how rank 0 receives the frame")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import raytracer_rs_b200 as rt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks (one process per GPU)" % (args.gpus, args.gpus))
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: raytracer_rs_b200 has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    fname, W, H, spp = WORKLOADS[args.workload]
+    scene = rt.load_scene(os.path.join(ROOT, "data", fname))
+    accel = rt.ACCEL_BVH if args.accel == "bvh" else rt.ACCEL_OCTREE
+    cfg = rt.Config(W, H, recursions=0, jitter_mode=rt.JITTER_FIXED_HALF if spp == 1 else rt.JITTER_HASHED, accel=accel,
+                    device=local_rank, shard_index=rank, shard_count=world, band_rows=8)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    tracer = rt.RayTracer.from_scene(scene, cfg)
+    stream = torch.cuda.Stream(device=dev)
+    tracer.set_stream(stream.cuda_stream)
+
+    # ---- multi-GPU plumbing -------------------------------------------------------------------------
+    from raytracer_rs_b200 import multi_gpu
+
+    gather = multi_gpu.FrameGather(tracer, rank, world, dev, stream, mode=args.gather) if world > 1 else None
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    host_frame = torch.empty(W * H, dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def device_step():
+        tracer.trace_rows(0, H, spp, want_shadow=False)
+        if gather is not None:
+            gather.device_gather()
+
+    # ---- ray counts of one step (deterministic: pinned camera) ----------------------------------------
+    n_primary, n_shadow = tracer.trace_rows(0, H, spp)
+    counts = torch.tensor([n_primary, n_shadow], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts)
+    n_primary_total, n_shadow_total = int(counts[0]), int(counts[1])
+    rays_per_step = n_primary_total + n_shadow_total
+
+    # ---- device-timed leg ------------------------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            flush.zero_()
+            device_step()
+    barrier()
+    launches0 = tracer.kernels_launched() + (gather.kernels if gather else 0)
+    sampler.ready.wait(timeout=10)
+    t_region0 = time.perf_counter()
+    events = []
+    kernel_ms = []
+    with torch.cuda.stream(stream):
+        for _ in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations (not inside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            device_step()
+            e1.record(stream)
+            events.append((e0, e1))
+    barrier()
+    clocks = sampler.window(t_region0, time.perf_counter())
+    launches = tracer.kernels_launched() + (gather.kernels if gather else 0) - launches0
+    step_ms = [a.elapsed_time(b) for a, b in events]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    value = rays_per_step * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- trace-kernel duration for the roofline (library's own CUDA events around the kernel, same stream) ----
+    with torch.cuda.stream(stream):
+        for _ in range(20):
+            flush.zero_()
+            tracer.trace_rows(0, H, spp, want_shadow=False)
+            kernel_ms.append(tracer.launch_stats()["trace_kernel_ms"])
+    kms = float(np.mean(kernel_ms))
+    kms_t = torch.tensor([kms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(kms_t, op=dist.ReduceOp.MAX)
+    kms = float(kms_t)
+
+    # ---- end-to-end leg: public API, host buffers, every step ---------------------------------------------------
+    def e2e_step(i):
+        # per-step input: camera state from the host (travels to the device as the kernel's launch parameters)
+        tracer.camera.set_state(0.0, 0.0, (0.0, 0.0, 0.0))
+        tracer.trace_rows(0, H, spp, want_shadow=False)
+        if gather is not None:
+            gather.device_gather()
+        if rank == 0:
+            tracer_or_gather_readback()
+
+    def tracer_or_gather_readback():
+        if gather is not None:
+            gather.read_frame_into(host_frame)
+        else:
+            tracer.get_tonemapped_pixels_into(host_frame.data_ptr())
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t)
+    e2e_value = rays_per_step * args.steps / e2e_s / 1e6
+    sampler.stop()
+
+    # ---- the reference's own call pattern: 50-row bands, full-frame readback after every band (main.rs:200-201) ----
+    band = None
+    if world == 1 and spp == 1:
+        tracer.set_rows_per_call(50)
+        calls = (H + 49) // 50
+        for _ in range(2 * calls):
+            tracer.trace_frame_additive()
+            tracer.get_tonemapped_pixels_into(host_frame.data_ptr())
+        torch.cuda.synchronize(dev)
+        reps = max(1, min(args.steps, 40))
+        t0 = time.perf_counter()
+        for _ in range(reps * calls):
+            tracer.trace_frame_additive()
+            tracer.get_tonemapped_pixels_into(host_frame.data_ptr())
+        dtb = time.perf_counter() - t0
+        band_rays = rays_per_step * (calls * 50 / H) * reps
+        band = {"value": band_rays / dtb / 1e6, "unit": UNIT, "calls_per_frame": calls,
+                "d2h_bytes_per_call": W * H * 4, "note": "trace_frame_additive (50 rows) + get_tonemapped_pixels per call"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_hbm_peak()
+    alg = algorithmic_bytes(args.workload)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("%s/%s" % (args.workload, args.accel))
+    except Exception:
+        pass
+    roofline = None
+    if alg is not None and spp == 1:
+        per_launch = alg / world  # each rank's launch processes 1/N of the frame
+        achieved = per_launch / (kms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_source": peak_src, "kernel": "trace_shade_kernel<%s>" % args.accel, "kernel_ms": kms,
+                    "algorithmic_bytes_per_launch": per_launch,
+                    "note": "traffic-equivalent of the reference algorithm's reads; the <= 2 MB scene is L1/L2 resident, so frac may exceed 1"}
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "reference scene fixture data/%s (the upstream repository's own scene), pinned camera" % fname,
+        "config": {"workload": args.workload, "width": W, "height": H, "spp": spp, "recursions": 0,
+                   "jitter": "fixed 0.5" if spp == 1 else "hashed seed 0", "accel": args.accel, "l2_flush_between_steps": True,
+                   "step": "one full frame: trace %d rows x %d spp%s" % (H, spp, "" if world == 1 else " sharded by 8-row bands + gather to rank 0 (%s)" % args.gather),
+                   "primary_rays_per_step": n_primary_total, "shadow_rays_per_step": n_shadow_total},
+        "frames_per_s": args.steps / (total_ms * 1e-3),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rt.lib().rt_launch_param_bytes()), "d2h_bytes_per_step": W * H * 4 + 32,
+                "ms_per_step": e2e_s / args.steps * 1e3, "note": "camera state in (launch parameters), packed LDR frame out to pinned host memory, wall clock"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if band:
+        line["e2e_reference_call_pattern"] = band
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args.workload, rt, scene)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

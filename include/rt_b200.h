@@ -168,6 +168,20 @@ int rt_get_ldr_device_ptr(rt_raytracer* rt, void** dev_ptr);
 int rt_set_ldr_target(rt_raytracer* rt, void* dev_ptr);
 /* Copies only the rows owned by this shard, compacted (owned rows in ascending order), into dev_out. */
 int rt_get_owned_ldr_rows_device(rt_raytracer* rt, void* dev_out, uint32_t* n_rows);
+/* Device buffers owned by the library (plain cudaMalloc, therefore exportable over CUDA IPC), and IPC plumbing for
+   the one-process-per-GPU gather: rank 0 exports its frame buffer, the other ranks map it and pass the mapped
+   pointer to rt_set_ldr_target, so their trace kernel stores packed pixels straight into rank 0's memory over
+   NVLink. handle64 is a cudaIpcMemHandle_t (64 bytes). */
+int rt_device_alloc(rt_raytracer* rt, size_t bytes, void** dev_ptr);
+int rt_device_free(rt_raytracer* rt, void* dev_ptr);
+int rt_ipc_export(rt_raytracer* rt, void* dev_ptr, uint8_t* handle64);
+int rt_ipc_open(rt_raytracer* rt, const uint8_t* handle64, void** dev_ptr);
+int rt_ipc_close(rt_raytracer* rt, void* dev_ptr);
+/* Device pointer to the 4 uint64 ray counters of the last launch: shadow rays, primary hits, bounce rays, blocked
+   shadow rays (zeroed at the start of every trace call). */
+int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr);
+/* Bytes of per-launch parameters (camera + pointers) that travel host -> device with every trace launch. */
+uint32_t rt_launch_param_bytes(void);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {
     uint32_t kernels_launched; /* CUDA kernels launched by the call */

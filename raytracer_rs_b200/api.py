@@ -95,6 +95,8 @@ ABI_SYMBOLS = [
     "rt_get_tonemapped_pixels", "rt_film_clear", "rt_get_film", "rt_get_primary_ids", "rt_camera_move_rel",
     "rt_camera_add_x_angle", "rt_camera_add_y_angle", "rt_camera_get", "rt_camera_set_state", "rt_set_stream",
     "rt_get_ldr_device_ptr", "rt_set_ldr_target", "rt_get_owned_ldr_rows_device", "rt_get_launch_stats",
+    "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_get_counters_device_ptr",
+    "rt_launch_param_bytes",
     "rt_kernels_launched", "rt_octree_stats", "rt_octree_export", "rt_bvh_stats", "rt_bvh_export", "rt_stats_new",
     "rt_stats_free", "rt_stats_stats", "rt_stats_mean_stats", "rt_benchmark_new", "rt_benchmark_free",
     "rt_benchmark_start", "rt_benchmark_stop", "rt_benchmark_report", "rt_version",
@@ -151,6 +153,13 @@ def lib() -> C.CDLL:
         "rt_set_ldr_target": (C.c_int, [vp, vp]),
         "rt_get_owned_ldr_rows_device": (C.c_int, [vp, vp, P(u32)]),
         "rt_get_launch_stats": (C.c_int, [vp, P(CLaunchStats)]),
+        "rt_device_alloc": (C.c_int, [vp, sz, P(vp)]),
+        "rt_device_free": (C.c_int, [vp, vp]),
+        "rt_ipc_export": (C.c_int, [vp, vp, vp]),
+        "rt_ipc_open": (C.c_int, [vp, vp, P(vp)]),
+        "rt_ipc_close": (C.c_int, [vp, vp]),
+        "rt_get_counters_device_ptr": (C.c_int, [vp, P(vp)]),
+        "rt_launch_param_bytes": (u32, []),
         "rt_kernels_launched": (u64, [vp]),
         "rt_octree_stats": (C.c_int, [vp, vp]),
         "rt_octree_export": (C.c_int, [vp, vp, vp, vp, vp, P(u64)]),
@@ -428,6 +437,33 @@ class RayTracer:
         n = C.c_uint32()
         self._check(lib().rt_get_owned_ldr_rows_device(self._h, C.c_void_p(dev_ptr or 0), C.byref(n)))
         return n.value
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(lib().rt_device_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, dev_ptr: int) -> None:
+        self._check(lib().rt_device_free(self._h, C.c_void_p(dev_ptr)))
+
+    def ipc_export(self, dev_ptr: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._check(lib().rt_ipc_export(self._h, C.c_void_p(dev_ptr), buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (C.c_uint8 * 64)(*handle)
+        p = C.c_void_p()
+        self._check(lib().rt_ipc_open(self._h, buf, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, dev_ptr: int) -> None:
+        self._check(lib().rt_ipc_close(self._h, C.c_void_p(dev_ptr)))
+
+    def counters_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._check(lib().rt_get_counters_device_ptr(self._h, C.byref(p)))
+        return p.value
 
     def octree_stats(self) -> dict:
         raw = np.zeros(6, np.uint64)

@@ -163,8 +163,18 @@ struct rt_raytracer {
         RT_CUDA(cudaStreamSynchronize(stream));
     }
 
+    float root_lo[3], root_hi[3];  // scene AABB (= octree root cube, calc_extents :315-330), computed once
+
     void upload_scene() {
         const uint32_t nt = scene.num_triangles();
+        for (int a = 0; a < 3; ++a) {
+            root_lo[a] = 3.402823466e+38f;
+            root_hi[a] = -3.402823466e+38f;
+        }
+        for (size_t k = 0; k < scene.vertices.size(); ++k) {
+            root_lo[k % 3] = std::fmin(root_lo[k % 3], scene.vertices[k]);
+            root_hi[k % 3] = std::fmax(root_hi[k % 3], scene.vertices[k]);
+        }
         std::vector<float4> shade(nt);
         for (uint32_t t = 0; t < nt; ++t) {
             const float* v = &scene.vertices[9 * (size_t)t];
@@ -328,14 +338,8 @@ struct rt_raytracer {
         p->counters = d_counters.p;
         p->jitter_mode = (uint32_t)cfg.jitter_mode;
         p->seed = cfg.seed;
-        // scene AABB (= octree root cube, calc_extents :315-330)
-        float lo[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, hi[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
-        for (size_t k = 0; k < scene.vertices.size(); ++k) {
-            lo[k % 3] = std::fmin(lo[k % 3], scene.vertices[k]);
-            hi[k % 3] = std::fmax(hi[k % 3], scene.vertices[k]);
-        }
-        std::memcpy(p->root_lo, lo, 12);
-        std::memcpy(p->root_hi, hi, 12);
+        std::memcpy(p->root_lo, root_lo, 12);
+        std::memcpy(p->root_hi, root_hi, 12);
     }
 
     // rows [first_row, first_row + n_rows) modulo height, `spp` passes
@@ -700,6 +704,50 @@ int rt_get_owned_ldr_rows_device(rt_raytracer* rt, void* dev_out, uint32_t* n_ro
         }
     });
 }
+int rt_device_alloc(rt_raytracer* rt, size_t bytes, void** dev_ptr) {
+    RT_GUARD(rt, {
+        if (!dev_ptr || bytes == 0) throw std::invalid_argument("bad allocation request");
+        RT_CUDA(cudaMalloc(dev_ptr, bytes));
+        RT_CUDA(cudaMemsetAsync(*dev_ptr, 0xFF, bytes, rt->stream));
+    });
+}
+int rt_device_free(rt_raytracer* rt, void* dev_ptr) {
+    RT_GUARD(rt, {
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+        RT_CUDA(cudaFree(dev_ptr));
+    });
+}
+int rt_ipc_export(rt_raytracer* rt, void* dev_ptr, uint8_t* handle64) {
+    RT_GUARD(rt, {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        if (!dev_ptr || !handle64) throw std::invalid_argument("null argument");
+        cudaIpcMemHandle_t h;
+        RT_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+        std::memcpy(handle64, &h, 64);
+    });
+}
+int rt_ipc_open(rt_raytracer* rt, const uint8_t* handle64, void** dev_ptr) {
+    RT_GUARD(rt, {
+        if (!dev_ptr || !handle64) throw std::invalid_argument("null argument");
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle64, 64);
+        RT_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    });
+}
+int rt_ipc_close(rt_raytracer* rt, void* dev_ptr) {
+    RT_GUARD(rt, {
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+        if (rt->ldr_remote == dev_ptr) rt->ldr_remote = nullptr;
+        RT_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    });
+}
+int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr) {
+    if (!rt || !dev_ptr || rt->host_only) return RT_ERR_INVALID;
+    *dev_ptr = rt->d_counters.p;
+    return RT_OK;
+}
+uint32_t rt_launch_param_bytes(void) { return (uint32_t)sizeof(TraceParams); }
+
 int rt_get_launch_stats(const rt_raytracer* rt_c, rt_launch_stats* out) {
     rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
     RT_GUARD(rt, {

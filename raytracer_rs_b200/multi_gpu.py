@@ -1,0 +1,132 @@
+"""One-process-per-GPU plumbing for a sharded frame.
+
+The image is partitioned into interleaved bands of `band_rows` rows (band b belongs to rank b % world); scene, tree
+and camera are replicated; every rank owns the film entries of its bands. Rendering needs no exchange. What has to
+cross NVLink is the packed LDR frame, once per displayed frame, to rank 0:
+
+  mode "peer" (fused): rank 0 owns two frame buffers (plain cudaMalloc, exported over CUDA IPC); every rank maps
+      them, and the trace kernel's epilogue stores each packed pixel straight into rank 0's buffer (P2P store over
+      NVLink, raytracer_rs_b200/csrc/kernels.cu `ldr_remote`). One tiny all-reduce of the ray counters per frame is
+      both the global ray count and the completion fence: rank 0 reads the frame after it, on the same stream.
+      Frames alternate between the two buffers so that the next frame's stores never race with rank 0's readback.
+  mode "nccl" (baseline): every rank compacts its rows (rt_get_owned_ldr_rows_device) and rank 0 gathers them with
+      torch.distributed.gather, then scatters the rows into place.
+
+torch is plumbing here (process group, streams, the receive buffer); no render arithmetic happens in Python.
+`band_partition` is pure host logic and is what the CPU (gloo) tests exercise.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def band_partition(height: int, world: int, band_rows: int = 8):
+    """rows owned by every rank: band b (rows b*band_rows ...) belongs to rank b % world. Mirrors
+    rt_raytracer::owns_row (raytracer_rs_b200/csrc/raytracer.cu)."""
+    rows = np.arange(height, dtype=np.int64)
+    owner = (rows // band_rows) % world
+    return [rows[owner == r] for r in range(world)]
+
+
+def assemble_frame(parts, partition, width: int, height: int) -> np.ndarray:
+    """Inverse of the sharding: parts[r] holds rank r's owned rows compacted in ascending row order."""
+    frame = np.empty((height, width), dtype=np.uint32)
+    for part, rows in zip(parts, partition):
+        frame[rows] = np.asarray(part, dtype=np.uint32).reshape(-1, width)[: len(rows)]
+    return frame.reshape(-1)
+
+
+class _DevPtr:
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class FrameGather:
+    """Delivers full frames to rank 0. Call order per frame: tracer.trace_rows(0, H, spp) -> device_gather()
+    -> (rank 0) read_frame_into(pinned_host_tensor)."""
+
+    def __init__(self, tracer, rank: int, world: int, device, stream, mode: str = "peer", band_rows: int = 8):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.tracer, self.rank, self.world, self.device, self.stream, self.mode = tracer, rank, world, device, stream, mode
+        self.W, self.H = tracer.width, tracer.height
+        self.partition = band_partition(self.H, world, band_rows)
+        self.kernels = 0  # kernels of OURS launched by this object (row compaction)
+        self.frame_no = 0
+        nbytes = self.W * self.H * 4
+        cptr = tracer.counters_device_ptr()
+        self.counters = torch.as_tensor(_DevPtr(cptr, 32), device=device).view(torch.int64)  # zero copy view of the library's counters
+        if mode == "peer":
+            handles = [None, None]
+            self.local_bufs = []
+            if rank == 0:
+                self.local_bufs = [tracer.device_alloc(nbytes), tracer.device_alloc(nbytes)]
+                handles = [tracer.ipc_export(p) for p in self.local_bufs]
+            box = [handles]
+            dist.broadcast_object_list(box, src=0)
+            handles = box[0]
+            if rank == 0:
+                self.targets = list(self.local_bufs)
+            else:
+                self.targets = [tracer.ipc_open(h) for h in handles]
+            self.frames = None
+            if rank == 0:
+                self.frames = [torch.as_tensor(_DevPtr(p, nbytes), device=device).view(torch.int32) for p in self.local_bufs]
+            tracer.set_ldr_target(self.targets[0])
+        elif mode == "nccl":
+            self.max_rows = max(len(r) for r in self.partition)
+            self.compact = torch.zeros(self.max_rows * self.W, dtype=torch.int32, device=device)
+            self.recv = [torch.zeros_like(self.compact) for _ in range(world)] if rank == 0 else None
+            self.frame = torch.zeros(self.H, self.W, dtype=torch.int32, device=device) if rank == 0 else None
+            self.row_index = [torch.as_tensor(r, device=device) for r in self.partition] if rank == 0 else None
+        else:
+            raise ValueError("gather mode must be 'peer' or 'nccl'")
+        torch.cuda.synchronize(device)
+        dist.barrier()
+
+    def device_gather(self):
+        """Enqueue (on the tracer's stream) whatever makes the frame just traced complete on rank 0."""
+        torch, dist = self.torch, self.dist
+        with torch.cuda.stream(self.stream):
+            if self.mode == "peer":
+                # global ray counters + completion fence: once this all-reduce has finished on rank 0, every rank's
+                # trace kernel (earlier on its stream) has completed, so its peer stores are visible
+                dist.all_reduce(self.counters)
+                self.ready = self.frame_no & 1
+                self.frame_no += 1
+                self.tracer.set_ldr_target(self.targets[self.frame_no & 1])
+            else:
+                self.tracer.owned_ldr_rows_to(self.compact.data_ptr())
+                self.kernels += 1
+                dist.gather(self.compact, self.recv, dst=0)
+                if self.rank == 0:
+                    for r in range(self.world):
+                        n = len(self.partition[r])
+                        self.frame.index_copy_(0, self.row_index[r], self.recv[r][: n * self.W].view(n, self.W))
+
+    def read_frame_into(self, host_tensor):
+        """rank 0: device -> (pinned) host copy of the completed frame, synchronous."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            src = self.frames[self.ready] if self.mode == "peer" else self.frame.view(-1)
+            host_tensor.copy_(src, non_blocking=True)
+        self.stream.synchronize()
+
+    def global_counters(self):
+        """[shadow rays, primary hits, bounce rays, blocked] summed over ranks (valid after device_gather in peer mode)."""
+        self.stream.synchronize()
+        return [int(x) for x in self.counters.cpu()]
+
+    def close(self):
+        if self.mode == "peer":
+            self.tracer.set_ldr_target(None)
+            self.torch.cuda.synchronize(self.device)
+            self.dist.barrier()
+            if self.rank == 0:
+                for p in self.local_bufs:
+                    self.tracer.device_free(p)
+            else:
+                for p in self.targets:
+                    self.tracer.ipc_close(p)

@@ -1,0 +1,64 @@
+"""Two-rank NCCL run of the sharded render + gather to rank 0 (needs >= 2 GPUs; skipped on a single-GPU box, where
+tests/test_gpu_parity.py::test_sharded_handles_reassemble_the_frame and tests/test_sharding_gloo.py cover the logic)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, mode, result_path):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    import raytracer_rs_b200 as rt
+    from raytracer_rs_b200.multi_gpu import FrameGather
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
+    w, h = 640, 360
+    scene = rt.load_scene(os.path.join(ROOT, "data", "thai2.dae"))
+    cfg = dict(recursions=0, jitter_mode=rt.JITTER_FIXED_HALF, accel=rt.ACCEL_BVH)
+    t = rt.RayTracer.from_scene(scene, rt.Config(w, h, device=rank, shard_index=rank, shard_count=world, band_rows=8, **cfg))
+    stream = torch.cuda.Stream(device=dev)
+    t.set_stream(stream.cuda_stream)
+    g = FrameGather(t, rank, world, dev, stream, mode=mode)
+    host = torch.empty(w * h, dtype=torch.int32).pin_memory()
+    ok = True
+    for frame in range(3):  # alternates between the two peer buffers
+        t.trace_rows(0, h, 1, want_shadow=False)
+        g.device_gather()
+        if rank == 0:
+            g.read_frame_into(host)
+            if frame == 0:
+                full = rt.RayTracer.from_scene(scene, rt.Config(w, h, device=0, **cfg))
+                _, n_shadow = full.trace_rows(0, h, 1)
+                ref = full.get_tonemapped_pixels()
+                full.close()
+            ok = ok and bool(np.array_equal(host.numpy().view(np.uint32), ref))
+            if mode == "peer":
+                ok = ok and g.global_counters()[0] == n_shadow
+        dist.barrier()
+    if rank == 0:
+        open(result_path, "w").write(str(ok))
+    g.close()
+    t.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_two_rank_gather(tmp_path, mode):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    result = tmp_path / "r.txt"
+    mp.spawn(_worker, args=(2, 29600 + os.getpid() % 1000, mode, str(result)), nprocs=2, join=True)
+    assert result.read_text() == "True"

@@ -1,0 +1,279 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on identical flattened inputs.
+
+Bars (BASELINE.json north star): primary-hit primitive ids equal on >= 99.99 % of pixels, 8-bit colour within 1 LSB
+per channel. The exact-semantics octree kernel is additionally required to match ids on EVERY pixel. HDR film sums
+are compared bit for bit except where the specular term differs by the documented <= 1 ulp of powf.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import raytracer_rs_b200 as rt
+from conftest import CONFIGS, GOLDEN, channel_diff
+from oracle_lib import ISECT_BRUTE, JITTER_FIXED, JITTER_HASHED, Oracle
+
+pytestmark = pytest.mark.gpu
+
+ACCELS = [(rt.ACCEL_OCTREE, "octree"), (rt.ACCEL_BVH, "bvh")]
+ID_BAR = 0.9999  # north star
+LSB_BAR = 1
+
+
+def gpu_tracer(scene, w, h, accel, jitter=rt.JITTER_FIXED_HALF, seed=0, **kw):
+    return rt.RayTracer.from_scene(scene, rt.Config(w, h, recursions=0, jitter_mode=jitter, seed=seed, accel=accel, **kw))
+
+
+def check_frame(tracer, oracle, exact_ids):
+    ids, ldr = tracer.get_primary_ids(), tracer.get_tonemapped_pixels()
+    ids_o, ldr_o = oracle.get_primary_ids(), oracle.get_tonemapped_pixels()
+    agree = float((ids == ids_o).mean())
+    if exact_ids:
+        assert agree == 1.0, f"ids differ on {(ids != ids_o).sum()} pixels"
+    assert agree >= ID_BAR, agree
+    same = ids == ids_o
+    lsb = channel_diff(ldr[same], ldr_o[same])
+    assert lsb <= LSB_BAR, lsb
+    assert float((ldr == ldr_o).mean()) >= ID_BAR
+    return agree, lsb
+
+
+@pytest.fixture(scope="module")
+def oracle_frames(scenes):
+    """Full-resolution pinned-mode oracle frames of the four BASELINE configurations (computed once, all host threads)."""
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            _, w, h = CONFIGS[name]
+            o = Oracle(scenes(name), w, h)
+            o.configure(recursions=0, jitter=JITTER_FIXED)
+            o.trace_rows(0, h, 1, threads=0)
+            cache[name] = o
+        return cache[name]
+
+    return get
+
+
+@pytest.mark.parametrize("accel,aname", ACCELS)
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_full_resolution_parity(scenes, oracle_frames, name, accel, aname):
+    """BASELINE.json configs[0..3] at their full sizes, pinned mode (xi = 0.5, recursions = 0, 1 spp)."""
+    _, w, h = CONFIGS[name]
+    o = oracle_frames(name)
+    t = gpu_tracer(scenes(name), w, h, accel)
+    n_primary, n_shadow = t.trace_rows(0, h, 1)
+    c = o.counters()
+    assert n_primary == w * h == c["rays"]["primary"]
+    # a shadow ray is issued per (hit, light) with n.l >= 0 (mod.rs:218-226): identical hits -> identical count
+    assert n_shadow == c["rays"]["shadow"]
+    check_frame(t, o, exact_ids=True)  # on these four scenes the BVH path also agrees on every pixel
+    film, film_o = t.film.pixel_datas(), o.get_film()
+    assert np.array_equal(film[:, 6], film_o[:, 6])
+    bits_differ = (film.view(np.uint32) != film_o.view(np.uint32)).any(axis=1)
+    assert bits_differ.mean() < 1e-3  # only the <= 1 ulp powf cases
+    # <= 1 ulp in the specular term -> a few ulps in sum / sum of squares; atol absorbs the subnormal range, where
+    # one ulp is a large relative step (x^32 underflows for small |V.R|)
+    assert np.allclose(film[bits_differ], film_o[bits_differ], rtol=1e-6, atol=1e-30)
+    t.close()
+
+
+@pytest.mark.parametrize("accel,aname", ACCELS)
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_against_committed_golden(scenes, name, accel, aname):
+    """Committed oracle vectors (tests/golden): no oracle needed at run time."""
+    man = json.load(open(os.path.join(GOLDEN, "manifest.json")))[name]
+    g = np.load(os.path.join(GOLDEN, f"{name}_{man['width']}x{man['height']}.npz"))
+    w, h = man["width"], man["height"]
+    t = gpu_tracer(scenes(name), w, h, accel)
+    _, n_shadow = t.trace_rows(0, h, 1)
+    assert n_shadow == man["shadow_rays"]
+    assert np.array_equal(t.get_primary_ids(), g["ids"])
+    assert channel_diff(t.get_tonemapped_pixels(), g["ldr"]) <= LSB_BAR
+    t.film.clear()
+    t.configure(recursions=0, jitter_mode=rt.JITTER_HASHED, seed=man["seed"], accel=accel)
+    t.trace_rows(0, h, 2)
+    assert channel_diff(t.get_tonemapped_pixels(), g["ldr_jitter2"]) <= LSB_BAR
+    t.close()
+
+
+@pytest.mark.parametrize("accel,aname", ACCELS)
+def test_hashed_jitter_multi_sample(scenes, accel, aname):
+    """configs[4] in miniature: thai2, hashed jitter, several samples per pixel accumulated in the film."""
+    w, h, spp, seed = 480, 270, 4, 7
+    s = scenes("thai2")
+    o = Oracle(s, w, h)
+    o.configure(recursions=0, jitter=JITTER_HASHED, seed=seed)
+    o.trace_rows(0, h, spp, threads=0)
+    t = gpu_tracer(s, w, h, accel, jitter=rt.JITTER_HASHED, seed=seed)
+    n_primary, n_shadow = t.trace_rows(0, h, spp)
+    assert n_primary == w * h * spp and n_shadow == o.counters()["rays"]["shadow"]
+    check_frame(t, o, exact_ids=(accel == rt.ACCEL_OCTREE))
+    assert np.array_equal(t.film.pixel_datas()[:, 6], np.full(w * h, spp, np.float32))
+    t.close()
+
+
+def test_4k_16spp_properties(scenes):
+    """configs[4] at full size (3840x2160, 16 jittered spp = 132.7 M primary rays): size-independent properties
+    instead of a full oracle frame — sample counts, ray-count bounds, determinism (two runs give identical frames),
+    octree kernel == BVH kernel, and an exact oracle comparison on a band of rows."""
+    w, h, spp, seed = 3840, 2160, 16, 0
+    s = scenes("thai2")
+    frames = []
+    for accel, _ in ACCELS:
+        t = gpu_tracer(s, w, h, accel, jitter=rt.JITTER_HASHED, seed=seed)
+        n_primary, n_shadow = t.trace_rows(0, h, spp)
+        assert n_primary == w * h * spp
+        assert 0.2 * n_primary < n_shadow < 0.3 * n_primary  # ~0.25 shadow rays per primary ray on thai2
+        frames.append((t.get_tonemapped_pixels(), t.get_primary_ids(), n_shadow))
+        if accel == rt.ACCEL_BVH:
+            t.film.clear()
+            t.trace_rows(0, h, spp, want_shadow=False)
+            assert np.array_equal(t.get_tonemapped_pixels(), frames[-1][0])  # deterministic
+        t.close()
+    assert frames[0][2] == frames[1][2]
+    assert float((frames[0][1] == frames[1][1]).mean()) >= ID_BAR
+    assert float((frames[0][0] == frames[1][0]).mean()) >= ID_BAR
+    # exact check of 24 rows around the statue's centre against the oracle
+    r0, nr = 600, 24
+    o = Oracle(s, w, h)
+    o.configure(recursions=0, jitter=JITTER_HASHED, seed=seed)
+    o.trace_rows(r0, nr, spp, threads=0)
+    band = slice(r0 * w, (r0 + nr) * w)
+    assert channel_diff(frames[1][0][band], o.get_tonemapped_pixels()[band]) <= LSB_BAR
+
+
+@pytest.mark.parametrize("accel,aname", ACCELS)
+def test_trace_frame_additive_call_pattern(scenes, accel, aname):
+    """The reference's loop (raytracer/src/main.rs:200-201): 50-row bands wrapping modulo height, full-frame
+    get_tonemapped_pixels after every band, never-sampled pixels white (Q15), progressive accumulation."""
+    w, h = 320, 120
+    s = scenes("ico2")
+    o = Oracle(s, w, h)
+    o.configure(recursions=0, jitter=JITTER_HASHED, seed=3)
+    t = gpu_tracer(s, w, h, accel, jitter=rt.JITTER_HASHED, seed=3)
+    assert (t.get_tonemapped_pixels() == 0xFFFFFFFF).all()
+    for call in range(6):  # 300 rows = 2.5 laps
+        assert t.trace_frame_additive() == 50 * w == o.trace_frame_additive(threads=0)
+        ldr, ldr_o = t.get_tonemapped_pixels(), o.get_tonemapped_pixels()
+        assert np.array_equal(ldr == 0xFFFFFFFF, ldr_o == 0xFFFFFFFF), call
+        assert channel_diff(ldr, ldr_o) <= LSB_BAR, call
+    assert np.array_equal(t.film.pixel_datas()[:, 6], o.get_film()[:, 6])
+    t.close()
+
+
+def test_height_smaller_than_band(scenes):
+    """height < 50: one call visits rows more than once, sequentially (mod.rs:87-114)."""
+    w, h = 64, 20
+    s = scenes("4boxes")
+    o = Oracle(s, w, h)
+    o.configure(recursions=0, jitter=JITTER_HASHED, seed=1)
+    t = gpu_tracer(s, w, h, rt.ACCEL_BVH, jitter=rt.JITTER_HASHED, seed=1)
+    t.trace_frame_additive(), o.trace_frame_additive()
+    film, film_o = t.film.pixel_datas(), o.get_film()
+    assert np.array_equal(film[:, 6], film_o[:, 6]) and set(film[:, 6]) == {2.0, 3.0}
+    assert channel_diff(t.get_tonemapped_pixels(), o.get_tonemapped_pixels()) <= LSB_BAR
+    t.close()
+
+
+@pytest.mark.parametrize("accel,aname", ACCELS)
+def test_camera_moves_and_film_clear(scenes, accel, aname):
+    """The key handlers of raytracer/src/main.rs:124-162: camera.move_rel / add_*_angle then film.clear()."""
+    w, h = 384, 216
+    s = scenes("thai2")
+    o = Oracle(s, w, h)
+    o.configure(recursions=0, jitter=JITTER_FIXED)
+    t = gpu_tracer(s, w, h, accel)
+    for fn, args in [("move_rel", (0.1, 0.0, 0.0)), ("add_y_angle", (0.05,)), ("add_x_angle", (-0.03,)), ("move_rel", (0.0, 0.3, -0.5))]:
+        getattr(t.camera, fn)(*args)
+        getattr(o, fn)(*args)
+        t.film.clear()
+        o.film_clear()
+        t.trace_rows(0, h, 1)
+        o.trace_rows(0, h, 1, threads=0)
+        check_frame(t, o, exact_ids=(accel == rt.ACCEL_OCTREE))
+    t.close()
+
+
+@pytest.mark.parametrize("tpl", [5, 20, 100])
+def test_triangles_per_leaf_parameter(scenes, tpl):
+    """create_raytracer's triangles_per_leaf (lib.rs:15, collect.ps1 sweeps 5..100): the exact octree kernel follows
+    whatever tree the parameter produces."""
+    w, h = 320, 180
+    s = scenes("ico2")
+    o = Oracle(s, w, h, tpl)
+    o.configure(recursions=0, jitter=JITTER_FIXED)
+    o.trace_rows(0, h, 1, threads=0)
+    t = gpu_tracer(s, w, h, rt.ACCEL_OCTREE, triangles_per_leaf=tpl)
+    t.trace_rows(0, h, 1)
+    assert t.octree_stats() == o.octree_stats()
+    check_frame(t, o, exact_ids=True)
+    t.close()
+
+
+def test_bvh_equals_brute_force_closest_hit_inside_root_cube(scenes):
+    """The BVH only changes which triangles are tested: with the root-cube acceptance rule it must reproduce the
+    brute-force intersector (no_acceleration_intersector.rs) wherever the hit point lies inside the scene AABB."""
+    w, h = 480, 270
+    for name in ("thai2", "ico2"):
+        s = scenes(name)
+        o = Oracle(s, w, h)
+        o.configure(recursions=0, jitter=JITTER_FIXED, intersector=ISECT_BRUTE)
+        o.trace_rows(0, h, 1, threads=0)
+        t = gpu_tracer(s, w, h, rt.ACCEL_BVH)
+        t.trace_rows(0, h, 1)
+        assert np.array_equal(t.get_primary_ids(), o.get_primary_ids())
+        t.close()
+
+
+def test_create_raytracer_from_file_defaults(scenes):
+    """lib.rs:22-27 with the reference's compile-time defaults; a full default-mode frame must at least agree with the
+    pinned oracle on which pixels are hit (jitter moves edges by < 1 pixel) and accumulate one sample everywhere."""
+    path = os.path.join(os.path.dirname(GOLDEN), "..", "data", "ico2.dae")
+    t = rt.create_raytracer_from_file(os.path.abspath(path), rt.DEFAULT_TRIANGLES_PER_LEAF, 256, 150)
+    t.configure(recursions=0, jitter_mode=rt.JITTER_HASHED, seed=0, accel=rt.ACCEL_BVH)
+    for _ in range(3):
+        assert t.trace_frame_additive() == 50 * 256
+    assert (t.film.pixel_datas()[:, 6] == 1).all()
+    doc = open(os.path.abspath(path)).read()
+    t2 = rt.create_raytracer(doc, 70, 256, 150)
+    t2.configure(recursions=0, jitter_mode=rt.JITTER_HASHED, seed=0, accel=rt.ACCEL_BVH)
+    for _ in range(3):
+        t2.trace_frame_additive()
+    assert np.array_equal(t.get_tonemapped_pixels(), t2.get_tonemapped_pixels())
+    t.close(), t2.close()
+
+
+def test_sharded_handles_reassemble_the_frame(scenes):
+    """Two shards on one GPU (sequential, independent handles): owned rows compacted on the device, reassembled on
+    the host, equal to the unsharded frame — the single-GPU stand-in for the N-GPU gather."""
+    import torch
+
+    from raytracer_rs_b200.multi_gpu import _DevPtr, assemble_frame, band_partition
+
+    w, h, world = 320, 200, 3
+    s = scenes("ico3_tex")
+    full = gpu_tracer(s, w, h, rt.ACCEL_BVH)
+    full.trace_rows(0, h, 1)
+    ref = full.get_tonemapped_pixels()
+    parts = band_partition(h, world, 8)
+    compact = []
+    total_primary = 0
+    for r in range(world):
+        t = gpu_tracer(s, w, h, rt.ACCEL_BVH, shard_index=r, shard_count=world, band_rows=8)
+        n_primary, _ = t.trace_rows(0, h, 1)
+        total_primary += n_primary
+        nbytes = len(parts[r]) * w * 4
+        buf = t.device_alloc(nbytes)
+        assert t.owned_ldr_rows_to(buf) == len(parts[r])  # gather_rows_kernel: owned rows, compacted, on the device
+        ldr = t.get_tonemapped_pixels().reshape(h, w)  # also synchronises the handle's stream
+        assert (ldr[np.setdiff1d(np.arange(h), parts[r])] == 0xFFFFFFFF).all()  # rows of other shards stay unsampled
+        host = torch.as_tensor(_DevPtr(buf, nbytes), device="cuda").cpu().numpy().view(np.uint32).copy()
+        assert np.array_equal(host, ldr[parts[r]].reshape(-1))
+        compact.append(host)
+        t.device_free(buf)
+        t.close()
+    assert total_primary == w * h
+    assert np.array_equal(assemble_frame(compact, parts, w, h), ref)
+    full.close()

@@ -1,0 +1,218 @@
+"""Host-side logic of the product (CPU only, handles created with RT_DEVICE_NONE): Collada loader, octree build,
+BVH build, camera, Stats / BenchMark stand-ins — each against the oracle or an independent restatement."""
+import os
+import re
+import time
+
+import numpy as np
+import pytest
+
+import raytracer_rs_b200 as rt
+from collada_ref import load_collada
+from conftest import CONFIGS, DATA
+from oracle_lib import Oracle
+from raytracer_rs_b200.api import DEVICE_NONE
+
+F = np.float32
+
+
+def host_tracer(scene, w=64, h=36, **kw):
+    return rt.RayTracer.from_scene(scene, rt.Config(w, h, device=DEVICE_NONE, recursions=0, **kw))
+
+
+# ---- loader (colladaloader.rs) ---------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_loader_bit_identical_to_numpy_restatement(scenes, name):
+    """Every vertex, light, material, texel and camera float equals the independent restatement in collada_ref.py
+    (Q13, Q14: geometry order = node order, v * (reflect_z * M^T * swap_yz) in f32)."""
+    s, r = scenes(name), load_collada(os.path.join(DATA, CONFIGS[name][0]))
+    assert np.array_equal(s.vertices.view(np.uint32), r.vertices.view(np.uint32))
+    assert np.array_equal(s.tri_geom, r.tri_geom)
+    assert len(s.materials) == len(r.materials)
+    for a, b in zip(s.materials, r.materials):
+        assert a[0] == b[0] and a[2] == b[2] and all(F(x) == F(y) for x, y in zip(a[1], b[1]))
+    assert len(s.lights) == len(r.lights)
+    for a, b in zip(s.lights, r.lights):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(s.camera_orientation, r.camera_orientation) and s.camera_fov_deg == r.camera_fov_deg
+    assert len(s.textures) == len(r.textures)
+    for a, b in zip(s.textures, r.textures):
+        assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
+
+
+def test_scene_inventory(scenes):
+    """SURVEY.md section 8 scene table."""
+    expect = {"ico2": (608, 5, 1, 0), "4boxes": (48, 4, 1, 0), "ico3_tex": (608, 5, 1, 1), "thai2": (20049, 2, 1, 0)}
+    for name, (tris, geoms, lights, texs) in expect.items():
+        s = scenes(name)
+        assert (s.vertices.shape[0], len(s.materials), len(s.lights), len(s.textures)) == (tris, geoms, lights, texs)
+    tex = scenes("ico3_tex")
+    assert tex.textures[0][:2] == (640, 640) and tex.materials[1][0] == 1  # Cube_004 is textured
+    assert tex.textures[0][2].max() <= 255 / 256  # texels are byte / 256 (texture.rs:42-44)
+    assert tuple(scenes("thai2").lights[0][1]) == (1.0, 1.0, 1.0) and tuple(scenes("ico2").lights[0][1]) == (10.0, 10.0, 10.0)
+
+
+def test_loader_errors_mirror_reference_categories(tmp_path):
+    """SceneLoadError / ColladaError Display categories (colladaloader.rs:603-689, loaders/mod.rs:45-55)."""
+    with pytest.raises(rt.RtError) as e:
+        rt.load_scene(str(tmp_path / "missing.dae"))
+    assert "No such file" in e.value.message and e.value.code == -2
+    doc = open(os.path.join(DATA, "4boxes.dae")).read()
+
+    def load(text):
+        p = tmp_path / "x.dae"
+        p.write_text(text)
+        return rt.load_scene(str(p))
+
+    with pytest.raises(rt.RtError, match="XmlDefinition error"):
+        load(doc.replace('<?xml version="1.0" encoding="utf-8"?>', ""))
+    with pytest.raises(rt.RtError, match="Not a collada doc"):
+        load(doc.replace("<COLLADA", "<COLLADB").replace("</COLLADA>", "</COLLADB>"))
+    with pytest.raises(rt.RtError, match="LibraryCamerasParsing error"):
+        load(re.sub(r"<library_cameras>.*?</library_cameras>", "", doc, flags=re.S))  # fixed library order (:71-108)
+    with pytest.raises(rt.RtError, match="RemainingData error"):
+        load(doc + "<extra/>")
+    with pytest.raises(rt.RtError, match="VisualSceneConversion error; unsupported node type"):
+        load(doc.replace("<instance_camera", "<instance_controller"))
+    # a geometry whose material is unknown falls back to Material::default() = (1000, 0, 1000) (Q13)
+    s = load(doc.replace('material="Material_004-material"', 'material="nope"'))
+    assert any(tuple(m[1]) == (1000.0, 0.0, 1000.0) for m in s.materials)
+    with pytest.raises(rt.RtError) as e:  # texture file missing -> TextureLoadError text
+        bad = open(os.path.join(DATA, "ico3_tex.dae")).read()
+        load(bad)  # tmp dir has no png next to the .dae
+    assert e.value.code == -2
+
+
+def test_create_raytracer_from_str_and_file_errors():
+    """lib.rs:15-27: Result<RayTracer, String> -> error code + message, no exception escapes the C ABI."""
+    with pytest.raises(rt.RtError):
+        rt.create_raytracer("not xml", 70, 64, 36)
+    with pytest.raises(rt.RtError):
+        rt.create_raytracer_from_file("/nonexistent/file.dae", 70, 64, 36)
+
+
+# ---- octree build (oct_tree_intersector.rs:66-146, 274-330, 374-469) -----------------------------------------------
+
+
+@pytest.mark.parametrize("name,tpl", [("4boxes", 70), ("ico2", 70), ("ico2", 5), ("thai2", 70), ("ico3_tex", 20)])
+def test_octree_identical_to_oracle(scenes, name, tpl):
+    """Node numbering, cubes (bit patterns), child links and leaf triangle lists equal the oracle's recursive build."""
+    s = scenes(name)
+    r = host_tracer(s, triangles_per_leaf=tpl)
+    o = Oracle(s, 64, 36, tpl)
+    assert r.octree_stats() == o.octree_stats()
+    for mine, ref in zip(r.octree_export(), o.octree_export()):
+        assert mine.dtype == ref.dtype and np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+
+
+def test_octree_depth_cap_and_leaf_order(scenes):
+    """depth cap: a node is split only while recurse_level <= 8 (:108); leaf lists stay in ascending triangle order
+    (:332-342), which is what makes 'first wins ties' well defined (Q7)."""
+    r = host_tracer(scenes("thai2"), triangles_per_leaf=1)
+    st = r.octree_stats()
+    assert st["depth"] == 9
+    cubes, first_child, leaf_offset, leaf_tris = r.octree_export()
+    for i in np.nonzero(first_child < 0)[0][:500]:
+        seg = leaf_tris[leaf_offset[i]:leaf_offset[i + 1]]
+        assert (np.diff(seg.astype(np.int64)) > 0).all()
+
+
+# ---- BVH build ------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name", ["4boxes", "ico2", "thai2"])
+def test_bvh_invariants(scenes, name):
+    s = scenes(name)
+    r = host_tracer(s)
+    boxes, children, counts, order = r.bvh_export()
+    n_tri = s.vertices.shape[0]
+    assert sorted(order.tolist()) == list(range(n_tri))  # every triangle in exactly one leaf slot
+    st = r.bvh_stats()
+    assert st["max_leaf"] <= 4 and st["leaves"] == (children < 0).sum() - (counts[children < 0] == 0).sum()
+    verts = s.vertices.reshape(n_tri, 3, 3)
+    seen = np.zeros(n_tri, bool)
+
+    def subtree_box(node):  # returns exact AABB of the subtree, checks stored (padded) child boxes contain it
+        lo_all, hi_all = np.full(3, np.inf), np.full(3, -np.inf)
+        for k in range(2):
+            c, cnt = int(children[node, k]), int(counts[node, k])
+            if c >= 0:
+                lo, hi = subtree_box(c)
+            else:
+                first = ~c
+                tri = order[first:first + cnt]
+                assert not seen[tri].any()
+                seen[tri] = True
+                if cnt == 0:
+                    continue
+                assert (np.diff(tri.astype(np.int64)) > 0).all()  # ascending ids inside a leaf (tie-break order)
+                lo, hi = verts[tri].reshape(-1, 3).min(0), verts[tri].reshape(-1, 3).max(0)
+            assert (boxes[node, k, 0] < lo).all() and (boxes[node, k, 1] > hi).all()  # strictly padded outward
+            lo_all, hi_all = np.minimum(lo_all, lo), np.maximum(hi_all, hi)
+        return lo_all, hi_all
+
+    import sys
+    sys.setrecursionlimit(10000)
+    subtree_box(0)
+    assert seen.all()
+
+
+# ---- camera (camera.rs) ------------------------------------------------------------------------------------------------
+
+
+def test_camera_matches_oracle_through_interactive_moves(scenes):
+    s = scenes("thai2")
+    r, o = host_tracer(s, 1920, 1080), Oracle(s, 1920, 1080)
+    assert np.array_equal(r.camera.matrices().view(np.uint32), o.camera().view(np.uint32))
+    moves = [("move_rel", (0.1, 0.0, 0.0)), ("add_y_angle", (0.01,)), ("add_x_angle", (-0.01,)), ("move_rel", (0.0, -0.1, 0.1)),
+             ("add_y_angle", (0.01,)), ("add_x_angle", (0.5,))]  # the key handlers of raytracer/src/main.rs:124-162
+    for fn, args in moves:
+        getattr(r.camera, fn)(*args)
+        getattr(o, fn)(*args)
+        assert np.array_equal(r.camera.matrices().view(np.uint32), o.camera().view(np.uint32)), fn
+    r.camera.set_state(0.25, -0.5, (1.0, 2.0, 3.0))
+    o2 = Oracle(s, 1920, 1080)
+    o2.add_x_angle(0.25), o2.add_y_angle(-0.5), o2.move_rel(1.0, 2.0, 3.0)
+    assert np.array_equal(r.camera.matrices(), o2.camera())
+
+
+def test_render_calls_fail_loudly_without_a_device(scenes):
+    """No CPU fallback: a host-side handle refuses to render."""
+    r = host_tracer(scenes("4boxes"))
+    for call in (r.trace_frame_additive, r.get_tonemapped_pixels, r.film.clear, lambda: r.trace_rows(0, 1)):
+        with pytest.raises(rt.RtError) as e:
+            call()
+        assert e.value.code == -3
+
+
+# ---- stats.rs / timing crate ---------------------------------------------------------------------------------------------
+
+
+def test_stats_strings():
+    st = rt.Stats()
+    time.sleep(0.02)
+    line = st.stats(96000)
+    m = re.fullmatch(r"fps: ([0-9.]+)  primary rays/s: (\d+)", line)  # stats.rs:31
+    assert m and 5 < float(m.group(1)) < 60 and 96000 * 5 < int(m.group(2)) < 96000 * 60
+    time.sleep(0.01)
+    st.stats(96000)
+    assert re.fullmatch(r"mean fps: [0-9.]+  mean primary rays/s: [0-9.]+", st.mean_stats())  # stats.rs:35-39
+
+
+def test_benchmark_report_shape():
+    """timing/src/lib.rs:95-109 and the README example: sorted by total duration, '{name} total: {}ms, mean: {}ms, samples: {}'"""
+    bm = rt.BenchMark()
+    bm.start("foo")
+    time.sleep(0.02)
+    bm.stop("foo")
+    for _ in range(3):
+        with bm.time_scope("bar"):
+            time.sleep(0.002)
+    lines = str(bm).strip().split("\n")
+    assert [l.split(" ")[0] for l in lines] == ["foo", "bar"]
+    m = re.fullmatch(r"bar total: ([0-9.]+)ms, mean: ([0-9.]+)ms, samples: 3", lines[1])
+    assert m and abs(float(m.group(1)) / 3 - float(m.group(2))) < 0.01
+    with pytest.raises(KeyError):
+        bm.stop("never started")
