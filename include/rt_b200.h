@@ -182,6 +182,13 @@ int rt_ipc_close(rt_raytracer* rt, void* dev_ptr);
 int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr);
 /* Bytes of per-launch parameters (camera + pointers) that travel host -> device with every trace launch. */
 uint32_t rt_launch_param_bytes(void);
+/* Developer tuning knobs (results never change, only the schedule). RT_TUNE_KERNEL_VARIANT: 1 (default) persistent
+   warps pulling 8x4 pixel tiles from an atomic queue, while-while traversal; 0 one thread per pixel, single-loop. */
+#define RT_TUNE_KERNEL_VARIANT 0
+/* RT_TUNE_TILE_SCHEDULE: 1 (default) the persistent kernel hands out tiles heaviest-first using the cycle counts
+   recorded by the previous launch of the same view (longest-processing-time-first); 0 image order. */
+#define RT_TUNE_TILE_SCHEDULE 1
+int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {
     uint32_t kernels_launched; /* CUDA kernels launched by the call */

@@ -29,7 +29,7 @@ constexpr uint32_t kNoHit = 0xFFFFFFFFu;
 constexpr int kOctStack = 64;  // >= 7 * depth + 1 with depth <= 9 (oct_tree_intersector.rs:108)
 constexpr int kBvhStack = 48;
 
-enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3, CNT_SLOTS = 4 };
+enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3, CNT_TILE_QUEUE = 4, CNT_SLOTS = 5 };
 
 struct TraceParams {
     DevCamera cam;
@@ -51,6 +51,10 @@ struct TraceParams {
     uint32_t* ldr_remote;  // optional second target (peer-mapped framebuffer of rank 0), may be null
     uint32_t* primary_ids;
     unsigned long long* counters;
+    // cost-feedback tile schedule of the persistent kernel (either may be null): cycles spent per 8x4 tile in this
+    // launch (written), queue slot -> tile id (read)
+    uint32_t* tile_cost;
+    const uint32_t* tile_order;
     // work: compact rows [0, n_rows) -> image row (first_row + c) % height, or row_list[c] when non-null
     const uint32_t* row_list;
     uint32_t first_row, n_rows;

@@ -271,21 +271,195 @@ done:
     return true;
 }
 
-template <int ACCEL>
+
+// ------------------------------------------------------------------------------------------------------
+// "while-while" forms of the two traversals (same results, different control flow): the inner loop keeps
+// descending inner nodes until EVERY lane of the warp holds a leaf (or is finished), then all lanes test triangles
+// together. Lanes no longer alternate between node code and triangle code inside one loop body, which is what
+// made only ~11 of 32 lanes useful per instruction in the first version (profiles/r1_v1_*.csv).
+// ------------------------------------------------------------------------------------------------------
+constexpr int kSentinel = 0x7fffffff;
+
+__device__ __forceinline__ bool octree_closest_hit_ww(const TraceParams& P, const V3& o, const V3& d, HitRec* out) {
+    const V3 inv = {fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z)};
+    int stack[kOctStack + 1];
+    int sp = 0;
+    stack[sp++] = kSentinel;
+    int cur = 0;
+    float4 A, B;
+    for (;;) {
+        // ---- descend until a (non-empty) leaf is on top ----
+        for (;;) {
+            if (cur == kSentinel) return false;
+            A = __ldg(&P.oct_nodes[2 * cur]);
+            B = __ldg(&P.oct_nodes[2 * cur + 1]);
+            const uint32_t meta = __float_as_uint(B.w);
+            if (meta & kOctLeafFlag) break;
+            const int first_child = (int)__float_as_uint(A.w);
+            uint32_t live = meta & 0xffu;
+            const float midx = fmul(0.5f, fadd(B.x, A.x)), midy = fmul(0.5f, fadd(B.y, A.y)), midz = fmul(0.5f, fadd(B.z, A.z));
+            const float xl = fmul(fsub(A.x, o.x), inv.x), xm = fmul(fsub(midx, o.x), inv.x), xh = fmul(fsub(B.x, o.x), inv.x);
+            const float yl = fmul(fsub(A.y, o.y), inv.y), ym = fmul(fsub(midy, o.y), inv.y), yh = fmul(fsub(B.y, o.y), inv.y);
+            const float zl = fmul(fsub(A.z, o.z), inv.z), zm = fmul(fsub(midz, o.z), inv.z), zh = fmul(fsub(B.z, o.z), inv.z);
+            const float nx[2] = {fminf(xl, xm), fminf(xm, xh)}, fx[2] = {fmaxf(xl, xm), fmaxf(xm, xh)};
+            const float ny[2] = {fminf(yl, ym), fminf(ym, yh)}, fy[2] = {fmaxf(yl, ym), fmaxf(ym, yh)};
+            const float nz[2] = {fminf(zl, zm), fminf(zm, zh)}, fz[2] = {fmaxf(zl, zm), fmaxf(zm, zh)};
+            float tc[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float tmin = fmaxf(fmaxf(nx[c & 1], ny[(c >> 1) & 1]), nz[c >> 2]);
+                const float tmax = fminf(fminf(fx[c & 1], fy[(c >> 1) & 1]), fz[c >> 2]);
+                tc[c] = tmin;
+                if (!(tmax >= tmin && tmax > 0.0f)) live &= ~(1u << c);
+            }
+            while (live) {  // push in descending (t, child) order = pop in the reference's stable ascending order
+                int pick = -1;
+                float pt = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if ((live >> c) & 1u) {
+                        if (pick < 0 || tc[c] >= pt) {
+                            pick = c;
+                            pt = tc[c];
+                        }
+                    }
+                }
+                live &= ~(1u << pick);
+                stack[sp++] = first_child + pick;
+            }
+            cur = stack[--sp];
+        }
+        // ---- leaf: closest triangle of the list (strict <), then the in-cube acceptance test ----
+        const uint32_t count = __float_as_uint(B.w) & ~kOctLeafFlag;
+        const float4* tri = P.oct_tris + 3 * (size_t)__float_as_uint(A.w);
+        bool have = false;
+        HitRec best;
+        best.t = 0.f;
+        best.u = 0.f;
+        best.v = 0.f;
+        best.tri = kNoHit;
+        for (uint32_t i = 0; i < count; ++i) {
+            const float4 t0 = __ldg(tri + 3 * i), t1 = __ldg(tri + 3 * i + 1), t2 = __ldg(tri + 3 * i + 2);
+            float t, u, v;
+            if (!moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) continue;
+            if (!have || t < best.t) {
+                have = true;
+                best.t = t;
+                best.u = u;
+                best.v = v;
+                best.tri = __float_as_uint(t2.y);
+            }
+        }
+        if (have) {
+            const V3 hp = vadd(o, vscale(d, best.t));
+            const bool outside = hp.x < A.x || hp.x > B.x || hp.y < A.y || hp.y > B.y || hp.z < A.z || hp.z > B.z;
+            if (!outside) {
+                *out = best;
+                return true;
+            }
+        }
+        cur = stack[--sp];
+    }
+}
+
+__device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V3& o, const V3& d, float t_limit, float early_t, HitRec* out) {
+    const float ix = fdiv(1.0f, d.x), iy = fdiv(1.0f, d.y), iz = fdiv(1.0f, d.z);
+    const float ox = -o.x * ix, oy = -o.y * iy, oz = -o.z * iz;
+    int stack_node[kBvhStack];
+    float stack_t[kBvhStack];
+    stack_node[0] = kSentinel;
+    stack_t[0] = -FLT_MAX;
+    int sp = 1;
+    HitRec best;
+    best.t = t_limit;
+    best.u = 0.f;
+    best.v = 0.f;
+    best.tri = kNoHit;
+    int cur = 0;
+    while (cur != kSentinel) {
+        while ((unsigned)cur < (unsigned)kSentinel) {  // inner nodes
+            const float4* n = P.bvh_nodes + 4 * (size_t)cur;
+            const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+            const float a0x = fmaf(q0.x, ix, ox), b0x = fmaf(q0.w, ix, ox);
+            const float a0y = fmaf(q0.y, iy, oy), b0y = fmaf(q1.x, iy, oy);
+            const float a0z = fmaf(q0.z, iz, oz), b0z = fmaf(q1.y, iz, oz);
+            const float a1x = fmaf(q1.z, ix, ox), b1x = fmaf(q2.y, ix, ox);
+            const float a1y = fmaf(q1.w, iy, oy), b1y = fmaf(q2.z, iy, oy);
+            const float a1z = fmaf(q2.x, iz, oz), b1z = fmaf(q2.w, iz, oz);
+            const float n0 = fmaxf(fmaxf(fminf(a0x, b0x), fminf(a0y, b0y)), fmaxf(fminf(a0z, b0z), 0.0f));
+            const float f0 = fminf(fminf(fmaxf(a0x, b0x), fmaxf(a0y, b0y)), fminf(fmaxf(a0z, b0z), best.t));
+            const float n1 = fmaxf(fmaxf(fminf(a1x, b1x), fminf(a1y, b1y)), fmaxf(fminf(a1z, b1z), 0.0f));
+            const float f1 = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), best.t));
+            const bool h0 = n0 <= f0, h1 = n1 <= f1;
+            const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+            if (h0 && h1) {
+                const bool first0 = n0 <= n1;
+                stack_node[sp] = first0 ? c1 : c0;
+                stack_t[sp] = first0 ? n1 : n0;
+                ++sp;
+                cur = first0 ? c0 : c1;
+            } else if (h0) {
+                cur = c0;
+            } else if (h1) {
+                cur = c1;
+            } else {
+                do {
+                    --sp;
+                    cur = stack_node[sp];
+                } while (stack_t[sp] > best.t);
+            }
+        }
+        if (cur != kSentinel) {  // leaf
+            const uint32_t ref = (uint32_t)~cur;
+            const uint32_t count = ref & 15u;
+            const float4* tri = P.bvh_tris + 3 * (size_t)(ref >> 4);
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4 t0 = __ldg(tri + 3 * i), t1 = __ldg(tri + 3 * i + 1), t2 = __ldg(tri + 3 * i + 2);
+                float t, u, v;
+                if (!moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) continue;
+                const uint32_t id = __float_as_uint(t2.y);
+                if (t < best.t || (t == best.t && id < best.tri)) {
+                    best.t = t;
+                    best.u = u;
+                    best.v = v;
+                    best.tri = id;
+                    if (t <= early_t) {
+                        *out = best;
+                        return true;
+                    }
+                }
+            }
+            do {
+                --sp;
+                cur = stack_node[sp];
+            } while (stack_t[sp] > best.t);
+        }
+    }
+    if (best.tri == kNoHit) return false;
+    const V3 hp = vadd(o, vscale(d, best.t));
+    const bool outside = hp.x < P.root_lo[0] || hp.x > P.root_hi[0] || hp.y < P.root_lo[1] || hp.y > P.root_hi[1] || hp.z < P.root_lo[2] ||
+                         hp.z > P.root_hi[2];
+    if (outside) return false;
+    *out = best;
+    return true;
+}
+
+// ACCEL: 0 octree / 1 BVH; WW: 0 single-loop, 1 while-while
+template <int ACCEL, int WW>
 __device__ __forceinline__ bool closest_hit(const TraceParams& P, const V3& o, const V3& d, HitRec* out) {
-    if (ACCEL == 0) return octree_closest_hit(P, o, d, out);
-    return bvh_closest_hit(P, o, d, FLT_MAX, -1.0f, out);
+    if (ACCEL == 0) return WW ? octree_closest_hit_ww(P, o, d, out) : octree_closest_hit(P, o, d, out);
+    return WW ? bvh_closest_hit_ww(P, o, d, FLT_MAX, -1.0f, out) : bvh_closest_hit(P, o, d, FLT_MAX, -1.0f, out);
 }
 // blocked <=> the closest hit has 0.01 < t < 1.0 (mod.rs:226-230)
-template <int ACCEL>
+template <int ACCEL, int WW>
 __device__ __forceinline__ bool shadow_blocked(const TraceParams& P, const V3& o, const V3& d) {
     HitRec h;
     if (ACCEL == 0) {
-        if (!octree_closest_hit(P, o, d, &h)) return false;
+        if (!(WW ? octree_closest_hit_ww(P, o, d, &h) : octree_closest_hit(P, o, d, &h))) return false;
         return h.t > 0.01f && h.t < 1.0f;
     }
     // BVH: hits with t >= 1 can never block, a hit with t <= 0.01 decides "lit" immediately
-    if (!bvh_closest_hit(P, o, d, 1.0f, 0.01f, &h)) return false;
+    if (!(WW ? bvh_closest_hit_ww(P, o, d, 1.0f, 0.01f, &h) : bvh_closest_hit(P, o, d, 1.0f, 0.01f, &h))) return false;
     return h.t > 0.01f && h.t < 1.0f;
 }
 
@@ -312,108 +486,197 @@ __device__ __forceinline__ uint32_t tonemap_pack(float sr, float sg, float sb, u
 }
 
 // ------------------------------------------------------------------------------------------------------
-// the fused trace + shade + film kernel.  Block = 8 warps, each warp an 8x4 pixel tile, block = 32x8 pixels.
+// one pixel sample: camera ray -> closest hit -> shading with shadow rays -> film -> packed LDR pixel
+// ------------------------------------------------------------------------------------------------------
+struct LaneCounters {
+    uint32_t shadow_rays = 0, prim_hit = 0, blocked = 0;
+};
+
+template <int ACCEL, int WW>
+__device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, uint32_t crow, LaneCounters& cnt) {
+    const uint32_t W = P.cam.width, H = P.cam.height;
+    const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % H;
+    const uint32_t idx = row * W + col;
+    float4 fs_ = P.film_sum[idx];
+    const uint32_t nsamp = __float_as_uint(fs_.w);
+    float xi1 = 0.5f, xi2 = 0.5f;
+    if (P.jitter_mode == 1) {
+        xi1 = u01(hash4(P.seed, idx, nsamp, 0));
+        xi2 = u01(hash4(P.seed, idx, nsamp, 1));
+    }
+    // camera.rs:80-90 with (u, v) = (idx % width, idx / height)  [sic, mod.rs:96]
+    const uint32_t pu = idx % W, pv = idx / H;
+    const float dir_x = fadd(-P.cam.max_x, fmul(fmul(2.0f, P.cam.max_x), fdiv(fadd((float)pu, xi1), (float)W)));
+    const float dir_y = fadd(-P.cam.max_y, fmul(fmul(2.0f, P.cam.max_y), fdiv(fadd((float)pv, xi2), (float)H)));
+    const float ndy = -dir_y;
+    const float* R = P.cam.rot;
+    V3 d;
+    d.x = fadd(fadd(fadd(fmul(dir_x, R[0]), fmul(ndy, R[4])), fmul(1.0f, R[8])), fmul(1.0f, R[12]));
+    d.y = fadd(fadd(fadd(fmul(dir_x, R[1]), fmul(ndy, R[5])), fmul(1.0f, R[9])), fmul(1.0f, R[13]));
+    d.z = fadd(fadd(fadd(fmul(dir_x, R[2]), fmul(ndy, R[6])), fmul(1.0f, R[10])), fmul(1.0f, R[14]));
+    const V3 o = {P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]};
+
+    float cr = 0.f, cg = 0.f, cb = 0.f;
+    HitRec hit;
+    uint32_t id = kNoHit;
+    if (closest_hit<ACCEL, WW>(P, o, d, &hit)) {
+        cnt.prim_hit += 1;
+        id = hit.tri;
+        const float4 sh = __ldg(&P.tri_shade[hit.tri]);
+        const V3 nrm = {sh.x, sh.y, sh.z};
+        const uint32_t geom = __float_as_uint(sh.w);
+        const V3 hp = vadd(o, vscale(d, hit.t));  // ray.pos + t * ray.dir  (mod.rs:212)
+        for (uint32_t li = 0; li < P.num_lights; ++li) {
+            const float4 lp = __ldg(&P.lights[2 * li]), lc = __ldg(&P.lights[2 * li + 1]);
+            const V3 L = vsub(V3{lp.x, lp.y, lp.z}, hp);
+            const V3 Ln = vunit(L);
+            const float ndl = vdot(nrm, Ln);
+            if (ndl < 0.0f) continue;
+            cnt.shadow_rays += 1;
+            const V3 so = vadd(hp, vscale(L, 0.01f));
+            if (shadow_blocked<ACCEL, WW>(P, so, L)) {
+                cnt.blocked += 1;
+                continue;
+            }
+            const float4 mat = __ldg(&P.materials[geom]);
+            float dr = mat.x, dg = mat.y, db = mat.z;
+            const int tex = __float_as_int(mat.w);
+            if (tex >= 0) {  // Texture::get_texel(hit.u, hit.v), texture.rs:21-27 (index clamped instead of panicking)
+                const DevTexture T = P.textures[tex];
+                const float fx = fmul(hit.u, (float)T.width), fy = fmul(hit.v, (float)T.height);
+                const size_t x = fx > 0.0f ? (size_t)__float2ull_rz(fx) : 0, y = fy > 0.0f ? (size_t)__float2ull_rz(fy) : 0;
+                size_t ti = y * T.width + x;
+                const size_t last = (size_t)T.width * T.height - 1;
+                if (ti > last) ti = last;
+                dr = T.rgb[3 * ti];
+                dg = T.rgb[3 * ti + 1];
+                db = T.rgb[3 * ti + 2];
+            }
+            const V3 view = vunit(d);
+            const V3 refl = vsub(vscale(nrm, fmul(2.0f, ndl)), Ln);  // 2.0 * ndl * normal - normalize(L)
+            const float spec = pow32(vdot(view, refl));
+            cr = fadd(cr, fmul(fadd(fmul(dr, ndl), spec), lc.x));
+            cg = fadd(cg, fmul(fadd(fmul(dg, ndl), spec), lc.y));
+            cb = fadd(cb, fmul(fadd(fmul(db, ndl), spec), lc.z));
+        }
+    }
+    // add_sample (film.rs:20-24)
+    float4 sq = P.film_sq[idx];
+    fs_.x = fadd(fs_.x, cr);
+    fs_.y = fadd(fs_.y, cg);
+    fs_.z = fadd(fs_.z, cb);
+    sq.x = fadd(sq.x, fmul(cr, cr));
+    sq.y = fadd(sq.y, fmul(cg, cg));
+    sq.z = fadd(sq.z, fmul(cb, cb));
+    const uint32_t n_new = nsamp + 1u;
+    fs_.w = __uint_as_float(n_new);
+    P.film_sum[idx] = fs_;
+    P.film_sq[idx] = sq;
+    P.primary_ids[idx] = id;
+    const uint32_t px = tonemap_pack(fs_.x, fs_.y, fs_.z, n_new);
+    P.ldr[idx] = px;
+    if (P.ldr_remote) P.ldr_remote[idx] = px;
+}
+
+__device__ __forceinline__ void flush_counters(const TraceParams& P, LaneCounters c, uint32_t lane) {
+    // ray counters: warp reduce, one atomic per warp and counter
+    const uint32_t s = __reduce_add_sync(0xffffffffu, c.shadow_rays);
+    const uint32_t h = __reduce_add_sync(0xffffffffu, c.prim_hit);
+    const uint32_t b = __reduce_add_sync(0xffffffffu, c.blocked);
+    if (lane == 0) {
+        if (s) atomicAdd(&P.counters[CNT_SHADOW], (unsigned long long)s);
+        if (h) atomicAdd(&P.counters[CNT_PRIMARY_HITS], (unsigned long long)h);
+        if (b) atomicAdd(&P.counters[CNT_BLOCKED], (unsigned long long)b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// variant 0: one thread per pixel, block = 8 warps, each warp an 8x4 pixel tile, block = 32x8 pixels
 // ------------------------------------------------------------------------------------------------------
 template <int ACCEL>
 __global__ void __launch_bounds__(256) trace_shade_kernel(const __grid_constant__ TraceParams P) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t col = blockIdx.x * 32u + (warp & 3u) * 8u + (lane & 7u);
     const uint32_t crow = blockIdx.y * 8u + (warp >> 2) * 4u + (lane >> 3);
-    const uint32_t W = P.cam.width, H = P.cam.height;
-    const bool active = col < W && crow < P.n_rows;
-    uint32_t shadow_rays = 0, prim_hit = 0, blocked_cnt = 0;
-    if (active) {
-        const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % H;
-        const uint32_t idx = row * W + col;
-        float4 fs_ = P.film_sum[idx];
-        const uint32_t nsamp = __float_as_uint(fs_.w);
-        float xi1 = 0.5f, xi2 = 0.5f;
-        if (P.jitter_mode == 1) {
-            xi1 = u01(hash4(P.seed, idx, nsamp, 0));
-            xi2 = u01(hash4(P.seed, idx, nsamp, 1));
-        }
-        // camera.rs:80-90 with (u, v) = (idx % width, idx / height)  [sic, mod.rs:96]
-        const uint32_t pu = idx % W, pv = idx / H;
-        const float dir_x = fadd(-P.cam.max_x, fmul(fmul(2.0f, P.cam.max_x), fdiv(fadd((float)pu, xi1), (float)W)));
-        const float dir_y = fadd(-P.cam.max_y, fmul(fmul(2.0f, P.cam.max_y), fdiv(fadd((float)pv, xi2), (float)H)));
-        const float ndy = -dir_y;
-        const float* R = P.cam.rot;
-        V3 d;
-        d.x = fadd(fadd(fadd(fmul(dir_x, R[0]), fmul(ndy, R[4])), fmul(1.0f, R[8])), fmul(1.0f, R[12]));
-        d.y = fadd(fadd(fadd(fmul(dir_x, R[1]), fmul(ndy, R[5])), fmul(1.0f, R[9])), fmul(1.0f, R[13]));
-        d.z = fadd(fadd(fadd(fmul(dir_x, R[2]), fmul(ndy, R[6])), fmul(1.0f, R[10])), fmul(1.0f, R[14]));
-        const V3 o = {P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]};
+    LaneCounters cnt;
+    if (col < P.cam.width && crow < P.n_rows) trace_pixel<ACCEL, 0>(P, col, crow, cnt);
+    flush_counters(P, cnt, lane);
+}
 
-        float cr = 0.f, cg = 0.f, cb = 0.f;
-        HitRec hit;
-        uint32_t id = kNoHit;
-        if (closest_hit<ACCEL>(P, o, d, &hit)) {
-            prim_hit = 1;
-            id = hit.tri;
-            const float4 sh = __ldg(&P.tri_shade[hit.tri]);
-            const V3 nrm = {sh.x, sh.y, sh.z};
-            const uint32_t geom = __float_as_uint(sh.w);
-            const V3 hp = vadd(o, vscale(d, hit.t));  // ray.pos + t * ray.dir  (mod.rs:212)
-            for (uint32_t li = 0; li < P.num_lights; ++li) {
-                const float4 lp = __ldg(&P.lights[2 * li]), lc = __ldg(&P.lights[2 * li + 1]);
-                const V3 L = vsub(V3{lp.x, lp.y, lp.z}, hp);
-                const V3 Ln = vunit(L);
-                const float ndl = vdot(nrm, Ln);
-                if (ndl < 0.0f) continue;
-                ++shadow_rays;
-                const V3 so = vadd(hp, vscale(L, 0.01f));
-                if (shadow_blocked<ACCEL>(P, so, L)) {
-                    ++blocked_cnt;
-                    continue;
-                }
-                const float4 mat = __ldg(&P.materials[geom]);
-                float dr = mat.x, dg = mat.y, db = mat.z;
-                const int tex = __float_as_int(mat.w);
-                if (tex >= 0) {  // Texture::get_texel(hit.u, hit.v), texture.rs:21-27 (index clamped instead of panicking)
-                    const DevTexture T = P.textures[tex];
-                    const float fx = fmul(hit.u, (float)T.width), fy = fmul(hit.v, (float)T.height);
-                    const size_t x = fx > 0.0f ? (size_t)__float2ull_rz(fx) : 0, y = fy > 0.0f ? (size_t)__float2ull_rz(fy) : 0;
-                    size_t ti = y * T.width + x;
-                    const size_t last = (size_t)T.width * T.height - 1;
-                    if (ti > last) ti = last;
-                    dr = T.rgb[3 * ti];
-                    dg = T.rgb[3 * ti + 1];
-                    db = T.rgb[3 * ti + 2];
-                }
-                const V3 view = vunit(d);
-                const V3 refl = vsub(vscale(nrm, fmul(2.0f, ndl)), Ln);  // 2.0 * ndl * normal - normalize(L)
-                const float spec = pow32(vdot(view, refl));
-                cr = fadd(cr, fmul(fadd(fmul(dr, ndl), spec), lc.x));
-                cg = fadd(cg, fmul(fadd(fmul(dg, ndl), spec), lc.y));
-                cb = fadd(cb, fmul(fadd(fmul(db, ndl), spec), lc.z));
-            }
+// ------------------------------------------------------------------------------------------------------
+// variant 1: persistent warps. Every warp pulls 8x4 pixel tiles from a global atomic queue until the frame is
+// done, so a slow tile (deep in the statue) never holds 7 finished warps' registers hostage and the tail of the
+// launch is made of the cheap all-miss tiles of the lower image rows. Traversal is while-while.
+// ------------------------------------------------------------------------------------------------------
+#ifndef RT_PERSISTENT_MIN_BLOCKS
+#define RT_PERSISTENT_MIN_BLOCKS 3
+#endif
+template <int ACCEL>
+__global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_persistent_kernel(const __grid_constant__ TraceParams P) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tiles_x = (P.cam.width + 7u) / 8u;
+    const uint32_t n_tiles = tiles_x * ((P.n_rows + 3u) / 4u);
+    LaneCounters cnt;
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) {
+            tile = (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], 1ull);
+            // cost-feedback schedule: queue slot -> tile id, heaviest tiles (by last frame's cycle count) first
+            if (P.tile_order && tile < n_tiles) tile = P.tile_order[tile];
         }
-        // add_sample (film.rs:20-24)
-        float4 sq = P.film_sq[idx];
-        fs_.x = fadd(fs_.x, cr);
-        fs_.y = fadd(fs_.y, cg);
-        fs_.z = fadd(fs_.z, cb);
-        sq.x = fadd(sq.x, fmul(cr, cr));
-        sq.y = fadd(sq.y, fmul(cg, cg));
-        sq.z = fadd(sq.z, fmul(cb, cb));
-        const uint32_t n_new = nsamp + 1u;
-        fs_.w = __uint_as_float(n_new);
-        P.film_sum[idx] = fs_;
-        P.film_sq[idx] = sq;
-        P.primary_ids[idx] = id;
-        const uint32_t px = tonemap_pack(fs_.x, fs_.y, fs_.z, n_new);
-        P.ldr[idx] = px;
-        if (P.ldr_remote) P.ldr_remote[idx] = px;
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const uint32_t col = (tile % tiles_x) * 8u + (lane & 7u);
+        const uint32_t crow = (tile / tiles_x) * 4u + (lane >> 3);
+        const long long t0 = clock64();
+        if (col < P.cam.width && crow < P.n_rows) trace_pixel<ACCEL, 1>(P, col, crow, cnt);
+        __syncwarp();
+        const long long dt = clock64() - t0;
+        if (lane == 0 && P.tile_cost) P.tile_cost[tile] = dt > 0xffffffffll ? 0xffffffffu : (uint32_t)dt;
+#ifdef RT_DEBUG_TILE_CLOCKS  // developer build only (tools/): per-tile cycle count instead of the primitive id
+        if (col < P.cam.width && crow < P.n_rows) {
+            const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % P.cam.height;
+            P.primary_ids[row * P.cam.width + col] = (uint32_t)dt;
+        }
+#endif
     }
-    // ray counters: warp reduce, one atomic per warp and counter
-    shadow_rays = __reduce_add_sync(0xffffffffu, shadow_rays);
-    prim_hit = __reduce_add_sync(0xffffffffu, prim_hit);
-    blocked_cnt = __reduce_add_sync(0xffffffffu, blocked_cnt);
-    if (lane == 0) {
-        if (shadow_rays) atomicAdd(&P.counters[CNT_SHADOW], (unsigned long long)shadow_rays);
-        if (prim_hit) atomicAdd(&P.counters[CNT_PRIMARY_HITS], (unsigned long long)prim_hit);
-        if (blocked_cnt) atomicAdd(&P.counters[CNT_BLOCKED], (unsigned long long)blocked_cnt);
+    flush_counters(P, cnt, lane);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// tile_sort_kernel: order[] = tile ids sorted by descending cost (counting sort on a log-scale key, one block).
+// Longest-processing-time-first: the tiles that took most cycles in the previous frame are handed out first, the
+// cheap all-miss tiles fill the end of the launch, so no warp is still inside a 500k-cycle tile when the queue
+// runs dry. Only the schedule depends on it; pixel results do not.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kSortBuckets = 2048;
+__global__ void __launch_bounds__(1024) tile_sort_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n) {
+    __shared__ uint32_t hist[kSortBuckets];
+    __shared__ uint32_t scan_tmp[1024];
+    for (int b = threadIdx.x; b < kSortBuckets; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    auto bucket = [](uint32_t c) {
+        // 64 buckets per octave; reversed so that bucket 0 holds the most expensive tiles
+        const int k = (int)(__log2f((float)c + 1.0f) * 64.0f);
+        return (uint32_t)(kSortBuckets - 1 - min(max(k, 0), kSortBuckets - 1));
+    };
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[bucket(cost[i])], 1u);
+    __syncthreads();
+    // exclusive scan of 2048 buckets: each thread owns two adjacent buckets
+    const uint32_t a = hist[2 * threadIdx.x], b2 = hist[2 * threadIdx.x + 1];
+    scan_tmp[threadIdx.x] = a + b2;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const uint32_t v = threadIdx.x >= (unsigned)off ? scan_tmp[threadIdx.x - off] : 0u;
+        __syncthreads();
+        scan_tmp[threadIdx.x] += v;
+        __syncthreads();
     }
+    const uint32_t base = scan_tmp[threadIdx.x] - (a + b2);
+    hist[2 * threadIdx.x] = base;
+    hist[2 * threadIdx.x + 1] = base + a;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&hist[bucket(cost[i])], 1u)] = i;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -458,14 +721,37 @@ __global__ void gather_rows_kernel(const uint32_t* __restrict__ ldr, const uint3
 // ------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------
-cudaError_t launch_trace(const TraceParams& p, int accel, cudaStream_t stream) {
+cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persistent_blocks, cudaStream_t stream) {
     if (p.n_rows == 0) return cudaSuccess;
-    dim3 grid((p.cam.width + 31u) / 32u, (p.n_rows + 7u) / 8u);
-    if (accel == 0)
-        trace_shade_kernel<0><<<grid, 256, 0, stream>>>(p);
-    else
-        trace_shade_kernel<1><<<grid, 256, 0, stream>>>(p);
+    if (variant == 0) {
+        dim3 grid((p.cam.width + 31u) / 32u, (p.n_rows + 7u) / 8u);
+        if (accel == 0)
+            trace_shade_kernel<0><<<grid, 256, 0, stream>>>(p);
+        else
+            trace_shade_kernel<1><<<grid, 256, 0, stream>>>(p);
+    } else {
+        const uint32_t tiles = ((p.cam.width + 7u) / 8u) * ((p.n_rows + 3u) / 4u);
+        uint32_t blocks = (uint32_t)persistent_blocks;
+        if (blocks * 8u > tiles) blocks = (tiles + 7u) / 8u;
+        if (accel == 0)
+            trace_shade_persistent_kernel<0><<<blocks, 256, 0, stream>>>(p);
+        else
+            trace_shade_persistent_kernel<1><<<blocks, 256, 0, stream>>>(p);
+    }
     return cudaGetLastError();
+}
+cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, cudaStream_t stream) {
+    tile_sort_kernel<<<1, 1024, 0, stream>>>(cost, order, n);
+    return cudaGetLastError();
+}
+// resident 256-thread blocks per SM of the persistent kernel (for sizing its grid)
+int persistent_blocks_per_sm(int accel) {
+    int n = 0;
+    if (accel == 0)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<0>, 256, 0);
+    else
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<1>, 256, 0);
+    return n > 0 ? n : 1;
 }
 cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream) {
     film_clear_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(sum, sq, ldr, ids, n);

@@ -98,6 +98,15 @@ struct rt_raytracer {
     std::vector<uint32_t> row_list_cache;   // rows of the last sharded / wrapped launch
     uint32_t cached_first = ~0u, cached_n = ~0u;
     uint64_t total_kernels = 0;
+    int variant = 1;            // RT_TUNE_KERNEL_VARIANT
+    int lpt_schedule = 1;       // RT_TUNE_TILE_SCHEDULE: 1 = heaviest tiles first (cost feedback), 0 = image order
+    // cost-feedback schedule state, valid for one launch geometry (first_row, rows, row list)
+    DevBuf<uint32_t> d_tile_cost, d_tile_order;
+    uint32_t sched_first = ~0u, sched_rows = ~0u, sched_tiles = 0;
+    uint32_t sched_launches = 0;  // launches recorded since the schedule geometry / camera last changed
+    bool sched_have_order = false;
+    int blocks_per_sm[2] = {0, 0};
+    int num_sms = 0;
     rt_launch_stats last{};
     bool stats_pending = false;
 
@@ -147,6 +156,7 @@ struct rt_raytracer {
         bind_device();
         cudaDeviceProp prop;
         RT_CUDA(cudaGetDeviceProperties(&prop, device));
+        num_sms = prop.multiProcessorCount;
         if (prop.major != 10) throw CudaFail{std::string("device '") + prop.name + "' is not sm_100 (Blackwell B200); rt_b200 ships sm_100a code only"};
         RT_CUDA(cudaEventCreate(&ev_start));
         RT_CUDA(cudaEventCreate(&ev_stop));
@@ -342,6 +352,49 @@ struct rt_raytracer {
         std::memcpy(p->root_hi, root_hi, 12);
     }
 
+    void invalidate_schedule() {
+        sched_launches = 0;  // costs of the old view no longer predict the new one well: re-sort soon
+    }
+
+    cudaError_t launch_one(const TraceParams& p_in) {
+        TraceParams p = p_in;
+        const int a = cfg.accel == RT_ACCEL_OCTREE ? 0 : 1;
+        if (variant != 0 && lpt_schedule) {
+            const uint32_t tiles = ((p.cam.width + 7u) / 8u) * ((p.n_rows + 3u) / 4u);
+            if (tiles >= 4096) {  // short launches are latency bound; keep them in image order
+                if (sched_first != p.first_row || sched_rows != p.n_rows || sched_tiles != tiles) {
+                    if (d_tile_cost.n < tiles) {
+                        d_tile_cost.alloc(tiles);
+                        d_tile_order.alloc(tiles);
+                    }
+                    sched_first = p.first_row;
+                    sched_rows = p.n_rows;
+                    sched_tiles = tiles;
+                    sched_launches = 0;
+                    sched_have_order = false;
+                }
+                // re-sort after the 1st and 2nd recorded launch of a view, then every 8th
+                if (sched_launches == 1 || sched_launches == 2 || (sched_launches > 2 && sched_launches % 8 == 0)) {
+                    cudaError_t e = launch_tile_sort(d_tile_cost.p, d_tile_order.p, tiles, stream);
+                    if (e != cudaSuccess) return e;
+                    ++total_kernels;
+                    ++last.kernels_launched;
+                    sched_have_order = true;
+                }
+                p.tile_cost = d_tile_cost.p;
+                p.tile_order = sched_have_order ? d_tile_order.p : nullptr;
+                ++sched_launches;
+            }
+        }
+        if (variant != 0) {
+            if (blocks_per_sm[a] == 0) blocks_per_sm[a] = persistent_blocks_per_sm(a);
+            // the tile queue lives next to the ray counters; every launch starts it at zero
+            cudaError_t e = cudaMemsetAsync(d_counters.p + CNT_TILE_QUEUE, 0, sizeof(unsigned long long), stream);
+            if (e != cudaSuccess) return e;
+        }
+        return launch_trace(p, a, variant, blocks_per_sm[a] * num_sms, stream);
+    }
+
     // rows [first_row, first_row + n_rows) modulo height, `spp` passes
     void trace_rows(uint32_t first_row, uint32_t n_rows, uint32_t spp) {
         if (cfg.recursions != 0) throw CudaFail{"recursions > 0 (bounce rays) is not available in this build; call rt_configure(recursions = 0)"};
@@ -367,6 +420,7 @@ struct rt_raytracer {
         }
         p.first_row = first_row;
         RT_CUDA(cudaMemsetAsync(d_counters.p, 0, CNT_SLOTS * sizeof(unsigned long long), stream));
+        last = rt_launch_stats{};
         RT_CUDA(cudaEventRecord(ev_start, stream));
         uint32_t launches = 0;
         if (wraps_twice && !sharded()) {
@@ -376,21 +430,20 @@ struct rt_raytracer {
                     TraceParams q = p;
                     q.row_list = d_row_list.p + off;
                     q.n_rows = std::min(cfg.height, launch_rows - off);
-                    RT_CUDA(launch_trace(q, cfg.accel, stream));
+                    RT_CUDA(launch_one(q));
                     ++launches;
                 }
         } else {
             p.n_rows = launch_rows;
             for (uint32_t s = 0; s < spp; ++s) {
-                RT_CUDA(launch_trace(p, cfg.accel, stream));
+                RT_CUDA(launch_one(p));
                 ++launches;
             }
         }
         RT_CUDA(cudaEventRecord(ev_stop, stream));
         RT_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, CNT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         total_kernels += launches;
-        last = rt_launch_stats{};
-        last.kernels_launched = launches;
+        last.kernels_launched += launches;
         last.n_primary = (uint64_t)launch_rows * cfg.width * spp;
         stats_pending = true;
     }
@@ -649,16 +702,19 @@ int rt_get_primary_ids(rt_raytracer* rt, uint32_t* out) {
 int rt_camera_move_rel(rt_raytracer* rt, float x, float y, float z) {
     if (!rt) return RT_ERR_INVALID;
     rt->camera.move_rel(x, y, z);
+    rt->invalidate_schedule();
     return RT_OK;
 }
 int rt_camera_add_x_angle(rt_raytracer* rt, float radians) {
     if (!rt) return RT_ERR_INVALID;
     rt->camera.add_x_angle(radians);
+    rt->invalidate_schedule();
     return RT_OK;
 }
 int rt_camera_add_y_angle(rt_raytracer* rt, float radians) {
     if (!rt) return RT_ERR_INVALID;
     rt->camera.add_y_angle(radians);
+    rt->invalidate_schedule();
     return RT_OK;
 }
 int rt_camera_get(const rt_raytracer* rt, float* out34) {
@@ -671,10 +727,13 @@ int rt_camera_get(const rt_raytracer* rt, float* out34) {
 }
 int rt_camera_set_state(rt_raytracer* rt, float x_angle, float y_angle, const float pos[3]) {
     if (!rt || !pos) return RT_ERR_INVALID;
+    const bool changed = rt->camera.x_angle != x_angle || rt->camera.y_angle != y_angle || rt->camera.pos.x != pos[0] ||
+                         rt->camera.pos.y != pos[1] || rt->camera.pos.z != pos[2];
     rt->camera.x_angle = x_angle;
     rt->camera.y_angle = y_angle;
     rt->camera.pos = f3{pos[0], pos[1], pos[2]};
     rt->camera.update_matrices();
+    if (changed) rt->invalidate_schedule();
     return RT_OK;
 }
 
@@ -747,6 +806,22 @@ int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr) {
     return RT_OK;
 }
 uint32_t rt_launch_param_bytes(void) { return (uint32_t)sizeof(TraceParams); }
+
+int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
+    if (!rt) return RT_ERR_INVALID;
+    if (key == RT_TUNE_KERNEL_VARIANT && (value == 0 || value == 1)) {
+        rt->variant = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_TILE_SCHEDULE && (value == 0 || value == 1)) {
+        rt->lpt_schedule = value;
+        rt->sched_have_order = false;
+        rt->sched_launches = 0;
+        return RT_OK;
+    }
+    rt->last_error = "unknown tuning key or value";
+    return RT_ERR_INVALID;
+}
 
 int rt_get_launch_stats(const rt_raytracer* rt_c, rt_launch_stats* out) {
     rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
