@@ -279,6 +279,12 @@ done:
 // made only ~11 of 32 lanes useful per instruction in the first version (profiles/r1_v1_*.csv).
 // ------------------------------------------------------------------------------------------------------
 constexpr int kSentinel = 0x7fffffff;
+#ifdef RT_DEBUG_STEP_COUNTS
+#define g_dbg_nodes (*dbg_nodes_ptr())
+#define g_dbg_tris (*dbg_tris_ptr())
+__device__ __forceinline__ uint32_t* dbg_nodes_ptr() { extern __shared__ uint32_t dbg_sm[]; return &dbg_sm[threadIdx.x]; }
+__device__ __forceinline__ uint32_t* dbg_tris_ptr() { extern __shared__ uint32_t dbg_sm[]; return &dbg_sm[256 + threadIdx.x]; }
+#endif
 
 __device__ __forceinline__ bool octree_closest_hit_ww(const TraceParams& P, const V3& o, const V3& d, HitRec* out) {
     const V3 inv = {fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z)};
@@ -378,6 +384,9 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
     int cur = 0;
     while (cur != kSentinel) {
         while ((unsigned)cur < (unsigned)kSentinel) {  // inner nodes
+#ifdef RT_DEBUG_STEP_COUNTS
+            ++g_dbg_nodes;
+#endif
             const float4* n = P.bvh_nodes + 4 * (size_t)cur;
             const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
             const float a0x = fmaf(q0.x, ix, ox), b0x = fmaf(q0.w, ix, ox);
@@ -414,6 +423,9 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
             const uint32_t count = ref & 15u;
             const float4* tri = P.bvh_tris + 3 * (size_t)(ref >> 4);
             for (uint32_t i = 0; i < count; ++i) {
+#ifdef RT_DEBUG_STEP_COUNTS
+                ++g_dbg_tris;
+#endif
                 const float4 t0 = __ldg(tri + 3 * i), t1 = __ldg(tri + 3 * i + 1), t2 = __ldg(tri + 3 * i + 2);
                 float t, u, v;
                 if (!moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) continue;
@@ -629,8 +641,18 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         const uint32_t col = (tile % tiles_x) * 8u + (lane & 7u);
         const uint32_t crow = (tile / tiles_x) * 4u + (lane >> 3);
         const long long t0 = clock64();
+#ifdef RT_DEBUG_STEP_COUNTS
+        g_dbg_nodes = 0;
+        g_dbg_tris = 0;
+#endif
         if (col < P.cam.width && crow < P.n_rows) trace_pixel<ACCEL, 1>(P, col, crow, cnt);
         __syncwarp();
+#ifdef RT_DEBUG_STEP_COUNTS  // developer build only: (inner nodes visited | triangles tested << 16) instead of the primitive id
+        if (col < P.cam.width && crow < P.n_rows) {
+            const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % P.cam.height;
+            P.primary_ids[row * P.cam.width + col] = min(g_dbg_nodes, 65535u) | (min(g_dbg_tris, 65535u) << 16);
+        }
+#endif
         const long long dt = clock64() - t0;
         if (lane == 0 && P.tile_cost) P.tile_cost[tile] = dt > 0xffffffffll ? 0xffffffffu : (uint32_t)dt;
 #ifdef RT_DEBUG_TILE_CLOCKS  // developer build only (tools/): per-tile cycle count instead of the primitive id
@@ -736,7 +758,11 @@ cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persi
         if (accel == 0)
             trace_shade_persistent_kernel<0><<<blocks, 256, 0, stream>>>(p);
         else
+#ifdef RT_DEBUG_STEP_COUNTS
+            trace_shade_persistent_kernel<1><<<blocks, 256, 2048, stream>>>(p);
+#else
             trace_shade_persistent_kernel<1><<<blocks, 256, 0, stream>>>(p);
+#endif
     }
     return cudaGetLastError();
 }
