@@ -59,6 +59,9 @@ struct TraceParams {
     const uint32_t* row_list;
     uint32_t first_row, n_rows;
     uint32_t jitter_mode, seed;
+    int32_t recursions;          // RECURSIONS (mod.rs:81); 0 = primary + shadow only
+    uint32_t sub_spread;         // SUB_SPREAD (mod.rs:82)
+    const float* sample_table;   // 65 536 unit vectors (sample_generator.rs), 3 floats each
     float root_lo[3], root_hi[3];  // scene AABB = octree root cube (acceptance rule of the BVH path)
 };
 

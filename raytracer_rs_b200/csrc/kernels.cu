@@ -501,10 +501,148 @@ __device__ __forceinline__ uint32_t tonemap_pack(float sr, float sg, float sb, u
 // one pixel sample: camera ray -> closest hit -> shading with shadow rays -> film -> packed LDR pixel
 // ------------------------------------------------------------------------------------------------------
 struct LaneCounters {
-    uint32_t shadow_rays = 0, prim_hit = 0, blocked = 0;
+    uint32_t shadow_rays = 0, prim_hit = 0, blocked = 0, bounce_rays = 0;
 };
 
+// shade (mod.rs:207-261): direct light with one closest-hit shadow ray per light the surface faces
 template <int ACCEL, int WW>
+__device__ __forceinline__ void shade_hit(const TraceParams& P, const V3& o, const V3& d, const HitRec& hit, V3* normal_out, float* out_r,
+                                          float* out_g, float* out_b, LaneCounters& cnt) {
+    float cr = 0.f, cg = 0.f, cb = 0.f;
+    const float4 sh = __ldg(&P.tri_shade[hit.tri]);
+    const V3 nrm = {sh.x, sh.y, sh.z};
+    *normal_out = nrm;
+    const uint32_t geom = __float_as_uint(sh.w);
+    const V3 hp = vadd(o, vscale(d, hit.t));  // ray.pos + t * ray.dir  (mod.rs:212)
+    for (uint32_t li = 0; li < P.num_lights; ++li) {
+        const float4 lp = __ldg(&P.lights[2 * li]), lc = __ldg(&P.lights[2 * li + 1]);
+        const V3 L = vsub(V3{lp.x, lp.y, lp.z}, hp);
+        const V3 Ln = vunit(L);
+        const float ndl = vdot(nrm, Ln);
+        if (ndl < 0.0f) continue;
+        cnt.shadow_rays += 1;
+        const V3 so = vadd(hp, vscale(L, 0.01f));
+        if (shadow_blocked<ACCEL, WW>(P, so, L)) {
+            cnt.blocked += 1;
+            continue;
+        }
+        const float4 mat = __ldg(&P.materials[geom]);
+        float dr = mat.x, dg = mat.y, db = mat.z;
+        const int tex = __float_as_int(mat.w);
+        if (tex >= 0) {  // Texture::get_texel(hit.u, hit.v), texture.rs:21-27 (index clamped instead of panicking)
+            const DevTexture T = P.textures[tex];
+            const float fx = fmul(hit.u, (float)T.width), fy = fmul(hit.v, (float)T.height);
+            const size_t x = fx > 0.0f ? (size_t)__float2ull_rz(fx) : 0, y = fy > 0.0f ? (size_t)__float2ull_rz(fy) : 0;
+            size_t ti = y * T.width + x;
+            const size_t last = (size_t)T.width * T.height - 1;
+            if (ti > last) ti = last;
+            dr = T.rgb[3 * ti];
+            dg = T.rgb[3 * ti + 1];
+            db = T.rgb[3 * ti + 2];
+        }
+        const V3 view = vunit(d);
+        const V3 refl = vsub(vscale(nrm, fmul(2.0f, ndl)), Ln);  // 2.0 * ndl * normal - normalize(L)
+        const float spec = pow32(vdot(view, refl));
+        cr = fadd(cr, fmul(fadd(fmul(dr, ndl), spec), lc.x));
+        cg = fadd(cg, fmul(fadd(fmul(dg, ndl), spec), lc.y));
+        cb = fadd(cb, fmul(fadd(fmul(db, ndl), spec), lc.z));
+    }
+    *out_r = cr;
+    *out_g = cg;
+    *out_b = cb;
+}
+
+// compute_radiance (mod.rs:132-176) with bounce rays, as an explicit depth-first walk of the recursion tree.
+// Level l traces spread * (recursions - l) bounce rays (mod.rs:150); a bounce direction is the first entry of the
+// 65 536-entry unit-vector table, starting at a hashed index and stepping (idx + 1) % 65535, that lies in the
+// hemisphere of the normal (mod.rs:186-189, sample_generator.rs:25-33). `path` names the ray inside the tree so its
+// random numbers do not depend on evaluation order (shared definition with oracle/rt_oracle.cpp).
+constexpr int kMaxRecursions = 4;
+struct BounceFrame {
+    V3 o, d, normal;
+    HitRec hit;
+    float rr, rg, rb;  // radiance of this hit
+    float sr, sg, sb;  // sum over finished sub rays
+    uint32_t k, n, path;
+};
+template <int ACCEL, int WW>
+__device__ __noinline__ void radiance_with_bounces(const TraceParams& P, const V3& o0, const V3& d0, const HitRec& hit0, uint32_t pixel,
+                                                   uint32_t sample, float* out_r, float* out_g, float* out_b, LaneCounters& cnt) {
+    BounceFrame fr[kMaxRecursions + 1];
+    int lvl = 0;
+    fr[0].o = o0;
+    fr[0].d = d0;
+    fr[0].hit = hit0;
+    fr[0].path = 0u;
+    bool entering = true;
+    float ret_r = 0.f, ret_g = 0.f, ret_b = 0.f;
+    for (;;) {
+        BounceFrame& F = fr[lvl];
+        if (entering) {
+            shade_hit<ACCEL, WW>(P, F.o, F.d, F.hit, &F.normal, &F.rr, &F.rg, &F.rb, cnt);
+            const int rec = P.recursions - lvl;
+            F.k = 0u;
+            F.n = rec < 1 ? 0u : P.sub_spread * (uint32_t)rec;
+            F.sr = F.sg = F.sb = 0.f;
+            entering = false;
+            if (rec < 1) {  // `if recursions < 1 { return radiance; }`
+                ret_r = F.rr;
+                ret_g = F.rg;
+                ret_b = F.rb;
+                if (lvl == 0) break;
+                --lvl;
+                fr[lvl].sr = fadd(fr[lvl].sr, ret_r);
+                fr[lvl].sg = fadd(fr[lvl].sg, ret_g);
+                fr[lvl].sb = fadd(fr[lvl].sb, ret_b);
+                continue;
+            }
+        }
+        if (F.k < F.n) {
+            const uint32_t sub_path = F.path * 31u + F.k + 1u;
+            F.k += 1u;
+            // normalized_vec_pseudo: random_range(0..NUM_SAMPLES - 1)
+            uint32_t idx = (uint32_t)(((unsigned long long)hash4(P.seed ^ 0xb0c0ffeeU, pixel, sample, sub_path) * 65535ull) >> 32);
+            V3 rd = {P.sample_table[3 * idx], P.sample_table[3 * idx + 1], P.sample_table[3 * idx + 2]};
+            while (vdot(rd, F.normal) <= 0.0f) {
+                idx = (idx + 1u) % 65535u;  // normalized_vec_lookup: (sample_idx + 1) % SAMPLE_MAX
+                rd = V3{P.sample_table[3 * idx], P.sample_table[3 * idx + 1], P.sample_table[3 * idx + 2]};
+            }
+            V3 hp = vadd(F.o, vscale(F.d, F.hit.t));       // ray.pos + t * ray.dir       (mod.rs:192)
+            hp = vadd(hp, vscale(rd, 0.00001f));           // + 0.00001 * random_dir      (mod.rs:193)
+            cnt.bounce_rays += 1;
+            HitRec h;
+            if (closest_hit<ACCEL, WW>(P, hp, rd, &h) && lvl < kMaxRecursions) {
+                BounceFrame& N = fr[lvl + 1];
+                N.o = hp;
+                N.d = rd;
+                N.hit = h;
+                N.path = sub_path;
+                ++lvl;
+                entering = true;
+            } else {  // None => RGB::black()
+                F.sr = fadd(F.sr, 0.0f);
+                F.sg = fadd(F.sg, 0.0f);
+                F.sb = fadd(F.sb, 0.0f);
+            }
+            continue;
+        }
+        // radiance + fold(sum) * (1.0 / num_sub_rays)
+        const float inv = fdiv(1.0f, (float)F.n);
+        ret_r = fadd(F.rr, fmul(F.sr, inv));
+        ret_g = fadd(F.rg, fmul(F.sg, inv));
+        ret_b = fadd(F.rb, fmul(F.sb, inv));
+        if (lvl == 0) break;
+        --lvl;
+        fr[lvl].sr = fadd(fr[lvl].sr, ret_r);
+        fr[lvl].sg = fadd(fr[lvl].sg, ret_g);
+        fr[lvl].sb = fadd(fr[lvl].sb, ret_b);
+    }
+    *out_r = ret_r;
+    *out_g = ret_g;
+    *out_b = ret_b;
+}
+
+template <int ACCEL, int WW, int BOUNCE>
 __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, uint32_t crow, LaneCounters& cnt) {
     const uint32_t W = P.cam.width, H = P.cam.height;
     const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % H;
@@ -534,42 +672,11 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, 
     if (closest_hit<ACCEL, WW>(P, o, d, &hit)) {
         cnt.prim_hit += 1;
         id = hit.tri;
-        const float4 sh = __ldg(&P.tri_shade[hit.tri]);
-        const V3 nrm = {sh.x, sh.y, sh.z};
-        const uint32_t geom = __float_as_uint(sh.w);
-        const V3 hp = vadd(o, vscale(d, hit.t));  // ray.pos + t * ray.dir  (mod.rs:212)
-        for (uint32_t li = 0; li < P.num_lights; ++li) {
-            const float4 lp = __ldg(&P.lights[2 * li]), lc = __ldg(&P.lights[2 * li + 1]);
-            const V3 L = vsub(V3{lp.x, lp.y, lp.z}, hp);
-            const V3 Ln = vunit(L);
-            const float ndl = vdot(nrm, Ln);
-            if (ndl < 0.0f) continue;
-            cnt.shadow_rays += 1;
-            const V3 so = vadd(hp, vscale(L, 0.01f));
-            if (shadow_blocked<ACCEL, WW>(P, so, L)) {
-                cnt.blocked += 1;
-                continue;
-            }
-            const float4 mat = __ldg(&P.materials[geom]);
-            float dr = mat.x, dg = mat.y, db = mat.z;
-            const int tex = __float_as_int(mat.w);
-            if (tex >= 0) {  // Texture::get_texel(hit.u, hit.v), texture.rs:21-27 (index clamped instead of panicking)
-                const DevTexture T = P.textures[tex];
-                const float fx = fmul(hit.u, (float)T.width), fy = fmul(hit.v, (float)T.height);
-                const size_t x = fx > 0.0f ? (size_t)__float2ull_rz(fx) : 0, y = fy > 0.0f ? (size_t)__float2ull_rz(fy) : 0;
-                size_t ti = y * T.width + x;
-                const size_t last = (size_t)T.width * T.height - 1;
-                if (ti > last) ti = last;
-                dr = T.rgb[3 * ti];
-                dg = T.rgb[3 * ti + 1];
-                db = T.rgb[3 * ti + 2];
-            }
-            const V3 view = vunit(d);
-            const V3 refl = vsub(vscale(nrm, fmul(2.0f, ndl)), Ln);  // 2.0 * ndl * normal - normalize(L)
-            const float spec = pow32(vdot(view, refl));
-            cr = fadd(cr, fmul(fadd(fmul(dr, ndl), spec), lc.x));
-            cg = fadd(cg, fmul(fadd(fmul(dg, ndl), spec), lc.y));
-            cb = fadd(cb, fmul(fadd(fmul(db, ndl), spec), lc.z));
+        if (BOUNCE) {
+            radiance_with_bounces<ACCEL, WW>(P, o, d, hit, idx, nsamp, &cr, &cg, &cb, cnt);
+        } else {
+            V3 nrm;
+            shade_hit<ACCEL, WW>(P, o, d, hit, &nrm, &cr, &cg, &cb, cnt);
         }
     }
     // add_sample (film.rs:20-24)
@@ -595,7 +702,9 @@ __device__ __forceinline__ void flush_counters(const TraceParams& P, LaneCounter
     const uint32_t s = __reduce_add_sync(0xffffffffu, c.shadow_rays);
     const uint32_t h = __reduce_add_sync(0xffffffffu, c.prim_hit);
     const uint32_t b = __reduce_add_sync(0xffffffffu, c.blocked);
+    const uint32_t r = __reduce_add_sync(0xffffffffu, c.bounce_rays);
     if (lane == 0) {
+        if (r) atomicAdd(&P.counters[CNT_BOUNCE], (unsigned long long)r);
         if (s) atomicAdd(&P.counters[CNT_SHADOW], (unsigned long long)s);
         if (h) atomicAdd(&P.counters[CNT_PRIMARY_HITS], (unsigned long long)h);
         if (b) atomicAdd(&P.counters[CNT_BLOCKED], (unsigned long long)b);
@@ -605,13 +714,13 @@ __device__ __forceinline__ void flush_counters(const TraceParams& P, LaneCounter
 // ------------------------------------------------------------------------------------------------------
 // variant 0: one thread per pixel, block = 8 warps, each warp an 8x4 pixel tile, block = 32x8 pixels
 // ------------------------------------------------------------------------------------------------------
-template <int ACCEL>
+template <int ACCEL, int BOUNCE>
 __global__ void __launch_bounds__(256) trace_shade_kernel(const __grid_constant__ TraceParams P) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t col = blockIdx.x * 32u + (warp & 3u) * 8u + (lane & 7u);
     const uint32_t crow = blockIdx.y * 8u + (warp >> 2) * 4u + (lane >> 3);
     LaneCounters cnt;
-    if (col < P.cam.width && crow < P.n_rows) trace_pixel<ACCEL, 0>(P, col, crow, cnt);
+    if (col < P.cam.width && crow < P.n_rows) trace_pixel<ACCEL, 0, BOUNCE>(P, col, crow, cnt);
     flush_counters(P, cnt, lane);
 }
 
@@ -623,7 +732,7 @@ __global__ void __launch_bounds__(256) trace_shade_kernel(const __grid_constant_
 #ifndef RT_PERSISTENT_MIN_BLOCKS
 #define RT_PERSISTENT_MIN_BLOCKS 3
 #endif
-template <int ACCEL>
+template <int ACCEL, int BOUNCE>
 __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_persistent_kernel(const __grid_constant__ TraceParams P) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t tiles_x = (P.cam.width + 7u) / 8u;
@@ -645,7 +754,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         g_dbg_nodes = 0;
         g_dbg_tris = 0;
 #endif
-        if (col < P.cam.width && crow < P.n_rows) trace_pixel<ACCEL, 1>(P, col, crow, cnt);
+        if (col < P.cam.width && crow < P.n_rows) trace_pixel<ACCEL, 1, BOUNCE>(P, col, crow, cnt);
         __syncwarp();
 #ifdef RT_DEBUG_STEP_COUNTS  // developer build only: (inner nodes visited | triangles tested << 16) instead of the primitive id
         if (col < P.cam.width && crow < P.n_rows) {
@@ -743,41 +852,57 @@ __global__ void gather_rows_kernel(const uint32_t* __restrict__ ldr, const uint3
 // ------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------
-cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persistent_blocks, cudaStream_t stream) {
-    if (p.n_rows == 0) return cudaSuccess;
+template <int ACCEL, int BOUNCE>
+static void launch_trace_t(const TraceParams& p, int variant, uint32_t blocks, cudaStream_t stream) {
     if (variant == 0) {
         dim3 grid((p.cam.width + 31u) / 32u, (p.n_rows + 7u) / 8u);
-        if (accel == 0)
-            trace_shade_kernel<0><<<grid, 256, 0, stream>>>(p);
-        else
-            trace_shade_kernel<1><<<grid, 256, 0, stream>>>(p);
+        trace_shade_kernel<ACCEL, BOUNCE><<<grid, 256, 0, stream>>>(p);
     } else {
-        const uint32_t tiles = ((p.cam.width + 7u) / 8u) * ((p.n_rows + 3u) / 4u);
-        uint32_t blocks = (uint32_t)persistent_blocks;
-        if (blocks * 8u > tiles) blocks = (tiles + 7u) / 8u;
-        if (accel == 0)
-            trace_shade_persistent_kernel<0><<<blocks, 256, 0, stream>>>(p);
-        else
 #ifdef RT_DEBUG_STEP_COUNTS
-            trace_shade_persistent_kernel<1><<<blocks, 256, 2048, stream>>>(p);
+        trace_shade_persistent_kernel<ACCEL, BOUNCE><<<blocks, 256, 2048, stream>>>(p);
 #else
-            trace_shade_persistent_kernel<1><<<blocks, 256, 0, stream>>>(p);
+        trace_shade_persistent_kernel<ACCEL, BOUNCE><<<blocks, 256, 0, stream>>>(p);
 #endif
     }
+}
+cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persistent_blocks, cudaStream_t stream) {
+    if (p.n_rows == 0) return cudaSuccess;
+    const uint32_t tiles = ((p.cam.width + 7u) / 8u) * ((p.n_rows + 3u) / 4u);
+    uint32_t blocks = (uint32_t)persistent_blocks;
+    if (blocks * 8u > tiles) blocks = (tiles + 7u) / 8u;
+    const bool bounce = p.recursions > 0;
+    if (accel == 0) {
+        if (bounce)
+            launch_trace_t<0, 1>(p, variant, blocks, stream);
+        else
+            launch_trace_t<0, 0>(p, variant, blocks, stream);
+    } else {
+        if (bounce)
+            launch_trace_t<1, 1>(p, variant, blocks, stream);
+        else
+            launch_trace_t<1, 0>(p, variant, blocks, stream);
+    }
     return cudaGetLastError();
+}
+// resident 256-thread blocks per SM of the persistent kernel (for sizing its grid)
+int persistent_blocks_per_sm(int accel, int bounce) {
+    int n = 0;
+    if (accel == 0) {
+        if (bounce)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<0, 1>, 256, 0);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<0, 0>, 256, 0);
+    } else {
+        if (bounce)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<1, 1>, 256, 0);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<1, 0>, 256, 0);
+    }
+    return n > 0 ? n : 1;
 }
 cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, cudaStream_t stream) {
     tile_sort_kernel<<<1, 1024, 0, stream>>>(cost, order, n);
     return cudaGetLastError();
-}
-// resident 256-thread blocks per SM of the persistent kernel (for sizing its grid)
-int persistent_blocks_per_sm(int accel) {
-    int n = 0;
-    if (accel == 0)
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<0>, 256, 0);
-    else
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<1>, 256, 0);
-    return n > 0 ? n : 1;
 }
 cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream) {
     film_clear_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(sum, sq, ldr, ids, n);

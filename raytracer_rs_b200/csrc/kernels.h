@@ -9,7 +9,7 @@ namespace rtb {
 // fused primary ray -> closest hit -> shadow rays -> Phong/texture -> film -> tonemap/pack
 // variant 0: one thread per pixel; variant 1: persistent warps pulling 8x4 tiles from an atomic queue
 cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persistent_blocks, cudaStream_t stream);
-int persistent_blocks_per_sm(int accel);
+int persistent_blocks_per_sm(int accel, int bounce);
 // order[] = tile ids by descending cost (longest-processing-time-first schedule for the persistent kernel)
 cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, cudaStream_t stream);
 cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream);

@@ -105,7 +105,7 @@ struct rt_raytracer {
     uint32_t sched_first = ~0u, sched_rows = ~0u, sched_tiles = 0;
     uint32_t sched_launches = 0;  // launches recorded since the schedule geometry / camera last changed
     bool sched_have_order = false;
-    int blocks_per_sm[2] = {0, 0};
+    int blocks_per_sm[2][2] = {{0, 0}, {0, 0}};  // [accel][bounce]
     int num_sms = 0;
     rt_launch_stats last{};
     bool stats_pending = false;
@@ -234,6 +234,53 @@ struct rt_raytracer {
         out[2] = make_float4(e2z, idw, 0.f, 0.f);
     }
 
+    // SampleGenerator::new (sample_generator.rs:15-24, 35-52): 65 536 unit vectors, rejection sampled in the unit
+    // ball. The reference draws them from rand::rng(); here they come from the shared counter-based hash so that
+    // oracle and GPU hold the same table for a given seed.
+    DevBuf<float> d_sample_table;
+    uint32_t sample_table_seed = 0;
+    bool sample_table_ready = false;
+    static uint32_t mix32(uint32_t h) {
+        h ^= h >> 16;
+        h *= 0x7feb352dU;
+        h ^= h >> 15;
+        h *= 0x846ca68bU;
+        h ^= h >> 16;
+        return h;
+    }
+    static uint32_t hash4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+        uint32_t h = mix32(a + 0x9e3779b9U);
+        h = mix32(h ^ (b + 0x85ebca6bU));
+        h = mix32(h ^ (c + 0xc2b2ae35U));
+        h = mix32(h ^ (d + 0x27d4eb2fU));
+        return h;
+    }
+    void ensure_sample_table() {
+        if (sample_table_ready && sample_table_seed == cfg.seed) return;
+        std::vector<float> table(65536 * 3);
+        const uint32_t key = cfg.seed ^ 0x5a17ab1eU;
+        for (uint32_t i = 0; i < 65536; ++i) {
+            for (uint32_t attempt = 0;; ++attempt) {
+                f3 v;
+                v.x = (float)(hash4(key, i, attempt, 0) >> 8) * (1.0f / 16777216.0f) * 2.0f - 1.0f;
+                v.y = (float)(hash4(key, i, attempt, 1) >> 8) * (1.0f / 16777216.0f) * 2.0f - 1.0f;
+                v.z = (float)(hash4(key, i, attempt, 2) >> 8) * (1.0f / 16777216.0f) * 2.0f - 1.0f;
+                const float len2 = dot3(v, v);
+                if (len2 < 1.0f && len2 > 0.0f) {
+                    const f3 u = unit3(v);
+                    table[3 * i] = u.x;
+                    table[3 * i + 1] = u.y;
+                    table[3 * i + 2] = u.z;
+                    break;
+                }
+            }
+        }
+        d_sample_table.upload(table, stream);
+        RT_CUDA(cudaStreamSynchronize(stream));  // `table` goes out of scope
+        sample_table_seed = cfg.seed;
+        sample_table_ready = true;
+    }
+
     void ensure_octree_host() {
         if (octree_built) return;
         octree = build_octree(scene, cfg.triangles_per_leaf);
@@ -348,6 +395,9 @@ struct rt_raytracer {
         p->counters = d_counters.p;
         p->jitter_mode = (uint32_t)cfg.jitter_mode;
         p->seed = cfg.seed;
+        p->recursions = cfg.recursions;
+        p->sub_spread = cfg.sub_spread;
+        p->sample_table = d_sample_table.p;
         std::memcpy(p->root_lo, root_lo, 12);
         std::memcpy(p->root_hi, root_hi, 12);
     }
@@ -359,6 +409,7 @@ struct rt_raytracer {
     cudaError_t launch_one(const TraceParams& p_in) {
         TraceParams p = p_in;
         const int a = cfg.accel == RT_ACCEL_OCTREE ? 0 : 1;
+        const int b = cfg.recursions > 0 ? 1 : 0;
         if (variant != 0 && lpt_schedule) {
             const uint32_t tiles = ((p.cam.width + 7u) / 8u) * ((p.n_rows + 3u) / 4u);
             if (tiles >= 4096) {  // short launches are latency bound; keep them in image order
@@ -387,17 +438,18 @@ struct rt_raytracer {
             }
         }
         if (variant != 0) {
-            if (blocks_per_sm[a] == 0) blocks_per_sm[a] = persistent_blocks_per_sm(a);
+            if (blocks_per_sm[a][b] == 0) blocks_per_sm[a][b] = persistent_blocks_per_sm(a, b);
             // the tile queue lives next to the ray counters; every launch starts it at zero
             cudaError_t e = cudaMemsetAsync(d_counters.p + CNT_TILE_QUEUE, 0, sizeof(unsigned long long), stream);
             if (e != cudaSuccess) return e;
         }
-        return launch_trace(p, a, variant, blocks_per_sm[a] * num_sms, stream);
+        return launch_trace(p, a, variant, blocks_per_sm[a][b] * num_sms, stream);
     }
 
     // rows [first_row, first_row + n_rows) modulo height, `spp` passes
     void trace_rows(uint32_t first_row, uint32_t n_rows, uint32_t spp) {
-        if (cfg.recursions != 0) throw CudaFail{"recursions > 0 (bounce rays) is not available in this build; call rt_configure(recursions = 0)"};
+        if (cfg.recursions > 4) throw CudaFail{"recursions > 4 is not supported (the reference uses 2)"};
+        if (cfg.recursions > 0) ensure_sample_table();
         ensure_accel(cfg.accel);
         TraceParams p;
         fill_params(&p);
