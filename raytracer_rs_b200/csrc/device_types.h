@@ -29,7 +29,7 @@ constexpr uint32_t kNoHit = 0xFFFFFFFFu;
 constexpr int kOctStack = 64;  // >= 7 * depth + 1 with depth <= 9 (oct_tree_intersector.rs:108)
 constexpr int kBvhStack = 48;
 
-enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3, CNT_TILE_QUEUE = 4, CNT_SLOTS = 5 };
+enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3, CNT_TILE_QUEUE = 4, CNT_QUEUE_ITEMS = 5, CNT_SLOTS = 6 };
 
 struct TraceParams {
     DevCamera cam;

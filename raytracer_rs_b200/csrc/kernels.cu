@@ -279,6 +279,10 @@ done:
 // made only ~11 of 32 lanes useful per instruction in the first version (profiles/r1_v1_*.csv).
 // ------------------------------------------------------------------------------------------------------
 constexpr int kSentinel = 0x7fffffff;
+constexpr uint32_t kItemTileMask = 0x0fffffffu, kItemSplitFlag = 0x80000000u;
+constexpr int kItemPartShift = 28;
+constexpr uint32_t kSplitRatio = 2u;          // split tiles costing more than (sum of costs / resident warps) / 2 ...
+constexpr uint32_t kSplitMinCycles = 40000u;  // ... and at least this many cycles
 #ifdef RT_DEBUG_STEP_COUNTS
 #define g_dbg_nodes (*dbg_nodes_ptr())
 #define g_dbg_tris (*dbg_tris_ptr())
@@ -401,16 +405,13 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
             const float f1 = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), best.t));
             const bool h0 = n0 <= f0, h1 = n1 <= f1;
             const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-            if (h0 && h1) {
-                const bool first0 = n0 <= n1;
-                stack_node[sp] = first0 ? c1 : c0;
-                stack_t[sp] = first0 ? n1 : n0;
-                ++sp;
-                cur = first0 ? c0 : c1;
-            } else if (h0) {
-                cur = c0;
-            } else if (h1) {
-                cur = c1;
+            // one branch instead of four: the far child is stored unconditionally and kept only if both children hit
+            const bool go1 = h1 && (!h0 || n1 < n0);  // child 1 first (child 0 wins ties, as before)
+            stack_node[sp] = go1 ? c0 : c1;
+            stack_t[sp] = go1 ? n0 : n1;
+            sp += (h0 && h1) ? 1 : 0;
+            if (h0 || h1) {
+                cur = go1 ? c1 : c0;
             } else {
                 do {
                     --sp;
@@ -738,34 +739,47 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
     const uint32_t tiles_x = (P.cam.width + 7u) / 8u;
     const uint32_t n_tiles = tiles_x * ((P.n_rows + 3u) / 4u);
     LaneCounters cnt;
+    // queue length: n_tiles in image order, or the item count the last tile_sort_kernel produced (heavy tiles are
+    // split into four 8-pixel items so that their serial divergent chain is spread over four warps)
+    const uint32_t n_items = P.tile_order ? (uint32_t)P.counters[CNT_QUEUE_ITEMS] : n_tiles;
     for (;;) {
-        uint32_t tile = 0;
+        uint32_t item = 0;
         if (lane == 0) {
-            tile = (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], 1ull);
-            // cost-feedback schedule: queue slot -> tile id, heaviest tiles (by last frame's cycle count) first
-            if (P.tile_order && tile < n_tiles) tile = P.tile_order[tile];
+            item = (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], 1ull);
+            // cost-feedback schedule: queue slot -> work item, heaviest tiles (by last frame's cycle count) first
+            if (item < n_items) item = P.tile_order ? P.tile_order[item] : item;
+            else item = 0xffffffffu;
         }
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item == 0xffffffffu) break;
+        const uint32_t tile = item & kItemTileMask;
+        const bool split = (item & kItemSplitFlag) != 0u;
+        const uint32_t part = (item >> kItemPartShift) & 3u;
         const uint32_t col = (tile % tiles_x) * 8u + (lane & 7u);
         const uint32_t crow = (tile / tiles_x) * 4u + (lane >> 3);
+        const bool mine = col < P.cam.width && crow < P.n_rows && (!split || (lane >> 3) == part);
         const long long t0 = clock64();
 #ifdef RT_DEBUG_STEP_COUNTS
         g_dbg_nodes = 0;
         g_dbg_tris = 0;
 #endif
-        if (col < P.cam.width && crow < P.n_rows) trace_pixel<ACCEL, 1, BOUNCE>(P, col, crow, cnt);
+        if (mine) trace_pixel<ACCEL, 1, BOUNCE>(P, col, crow, cnt);
         __syncwarp();
 #ifdef RT_DEBUG_STEP_COUNTS  // developer build only: (inner nodes visited | triangles tested << 16) instead of the primitive id
-        if (col < P.cam.width && crow < P.n_rows) {
+        if (mine) {
             const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % P.cam.height;
             P.primary_ids[row * P.cam.width + col] = min(g_dbg_nodes, 65535u) | (min(g_dbg_tris, 65535u) << 16);
         }
 #endif
         const long long dt = clock64() - t0;
-        if (lane == 0 && P.tile_cost) P.tile_cost[tile] = dt > 0xffffffffll ? 0xffffffffu : (uint32_t)dt;
-#ifdef RT_DEBUG_TILE_CLOCKS  // developer build only (tools/): per-tile cycle count instead of the primitive id
-        if (col < P.cam.width && crow < P.n_rows) {
+        if (lane == 0 && P.tile_cost) {
+            const uint32_t c = dt > 0x3fffffffll ? 0x3fffffffu : (uint32_t)dt;
+            // a split tile keeps the largest 4 x part cost seen (sticky, so it stays split while the view lasts)
+            if (split) atomicMax(&P.tile_cost[tile], 4u * c);
+            else P.tile_cost[tile] = c;
+        }
+#ifdef RT_DEBUG_TILE_CLOCKS  // developer build only (tools/): per-item cycle count instead of the primitive id
+        if (mine) {
             const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % P.cam.height;
             P.primary_ids[row * P.cam.width + col] = (uint32_t)dt;
         }
@@ -781,17 +795,37 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
 // runs dry. Only the schedule depends on it; pixel results do not.
 // ------------------------------------------------------------------------------------------------------
 constexpr int kSortBuckets = 2048;
-__global__ void __launch_bounds__(1024) tile_sort_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n) {
+// Items: bits 0..27 tile id, bits 28..29 part (pixel row of the 8x4 tile), bit 31 "split" flag.
+// A tile whose cost exceeds 1/kSplitRatio of the balanced launch time becomes four items (one pixel row each):
+// the end of a launch is bounded by the slowest single item, and a warp that works on 8 instead of 32 divergent
+// rays has a much shorter serial chain. The extra items cost lanes, not time: they run while the GPU is full.
+__global__ void __launch_bounds__(1024) tile_sort_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n,
+                                                         uint32_t n_warps, uint32_t allow_split, unsigned long long* __restrict__ counters) {
     __shared__ uint32_t hist[kSortBuckets];
     __shared__ uint32_t scan_tmp[1024];
+    __shared__ unsigned long long total_cost;
     for (int b = threadIdx.x; b < kSortBuckets; b += blockDim.x) hist[b] = 0;
+    if (threadIdx.x == 0) total_cost = 0;
     __syncthreads();
+    unsigned long long local_sum = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) local_sum += cost[i];
+    atomicAdd(&total_cost, local_sum);
+    __syncthreads();
+    // a perfectly balanced launch would take total / n_warps; only tiles that alone exceed a fraction of that can
+    // stretch the tail, so only those are split (a launch of uniformly heavy tiles is left alone)
+    const unsigned long long balanced = total_cost / (unsigned long long)max(n_warps, 1u);
+    const uint32_t split_above =
+        allow_split ? (uint32_t)min((unsigned long long)0x7fffffffu, max(balanced / kSplitRatio, (unsigned long long)kSplitMinCycles)) : 0xffffffffu;
     auto bucket = [](uint32_t c) {
-        // 64 buckets per octave; reversed so that bucket 0 holds the most expensive tiles
+        // 64 buckets per octave; reversed so that bucket 0 holds the most expensive items
         const int k = (int)(__log2f((float)c + 1.0f) * 64.0f);
         return (uint32_t)(kSortBuckets - 1 - min(max(k, 0), kSortBuckets - 1));
     };
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[bucket(cost[i])], 1u);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t c = cost[i];
+        if (c >= split_above) atomicAdd(&hist[bucket(c / 4u)], 4u);
+        else atomicAdd(&hist[bucket(c)], 1u);
+    }
     __syncthreads();
     // exclusive scan of 2048 buckets: each thread owns two adjacent buckets
     const uint32_t a = hist[2 * threadIdx.x], b2 = hist[2 * threadIdx.x + 1];
@@ -803,11 +837,20 @@ __global__ void __launch_bounds__(1024) tile_sort_kernel(const uint32_t* __restr
         scan_tmp[threadIdx.x] += v;
         __syncthreads();
     }
+    if (threadIdx.x == 1023) counters[CNT_QUEUE_ITEMS] = scan_tmp[1023];
     const uint32_t base = scan_tmp[threadIdx.x] - (a + b2);
     hist[2 * threadIdx.x] = base;
     hist[2 * threadIdx.x + 1] = base + a;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&hist[bucket(cost[i])], 1u)] = i;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t c = cost[i];
+        if (c >= split_above) {
+            const uint32_t at = atomicAdd(&hist[bucket(c / 4u)], 4u);
+            for (uint32_t part = 0; part < 4u; ++part) order[at + part] = i | (part << kItemPartShift) | kItemSplitFlag;
+        } else {
+            order[atomicAdd(&hist[bucket(c)], 1u)] = i;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -900,8 +943,9 @@ int persistent_blocks_per_sm(int accel, int bounce) {
     }
     return n > 0 ? n : 1;
 }
-cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, cudaStream_t stream) {
-    tile_sort_kernel<<<1, 1024, 0, stream>>>(cost, order, n);
+cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, uint32_t n_warps, bool allow_split,
+                             unsigned long long* counters, cudaStream_t stream) {
+    tile_sort_kernel<<<1, 1024, 0, stream>>>(cost, order, n, n_warps, allow_split ? 1u : 0u, counters);
     return cudaGetLastError();
 }
 cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream) {

@@ -11,7 +11,11 @@ namespace rtb {
 cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persistent_blocks, cudaStream_t stream);
 int persistent_blocks_per_sm(int accel, int bounce);
 // order[] = tile ids by descending cost (longest-processing-time-first schedule for the persistent kernel)
-cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, cudaStream_t stream);
+// order must hold 4 * n entries (heavy tiles become four items); counters[CNT_QUEUE_ITEMS] receives the item count
+// allow_split: heavy tiles may become four quarter-tile items (pays off for the divergent BVH kernel, not for the octree's
+// long coherent leaf loops)
+cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, uint32_t n_warps, bool allow_split,
+                             unsigned long long* counters, cudaStream_t stream);
 cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream);
 cudaError_t launch_tonemap(const float4* sum, uint32_t* ldr, uint32_t n, cudaStream_t stream);
 cudaError_t launch_gather_rows(const uint32_t* ldr, const uint32_t* row_list, uint32_t n_rows, uint32_t width, uint32_t* out,

@@ -30,6 +30,11 @@ namespace {
 struct CudaFail {
     std::string what;
 };
+#define RT_CUDA_RET(expr)                      \
+    do {                                       \
+        cudaError_t e__ = (expr);              \
+        if (e__ != cudaSuccess) return e__;    \
+    } while (0)
 #define RT_CUDA(expr)                                                                                   \
     do {                                                                                                \
         cudaError_t e__ = (expr);                                                                       \
@@ -416,17 +421,23 @@ struct rt_raytracer {
                 if (sched_first != p.first_row || sched_rows != p.n_rows || sched_tiles != tiles) {
                     if (d_tile_cost.n < tiles) {
                         d_tile_cost.alloc(tiles);
-                        d_tile_order.alloc(tiles);
+                        d_tile_order.alloc(4 * (size_t)tiles);
                     }
                     sched_first = p.first_row;
                     sched_rows = p.n_rows;
                     sched_tiles = tiles;
                     sched_launches = 0;
                     sched_have_order = false;
+                    RT_CUDA_RET(cudaMemsetAsync(d_tile_cost.p, 0, tiles * sizeof(uint32_t), stream));
+                }
+                if (sched_launches == 0 && sched_have_order) {  // the view changed: forget the old costs and order
+                    RT_CUDA_RET(cudaMemsetAsync(d_tile_cost.p, 0, tiles * sizeof(uint32_t), stream));
+                    sched_have_order = false;
                 }
                 // re-sort after the 1st and 2nd recorded launch of a view, then every 8th
                 if (sched_launches == 1 || sched_launches == 2 || (sched_launches > 2 && sched_launches % 8 == 0)) {
-                    cudaError_t e = launch_tile_sort(d_tile_cost.p, d_tile_order.p, tiles, stream);
+                    if (blocks_per_sm[a][b] == 0) blocks_per_sm[a][b] = persistent_blocks_per_sm(a, b);
+                    cudaError_t e = launch_tile_sort(d_tile_cost.p, d_tile_order.p, tiles, (uint32_t)(blocks_per_sm[a][b] * num_sms * 8), a == 1, d_counters.p, stream);
                     if (e != cudaSuccess) return e;
                     ++total_kernels;
                     ++last.kernels_launched;
@@ -471,7 +482,7 @@ struct rt_raytracer {
             launch_rows = (uint32_t)row_list_cache.size();
         }
         p.first_row = first_row;
-        RT_CUDA(cudaMemsetAsync(d_counters.p, 0, CNT_SLOTS * sizeof(unsigned long long), stream));
+        RT_CUDA(cudaMemsetAsync(d_counters.p, 0, CNT_QUEUE_ITEMS * sizeof(unsigned long long), stream));  // keeps the item count
         last = rt_launch_stats{};
         RT_CUDA(cudaEventRecord(ev_start, stream));
         uint32_t launches = 0;
