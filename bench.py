@@ -227,6 +227,9 @@ def main():
     ap.add_argument("--accel", default="bvh", choices=["bvh", "octree"])
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N>1: how rank 0 receives the frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--zero-copy", action="store_true",
+                    help="e2e leg: let the kernel store packed pixels straight into the pinned host frame (rt_set_host_frame) instead of "
+                         "copying the frame after the kernel; measured slower on PCIe (32-byte writes), kept as an option")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -348,6 +351,8 @@ def main():
         else:
             tracer.get_tonemapped_pixels_into(host_frame.data_ptr())
 
+    if gather is None and args.zero_copy:
+        tracer.set_host_frame(host_frame.data_ptr())  # the kernel stores packed pixels straight into the pinned frame
     for i in range(args.warmup):
         e2e_step(i)
     barrier()
@@ -362,6 +367,13 @@ def main():
     e2e_s = float(e2e_t)
     e2e_value = rays_per_step * args.steps / e2e_s / 1e6
     sampler.stop()
+    e2e_frame_ok = None
+    if rank == 0 and gather is None:
+        # the frame delivered by the last e2e step must equal the device frame
+        check = np.empty(W * H, np.uint32)
+        tracer.set_host_frame(None)
+        tracer.get_tonemapped_pixels(check)
+        e2e_frame_ok = bool(np.array_equal(check, host_frame.numpy().view(np.uint32)))
 
     # ---- the reference's own call pattern: 50-row bands, full-frame readback after every band (main.rs:200-201) ----
     band = None
@@ -423,7 +435,9 @@ def main():
         "frames_per_s": args.steps / (total_ms * 1e-3),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rt.lib().rt_launch_param_bytes()), "d2h_bytes_per_step": W * H * 4 + 32,
-                "ms_per_step": e2e_s / args.steps * 1e3, "note": "camera state in (launch parameters), packed LDR frame out to pinned host memory, wall clock"},
+                "ms_per_step": e2e_s / args.steps * 1e3, "readback": "nccl/peer gather + copy" if world > 1 else ("zero-copy stores from the trace kernel into the pinned frame" if args.zero_copy else "cudaMemcpyAsync after the kernel"),
+                "frame_matches_device": e2e_frame_ok,
+                "note": "camera state in (launch parameters), packed LDR frame out to pinned host memory, wall clock"},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }

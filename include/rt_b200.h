@@ -166,6 +166,11 @@ int rt_get_ldr_device_ptr(rt_raytracer* rt, void** dev_ptr);
 /* Redirect the LDR stores of the rows this instance owns into `dev_ptr` (e.g. a peer-mapped framebuffer of
    rank 0, or a torch tensor): the fused trace+gather path. NULL restores the internal buffer. */
 int rt_set_ldr_target(rt_raytracer* rt, void* dev_ptr);
+/* Zero-copy readback: register a page-locked (cudaHostAlloc / cudaHostRegister, mapped) host buffer of width*height
+   u32. From then on the trace kernel's epilogue also stores every packed pixel straight into that buffer over PCIe
+   while it renders, and rt_get_tonemapped_pixels(rt, same pointer) only synchronises the stream (no device->host
+   copy after the fact). NULL unregisters. Rows this handle never traces keep whatever the buffer held. */
+int rt_set_host_frame(rt_raytracer* rt, uint32_t* pinned_host_frame);
 /* Copies only the rows owned by this shard, compacted (owned rows in ascending order), into dev_out. */
 int rt_get_owned_ldr_rows_device(rt_raytracer* rt, void* dev_out, uint32_t* n_rows);
 /* Device buffers owned by the library (plain cudaMalloc, therefore exportable over CUDA IPC), and IPC plumbing for

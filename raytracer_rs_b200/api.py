@@ -96,7 +96,7 @@ ABI_SYMBOLS = [
     "rt_camera_add_x_angle", "rt_camera_add_y_angle", "rt_camera_get", "rt_camera_set_state", "rt_set_stream",
     "rt_get_ldr_device_ptr", "rt_set_ldr_target", "rt_get_owned_ldr_rows_device", "rt_get_launch_stats",
     "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_get_counters_device_ptr",
-    "rt_launch_param_bytes", "rt_set_tuning",
+    "rt_launch_param_bytes", "rt_set_tuning", "rt_set_host_frame",
     "rt_kernels_launched", "rt_octree_stats", "rt_octree_export", "rt_bvh_stats", "rt_bvh_export", "rt_stats_new",
     "rt_stats_free", "rt_stats_stats", "rt_stats_mean_stats", "rt_benchmark_new", "rt_benchmark_free",
     "rt_benchmark_start", "rt_benchmark_stop", "rt_benchmark_report", "rt_version",
@@ -161,6 +161,7 @@ def lib() -> C.CDLL:
         "rt_get_counters_device_ptr": (C.c_int, [vp, P(vp)]),
         "rt_launch_param_bytes": (u32, []),
         "rt_set_tuning": (C.c_int, [vp, i32, i32]),
+        "rt_set_host_frame": (C.c_int, [vp, vp]),
         "rt_kernels_launched": (u64, [vp]),
         "rt_octree_stats": (C.c_int, [vp, vp]),
         "rt_octree_export": (C.c_int, [vp, vp, vp, vp, vp, P(u64)]),
@@ -438,6 +439,10 @@ class RayTracer:
         n = C.c_uint32()
         self._check(lib().rt_get_owned_ldr_rows_device(self._h, C.c_void_p(dev_ptr or 0), C.byref(n)))
         return n.value
+
+    def set_host_frame(self, pinned_host_ptr: int | None) -> None:
+        """Zero-copy readback into a page-locked host buffer (rt_set_host_frame)."""
+        self._check(lib().rt_set_host_frame(self._h, C.c_void_p(pinned_host_ptr or 0)))
 
     def set_tuning(self, key: int, value: int) -> None:
         self._check(lib().rt_set_tuning(self._h, key, value))

@@ -95,6 +95,9 @@ struct rt_raytracer {
     DevBuf<unsigned long long> d_counters;
     unsigned long long* h_counters = nullptr;  // pinned
     uint32_t* ldr_remote = nullptr;
+    uint32_t* host_frame = nullptr;       // registered zero-copy frame (host address)
+    uint32_t* host_frame_dev = nullptr;   // its device-visible address
+    bool host_frame_stale = true;         // rows traced before registration / film clear are not in it yet
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 
     // host state
@@ -368,6 +371,7 @@ struct rt_raytracer {
     }
 
     void film_clear() {
+        host_frame_stale = true;
         RT_CUDA(launch_film_clear(d_film_sum.p, d_film_sq.p, d_ldr.p, d_ids.p, npix(), stream));
         ++total_kernels;
     }
@@ -724,8 +728,31 @@ int rt_trace_rows(rt_raytracer* rt, uint32_t first_row, uint32_t n_rows, uint32_
 int rt_get_tonemapped_pixels(rt_raytracer* rt, uint32_t* out) {
     RT_GUARD(rt, {
         if (!out) throw std::invalid_argument("null output");
-        RT_CUDA(cudaMemcpyAsync(out, rt->d_ldr.p, (size_t)rt->npix() * 4, cudaMemcpyDeviceToHost, rt->stream));
-        RT_CUDA(cudaStreamSynchronize(rt->stream));
+        if (out == rt->host_frame && !rt->host_frame_stale) {
+            RT_CUDA(cudaStreamSynchronize(rt->stream));  // the kernel already stored the pixels into this buffer
+        } else {
+            RT_CUDA(cudaMemcpyAsync(out, rt->d_ldr.p, (size_t)rt->npix() * 4, cudaMemcpyDeviceToHost, rt->stream));
+            RT_CUDA(cudaStreamSynchronize(rt->stream));
+            if (out == rt->host_frame) rt->host_frame_stale = false;
+        }
+    });
+}
+
+int rt_set_host_frame(rt_raytracer* rt, uint32_t* pinned_host_frame) {
+    RT_GUARD(rt, {
+        if (rt->ldr_remote && rt->ldr_remote != rt->host_frame_dev) throw std::invalid_argument("an LDR target is already set (rt_set_ldr_target)");
+        if (!pinned_host_frame) {
+            rt->host_frame = nullptr;
+            rt->host_frame_dev = nullptr;
+            rt->ldr_remote = nullptr;
+            return RT_OK;
+        }
+        void* dev = nullptr;
+        RT_CUDA(cudaHostGetDevicePointer(&dev, pinned_host_frame, 0));  // fails unless the buffer is page-locked and mapped
+        rt->host_frame = pinned_host_frame;
+        rt->host_frame_dev = (uint32_t*)dev;
+        rt->ldr_remote = (uint32_t*)dev;
+        rt->host_frame_stale = true;  // the first readback copies the whole frame, later ones only synchronise
     });
 }
 
