@@ -73,7 +73,8 @@ typedef struct rt_scene_desc {
 /* ---- configuration ------------------------------------------------------------------------------------ */
 
 enum { RT_ACCEL_OCTREE = 0, /* flattened reference octree, traversal bit-identical to oct_tree_intersector.rs:148-272 */
-       RT_ACCEL_BVH = 1 };  /* SAH BVH, closest hit + lowest-index tie break + root-cube acceptance */
+       RT_ACCEL_BVH = 1,    /* binary SAH BVH, closest hit + lowest-index tie break + root-cube acceptance */
+       RT_ACCEL_CWBVH = 2 };/* compressed 8-wide BVH (same hit rules as RT_ACCEL_BVH, shorter dependent-load chain) */
 enum { RT_JITTER_FIXED_HALF = 0, /* xi = (0.5, 0.5): the pinned parity mode */
        RT_JITTER_HASHED = 1 };   /* xi = hash(seed, pixel, sample, axis) * 2^-24: stands in for StdRng::from_os_rng
                                     (raytracer/mod.rs:84, scene/camera.rs:82-84) */
@@ -217,6 +218,11 @@ int rt_bvh_stats(const rt_raytracer* rt, uint64_t* out);
 /* boxes: nodes*12 (child0 lo xyz, hi xyz, child1 lo xyz, hi xyz); children: nodes*2 (>= 0 inner node, < 0 leaf with
    ~child = first triangle slot); counts: nodes*2 (triangles of a leaf child); tri_order: slot -> global triangle. */
 int rt_bvh_export(const rt_raytracer* rt, float* boxes, int32_t* children, int32_t* counts, uint32_t* tri_order);
+/* compressed 8-wide BVH (RT_ACCEL_CWBVH). out[4]: nodes, leaf children, triangle slots, depth */
+int rt_cwbvh_stats(const rt_raytracer* rt, uint64_t* out);
+/* node_words: nodes*20 u32 (five 16-byte words per node, layout in csrc/cwbvh_build.cpp); tri_order: slot -> global
+   triangle. Either pointer may be NULL. */
+int rt_cwbvh_export(const rt_raytracer* rt, uint32_t* node_words, uint32_t* tri_order);
 
 /* ---- stats.rs / timing crate stand-ins ---------------------------------------------------------------- */
 

@@ -16,6 +16,7 @@ without a GPU (so the ABI can be inspected), rendering raises RtError.
 from .api import (  # noqa: F401
     DEFAULT_TRIANGLES_PER_LEAF,
     ACCEL_BVH,
+    ACCEL_CWBVH,
     ACCEL_OCTREE,
     JITTER_FIXED_HALF,
     JITTER_HASHED,
@@ -36,6 +37,7 @@ from .api import (  # noqa: F401
 __all__ = [
     "DEFAULT_TRIANGLES_PER_LEAF",
     "ACCEL_BVH",
+    "ACCEL_CWBVH",
     "ACCEL_OCTREE",
     "JITTER_FIXED_HALF",
     "JITTER_HASHED",

@@ -36,4 +36,17 @@ struct FlatBvh {
 };
 FlatBvh build_bvh(const HostScene& scene, uint32_t max_leaf_size);
 
+// Compressed 8-wide BVH (layout documented in cwbvh_build.cpp): 5 x 16-byte words per node.
+struct CwWord {
+    uint32_t x, y, z, w;
+};
+struct FlatCwbvh {
+    std::vector<CwWord> nodes;        // 5 words per node, node 0 = root
+    std::vector<uint32_t> tri_order;  // triangle slot -> global triangle index (a node's leaf triangles are contiguous)
+    uint32_t depth = 0, num_leaves = 0;
+    float root_lo[3], root_hi[3];
+    size_t num_nodes() const { return nodes.size() / 5; }
+};
+FlatCwbvh build_cwbvh(const HostScene& scene);
+
 }  // namespace rtb

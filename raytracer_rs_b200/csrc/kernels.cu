@@ -457,10 +457,139 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
     return true;
 }
 
-// ACCEL: 0 octree / 1 BVH; WW: 0 single-loop, 1 while-while
+// ------------------------------------------------------------------------------------------------------
+// Compressed 8-wide BVH traversal (node layout: cwbvh_build.cpp; scheme after Ylitie, Karras, Laine, HPG 2017).
+// Same hit rules as bvh_closest_hit. One node visit = five 16-byte loads and eight box tests, so the chain of
+// dependent loads of a ray is ~3x shorter than in the binary tree. Traversal state is a "node group"
+// (first child node | hit bits of the not yet visited inner children, ordered by the ray's octant | imask) and a
+// "triangle group" (first triangle | hit bits); only node groups are ever pushed.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {  // every byte: 0xff if its top bit is set, else 0x00
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+    return r;
+}
+// byte j of w as a float without the quarter-rate I2F: place it in the mantissa of 2^23, subtract 2^23 (both exact)
+template <int J>
+__device__ __forceinline__ float byte_to_float(uint32_t w) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "n"(0x7650 + J));
+    return __fsub_rn(__uint_as_float(r), 8388608.0f);
+}
+
+__device__ __forceinline__ bool cwbvh_closest_hit(const TraceParams& P, const V3& o, const V3& d, float t_limit, float early_t, HitRec* out) {
+    // box tests only: keep the reciprocal finite (the triangle test below uses the unmodified direction)
+    const float kTiny = 1e-18f;
+    const float ix = 1.0f / (fabsf(d.x) > kTiny ? d.x : copysignf(kTiny, d.x));
+    const float iy = 1.0f / (fabsf(d.y) > kTiny ? d.y : copysignf(kTiny, d.y));
+    const float iz = 1.0f / (fabsf(d.z) > kTiny ? d.z : copysignf(kTiny, d.z));
+    // slot s holds the child towards +axis where bit a of s is set; a ray travelling towards +a meets the children
+    // with that bit clear first: priority of slot s = s ^ octinv, highest first
+    const uint32_t octinv = (d.x < 0.0f ? 0u : 1u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 4u);
+    const uint32_t octinv4 = octinv * 0x01010101u;
+    uint2 stack[kCwStack];
+    int sp = 0;
+    HitRec best;
+    best.t = t_limit;
+    best.u = 0.f;
+    best.v = 0.f;
+    best.tri = kNoHit;
+    uint2 G = make_uint2(0u, 0x80000000u);  // the root as a one-child group
+    uint2 T = make_uint2(0u, 0u);
+    for (;;) {
+        // ---- node phase: descend until some triangles are waiting (or the traversal is over) ----
+        while (T.y == 0u) {
+            if ((G.y & 0xff000000u) == 0u) {
+                if (sp == 0) goto done;
+                G = stack[--sp];
+            }
+            const uint32_t bit = 31u - (uint32_t)__clz((int)G.y);
+            G.y &= ~(1u << bit);
+            if (G.y & 0xff000000u) stack[sp++] = G;
+            const uint32_t slot = (bit - 24u) ^ octinv;
+            const uint32_t rel = (uint32_t)__popc(G.y & ~(0xffffffffu << slot));  // inner children in lower slots
+            const uint4* n = P.cw_nodes + 5 * (size_t)(G.x + rel);
+#ifdef RT_DEBUG_STEP_COUNTS
+            ++g_dbg_nodes;
+#endif
+            const uint4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3), n4 = __ldg(n + 4);
+            const float ax = __uint_as_float((n0.w & 0xffu) << 23) * ix;
+            const float ay = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * iy;
+            const float az = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * iz;
+            const float bx = (__uint_as_float(n0.x) - o.x) * ix;
+            const float by = (__uint_as_float(n0.y) - o.y) * iy;
+            const float bz = (__uint_as_float(n0.z) - o.z) * iz;
+            uint32_t hitmask = 0u;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t meta4 = half ? n1.w : n1.z;
+                const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+                const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+                const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z, qlz = half ? n3.y : n3.x;
+                const uint32_t qhx = half ? n3.w : n3.z, qhy = half ? n4.y : n4.x, qhz = half ? n4.w : n4.z;
+                // entry / exit planes by the sign of the direction
+                const uint32_t nx = d.x < 0.0f ? qhx : qlx, fx = d.x < 0.0f ? qlx : qhx;
+                const uint32_t ny = d.y < 0.0f ? qhy : qly, fy = d.y < 0.0f ? qly : qhy;
+                const uint32_t nz = d.z < 0.0f ? qhz : qlz, fz = d.z < 0.0f ? qlz : qhz;
+#define RT_CW_CHILD(J)                                                                                                   \
+    {                                                                                                                    \
+        const float t0x = fmaf(byte_to_float<J>(nx), ax, bx), t1x = fmaf(byte_to_float<J>(fx), ax, bx);                  \
+        const float t0y = fmaf(byte_to_float<J>(ny), ay, by), t1y = fmaf(byte_to_float<J>(fy), ay, by);                  \
+        const float t0z = fmaf(byte_to_float<J>(nz), az, bz), t1z = fmaf(byte_to_float<J>(fz), az, bz);                  \
+        const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));                                                       \
+        const float tf = fminf(fminf(t1x, t1y), fminf(t1z, best.t));                                                     \
+        if (tn <= tf) hitmask |= ((child_bits4 >> (8 * J)) & 0xffu) << ((bit_index4 >> (8 * J)) & 0xffu);                \
+    }
+                RT_CW_CHILD(0)
+                RT_CW_CHILD(1)
+                RT_CW_CHILD(2)
+                RT_CW_CHILD(3)
+#undef RT_CW_CHILD
+            }
+            G = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+            T = make_uint2(n1.y, hitmask & 0x00ffffffu);
+        }
+        // ---- triangle phase ----
+        while (T.y != 0u) {
+            const uint32_t bit = 31u - (uint32_t)__clz((int)T.y);
+            T.y &= ~(1u << bit);
+#ifdef RT_DEBUG_STEP_COUNTS
+            ++g_dbg_tris;
+#endif
+            const float4* tri = P.cw_tris + 3 * (size_t)(T.x + bit);
+            const float4 t0 = __ldg(tri), t1 = __ldg(tri + 1), t2 = __ldg(tri + 2);
+            float t, u, v;
+            if (!moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) continue;
+            const uint32_t id = __float_as_uint(t2.y);
+            if (t < best.t || (t == best.t && id < best.tri)) {
+                best.t = t;
+                best.u = u;
+                best.v = v;
+                best.tri = id;
+                if (t <= early_t) {
+                    *out = best;
+                    return true;
+                }
+            }
+        }
+    }
+done:
+    if (best.tri == kNoHit) return false;
+    const V3 hp = vadd(o, vscale(d, best.t));
+    const bool outside = hp.x < P.root_lo[0] || hp.x > P.root_hi[0] || hp.y < P.root_lo[1] || hp.y > P.root_hi[1] || hp.z < P.root_lo[2] ||
+                         hp.z > P.root_hi[2];
+    if (outside) return false;
+    *out = best;
+    return true;
+}
+
+// ACCEL: 0 octree / 1 binary BVH / 2 compressed 8-wide BVH; WW: 0 single-loop, 1 while-while
 template <int ACCEL, int WW>
 __device__ __forceinline__ bool closest_hit(const TraceParams& P, const V3& o, const V3& d, HitRec* out) {
     if (ACCEL == 0) return WW ? octree_closest_hit_ww(P, o, d, out) : octree_closest_hit(P, o, d, out);
+    if (ACCEL == 2) return cwbvh_closest_hit(P, o, d, FLT_MAX, -1.0f, out);
     return WW ? bvh_closest_hit_ww(P, o, d, FLT_MAX, -1.0f, out) : bvh_closest_hit(P, o, d, FLT_MAX, -1.0f, out);
 }
 // blocked <=> the closest hit has 0.01 < t < 1.0 (mod.rs:226-230)
@@ -472,6 +601,10 @@ __device__ __forceinline__ bool shadow_blocked(const TraceParams& P, const V3& o
         return h.t > 0.01f && h.t < 1.0f;
     }
     // BVH: hits with t >= 1 can never block, a hit with t <= 0.01 decides "lit" immediately
+    if (ACCEL == 2) {
+        if (!cwbvh_closest_hit(P, o, d, 1.0f, 0.01f, &h)) return false;
+        return h.t > 0.01f && h.t < 1.0f;
+    }
     if (!(WW ? bvh_closest_hit_ww(P, o, d, 1.0f, 0.01f, &h) : bvh_closest_hit(P, o, d, 1.0f, 0.01f, &h))) return false;
     return h.t > 0.01f && h.t < 1.0f;
 }
@@ -914,32 +1047,28 @@ cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persi
     uint32_t blocks = (uint32_t)persistent_blocks;
     if (blocks * 8u > tiles) blocks = (tiles + 7u) / 8u;
     const bool bounce = p.recursions > 0;
-    if (accel == 0) {
-        if (bounce)
-            launch_trace_t<0, 1>(p, variant, blocks, stream);
-        else
-            launch_trace_t<0, 0>(p, variant, blocks, stream);
-    } else {
-        if (bounce)
-            launch_trace_t<1, 1>(p, variant, blocks, stream);
-        else
-            launch_trace_t<1, 0>(p, variant, blocks, stream);
+    switch (accel * 2 + (bounce ? 1 : 0)) {
+        case 0: launch_trace_t<0, 0>(p, variant, blocks, stream); break;
+        case 1: launch_trace_t<0, 1>(p, variant, blocks, stream); break;
+        case 2: launch_trace_t<1, 0>(p, variant, blocks, stream); break;
+        case 3: launch_trace_t<1, 1>(p, variant, blocks, stream); break;
+        case 4: launch_trace_t<2, 0>(p, variant, blocks, stream); break;
+        case 5: launch_trace_t<2, 1>(p, variant, blocks, stream); break;
+        default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 // resident 256-thread blocks per SM of the persistent kernel (for sizing its grid)
 int persistent_blocks_per_sm(int accel, int bounce) {
     int n = 0;
-    if (accel == 0) {
-        if (bounce)
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<0, 1>, 256, 0);
-        else
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<0, 0>, 256, 0);
-    } else {
-        if (bounce)
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<1, 1>, 256, 0);
-        else
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<1, 0>, 256, 0);
+    switch (accel * 2 + (bounce ? 1 : 0)) {
+        case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<0, 0>, 256, 0); break;
+        case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<0, 1>, 256, 0); break;
+        case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<1, 0>, 256, 0); break;
+        case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<1, 1>, 256, 0); break;
+        case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<2, 0>, 256, 0); break;
+        case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<2, 1>, 256, 0); break;
+        default: break;
     }
     return n > 0 ? n : 1;
 }

@@ -82,12 +82,15 @@ struct rt_raytracer {
     bool octree_built = false;
     FlatBvh bvh;
     bool bvh_built = false;
+    FlatCwbvh cwbvh;
+    bool cwbvh_built = false;
     std::string last_error;
     int device = 0;
     cudaStream_t stream = nullptr;
 
     // device data
-    DevBuf<float4> d_oct_nodes, d_oct_tris, d_bvh_nodes, d_bvh_tris, d_tri_shade, d_materials, d_lights;
+    DevBuf<float4> d_oct_nodes, d_oct_tris, d_bvh_nodes, d_bvh_tris, d_cw_tris, d_tri_shade, d_materials, d_lights;
+    DevBuf<CwWord> d_cw_nodes;
     std::vector<std::unique_ptr<DevBuf<float>>> d_tex_data;
     DevBuf<DevTexture> d_textures;
     DevBuf<float4> d_film_sum, d_film_sq;
@@ -113,7 +116,7 @@ struct rt_raytracer {
     uint32_t sched_first = ~0u, sched_rows = ~0u, sched_tiles = 0;
     uint32_t sched_launches = 0;  // launches recorded since the schedule geometry / camera last changed
     bool sched_have_order = false;
-    int blocks_per_sm[2][2] = {{0, 0}, {0, 0}};  // [accel][bounce]
+    int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // [accel][bounce]
     int num_sms = 0;
     rt_launch_stats last{};
     bool stats_pending = false;
@@ -301,6 +304,12 @@ struct rt_raytracer {
         bvh_built = true;
     }
 
+    void ensure_cwbvh_host() {
+        if (cwbvh_built) return;
+        cwbvh = build_cwbvh(scene);
+        cwbvh_built = true;
+    }
+
     void ensure_accel(int accel) {
         if (accel == RT_ACCEL_OCTREE) {
             ensure_octree_host();
@@ -365,6 +374,17 @@ struct rt_raytracer {
             }
             d_bvh_nodes.upload(nodes, stream);
             d_bvh_tris.upload(tris, stream);
+        } else if (accel == RT_ACCEL_CWBVH) {
+            if (d_cw_nodes.p) return;
+            ensure_cwbvh_host();
+            if (cwbvh.depth + 3 > (uint32_t)kCwStack) throw CudaFail{"wide BVH deeper than the traversal stack"};
+            std::vector<float4> tris(3 * cwbvh.tri_order.size());
+            for (size_t s = 0; s < cwbvh.tri_order.size(); ++s) {
+                const uint32_t t = cwbvh.tri_order[s];
+                pack_triangle(&scene.vertices[9 * (size_t)t], t, &tris[3 * s]);
+            }
+            d_cw_nodes.upload(cwbvh.nodes, stream);
+            d_cw_tris.upload(tris, stream);
         } else {
             throw CudaFail{"unknown accel"};
         }
@@ -391,6 +411,8 @@ struct rt_raytracer {
         p->oct_tris = d_oct_tris.p;
         p->bvh_nodes = d_bvh_nodes.p;
         p->bvh_tris = d_bvh_tris.p;
+        p->cw_nodes = reinterpret_cast<const uint4*>(d_cw_nodes.p);
+        p->cw_tris = d_cw_tris.p;
         p->tri_shade = d_tri_shade.p;
         p->materials = d_materials.p;
         p->lights = d_lights.p;
@@ -417,7 +439,7 @@ struct rt_raytracer {
 
     cudaError_t launch_one(const TraceParams& p_in) {
         TraceParams p = p_in;
-        const int a = cfg.accel == RT_ACCEL_OCTREE ? 0 : 1;
+        const int a = cfg.accel == RT_ACCEL_OCTREE ? 0 : (cfg.accel == RT_ACCEL_CWBVH ? 2 : 1);
         const int b = cfg.recursions > 0 ? 1 : 0;
         if (variant != 0 && lpt_schedule) {
             const uint32_t tiles = ((p.cam.width + 7u) / 8u) * ((p.n_rows + 3u) / 4u);
@@ -441,7 +463,7 @@ struct rt_raytracer {
                 // re-sort after the 1st and 2nd recorded launch of a view, then every 8th
                 if (sched_launches == 1 || sched_launches == 2 || (sched_launches > 2 && sched_launches % 8 == 0)) {
                     if (blocks_per_sm[a][b] == 0) blocks_per_sm[a][b] = persistent_blocks_per_sm(a, b);
-                    cudaError_t e = launch_tile_sort(d_tile_cost.p, d_tile_order.p, tiles, (uint32_t)(blocks_per_sm[a][b] * num_sms * 8), a == 1, d_counters.p, stream);
+                    cudaError_t e = launch_tile_sort(d_tile_cost.p, d_tile_order.p, tiles, (uint32_t)(blocks_per_sm[a][b] * num_sms * 8), a != 0, d_counters.p, stream);
                     if (e != cudaSuccess) return e;
                     ++total_kernels;
                     ++last.kernels_launched;
@@ -683,7 +705,7 @@ const char* rt_last_error(const rt_raytracer* rt) { return rt ? rt->last_error.c
 
 int rt_configure(rt_raytracer* rt, int32_t recursions, uint32_t sub_spread, int32_t jitter_mode, uint32_t seed, int32_t accel) {
     RT_GUARD_HOST(rt, {
-        if (accel != RT_ACCEL_OCTREE && accel != RT_ACCEL_BVH) throw std::invalid_argument("unknown accel");
+        if (accel != RT_ACCEL_OCTREE && accel != RT_ACCEL_BVH && accel != RT_ACCEL_CWBVH) throw std::invalid_argument("unknown accel");
         if (jitter_mode != RT_JITTER_FIXED_HALF && jitter_mode != RT_JITTER_HASHED) throw std::invalid_argument("unknown jitter mode");
         if (recursions < 0) throw std::invalid_argument("negative recursions");
         rt->cfg.recursions = recursions;
@@ -983,6 +1005,24 @@ int rt_bvh_export(const rt_raytracer* rt_c, float* boxes, int32_t* children, int
         }
     }
     if (tri_order && !rt->bvh.tri_order.empty()) std::memcpy(tri_order, rt->bvh.tri_order.data(), rt->bvh.tri_order.size() * 4);
+    return RT_OK;
+}
+int rt_cwbvh_stats(const rt_raytracer* rt_c, uint64_t* out) {
+    rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
+    if (!rt || !out) return RT_ERR_INVALID;
+    rt->ensure_cwbvh_host();
+    out[0] = rt->cwbvh.num_nodes();
+    out[1] = rt->cwbvh.num_leaves;
+    out[2] = rt->cwbvh.tri_order.size();
+    out[3] = rt->cwbvh.depth;
+    return RT_OK;
+}
+int rt_cwbvh_export(const rt_raytracer* rt_c, uint32_t* node_words, uint32_t* tri_order) {
+    rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
+    if (!rt) return RT_ERR_INVALID;
+    rt->ensure_cwbvh_host();
+    if (node_words) std::memcpy(node_words, rt->cwbvh.nodes.data(), rt->cwbvh.nodes.size() * sizeof(CwWord));
+    if (tri_order && !rt->cwbvh.tri_order.empty()) std::memcpy(tri_order, rt->cwbvh.tri_order.data(), rt->cwbvh.tri_order.size() * 4);
     return RT_OK;
 }
 

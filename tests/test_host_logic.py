@@ -159,6 +159,71 @@ def test_bvh_invariants(scenes, name):
     assert seen.all()
 
 
+@pytest.mark.parametrize("name", ["4boxes", "ico2", "thai2"])
+def test_cwbvh_invariants(scenes, name):
+    """Compressed 8-wide BVH (csrc/cwbvh_build.cpp): every triangle sits in exactly one leaf child, every quantised child
+    box (decoded with the f32 expression the traversal uses, plane = p + q * 2^e) contains its subtree, inner
+    children are numbered consecutively in slot order."""
+    s = scenes(name)
+    r = host_tracer(s)
+    words, order = r.cwbvh_export()
+    st = r.cwbvh_stats()
+    n_tri = s.vertices.shape[0]
+    assert sorted(order.tolist()) == list(range(n_tri))
+    assert st["nodes"] == words.shape[0] and st["depth"] + 3 <= 32
+    verts = s.vertices.reshape(n_tri, 3, 3)
+    seen = np.zeros(n_tri, bool)
+    visited = np.zeros(st["nodes"], bool)
+
+    def bytes_of(w):
+        return [(int(w) >> (8 * k)) & 255 for k in range(4)]
+
+    def decode(node):
+        w = words[node]
+        p = w[0, :3].copy().view(np.float32)
+        e = bytes_of(w[0, 3])
+        scale = np.array([np.float32(2.0) ** np.float32(e[a] - 127) for a in range(3)], np.float32)
+        imask = e[3]
+        meta = bytes_of(w[1, 2]) + bytes_of(w[1, 3])
+        q = [bytes_of(w[2, 0]) + bytes_of(w[2, 1]), bytes_of(w[2, 2]) + bytes_of(w[2, 3]), bytes_of(w[3, 0]) + bytes_of(w[3, 1]),
+             bytes_of(w[3, 2]) + bytes_of(w[3, 3]), bytes_of(w[4, 0]) + bytes_of(w[4, 1]), bytes_of(w[4, 2]) + bytes_of(w[4, 3])]
+        lo = np.array([[p[a] + np.float32(q[a][sl]) * scale[a] for a in range(3)] for sl in range(8)], np.float32)
+        hi = np.array([[p[a] + np.float32(q[3 + a][sl]) * scale[a] for a in range(3)] for sl in range(8)], np.float32)
+        return int(w[1, 0]), int(w[1, 1]), imask, meta, lo, hi
+
+    def walk(node):
+        assert not visited[node]
+        visited[node] = True
+        child_base, tri_base, imask, meta, lo, hi = decode(node)
+        lo_all, hi_all = np.full(3, np.inf), np.full(3, -np.inf)
+        rel = 0
+        for sl in range(8):
+            m = meta[sl]
+            if m == 0:
+                assert not (imask >> sl) & 1
+                continue
+            if (imask >> sl) & 1:
+                assert m == (1 << 5) | (24 + sl)
+                clo, chi = walk(child_base + rel)
+                rel += 1
+            else:
+                cnt = {1: 1, 3: 2, 7: 3}[m >> 5]
+                off = m & 31
+                assert off + cnt <= 24
+                tri = order[tri_base + off: tri_base + off + cnt]
+                assert not seen[tri].any()
+                seen[tri] = True
+                clo, chi = verts[tri].reshape(-1, 3).min(0), verts[tri].reshape(-1, 3).max(0)
+            assert (lo[sl] <= clo).all() and (hi[sl] >= chi).all(), (node, sl)
+            lo_all, hi_all = np.minimum(lo_all, clo), np.maximum(hi_all, chi)
+        return lo_all, hi_all
+
+    import sys
+    sys.setrecursionlimit(10000)
+    walk(0)
+    assert seen.all() and visited.all()
+
+
 # ---- camera (camera.rs) ------------------------------------------------------------------------------------------------
 
 

@@ -5,10 +5,10 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import raytracer_rs_b200 as rt
 scenes = [('4boxes',1920,1080),('ico2',1024,768),('ico3_tex',1920,1080),('thai2',1920,1080)]
-variants = [(0,0),(1,0),(1,1)]
+variants = [(1,1)]
 for name,w,h in scenes:
     s = rt.load_scene(os.path.join(ROOT, f'data/{name}.dae'))
-    for accel, an in [(rt.ACCEL_OCTREE,'octree'),(rt.ACCEL_BVH,'bvh')]:
+    for accel, an in [(rt.ACCEL_BVH,'bvh'),(rt.ACCEL_CWBVH,'cwbvh')]:
         ref=None; line=f'{name:9s} {an:7s}'
         for v in variants:
             r = rt.RayTracer.from_scene(s, rt.Config(w,h,recursions=0,jitter_mode=rt.JITTER_FIXED_HALF,accel=accel))
