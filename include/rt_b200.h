@@ -188,12 +188,21 @@ int rt_ipc_close(rt_raytracer* rt, void* dev_ptr);
 int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr);
 /* Bytes of per-launch parameters (camera + pointers) that travel host -> device with every trace launch. */
 uint32_t rt_launch_param_bytes(void);
-/* Developer tuning knobs (results never change, only the schedule). RT_TUNE_KERNEL_VARIANT: 1 (default) persistent
-   warps pulling 8x4 pixel tiles from an atomic queue, while-while traversal; 0 one thread per pixel, single-loop. */
+/* Developer tuning knobs (results never change, only the schedule). RT_TUNE_KERNEL_VARIANT: 2 (default) ray pool —
+   lanes are decoupled from pixels through per-warp shared-memory ray rings (binary BVH, recursions 0, one light;
+   other configurations run variant 1); 1 persistent warps pulling 8x4 pixel tiles from an atomic queue, while-while
+   traversal; 0 one thread per pixel, single-loop. */
 #define RT_TUNE_KERNEL_VARIANT 0
 /* RT_TUNE_TILE_SCHEDULE: 1 (default) the persistent kernel hands out tiles heaviest-first using the cycle counts
    recorded by the previous launch of the same view (longest-processing-time-first); 0 image order. */
 #define RT_TUNE_TILE_SCHEDULE 1
+/* RT_TUNE_POOL_REFILL: idle lanes of a warp that trigger a refill from the ray rings (1..32, default 8).
+   RT_TUNE_POOL_BLOCKS: resident 256-thread blocks per SM of the ray-pool kernel (0 = as many as fit). */
+#define RT_TUNE_POOL_REFILL 2
+#define RT_TUNE_POOL_BLOCKS 3
+/* RT_TUNE_POOL_MIN_INNER: the ray-pool kernel leaves its inner-node loop when fewer lanes than this are still
+   descending while other lanes wait at a leaf or with a finished ray (0..32, default 16; 0 = classic while-while). */
+#define RT_TUNE_POOL_MIN_INNER 4
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {

@@ -65,6 +65,9 @@ struct TraceParams {
     int32_t recursions;          // RECURSIONS (mod.rs:81); 0 = primary + shadow only
     uint32_t sub_spread;         // SUB_SPREAD (mod.rs:82)
     const float* sample_table;   // 65 536 unit vectors (sample_generator.rs), 3 floats each
+    uint32_t pool_refill;        // ray-pool kernel: idle lanes of a warp that trigger a refill
+    uint32_t pool_min_inner;     // ray-pool kernel: the inner-node loop yields when fewer lanes than this still descend
+    uint32_t magic_w, magic_h, magic_tiles_x;  // floor(2^32 / d) for d = width, height, tiles per row (udiv_magic)
     float root_lo[3], root_hi[3];  // scene AABB = octree root cube (acceptance rule of the BVH path)
 };
 

@@ -776,20 +776,21 @@ __device__ __noinline__ void radiance_with_bounces(const TraceParams& P, const V
     *out_b = ret_b;
 }
 
-template <int ACCEL, int WW, int BOUNCE>
-__device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, uint32_t crow, LaneCounters& cnt) {
+// camera.rs:80-90 with (u, v) = (idx % width, idx / height)  [sic, mod.rs:96]; `nsamp` numbers the sample of the pixel
+// n / d for 32-bit unsigned n with magic = floor(2^32 / d) (0xffffffff for d = 1): the estimate is at most one too small
+__device__ __forceinline__ uint32_t udiv_magic(uint32_t n, uint32_t d, uint32_t magic) {
+    uint32_t q = __umulhi(n, magic);
+    if (n - q * d >= d) ++q;
+    return q;
+}
+__device__ __forceinline__ V3 camera_ray_dir(const TraceParams& P, uint32_t idx, uint32_t col, uint32_t nsamp) {
     const uint32_t W = P.cam.width, H = P.cam.height;
-    const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % H;
-    const uint32_t idx = row * W + col;
-    float4 fs_ = P.film_sum[idx];
-    const uint32_t nsamp = __float_as_uint(fs_.w);
     float xi1 = 0.5f, xi2 = 0.5f;
     if (P.jitter_mode == 1) {
         xi1 = u01(hash4(P.seed, idx, nsamp, 0));
         xi2 = u01(hash4(P.seed, idx, nsamp, 1));
     }
-    // camera.rs:80-90 with (u, v) = (idx % width, idx / height)  [sic, mod.rs:96]
-    const uint32_t pu = idx % W, pv = idx / H;
+    const uint32_t pu = col /* = idx % W */, pv = udiv_magic(idx, H, P.magic_h);
     const float dir_x = fadd(-P.cam.max_x, fmul(fmul(2.0f, P.cam.max_x), fdiv(fadd((float)pu, xi1), (float)W)));
     const float dir_y = fadd(-P.cam.max_y, fmul(fmul(2.0f, P.cam.max_y), fdiv(fadd((float)pv, xi2), (float)H)));
     const float ndy = -dir_y;
@@ -798,6 +799,38 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, 
     d.x = fadd(fadd(fadd(fmul(dir_x, R[0]), fmul(ndy, R[4])), fmul(1.0f, R[8])), fmul(1.0f, R[12]));
     d.y = fadd(fadd(fadd(fmul(dir_x, R[1]), fmul(ndy, R[5])), fmul(1.0f, R[9])), fmul(1.0f, R[13]));
     d.z = fadd(fadd(fadd(fmul(dir_x, R[2]), fmul(ndy, R[6])), fmul(1.0f, R[10])), fmul(1.0f, R[14]));
+    return d;
+}
+
+// add_sample (film.rs:20-24) + mean, tonemap, pack of the updated pixel (film.rs:43-48, tonemap.rs:4-10, color.rs:89-95)
+__device__ __forceinline__ void film_add_sample(const TraceParams& P, uint32_t idx, float4 fs_, float cr, float cg, float cb) {
+    fs_.x = fadd(fs_.x, cr);
+    fs_.y = fadd(fs_.y, cg);
+    fs_.z = fadd(fs_.z, cb);
+    if (cr != 0.0f || cg != 0.0f || cb != 0.0f) {  // a black sample adds +0 to sums of squares that are never -0: nothing to write
+        float4 sq = P.film_sq[idx];
+        sq.x = fadd(sq.x, fmul(cr, cr));
+        sq.y = fadd(sq.y, fmul(cg, cg));
+        sq.z = fadd(sq.z, fmul(cb, cb));
+        P.film_sq[idx] = sq;
+    }
+    const uint32_t n_new = __float_as_uint(fs_.w) + 1u;
+    fs_.w = __uint_as_float(n_new);
+    P.film_sum[idx] = fs_;
+    // a pixel whose sums are all zero maps to opaque black whatever n is: 0 * (1/n) = 0, 0 / (1 + 0) = 0
+    const uint32_t px = (fs_.x == 0.0f && fs_.y == 0.0f && fs_.z == 0.0f) ? 0xff000000u : tonemap_pack(fs_.x, fs_.y, fs_.z, n_new);
+    P.ldr[idx] = px;
+    if (P.ldr_remote) P.ldr_remote[idx] = px;
+}
+
+template <int ACCEL, int WW, int BOUNCE>
+__device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, uint32_t crow, LaneCounters& cnt) {
+    const uint32_t W = P.cam.width, H = P.cam.height;
+    const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % H;
+    const uint32_t idx = row * W + col;
+    const float4 fs_ = P.film_sum[idx];
+    const uint32_t nsamp = __float_as_uint(fs_.w);
+    const V3 d = camera_ray_dir(P, idx, col, nsamp);
     const V3 o = {P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]};
 
     float cr = 0.f, cg = 0.f, cb = 0.f;
@@ -813,22 +846,8 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, 
             shade_hit<ACCEL, WW>(P, o, d, hit, &nrm, &cr, &cg, &cb, cnt);
         }
     }
-    // add_sample (film.rs:20-24)
-    float4 sq = P.film_sq[idx];
-    fs_.x = fadd(fs_.x, cr);
-    fs_.y = fadd(fs_.y, cg);
-    fs_.z = fadd(fs_.z, cb);
-    sq.x = fadd(sq.x, fmul(cr, cr));
-    sq.y = fadd(sq.y, fmul(cg, cg));
-    sq.z = fadd(sq.z, fmul(cb, cb));
-    const uint32_t n_new = nsamp + 1u;
-    fs_.w = __uint_as_float(n_new);
-    P.film_sum[idx] = fs_;
-    P.film_sq[idx] = sq;
     P.primary_ids[idx] = id;
-    const uint32_t px = tonemap_pack(fs_.x, fs_.y, fs_.z, n_new);
-    P.ldr[idx] = px;
-    if (P.ldr_remote) P.ldr_remote[idx] = px;
+    film_add_sample(P, idx, fs_, cr, cg, cb);
 }
 
 __device__ __forceinline__ void flush_counters(const TraceParams& P, LaneCounters c, uint32_t lane) {
@@ -918,6 +937,420 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         }
 #endif
     }
+    flush_counters(P, cnt, lane);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// variant 2: ray pool (binary BVH, recursions = 0, one light). A warp is a small wavefront machine whose queues live
+// in shared memory; lanes are decoupled from pixels:
+//   traverse : every lane owns ONE ray (camera or shadow). A lane whose ray ends pushes the result into a ring and,
+//              as soon as `pool_refill` lanes are idle, takes the next ray: a waiting shadow ray first, else the
+//              camera ray of the next pixel of the warp's current 8x4 tile. The traversal loops therefore run with
+//              (almost) all lanes busy instead of waiting for the slowest pixel of a tile; the inner-node loop is
+//              left as soon as fewer than `pool_min_inner` lanes are still descending while others wait at a leaf
+//   shade    : 32 camera-ray hits at a time: normal, facing test, Phong/texture -> shadow-ray ring (the colour the
+//              pixel gets if the light is visible travels with the ray) or, when the surface faces away, -> film ring
+//   film     : 32 finished pixels at a time: add_sample, mean, tonemap, pack, LDR store
+// Ring pushes/pops are compactions with __ballot_sync/__popc. Every stage evaluates the same f32 expressions as
+// trace_pixel/shade_hit, so results are bit-identical to variants 0/1; only the order in which pixels finish differs.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kPoolShadowCap = 64, kPoolShadeCap = 96, kPoolFinalCap = 64;
+constexpr int kPoolShadowWords = 10; // pixel | hit point xyz | 1/L.xyz | colour if lit rgb
+constexpr int kPoolShadeWords = 5;   // pixel | t u v | triangle
+constexpr int kPoolFinalWords = 4;   // pixel | rgb
+constexpr int kPoolWarpWords = kPoolShadowCap * kPoolShadowWords + kPoolShadeCap * kPoolShadeWords + kPoolFinalCap * kPoolFinalWords;
+constexpr int kPoolWarps = 8;
+constexpr size_t kPoolSmemBytes = (size_t)kPoolWarps * kPoolWarpWords * 4;
+constexpr uint32_t kPoolHitCost = 48u;  // schedule cost of a camera-ray hit (its shade + shadow ray), in traversal steps
+
+template <int CAP>
+__device__ __forceinline__ uint32_t ring_wrap(uint32_t x) {
+    return x >= (uint32_t)CAP ? x - (uint32_t)CAP : x;
+}
+
+__global__ void __launch_bounds__(32 * kPoolWarps, 3) trace_shade_pool_kernel(const __grid_constant__ TraceParams P) {
+    extern __shared__ uint32_t pool_smem[];
+    const uint32_t full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t* const q_shadow = pool_smem + warp * kPoolWarpWords;
+    uint32_t* const q_shade = q_shadow + kPoolShadowCap * kPoolShadowWords;
+    uint32_t* const q_final = q_shade + kPoolShadeCap * kPoolShadeWords;
+    uint32_t shadow_head = 0, shadow_cnt = 0, shade_head = 0, shade_cnt = 0, final_head = 0, final_cnt = 0;
+
+    const uint32_t W = P.cam.width, H = P.cam.height;
+    const uint32_t tiles_x = (W + 7u) / 8u;
+    const uint32_t n_tiles = tiles_x * ((P.n_rows + 3u) / 4u);
+    const uint32_t n_items = P.tile_order ? (uint32_t)P.counters[CNT_QUEUE_ITEMS] : n_tiles;
+    const uint32_t refill_at = P.pool_refill, min_inner = P.pool_min_inner;
+    bool queue_done = false;
+    uint32_t tile_id = 0, tile_px = 32u;  // the warp's current tile and its next unassigned pixel (32 = used up)
+    const V3 cam_o = {P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]};
+    const float4 lp4 = __ldg(&P.lights[0]), lc4 = __ldg(&P.lights[1]);
+    const V3 light_pos = {lp4.x, lp4.y, lp4.z};
+    LaneCounters cnt;
+
+#ifdef RT_DEBUG_WARP_EXIT
+    if (lane == 0) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        P.primary_ids[(gridDim.x + blockIdx.x) * kPoolWarps + warp] = (uint32_t)ns;
+    }
+#endif
+    // the ray this lane traverses
+    int stack_node[kBvhStack];
+    float stack_t[kBvhStack];
+    stack_node[0] = kSentinel;
+    stack_t[0] = -FLT_MAX;
+    bool active = false, is_shadow = false;
+    uint32_t pix = 0, ray_tile = 0, steps = 0;
+    V3 o = cam_o, d = {0.f, 0.f, 0.f};
+    float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+    float pen_r = 0.f, pen_g = 0.f, pen_b = 0.f, early_t = -1.0f;
+    HitRec best;
+    best.t = 0.f;
+    best.u = 0.f;
+    best.v = 0.f;
+    best.tri = kNoHit;
+    int cur = kSentinel, sp = 1;
+
+    // ---- film stage: n <= 32 finished pixels ----
+    auto film_stage = [&](uint32_t n) {
+        if (lane < n) {
+            const uint32_t s = ring_wrap<kPoolFinalCap>(final_head + lane);
+            const uint32_t idx = q_final[s];
+            const float r = __uint_as_float(q_final[kPoolFinalCap + s]);
+            const float g = __uint_as_float(q_final[2 * kPoolFinalCap + s]);
+            const float b = __uint_as_float(q_final[3 * kPoolFinalCap + s]);
+            film_add_sample(P, idx, P.film_sum[idx], r, g, b);
+        }
+        final_head = ring_wrap<kPoolFinalCap>(final_head + n);
+        final_cnt -= n;
+        __syncwarp();
+    };
+    auto push_final = [&](bool want, uint32_t idx, float r, float g, float b) {
+        const uint32_t mask = __ballot_sync(full, want);
+        if (want) {
+            const uint32_t s = ring_wrap<kPoolFinalCap>(ring_wrap<kPoolFinalCap>(final_head + final_cnt) + (uint32_t)__popc(mask & lt));
+            q_final[s] = idx;
+            q_final[kPoolFinalCap + s] = __float_as_uint(r);
+            q_final[2 * kPoolFinalCap + s] = __float_as_uint(g);
+            q_final[3 * kPoolFinalCap + s] = __float_as_uint(b);
+        }
+        final_cnt += (uint32_t)__popc(mask);
+    };
+
+    // ---- shade stage: n <= 32 camera-ray hits (shade, mod.rs:207-261, for the single light) ----
+    auto shade_stage = [&](uint32_t n) {
+        const bool have = lane < n;
+        uint32_t idx = 0;
+        HitRec hit;
+        hit.t = hit.u = hit.v = 0.f;
+        hit.tri = 0;
+        if (have) {
+            const uint32_t s = ring_wrap<kPoolShadeCap>(shade_head + lane);
+            idx = q_shade[s];
+            hit.t = __uint_as_float(q_shade[kPoolShadeCap + s]);
+            hit.u = __uint_as_float(q_shade[2 * kPoolShadeCap + s]);
+            hit.v = __uint_as_float(q_shade[3 * kPoolShadeCap + s]);
+            hit.tri = q_shade[4 * kPoolShadeCap + s];
+        }
+        shade_head = ring_wrap<kPoolShadeCap>(shade_head + n);
+        shade_cnt -= n;
+        bool to_shadow = false;
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        V3 hp = {0.f, 0.f, 0.f}, inv = {0.f, 0.f, 0.f};
+        if (have) {
+            const uint32_t nsamp = P.jitter_mode == 1 ? __float_as_uint(P.film_sum[idx].w) : 0u;
+            const V3 d0 = camera_ray_dir(P, idx, idx - udiv_magic(idx, W, P.magic_w) * W, nsamp);
+            const float4 sh = __ldg(&P.tri_shade[hit.tri]);
+            const V3 nrm = {sh.x, sh.y, sh.z};
+            const uint32_t geom = __float_as_uint(sh.w);
+            hp = vadd(cam_o, vscale(d0, hit.t));
+            const V3 L = vsub(light_pos, hp);
+            const V3 Ln = vunit(L);
+            const float ndl = vdot(nrm, Ln);
+            if (!(ndl < 0.0f)) {
+                to_shadow = true;
+                cnt.shadow_rays += 1;
+                const float4 mat = __ldg(&P.materials[geom]);
+                float dr = mat.x, dg = mat.y, db = mat.z;
+                const int tex = __float_as_int(mat.w);
+                if (tex >= 0) {
+                    const DevTexture T = P.textures[tex];
+                    const float fx = fmul(hit.u, (float)T.width), fy = fmul(hit.v, (float)T.height);
+                    const size_t x = fx > 0.0f ? (size_t)__float2ull_rz(fx) : 0, y = fy > 0.0f ? (size_t)__float2ull_rz(fy) : 0;
+                    size_t ti = y * T.width + x;
+                    const size_t last = (size_t)T.width * T.height - 1;
+                    if (ti > last) ti = last;
+                    dr = T.rgb[3 * ti];
+                    dg = T.rgb[3 * ti + 1];
+                    db = T.rgb[3 * ti + 2];
+                }
+                const V3 view = vunit(d0);
+                const V3 refl = vsub(vscale(nrm, fmul(2.0f, ndl)), Ln);
+                const float spec = pow32(vdot(view, refl));
+                cr = fadd(0.0f, fmul(fadd(fmul(dr, ndl), spec), lc4.x));
+                cg = fadd(0.0f, fmul(fadd(fmul(dg, ndl), spec), lc4.y));
+                cb = fadd(0.0f, fmul(fadd(fmul(db, ndl), spec), lc4.z));
+                inv = V3{fdiv(1.0f, L.x), fdiv(1.0f, L.y), fdiv(1.0f, L.z)};
+            }
+        }
+        const uint32_t mask = __ballot_sync(full, to_shadow);
+        if (to_shadow) {
+            const uint32_t s = ring_wrap<kPoolShadowCap>(ring_wrap<kPoolShadowCap>(shadow_head + shadow_cnt) + (uint32_t)__popc(mask & lt));
+            q_shadow[s] = idx;
+            q_shadow[kPoolShadowCap + s] = __float_as_uint(hp.x);
+            q_shadow[2 * kPoolShadowCap + s] = __float_as_uint(hp.y);
+            q_shadow[3 * kPoolShadowCap + s] = __float_as_uint(hp.z);
+            q_shadow[4 * kPoolShadowCap + s] = __float_as_uint(inv.x);
+            q_shadow[5 * kPoolShadowCap + s] = __float_as_uint(inv.y);
+            q_shadow[6 * kPoolShadowCap + s] = __float_as_uint(inv.z);
+            q_shadow[7 * kPoolShadowCap + s] = __float_as_uint(cr);
+            q_shadow[8 * kPoolShadowCap + s] = __float_as_uint(cg);
+            q_shadow[9 * kPoolShadowCap + s] = __float_as_uint(cb);
+        }
+        shadow_cnt += (uint32_t)__popc(mask);
+        push_final(have && !to_shadow, idx, 0.f, 0.f, 0.f);  // the surface faces away from the light: black
+        __syncwarp();
+    };
+
+    for (;;) {
+        // ---- full batches of the 32-wide stages ----
+        while (final_cnt >= 32u) film_stage(32u);
+        while (shade_cnt >= 32u && shadow_cnt <= (uint32_t)kPoolShadowCap - 32u) {
+            shade_stage(32u);
+            while (final_cnt >= 32u) film_stage(32u);
+        }
+        // ---- refill idle lanes: waiting shadow rays first, then camera rays of the next pixels ----
+        const uint32_t idle_mask = __ballot_sync(full, !active);
+        const uint32_t n_idle = (uint32_t)__popc(idle_mask);
+        if (n_idle >= refill_at) {
+            const uint32_t rank = (uint32_t)__popc(idle_mask & lt);
+            const uint32_t n_sh = min(n_idle, shadow_cnt);
+            bool fresh = false;
+            if (!active && rank < n_sh) {
+                const uint32_t s = ring_wrap<kPoolShadowCap>(shadow_head + rank);
+                pix = q_shadow[s];
+                const V3 hp = {__uint_as_float(q_shadow[kPoolShadowCap + s]), __uint_as_float(q_shadow[2 * kPoolShadowCap + s]),
+                               __uint_as_float(q_shadow[3 * kPoolShadowCap + s])};
+                ix = __uint_as_float(q_shadow[4 * kPoolShadowCap + s]);
+                iy = __uint_as_float(q_shadow[5 * kPoolShadowCap + s]);
+                iz = __uint_as_float(q_shadow[6 * kPoolShadowCap + s]);
+                pen_r = __uint_as_float(q_shadow[7 * kPoolShadowCap + s]);
+                pen_g = __uint_as_float(q_shadow[8 * kPoolShadowCap + s]);
+                pen_b = __uint_as_float(q_shadow[9 * kPoolShadowCap + s]);
+                d = vsub(light_pos, hp);         // L = light.pos - hit_point           (mod.rs:215)
+                o = vadd(hp, vscale(d, 0.01f));  // hit_point + 0.01 * L                (mod.rs:224)
+                is_shadow = true;
+                best.t = 1.0f;    // hits with t >= 1 can never block ...
+                early_t = 0.01f;  // ... and a hit with t <= 0.01 decides "lit" at once (mod.rs:226-230)
+                fresh = true;
+            }
+            shadow_head = ring_wrap<kPoolShadowCap>(shadow_head + n_sh);
+            shadow_cnt -= n_sh;
+            // camera rays: idle lane number (rank - n_sh) takes the next unassigned pixel of the warp's tile(s)
+            const uint32_t need = n_idle - n_sh;
+            const uint32_t mine = rank - n_sh;
+            const bool want_cam = !active && rank >= n_sh;
+            uint32_t given = 0, my_tile = 0, my_px = 0;
+            bool take = false;
+            while (given < need && !queue_done) {
+                if (tile_px >= 32u) {
+                    uint32_t item = 0;
+                    if (lane == 0) {
+                        item = (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], 1ull);
+                        if (item < n_items) item = P.tile_order ? (P.tile_order[item] & kItemTileMask) : item;
+                        else item = 0xffffffffu;
+                    }
+                    item = __shfl_sync(full, item, 0);
+                    if (item == 0xffffffffu) {
+                        queue_done = true;
+                        break;
+                    }
+                    tile_id = item;
+                    tile_px = 0u;
+                }
+                const uint32_t n = min(32u - tile_px, need - given);
+                if (want_cam && mine >= given && mine < given + n) {
+                    my_tile = tile_id;
+                    my_px = tile_px + (mine - given);
+                    take = true;
+                }
+                tile_px += n;
+                given += n;
+            }
+            if (take) {
+                const uint32_t ty = udiv_magic(my_tile, tiles_x, P.magic_tiles_x);
+                const uint32_t col = (my_tile - ty * tiles_x) * 8u + (my_px & 7u);
+                const uint32_t crow = ty * 4u + (my_px >> 3);
+                if (col < W && crow < P.n_rows) {
+                    uint32_t row;
+                    if (P.row_list) {
+                        row = P.row_list[crow];
+                    } else {
+                        row = P.first_row + crow;
+                        if (row >= H) row -= H;
+                    }
+                    pix = row * W + col;
+                    const uint32_t nsamp = P.jitter_mode == 1 ? __float_as_uint(P.film_sum[pix].w) : 0u;
+                    d = camera_ray_dir(P, pix, col, nsamp);
+                    ix = fdiv(1.0f, d.x);
+                    iy = fdiv(1.0f, d.y);
+                    iz = fdiv(1.0f, d.z);
+                    o = cam_o;
+                    is_shadow = false;
+                    ray_tile = my_tile;
+                    best.t = FLT_MAX;
+                    early_t = -1.0f;
+                    fresh = true;
+                }
+            }
+            if (fresh) {
+                ox = -o.x * ix;
+                oy = -o.y * iy;
+                oz = -o.z * iz;
+                best.u = 0.f;
+                best.v = 0.f;
+                best.tri = kNoHit;
+                cur = 0;
+                sp = 1;
+                steps = 0;
+                active = true;
+            }
+            __syncwarp();
+        }
+        if (!__any_sync(full, active)) {
+            // no ray left to traverse: flush partial batches; a shade batch may produce new shadow rays
+            if (shade_cnt > 0u) {
+                shade_stage(min(shade_cnt, 32u));
+                continue;
+            }
+            if (final_cnt > 0u) {
+                film_stage(min(final_cnt, 32u));
+                continue;
+            }
+            if (queue_done) break;
+            continue;  // every pixel handed out so far lay outside the image (partial edge tiles): fetch more
+        }
+
+        // ---- one round of the BVH traversal (same steps as bvh_closest_hit_ww) ----
+        for (;;) {
+            const bool inner = (unsigned)cur < (unsigned)kSentinel;
+            const uint32_t m_in = __ballot_sync(full, inner);
+            if (m_in == 0u) break;
+            // few lanes still descend and others wait at a leaf / with a finished ray: serve those first
+            if ((uint32_t)__popc(m_in) < min_inner && __any_sync(full, active && !inner)) break;
+            if (inner) {
+                const float4* n = P.bvh_nodes + 4 * (size_t)cur;
+                const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+                const float a0x = fmaf(q0.x, ix, ox), b0x = fmaf(q0.w, ix, ox);
+                const float a0y = fmaf(q0.y, iy, oy), b0y = fmaf(q1.x, iy, oy);
+                const float a0z = fmaf(q0.z, iz, oz), b0z = fmaf(q1.y, iz, oz);
+                const float a1x = fmaf(q1.z, ix, ox), b1x = fmaf(q2.y, ix, ox);
+                const float a1y = fmaf(q1.w, iy, oy), b1y = fmaf(q2.z, iy, oy);
+                const float a1z = fmaf(q2.x, iz, oz), b1z = fmaf(q2.w, iz, oz);
+                const float n0 = fmaxf(fmaxf(fminf(a0x, b0x), fminf(a0y, b0y)), fmaxf(fminf(a0z, b0z), 0.0f));
+                const float f0 = fminf(fminf(fmaxf(a0x, b0x), fmaxf(a0y, b0y)), fminf(fmaxf(a0z, b0z), best.t));
+                const float n1 = fmaxf(fmaxf(fminf(a1x, b1x), fminf(a1y, b1y)), fmaxf(fminf(a1z, b1z), 0.0f));
+                const float f1 = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), best.t));
+                const bool h0 = n0 <= f0, h1 = n1 <= f1;
+                const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+                const bool go1 = h1 && (!h0 || n1 < n0);
+                stack_node[sp] = go1 ? c0 : c1;
+                stack_t[sp] = go1 ? n0 : n1;
+                sp += (h0 && h1) ? 1 : 0;
+                ++steps;
+                if (h0 || h1) {
+                    cur = go1 ? c1 : c0;
+                } else {
+                    do {
+                        --sp;
+                        cur = stack_node[sp];
+                    } while (stack_t[sp] > best.t);
+                }
+            }
+        }
+        if (cur < 0) {  // leaf
+            const uint32_t ref = (uint32_t)~cur;
+            const uint32_t count = ref & 15u;
+            const float4* tri = P.bvh_tris + 3 * (size_t)(ref >> 4);
+            bool ended = false;
+            steps += count;
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4 t0 = __ldg(tri + 3 * i), t1 = __ldg(tri + 3 * i + 1), t2 = __ldg(tri + 3 * i + 2);
+                float t, u, v;
+                if (!moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) continue;
+                const uint32_t id = __float_as_uint(t2.y);
+                if (t < best.t || (t == best.t && id < best.tri)) {
+                    best.t = t;
+                    best.u = u;
+                    best.v = v;
+                    best.tri = id;
+                    if (t <= early_t) {
+                        ended = true;
+                        break;
+                    }
+                }
+            }
+            if (ended) {
+                cur = kSentinel;
+            } else {
+                do {
+                    --sp;
+                    cur = stack_node[sp];
+                } while (stack_t[sp] > best.t);
+            }
+        }
+
+        // ---- rays that ended in this round ----
+        const bool done = active && cur == kSentinel;
+        if (__any_sync(full, done)) {
+            bool hit = false;
+            if (done) {
+                hit = best.tri != kNoHit;
+                if (hit) {  // root-cube acceptance rule (oct_tree_intersector.rs:164-169 on the scene AABB)
+                    const V3 hp = vadd(o, vscale(d, best.t));
+                    if (hp.x < P.root_lo[0] || hp.x > P.root_hi[0] || hp.y < P.root_lo[1] || hp.y > P.root_hi[1] || hp.z < P.root_lo[2] ||
+                        hp.z > P.root_hi[2])
+                        hit = false;
+                }
+                active = false;
+            }
+            const bool prim_done = done && !is_shadow, shadow_done = done && is_shadow;
+            if (prim_done) {
+                P.primary_ids[pix] = hit ? best.tri : kNoHit;
+                if (hit) cnt.prim_hit += 1;
+                // cost feedback for the next launch of this view: tiles are started in the order of their longest
+                // dependent chain (a ray's steps are serial, the rays of a tile run side by side)
+                if (P.tile_cost) atomicMax(&P.tile_cost[ray_tile], steps + (hit ? kPoolHitCost : 0u));
+            }
+            const bool to_shade = prim_done && hit;
+            const uint32_t mask = __ballot_sync(full, to_shade);
+            if (to_shade) {
+                const uint32_t s = ring_wrap<kPoolShadeCap>(ring_wrap<kPoolShadeCap>(shade_head + shade_cnt) + (uint32_t)__popc(mask & lt));
+                q_shade[s] = pix;
+                q_shade[kPoolShadeCap + s] = __float_as_uint(best.t);
+                q_shade[2 * kPoolShadeCap + s] = __float_as_uint(best.u);
+                q_shade[3 * kPoolShadeCap + s] = __float_as_uint(best.v);
+                q_shade[4 * kPoolShadeCap + s] = best.tri;
+            }
+            shade_cnt += (uint32_t)__popc(mask);
+            // blocked <=> the closest hit has 0.01 < t < 1.0 (mod.rs:226-230)
+            const bool blocked = shadow_done && hit && best.t > 0.01f && best.t < 1.0f;
+            if (blocked) cnt.blocked += 1;
+            const bool lit = shadow_done && !blocked;
+            push_final(done && !to_shade, pix, lit ? pen_r : 0.f, lit ? pen_g : 0.f, lit ? pen_b : 0.f);
+            __syncwarp();
+        }
+    }
+#ifdef RT_DEBUG_WARP_EXIT  // developer build only (tools/): when every warp ran out of work, instead of the primitive ids
+    if (lane == 0) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        P.primary_ids[blockIdx.x * kPoolWarps + warp] = (uint32_t)ns;
+    }
+#endif
     flush_counters(P, cnt, lane);
 }
 
@@ -1030,6 +1463,11 @@ __global__ void gather_rows_kernel(const uint32_t* __restrict__ ldr, const uint3
 // ------------------------------------------------------------------------------------------------------
 template <int ACCEL, int BOUNCE>
 static void launch_trace_t(const TraceParams& p, int variant, uint32_t blocks, cudaStream_t stream) {
+    if (variant == 2 && ACCEL == 1 && BOUNCE == 0 && p.num_lights == 1) {
+        // > 48 KB of dynamic shared memory needs the opt-in (set per device by pool_blocks_per_sm, which every handle calls first)
+        trace_shade_pool_kernel<<<blocks, 32 * kPoolWarps, kPoolSmemBytes, stream>>>(p);
+        return;
+    }
     if (variant == 0) {
         dim3 grid((p.cam.width + 31u) / 32u, (p.n_rows + 7u) / 8u);
         trace_shade_kernel<ACCEL, BOUNCE><<<grid, 256, 0, stream>>>(p);
@@ -1057,6 +1495,12 @@ cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persi
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
+}
+int pool_blocks_per_sm() {
+    int n = 0;
+    cudaFuncSetAttribute(trace_shade_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmemBytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_pool_kernel, 32 * kPoolWarps, kPoolSmemBytes);
+    return n > 0 ? n : 1;
 }
 // resident 256-thread blocks per SM of the persistent kernel (for sizing its grid)
 int persistent_blocks_per_sm(int accel, int bounce) {

@@ -7,9 +7,12 @@
 namespace rtb {
 
 // fused primary ray -> closest hit -> shadow rays -> Phong/texture -> film -> tonemap/pack
-// variant 0: one thread per pixel; variant 1: persistent warps pulling 8x4 tiles from an atomic queue
+// variant 0: one thread per pixel; variant 1: persistent warps pulling 8x4 tiles from an atomic queue;
+// variant 2: ray pool, lanes decoupled from pixels through per-warp shared-memory ray rings
 cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persistent_blocks, cudaStream_t stream);
 int persistent_blocks_per_sm(int accel, int bounce);
+// variant 2 (ray pool: binary BVH, recursions 0, one light; other configurations run variant 1)
+int pool_blocks_per_sm();
 // order[] = tile ids by descending cost (longest-processing-time-first schedule for the persistent kernel)
 // order must hold 4 * n entries (heavy tiles become four items); counters[CNT_QUEUE_ITEMS] receives the item count
 // allow_split: heavy tiles may become four quarter-tile items (pays off for the divergent BVH kernel, not for the octree's

@@ -109,7 +109,10 @@ struct rt_raytracer {
     std::vector<uint32_t> row_list_cache;   // rows of the last sharded / wrapped launch
     uint32_t cached_first = ~0u, cached_n = ~0u;
     uint64_t total_kernels = 0;
-    int variant = 1;            // RT_TUNE_KERNEL_VARIANT
+    int variant = 2;            // RT_TUNE_KERNEL_VARIANT
+    int pool_refill = 8;        // RT_TUNE_POOL_REFILL
+    int pool_min_inner = 16;    // RT_TUNE_POOL_MIN_INNER
+    int pool_blocks = 0;        // resident blocks per SM of the ray-pool kernel
     int lpt_schedule = 1;       // RT_TUNE_TILE_SCHEDULE: 1 = heaviest tiles first (cost feedback), 0 = image order
     // cost-feedback schedule state, valid for one launch geometry (first_row, rows, row list)
     DevBuf<uint32_t> d_tile_cost, d_tile_order;
@@ -429,6 +432,9 @@ struct rt_raytracer {
         p->recursions = cfg.recursions;
         p->sub_spread = cfg.sub_spread;
         p->sample_table = d_sample_table.p;
+        p->magic_w = udiv_magic_of(cfg.width);
+        p->magic_h = udiv_magic_of(cfg.height);
+        p->magic_tiles_x = udiv_magic_of((cfg.width + 7u) / 8u);
         std::memcpy(p->root_lo, root_lo, 12);
         std::memcpy(p->root_hi, root_hi, 12);
     }
@@ -437,10 +443,18 @@ struct rt_raytracer {
         sched_launches = 0;  // costs of the old view no longer predict the new one well: re-sort soon
     }
 
+    static uint32_t udiv_magic_of(uint32_t d) { return d <= 1u ? 0xffffffffu : (uint32_t)((1ull << 32) / d); }
+
     cudaError_t launch_one(const TraceParams& p_in) {
         TraceParams p = p_in;
         const int a = cfg.accel == RT_ACCEL_OCTREE ? 0 : (cfg.accel == RT_ACCEL_CWBVH ? 2 : 1);
         const int b = cfg.recursions > 0 ? 1 : 0;
+        // the ray-pool kernel covers the headline configuration; everything else runs the persistent tile kernel
+        const bool use_pool = variant == 2 && a == 1 && b == 0 && scene.lights.size() == 1;
+        if (use_pool && pool_blocks == 0) pool_blocks = pool_blocks_per_sm();
+        if (!use_pool && variant != 0 && blocks_per_sm[a][b] == 0) blocks_per_sm[a][b] = persistent_blocks_per_sm(a, b);
+        p.pool_refill = (uint32_t)pool_refill;
+        p.pool_min_inner = (uint32_t)pool_min_inner;
         if (variant != 0 && lpt_schedule) {
             const uint32_t tiles = ((p.cam.width + 7u) / 8u) * ((p.n_rows + 3u) / 4u);
             if (tiles >= 4096) {  // short launches are latency bound; keep them in image order
@@ -462,25 +476,33 @@ struct rt_raytracer {
                 }
                 // re-sort after the 1st and 2nd recorded launch of a view, then every 8th
                 if (sched_launches == 1 || sched_launches == 2 || (sched_launches > 2 && sched_launches % 8 == 0)) {
-                    if (blocks_per_sm[a][b] == 0) blocks_per_sm[a][b] = persistent_blocks_per_sm(a, b);
-                    cudaError_t e = launch_tile_sort(d_tile_cost.p, d_tile_order.p, tiles, (uint32_t)(blocks_per_sm[a][b] * num_sms * 8), a != 0, d_counters.p, stream);
+                    const uint32_t warps = (uint32_t)((use_pool ? pool_blocks : blocks_per_sm[a][b]) * num_sms * 8);
+                    cudaError_t e = launch_tile_sort(d_tile_cost.p, d_tile_order.p, tiles, warps, a != 0 && !use_pool, d_counters.p, stream);
                     if (e != cudaSuccess) return e;
                     ++total_kernels;
                     ++last.kernels_launched;
                     sched_have_order = true;
                 }
-                p.tile_cost = d_tile_cost.p;
+                if (use_pool) {
+                    // the pool kernel ADDS every camera ray's steps to its tile's cost: record only the launches a sort
+                    // will read (the one before each re-sort), starting from zero
+                    const bool record = sched_launches <= 1 || sched_launches % 8 == 7;
+                    if (record && sched_launches > 0) RT_CUDA_RET(cudaMemsetAsync(d_tile_cost.p, 0, tiles * sizeof(uint32_t), stream));
+                    p.tile_cost = record ? d_tile_cost.p : nullptr;
+                } else {
+                    p.tile_cost = d_tile_cost.p;
+                }
                 p.tile_order = sched_have_order ? d_tile_order.p : nullptr;
                 ++sched_launches;
             }
         }
         if (variant != 0) {
-            if (blocks_per_sm[a][b] == 0) blocks_per_sm[a][b] = persistent_blocks_per_sm(a, b);
             // the tile queue lives next to the ray counters; every launch starts it at zero
             cudaError_t e = cudaMemsetAsync(d_counters.p + CNT_TILE_QUEUE, 0, sizeof(unsigned long long), stream);
             if (e != cudaSuccess) return e;
         }
-        return launch_trace(p, a, variant, blocks_per_sm[a][b] * num_sms, stream);
+        if (use_pool) return launch_trace(p, a, 2, pool_blocks * num_sms, stream);
+        return launch_trace(p, a, variant == 0 ? 0 : 1, blocks_per_sm[a][b] * num_sms, stream);
     }
 
     // rows [first_row, first_row + n_rows) modulo height, `spp` passes
@@ -921,8 +943,20 @@ uint32_t rt_launch_param_bytes(void) { return (uint32_t)sizeof(TraceParams); }
 
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     if (!rt) return RT_ERR_INVALID;
-    if (key == RT_TUNE_KERNEL_VARIANT && (value == 0 || value == 1)) {
+    if (key == RT_TUNE_KERNEL_VARIANT && value >= 0 && value <= 2) {
         rt->variant = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_POOL_REFILL && value >= 1 && value <= 32) {
+        rt->pool_refill = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_POOL_MIN_INNER && value >= 0 && value <= 32) {
+        rt->pool_min_inner = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_POOL_BLOCKS && value >= 0 && value <= 8) {
+        rt->pool_blocks = value;  // 0 = as many as fit
         return RT_OK;
     }
     if (key == RT_TUNE_TILE_SCHEDULE && (value == 0 || value == 1)) {
