@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="thai2_1080p", choices=sorted(WORKLOADS))
-    ap.add_argument("--accel", default="bvh", choices=["bvh", "octree", "cwbvh"])
+    ap.add_argument("--accel", default="bvh", choices=["bvh", "octree", "cwbvh", "bvh4"])
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N>1: how rank 0 receives the frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--zero-copy", action="store_true",
@@ -259,7 +259,7 @@ def main():
 
     fname, W, H, spp = WORKLOADS[args.workload]
     scene = rt.load_scene(os.path.join(ROOT, "data", fname))
-    accel = {"bvh": rt.ACCEL_BVH, "octree": rt.ACCEL_OCTREE, "cwbvh": rt.ACCEL_CWBVH}[args.accel]
+    accel = {"bvh": rt.ACCEL_BVH, "octree": rt.ACCEL_OCTREE, "cwbvh": rt.ACCEL_CWBVH, "bvh4": rt.ACCEL_BVH4}[args.accel]
     cfg = rt.Config(W, H, recursions=0, jitter_mode=rt.JITTER_FIXED_HALF if spp == 1 else rt.JITTER_HASHED, accel=accel,
                     device=local_rank, shard_index=rank, shard_count=world, band_rows=8)
     sampler = ClockSampler(local_rank)

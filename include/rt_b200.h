@@ -74,7 +74,8 @@ typedef struct rt_scene_desc {
 
 enum { RT_ACCEL_OCTREE = 0, /* flattened reference octree, traversal bit-identical to oct_tree_intersector.rs:148-272 */
        RT_ACCEL_BVH = 1,    /* binary SAH BVH, closest hit + lowest-index tie break + root-cube acceptance */
-       RT_ACCEL_CWBVH = 2 };/* compressed 8-wide BVH (same hit rules as RT_ACCEL_BVH, shorter dependent-load chain) */
+       RT_ACCEL_CWBVH = 2,  /* compressed 8-wide BVH (same hit rules as RT_ACCEL_BVH; 80-byte nodes, costlier box decode) */
+       RT_ACCEL_BVH4 = 3 }; /* 4-wide BVH, full-precision boxes, one 128-byte node per visit (same hit rules) */
 enum { RT_JITTER_FIXED_HALF = 0, /* xi = (0.5, 0.5): the pinned parity mode */
        RT_JITTER_HASHED = 1 };   /* xi = hash(seed, pixel, sample, axis) * 2^-24: stands in for StdRng::from_os_rng
                                     (raytracer/mod.rs:84, scene/camera.rs:82-84) */
@@ -188,20 +189,20 @@ int rt_ipc_close(rt_raytracer* rt, void* dev_ptr);
 int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr);
 /* Bytes of per-launch parameters (camera + pointers) that travel host -> device with every trace launch. */
 uint32_t rt_launch_param_bytes(void);
-/* Developer tuning knobs (results never change, only the schedule). RT_TUNE_KERNEL_VARIANT: 2 (default) ray pool —
-   lanes are decoupled from pixels through per-warp shared-memory ray rings (binary BVH, recursions 0, one light;
-   other configurations run variant 1); 1 persistent warps pulling 8x4 pixel tiles from an atomic queue, while-while
-   traversal; 0 one thread per pixel, single-loop. */
+/* Developer tuning knobs (results never change, only the schedule). RT_TUNE_KERNEL_VARIANT: 1 (default) persistent
+   warps pulling 8x4 pixel tiles from an atomic queue, while-while traversal; 2 ray pool — lanes are decoupled from
+   pixels through per-warp shared-memory ray rings (binary BVH, recursions 0, one light; other configurations run
+   variant 1); 0 one thread per pixel, single-loop. */
 #define RT_TUNE_KERNEL_VARIANT 0
 /* RT_TUNE_TILE_SCHEDULE: 1 (default) the persistent kernel hands out tiles heaviest-first using the cycle counts
    recorded by the previous launch of the same view (longest-processing-time-first); 0 image order. */
 #define RT_TUNE_TILE_SCHEDULE 1
-/* RT_TUNE_POOL_REFILL: idle lanes of a warp that trigger a refill from the ray rings (1..32, default 8).
+/* RT_TUNE_POOL_REFILL: idle lanes of a warp that trigger a refill from the ray rings (1..32, default 16).
    RT_TUNE_POOL_BLOCKS: resident 256-thread blocks per SM of the ray-pool kernel (0 = as many as fit). */
 #define RT_TUNE_POOL_REFILL 2
 #define RT_TUNE_POOL_BLOCKS 3
 /* RT_TUNE_POOL_MIN_INNER: the ray-pool kernel leaves its inner-node loop when fewer lanes than this are still
-   descending while other lanes wait at a leaf or with a finished ray (0..32, default 16; 0 = classic while-while). */
+   descending while other lanes wait at a leaf or with a finished ray (0..32, default 8; 0 = classic while-while). */
 #define RT_TUNE_POOL_MIN_INNER 4
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
@@ -227,6 +228,11 @@ int rt_bvh_stats(const rt_raytracer* rt, uint64_t* out);
 /* boxes: nodes*12 (child0 lo xyz, hi xyz, child1 lo xyz, hi xyz); children: nodes*2 (>= 0 inner node, < 0 leaf with
    ~child = first triangle slot); counts: nodes*2 (triangles of a leaf child); tri_order: slot -> global triangle. */
 int rt_bvh_export(const rt_raytracer* rt, float* boxes, int32_t* children, int32_t* counts, uint32_t* tri_order);
+/* 4-wide BVH (RT_ACCEL_BVH4). out[4]: nodes, leaves, max leaf size, depth */
+int rt_bvh4_stats(const rt_raytracer* rt, uint64_t* out);
+/* boxes: nodes*24 (per child: lo xyz, hi xyz; an empty slot is lo = hi = +inf); children: nodes*4 (>= 0 inner node,
+   < 0 leaf with ~child = first triangle slot); counts: nodes*4; tri_order: slot -> global triangle. */
+int rt_bvh4_export(const rt_raytracer* rt, float* boxes, int32_t* children, int32_t* counts, uint32_t* tri_order);
 /* compressed 8-wide BVH (RT_ACCEL_CWBVH). out[4]: nodes, leaf children, triangle slots, depth */
 int rt_cwbvh_stats(const rt_raytracer* rt, uint64_t* out);
 /* node_words: nodes*20 u32 (five 16-byte words per node, layout in csrc/cwbvh_build.cpp); tri_order: slot -> global

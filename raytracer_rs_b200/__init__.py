@@ -16,6 +16,7 @@ without a GPU (so the ABI can be inspected), rendering raises RtError.
 from .api import (  # noqa: F401
     DEFAULT_TRIANGLES_PER_LEAF,
     ACCEL_BVH,
+    ACCEL_BVH4,
     ACCEL_CWBVH,
     ACCEL_OCTREE,
     JITTER_FIXED_HALF,
@@ -37,6 +38,7 @@ from .api import (  # noqa: F401
 __all__ = [
     "DEFAULT_TRIANGLES_PER_LEAF",
     "ACCEL_BVH",
+    "ACCEL_BVH4",
     "ACCEL_CWBVH",
     "ACCEL_OCTREE",
     "JITTER_FIXED_HALF",

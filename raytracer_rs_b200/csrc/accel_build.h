@@ -36,6 +36,20 @@ struct FlatBvh {
 };
 FlatBvh build_bvh(const HostScene& scene, uint32_t max_leaf_size);
 
+// 4-wide BVH with full-precision child boxes (bvh4_build.cpp): one node = one 128-byte line on the device.
+struct FlatBvh4 {
+    struct Node {
+        float lo[4][3], hi[4][3];  // child boxes (the binary builder's padded boxes); empty slot: lo = hi = +inf
+        int32_t child[4];          // >= 0: inner node index; < 0: leaf, ~child = first triangle slot
+        int32_t count[4];          // triangles in the leaf (0 for inner / empty)
+    };
+    std::vector<Node> nodes;          // nodes[0] = root
+    std::vector<uint32_t> tri_order;  // triangle slot -> global triangle index
+    uint32_t depth = 0, max_leaf = 0, num_leaves = 0;
+    float root_lo[3], root_hi[3];
+};
+FlatBvh4 build_bvh4(const HostScene& scene);
+
 // Compressed 8-wide BVH (layout documented in cwbvh_build.cpp): 5 x 16-byte words per node.
 struct CwWord {
     uint32_t x, y, z, w;

@@ -28,6 +28,7 @@ constexpr uint32_t kOctLeafFlag = 0x80000000u;
 constexpr uint32_t kNoHit = 0xFFFFFFFFu;
 constexpr int kOctStack = 64;  // >= 7 * depth + 1 with depth <= 9 (oct_tree_intersector.rs:108)
 constexpr int kBvhStack = 48;
+constexpr int kBvh4Stack = 64;  // up to three pushes per level
 constexpr int kCwStack = 32;  // node groups only: at most one per level plus slack
 
 enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3, CNT_TILE_QUEUE = 4, CNT_QUEUE_ITEMS = 5, CNT_SLOTS = 6 };
@@ -39,6 +40,8 @@ struct TraceParams {
     const float4* oct_tris;
     const float4* bvh_nodes;
     const float4* bvh_tris;
+    const float4* bvh4_nodes;  // 4-wide BVH, 8 float4 per node (bvh4_build.cpp)
+    const float4* bvh4_tris;
     const uint4* cw_nodes;   // compressed 8-wide BVH, 5 words per node
     const float4* cw_tris;
     // shading data

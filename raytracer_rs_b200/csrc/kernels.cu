@@ -458,6 +458,122 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
 }
 
 // ------------------------------------------------------------------------------------------------------
+// 4-wide BVH traversal (node layout: bvh4_build.cpp, one node = one 128-byte line). Same hit rules as
+// bvh_closest_hit; half as many dependent node visits per ray. The (up to four) children a ray enters are sorted by
+// entry distance with a five-exchange network; the nearest is visited next, the others are pushed far to near.
+// An empty slot is the box lo = hi = +inf, which no ray can enter (both slab planes lie at the same infinity).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cswap_near(float& da, int& ca, float& db, int& cb) {
+    const bool s = db < da;
+    const float td = s ? db : da;
+    const int tc = s ? cb : ca;
+    db = s ? da : db;
+    cb = s ? ca : cb;
+    da = td;
+    ca = tc;
+}
+__device__ __forceinline__ bool bvh4_closest_hit_ww(const TraceParams& P, const V3& o, const V3& d, float t_limit, float early_t, HitRec* out) {
+    const float ix = fdiv(1.0f, d.x), iy = fdiv(1.0f, d.y), iz = fdiv(1.0f, d.z);
+    const float ox = -o.x * ix, oy = -o.y * iy, oz = -o.z * iz;
+    int stack_node[kBvh4Stack];
+    float stack_t[kBvh4Stack];
+    stack_node[0] = kSentinel;
+    stack_t[0] = -FLT_MAX;
+    int sp = 1;
+    HitRec best;
+    best.t = t_limit;
+    best.u = 0.f;
+    best.v = 0.f;
+    best.tri = kNoHit;
+    int cur = 0;
+    const float kMiss = __int_as_float(0x7f800000);  // +inf
+    while (cur != kSentinel) {
+        while ((unsigned)cur < (unsigned)kSentinel) {  // inner nodes
+#ifdef RT_DEBUG_STEP_COUNTS
+            ++g_dbg_nodes;
+#endif
+            const float4* n = P.bvh4_nodes + 8 * (size_t)cur;
+            const float4 LX = __ldg(n), LY = __ldg(n + 1), LZ = __ldg(n + 2), HX = __ldg(n + 3), HY = __ldg(n + 4), HZ = __ldg(n + 5);
+            const float4 CR = __ldg(n + 6);
+            float d0, d1, d2, d3;
+#define RT_BOX4(K, DK)                                                                                          \
+    {                                                                                                           \
+        const float ax = fmaf(LX.K, ix, ox), bx = fmaf(HX.K, ix, ox);                                           \
+        const float ay = fmaf(LY.K, iy, oy), by = fmaf(HY.K, iy, oy);                                           \
+        const float az = fmaf(LZ.K, iz, oz), bz = fmaf(HZ.K, iz, oz);                                           \
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));                \
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best.t));              \
+        DK = tn <= tf ? tn : kMiss;                                                                             \
+    }
+            RT_BOX4(x, d0)
+            RT_BOX4(y, d1)
+            RT_BOX4(z, d2)
+            RT_BOX4(w, d3)
+#undef RT_BOX4
+            int c0 = __float_as_int(CR.x), c1 = __float_as_int(CR.y), c2 = __float_as_int(CR.z), c3 = __float_as_int(CR.w);
+            cswap_near(d0, c0, d1, c1);
+            cswap_near(d2, c2, d3, c3);
+            cswap_near(d0, c0, d2, c2);
+            cswap_near(d1, c1, d3, c3);
+            cswap_near(d1, c1, d2, c2);
+            // far to near; an entry is kept only if its child was entered (misses sort to the end as +inf)
+            stack_node[sp] = c3;
+            stack_t[sp] = d3;
+            sp += d3 < kMiss ? 1 : 0;
+            stack_node[sp] = c2;
+            stack_t[sp] = d2;
+            sp += d2 < kMiss ? 1 : 0;
+            stack_node[sp] = c1;
+            stack_t[sp] = d1;
+            sp += d1 < kMiss ? 1 : 0;
+            if (d0 < kMiss) {
+                cur = c0;
+            } else {
+                do {
+                    --sp;
+                    cur = stack_node[sp];
+                } while (stack_t[sp] > best.t);
+            }
+        }
+        if (cur != kSentinel) {  // leaf
+            const uint32_t ref = (uint32_t)~cur;
+            const uint32_t count = ref & 15u;
+            const float4* tri = P.bvh4_tris + 3 * (size_t)(ref >> 4);
+            for (uint32_t i = 0; i < count; ++i) {
+#ifdef RT_DEBUG_STEP_COUNTS
+                ++g_dbg_tris;
+#endif
+                const float4 t0 = __ldg(tri + 3 * i), t1 = __ldg(tri + 3 * i + 1), t2 = __ldg(tri + 3 * i + 2);
+                float t, u, v;
+                if (!moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) continue;
+                const uint32_t id = __float_as_uint(t2.y);
+                if (t < best.t || (t == best.t && id < best.tri)) {
+                    best.t = t;
+                    best.u = u;
+                    best.v = v;
+                    best.tri = id;
+                    if (t <= early_t) {
+                        *out = best;
+                        return true;
+                    }
+                }
+            }
+            do {
+                --sp;
+                cur = stack_node[sp];
+            } while (stack_t[sp] > best.t);
+        }
+    }
+    if (best.tri == kNoHit) return false;
+    const V3 hp = vadd(o, vscale(d, best.t));
+    const bool outside = hp.x < P.root_lo[0] || hp.x > P.root_hi[0] || hp.y < P.root_lo[1] || hp.y > P.root_hi[1] || hp.z < P.root_lo[2] ||
+                         hp.z > P.root_hi[2];
+    if (outside) return false;
+    *out = best;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Compressed 8-wide BVH traversal (node layout: cwbvh_build.cpp; scheme after Ylitie, Karras, Laine, HPG 2017).
 // Same hit rules as bvh_closest_hit. One node visit = five 16-byte loads and eight box tests, so the chain of
 // dependent loads of a ray is ~3x shorter than in the binary tree. Traversal state is a "node group"
@@ -585,11 +701,12 @@ done:
     return true;
 }
 
-// ACCEL: 0 octree / 1 binary BVH / 2 compressed 8-wide BVH; WW: 0 single-loop, 1 while-while
+// ACCEL: 0 octree / 1 binary BVH / 2 compressed 8-wide BVH / 3 4-wide BVH; WW: 0 single-loop, 1 while-while
 template <int ACCEL, int WW>
 __device__ __forceinline__ bool closest_hit(const TraceParams& P, const V3& o, const V3& d, HitRec* out) {
     if (ACCEL == 0) return WW ? octree_closest_hit_ww(P, o, d, out) : octree_closest_hit(P, o, d, out);
     if (ACCEL == 2) return cwbvh_closest_hit(P, o, d, FLT_MAX, -1.0f, out);
+    if (ACCEL == 3) return bvh4_closest_hit_ww(P, o, d, FLT_MAX, -1.0f, out);
     return WW ? bvh_closest_hit_ww(P, o, d, FLT_MAX, -1.0f, out) : bvh_closest_hit(P, o, d, FLT_MAX, -1.0f, out);
 }
 // blocked <=> the closest hit has 0.01 < t < 1.0 (mod.rs:226-230)
@@ -603,6 +720,10 @@ __device__ __forceinline__ bool shadow_blocked(const TraceParams& P, const V3& o
     // BVH: hits with t >= 1 can never block, a hit with t <= 0.01 decides "lit" immediately
     if (ACCEL == 2) {
         if (!cwbvh_closest_hit(P, o, d, 1.0f, 0.01f, &h)) return false;
+        return h.t > 0.01f && h.t < 1.0f;
+    }
+    if (ACCEL == 3) {
+        if (!bvh4_closest_hit_ww(P, o, d, 1.0f, 0.01f, &h)) return false;
         return h.t > 0.01f && h.t < 1.0f;
     }
     if (!(WW ? bvh_closest_hit_ww(P, o, d, 1.0f, 0.01f, &h) : bvh_closest_hit(P, o, d, 1.0f, 0.01f, &h))) return false;
@@ -1492,6 +1613,8 @@ cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persi
         case 3: launch_trace_t<1, 1>(p, variant, blocks, stream); break;
         case 4: launch_trace_t<2, 0>(p, variant, blocks, stream); break;
         case 5: launch_trace_t<2, 1>(p, variant, blocks, stream); break;
+        case 6: launch_trace_t<3, 0>(p, variant, blocks, stream); break;
+        case 7: launch_trace_t<3, 1>(p, variant, blocks, stream); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -1512,6 +1635,8 @@ int persistent_blocks_per_sm(int accel, int bounce) {
         case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<1, 1>, 256, 0); break;
         case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<2, 0>, 256, 0); break;
         case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<2, 1>, 256, 0); break;
+        case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<3, 0>, 256, 0); break;
+        case 7: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<3, 1>, 256, 0); break;
         default: break;
     }
     return n > 0 ? n : 1;

@@ -84,12 +84,14 @@ struct rt_raytracer {
     bool bvh_built = false;
     FlatCwbvh cwbvh;
     bool cwbvh_built = false;
+    FlatBvh4 bvh4;
+    bool bvh4_built = false;
     std::string last_error;
     int device = 0;
     cudaStream_t stream = nullptr;
 
     // device data
-    DevBuf<float4> d_oct_nodes, d_oct_tris, d_bvh_nodes, d_bvh_tris, d_cw_tris, d_tri_shade, d_materials, d_lights;
+    DevBuf<float4> d_oct_nodes, d_oct_tris, d_bvh_nodes, d_bvh_tris, d_cw_tris, d_bvh4_nodes, d_bvh4_tris, d_tri_shade, d_materials, d_lights;
     DevBuf<CwWord> d_cw_nodes;
     std::vector<std::unique_ptr<DevBuf<float>>> d_tex_data;
     DevBuf<DevTexture> d_textures;
@@ -109,9 +111,9 @@ struct rt_raytracer {
     std::vector<uint32_t> row_list_cache;   // rows of the last sharded / wrapped launch
     uint32_t cached_first = ~0u, cached_n = ~0u;
     uint64_t total_kernels = 0;
-    int variant = 2;            // RT_TUNE_KERNEL_VARIANT
-    int pool_refill = 8;        // RT_TUNE_POOL_REFILL
-    int pool_min_inner = 16;    // RT_TUNE_POOL_MIN_INNER
+    int variant = 1;            // RT_TUNE_KERNEL_VARIANT
+    int pool_refill = 16;       // RT_TUNE_POOL_REFILL
+    int pool_min_inner = 8;     // RT_TUNE_POOL_MIN_INNER
     int pool_blocks = 0;        // resident blocks per SM of the ray-pool kernel
     int lpt_schedule = 1;       // RT_TUNE_TILE_SCHEDULE: 1 = heaviest tiles first (cost feedback), 0 = image order
     // cost-feedback schedule state, valid for one launch geometry (first_row, rows, row list)
@@ -119,7 +121,7 @@ struct rt_raytracer {
     uint32_t sched_first = ~0u, sched_rows = ~0u, sched_tiles = 0;
     uint32_t sched_launches = 0;  // launches recorded since the schedule geometry / camera last changed
     bool sched_have_order = false;
-    int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // [accel][bounce]
+    int blocks_per_sm[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [accel][bounce]
     int num_sms = 0;
     rt_launch_stats last{};
     bool stats_pending = false;
@@ -307,6 +309,12 @@ struct rt_raytracer {
         bvh_built = true;
     }
 
+    void ensure_bvh4_host() {
+        if (bvh4_built) return;
+        bvh4 = build_bvh4(scene);
+        bvh4_built = true;
+    }
+
     void ensure_cwbvh_host() {
         if (cwbvh_built) return;
         cwbvh = build_cwbvh(scene);
@@ -377,6 +385,32 @@ struct rt_raytracer {
             }
             d_bvh_nodes.upload(nodes, stream);
             d_bvh_tris.upload(tris, stream);
+        } else if (accel == RT_ACCEL_BVH4) {
+            if (d_bvh4_nodes.p) return;
+            ensure_bvh4_host();
+            if (3 * bvh4.depth + 5 > (uint32_t)kBvh4Stack) throw CudaFail{"4-wide BVH deeper than the traversal stack"};
+            std::vector<float4> nodes(8 * bvh4.nodes.size());
+            for (size_t i = 0; i < bvh4.nodes.size(); ++i) {
+                const FlatBvh4::Node& n = bvh4.nodes[i];
+                float ref[4];
+                for (int k = 0; k < 4; ++k) {
+                    const int32_t r = n.child[k] >= 0 ? n.child[k] : ~(int32_t)(((uint32_t)(~n.child[k]) << 4) | (uint32_t)n.count[k]);
+                    std::memcpy(&ref[k], &r, 4);
+                }
+                for (int a = 0; a < 3; ++a) {
+                    nodes[8 * i + a] = make_float4(n.lo[0][a], n.lo[1][a], n.lo[2][a], n.lo[3][a]);
+                    nodes[8 * i + 3 + a] = make_float4(n.hi[0][a], n.hi[1][a], n.hi[2][a], n.hi[3][a]);
+                }
+                nodes[8 * i + 6] = make_float4(ref[0], ref[1], ref[2], ref[3]);
+                nodes[8 * i + 7] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            std::vector<float4> tris(3 * bvh4.tri_order.size());
+            for (size_t s = 0; s < bvh4.tri_order.size(); ++s) {
+                const uint32_t t = bvh4.tri_order[s];
+                pack_triangle(&scene.vertices[9 * (size_t)t], t, &tris[3 * s]);
+            }
+            d_bvh4_nodes.upload(nodes, stream);
+            d_bvh4_tris.upload(tris, stream);
         } else if (accel == RT_ACCEL_CWBVH) {
             if (d_cw_nodes.p) return;
             ensure_cwbvh_host();
@@ -414,6 +448,8 @@ struct rt_raytracer {
         p->oct_tris = d_oct_tris.p;
         p->bvh_nodes = d_bvh_nodes.p;
         p->bvh_tris = d_bvh_tris.p;
+        p->bvh4_nodes = d_bvh4_nodes.p;
+        p->bvh4_tris = d_bvh4_tris.p;
         p->cw_nodes = reinterpret_cast<const uint4*>(d_cw_nodes.p);
         p->cw_tris = d_cw_tris.p;
         p->tri_shade = d_tri_shade.p;
@@ -447,7 +483,7 @@ struct rt_raytracer {
 
     cudaError_t launch_one(const TraceParams& p_in) {
         TraceParams p = p_in;
-        const int a = cfg.accel == RT_ACCEL_OCTREE ? 0 : (cfg.accel == RT_ACCEL_CWBVH ? 2 : 1);
+        const int a = cfg.accel == RT_ACCEL_OCTREE ? 0 : (cfg.accel == RT_ACCEL_CWBVH ? 2 : (cfg.accel == RT_ACCEL_BVH4 ? 3 : 1));
         const int b = cfg.recursions > 0 ? 1 : 0;
         // the ray-pool kernel covers the headline configuration; everything else runs the persistent tile kernel
         const bool use_pool = variant == 2 && a == 1 && b == 0 && scene.lights.size() == 1;
@@ -727,7 +763,7 @@ const char* rt_last_error(const rt_raytracer* rt) { return rt ? rt->last_error.c
 
 int rt_configure(rt_raytracer* rt, int32_t recursions, uint32_t sub_spread, int32_t jitter_mode, uint32_t seed, int32_t accel) {
     RT_GUARD_HOST(rt, {
-        if (accel != RT_ACCEL_OCTREE && accel != RT_ACCEL_BVH && accel != RT_ACCEL_CWBVH) throw std::invalid_argument("unknown accel");
+        if (accel != RT_ACCEL_OCTREE && accel != RT_ACCEL_BVH && accel != RT_ACCEL_CWBVH && accel != RT_ACCEL_BVH4) throw std::invalid_argument("unknown accel");
         if (jitter_mode != RT_JITTER_FIXED_HALF && jitter_mode != RT_JITTER_HASHED) throw std::invalid_argument("unknown jitter mode");
         if (recursions < 0) throw std::invalid_argument("negative recursions");
         rt->cfg.recursions = recursions;
@@ -1039,6 +1075,34 @@ int rt_bvh_export(const rt_raytracer* rt_c, float* boxes, int32_t* children, int
         }
     }
     if (tri_order && !rt->bvh.tri_order.empty()) std::memcpy(tri_order, rt->bvh.tri_order.data(), rt->bvh.tri_order.size() * 4);
+    return RT_OK;
+}
+int rt_bvh4_stats(const rt_raytracer* rt_c, uint64_t* out) {
+    rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
+    if (!rt || !out) return RT_ERR_INVALID;
+    rt->ensure_bvh4_host();
+    out[0] = rt->bvh4.nodes.size();
+    out[1] = rt->bvh4.num_leaves;
+    out[2] = rt->bvh4.max_leaf;
+    out[3] = rt->bvh4.depth;
+    return RT_OK;
+}
+int rt_bvh4_export(const rt_raytracer* rt_c, float* boxes, int32_t* children, int32_t* counts, uint32_t* tri_order) {
+    rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
+    if (!rt) return RT_ERR_INVALID;
+    rt->ensure_bvh4_host();
+    for (size_t i = 0; i < rt->bvh4.nodes.size(); ++i) {
+        const FlatBvh4::Node& n = rt->bvh4.nodes[i];
+        for (int k = 0; k < 4; ++k) {
+            if (boxes) {
+                std::memcpy(boxes + 24 * i + 6 * k, n.lo[k], 12);
+                std::memcpy(boxes + 24 * i + 6 * k + 3, n.hi[k], 12);
+            }
+            if (children) children[4 * i + k] = n.child[k];
+            if (counts) counts[4 * i + k] = n.count[k];
+        }
+    }
+    if (tri_order && !rt->bvh4.tri_order.empty()) std::memcpy(tri_order, rt->bvh4.tri_order.data(), rt->bvh4.tri_order.size() * 4);
     return RT_OK;
 }
 int rt_cwbvh_stats(const rt_raytracer* rt_c, uint64_t* out) {

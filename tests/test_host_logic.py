@@ -160,6 +160,49 @@ def test_bvh_invariants(scenes, name):
 
 
 @pytest.mark.parametrize("name", ["4boxes", "ico2", "thai2"])
+def test_bvh4_invariants(scenes, name):
+    """4-wide BVH (csrc/bvh4_build.cpp): every triangle in exactly one leaf, stored child boxes strictly contain their
+    subtrees, empty slots are the unhittable box lo = hi = +inf, leaves hold at most 4 ascending triangle ids."""
+    s = scenes(name)
+    r = host_tracer(s)
+    boxes, children, counts, order = r.bvh4_export()
+    st = r.bvh4_stats()
+    n_tri = s.vertices.shape[0]
+    assert sorted(order.tolist()) == list(range(n_tri))
+    assert st["max_leaf"] <= 4 and 3 * st["depth"] + 5 <= 64
+    assert st["nodes"] < r.bvh_stats()["nodes"]  # the collapse removes inner nodes
+    verts = s.vertices.reshape(n_tri, 3, 3)
+    seen = np.zeros(n_tri, bool)
+    visited = np.zeros(st["nodes"], bool)
+
+    def subtree_box(node):
+        assert not visited[node]
+        visited[node] = True
+        lo_all, hi_all = np.full(3, np.inf), np.full(3, -np.inf)
+        for k in range(4):
+            c, cnt = int(children[node, k]), int(counts[node, k])
+            if c < 0 and cnt == 0:
+                assert np.isposinf(boxes[node, k]).all()
+                continue
+            if c >= 0:
+                lo, hi = subtree_box(c)
+            else:
+                tri = order[~c:~c + cnt]
+                assert not seen[tri].any()
+                seen[tri] = True
+                assert (np.diff(tri.astype(np.int64)) > 0).all()
+                lo, hi = verts[tri].reshape(-1, 3).min(0), verts[tri].reshape(-1, 3).max(0)
+            assert (boxes[node, k, 0] < lo).all() and (boxes[node, k, 1] > hi).all()
+            lo_all, hi_all = np.minimum(lo_all, lo), np.maximum(hi_all, hi)
+        return lo_all, hi_all
+
+    import sys
+    sys.setrecursionlimit(10000)
+    subtree_box(0)
+    assert seen.all() and visited.all()
+
+
+@pytest.mark.parametrize("name", ["4boxes", "ico2", "thai2"])
 def test_cwbvh_invariants(scenes, name):
     """Compressed 8-wide BVH (csrc/cwbvh_build.cpp): every triangle sits in exactly one leaf child, every quantised child
     box (decoded with the f32 expression the traversal uses, plane = p + q * 2^e) contains its subtree, inner
