@@ -11,7 +11,11 @@ rays (recursions = 0, fixed sub-pixel offset 0.5: the pinned parity mode), accum
   cpu_baseline / --impl reference : the CPU oracle (C++ restatement of the reference, oracle/) on the host cores
 
 N > 1 (torchrun, one process per GPU): the frame is sharded by interleaved 8-row bands, the scene is replicated,
-rank 0 receives the packed frame over NVLink (see --gather). scaling = "strong": total work per step is fixed.
+rank 0 receives the packed frame over NVLink (see --gather), no other exchange.
+  --scaling weak (default): a step renders N samples per pixel of the frame (hashed jitter), so every rank traces
+      H/N rows x N samples = as many camera rays as the single GPU does in its step; value = all rays of all ranks / time
+  --scaling strong: a step is one sample per pixel whatever N is (each rank traces H/N rows); a 0.23 ms frame cut in
+      N pieces is bounded by launch + fence latency and by the slowest tile, see DESIGN.md section 7
 """
 from __future__ import annotations
 
@@ -149,7 +153,7 @@ def run_reference(args):
         "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True,
-        "scaling": "strong",
+        "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "reference scene fixture data/%s (the upstream repository's own scene), pinned camera" % fname,
@@ -224,8 +228,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="thai2_1080p", choices=sorted(WORKLOADS))
-    ap.add_argument("--accel", default="bvh", choices=["bvh", "octree", "cwbvh", "bvh4"])
+    ap.add_argument("--accel", default="bvh", choices=["bvh", "octree", "cwbvh", "bvh4", "lbvh"])
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N>1: how rank 0 receives the frame")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: samples per pixel per step = N (weak) or 1 (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--zero-copy", action="store_true",
                     help="e2e leg: let the kernel store packed pixels straight into the pinned host frame (rt_set_host_frame) instead of "
@@ -258,8 +263,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     fname, W, H, spp = WORKLOADS[args.workload]
+    base_spp = spp
+    if world > 1 and args.scaling == "weak":
+        spp = spp * world  # per-GPU work stays what one GPU does at N = 1
     scene = rt.load_scene(os.path.join(ROOT, "data", fname))
-    accel = {"bvh": rt.ACCEL_BVH, "octree": rt.ACCEL_OCTREE, "cwbvh": rt.ACCEL_CWBVH, "bvh4": rt.ACCEL_BVH4}[args.accel]
+    accel = {"bvh": rt.ACCEL_BVH, "octree": rt.ACCEL_OCTREE, "cwbvh": rt.ACCEL_CWBVH, "bvh4": rt.ACCEL_BVH4, "lbvh": rt.ACCEL_LBVH}[args.accel]
     cfg = rt.Config(W, H, recursions=0, jitter_mode=rt.JITTER_FIXED_HALF if spp == 1 else rt.JITTER_HASHED, accel=accel,
                     device=local_rank, shard_index=rank, shard_count=world, band_rows=8)
     sampler = ClockSampler(local_rank)
@@ -286,13 +294,12 @@ def main():
         if gather is not None:
             gather.device_gather()
 
-    # ---- ray counts of one step (deterministic: pinned camera) ----------------------------------------
-    n_primary, n_shadow = tracer.trace_rows(0, H, spp)
-    counts = torch.tensor([n_primary, n_shadow], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(counts)
-    n_primary_total, n_shadow_total = int(counts[0]), int(counts[1])
-    rays_per_step = n_primary_total + n_shadow_total
+    def global_ray_totals():
+        t = tracer.ray_totals()  # exact device counters since the handle was created (synchronises this rank's stream)
+        v = torch.tensor([t["primary"], t["shadow"]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(v)
+        return int(v[0]), int(v[1])
 
     # ---- device-timed leg ------------------------------------------------------------------------------
     with torch.cuda.stream(stream):
@@ -300,6 +307,7 @@ def main():
             flush.zero_()
             device_step()
     barrier()
+    rays0 = global_ray_totals()
     launches0 = tracer.kernels_launched() + (gather.kernels if gather else 0)
     sampler.ready.wait(timeout=10)
     t_region0 = time.perf_counter()
@@ -316,6 +324,11 @@ def main():
     barrier()
     clocks = sampler.window(t_region0, time.perf_counter())
     launches = tracer.kernels_launched() + (gather.kernels if gather else 0) - launches0
+    rays1 = global_ray_totals()
+    # rays of the timed steps, counted on the device (with hashed jitter every step draws new samples, so the shadow-ray
+    # count differs slightly from step to step)
+    n_primary_total, n_shadow_total = (rays1[0] - rays0[0]) / args.steps, (rays1[1] - rays0[1]) / args.steps
+    rays_per_step = n_primary_total + n_shadow_total
     step_ms = [a.elapsed_time(b) for a, b in events]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -356,16 +369,19 @@ def main():
     for i in range(args.warmup):
         e2e_step(i)
     barrier()
+    rays0 = global_ray_totals()
     t0 = time.perf_counter()
     for i in range(args.steps):
         e2e_step(i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    rays1 = global_ray_totals()
+    e2e_rays = (rays1[0] - rays0[0]) + (rays1[1] - rays0[1])
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t)
-    e2e_value = rays_per_step * args.steps / e2e_s / 1e6
+    e2e_value = e2e_rays / e2e_s / 1e6
     sampler.stop()
     e2e_frame_ok = None
     if rank == 0 and gather is None:
@@ -408,13 +424,19 @@ def main():
     except Exception:
         pass
     roofline = None
-    if alg is not None and spp == 1:
-        per_launch = alg / world  # each rank's launch processes 1/N of the frame
+    if alg is not None:
+        note = "traffic-equivalent of the reference algorithm's reads; the <= 2 MB scene is L1/L2 resident, so frac may exceed 1"
+        if world == 1 and spp == 1:
+            per_launch = float(alg)  # exact oracle counters of the pinned frame
+        else:
+            # jittered / sharded launches: the pinned frame's average bytes per ray x the rays one rank traces per launch
+            p0, s0 = REFERENCE_WORK[args.workload][:2]
+            per_launch = alg / (p0 + s0) * rays_per_step / world
+            note += "; per-launch bytes estimated from the pinned frame's average bytes per ray"
         achieved = per_launch / (kms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": peak_src, "kernel": "trace_shade_kernel<%s>" % args.accel, "kernel_ms": kms,
-                    "algorithmic_bytes_per_launch": per_launch,
-                    "note": "traffic-equivalent of the reference algorithm's reads; the <= 2 MB scene is L1/L2 resident, so frac may exceed 1"}
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic if world == 1 and spp == 1 else None,
+                    "peak_source": peak_src, "kernel": "trace_shade_persistent_kernel<%s>" % args.accel, "kernel_ms": kms,
+                    "algorithmic_bytes_per_launch": per_launch, "note": note}
     line = {
         "metric": METRIC,
         "value": value,
@@ -424,13 +446,13 @@ def main():
         "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps,
         "higher_is_better": True,
-        "scaling": "strong",
+        "scaling": args.scaling if world > 1 else "weak",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "reference scene fixture data/%s (the upstream repository's own scene), pinned camera" % fname,
         "config": {"workload": args.workload, "width": W, "height": H, "spp": spp, "recursions": 0,
                    "jitter": "fixed 0.5" if spp == 1 else "hashed seed 0", "accel": args.accel, "l2_flush_between_steps": True,
-                   "step": "one full frame: trace %d rows x %d spp%s" % (H, spp, "" if world == 1 else " sharded by 8-row bands + gather to rank 0 (%s)" % args.gather),
+                   "step": "one full frame: trace %d rows x %d spp%s" % (H, spp, "" if world == 1 else " (%d spp per GPU-count unit: %s scaling), rows sharded by interleaved 8-row bands, every rank traces its rows x all samples in one launch, packed frame stored into rank 0's buffer over NVLink (%s)" % (base_spp, args.scaling, args.gather)),
                    "primary_rays_per_step": n_primary_total, "shadow_rays_per_step": n_shadow_total},
         "frames_per_s": args.steps / (total_ms * 1e-3),
         "clocks": clocks,

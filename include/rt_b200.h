@@ -75,7 +75,9 @@ typedef struct rt_scene_desc {
 enum { RT_ACCEL_OCTREE = 0, /* flattened reference octree, traversal bit-identical to oct_tree_intersector.rs:148-272 */
        RT_ACCEL_BVH = 1,    /* binary SAH BVH, closest hit + lowest-index tie break + root-cube acceptance */
        RT_ACCEL_CWBVH = 2,  /* compressed 8-wide BVH (same hit rules as RT_ACCEL_BVH; 80-byte nodes, costlier box decode) */
-       RT_ACCEL_BVH4 = 3 }; /* 4-wide BVH, full-precision boxes, one 128-byte node per visit (same hit rules) */
+       RT_ACCEL_BVH4 = 3,   /* 4-wide BVH, full-precision boxes, one 128-byte node per visit (same hit rules) */
+       RT_ACCEL_LBVH = 4 }; /* binary BVH built ON THE GPU (Morton codes, radix sort, Karras hierarchy, refit); same
+                               traversal kernel and hit rules as RT_ACCEL_BVH */
 enum { RT_JITTER_FIXED_HALF = 0, /* xi = (0.5, 0.5): the pinned parity mode */
        RT_JITTER_HASHED = 1 };   /* xi = hash(seed, pixel, sample, axis) * 2^-24: stands in for StdRng::from_os_rng
                                     (raytracer/mod.rs:84, scene/camera.rs:82-84) */
@@ -204,6 +206,9 @@ uint32_t rt_launch_param_bytes(void);
 /* RT_TUNE_POOL_MIN_INNER: the ray-pool kernel leaves its inner-node loop when fewer lanes than this are still
    descending while other lanes wait at a leaf or with a finished ray (0..32, default 8; 0 = classic while-while). */
 #define RT_TUNE_POOL_MIN_INNER 4
+/* RT_TUNE_MULTI_SAMPLE_LAUNCH: 1 (default) rt_trace_rows with spp > 1 traces all samples of the pass in one launch
+   (per-sample radiance planes + one ordered accumulation into the film); 0 one launch per sample. Same film either way. */
+#define RT_TUNE_MULTI_SAMPLE_LAUNCH 5
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {
@@ -212,6 +217,9 @@ typedef struct rt_launch_stats {
     uint64_t n_primary, n_shadow, n_bounce;
 } rt_launch_stats;
 int rt_get_launch_stats(const rt_raytracer* rt, rt_launch_stats* out);
+/* Rays issued by this handle since creation: out3 = primary, shadow, bounce (synchronises the stream). Exact totals
+   over any number of asynchronous trace calls. */
+int rt_get_ray_totals(rt_raytracer* rt, uint64_t* out3);
 /* Total kernels launched by this handle since creation. */
 uint64_t rt_kernels_launched(const rt_raytracer* rt);
 
@@ -228,6 +236,13 @@ int rt_bvh_stats(const rt_raytracer* rt, uint64_t* out);
 /* boxes: nodes*12 (child0 lo xyz, hi xyz, child1 lo xyz, hi xyz); children: nodes*2 (>= 0 inner node, < 0 leaf with
    ~child = first triangle slot); counts: nodes*2 (triangles of a leaf child); tri_order: slot -> global triangle. */
 int rt_bvh_export(const rt_raytracer* rt, float* boxes, int32_t* children, int32_t* counts, uint32_t* tri_order);
+/* GPU tree build (RT_ACCEL_LBVH): (re)builds the tree on the device and reports out3 = nodes, depth, triangles and
+   the device time of the build in milliseconds (CUDA events). Either output may be NULL. */
+int rt_lbvh_build(rt_raytracer* rt, uint64_t* out3, float* build_ms);
+/* The GPU-built tree in the layout of rt_bvh_export (boxes: nodes*12, children/counts: nodes*2, tri_order: slot ->
+   global triangle); nodes = max(triangles - 1, 1). Nodes that were folded into a leaf of their parent stay in the
+   array but are unreachable. */
+int rt_lbvh_export(rt_raytracer* rt, float* boxes, int32_t* children, int32_t* counts, uint32_t* tri_order);
 /* 4-wide BVH (RT_ACCEL_BVH4). out[4]: nodes, leaves, max leaf size, depth */
 int rt_bvh4_stats(const rt_raytracer* rt, uint64_t* out);
 /* boxes: nodes*24 (per child: lo xyz, hi xyz; an empty slot is lo = hi = +inf); children: nodes*4 (>= 0 inner node,

@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     ACCEL_BVH,
     ACCEL_BVH4,
     ACCEL_CWBVH,
+    ACCEL_LBVH,
     ACCEL_OCTREE,
     JITTER_FIXED_HALF,
     JITTER_HASHED,
@@ -40,6 +41,7 @@ __all__ = [
     "ACCEL_BVH",
     "ACCEL_BVH4",
     "ACCEL_CWBVH",
+    "ACCEL_LBVH",
     "ACCEL_OCTREE",
     "JITTER_FIXED_HALF",
     "JITTER_HASHED",

@@ -13,7 +13,7 @@ import numpy as np
 
 DEFAULT_TRIANGLES_PER_LEAF = 70  # oct_tree_intersector.rs:12, re-exported lib.rs:7
 DEVICE_NONE = -2  # RT_DEVICE_NONE: host-side handle for CPU-only tests of the host logic
-ACCEL_OCTREE, ACCEL_BVH, ACCEL_CWBVH, ACCEL_BVH4 = 0, 1, 2, 3
+ACCEL_OCTREE, ACCEL_BVH, ACCEL_CWBVH, ACCEL_BVH4, ACCEL_LBVH = 0, 1, 2, 3, 4
 JITTER_FIXED_HALF, JITTER_HASHED = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -97,7 +97,7 @@ ABI_SYMBOLS = [
     "rt_get_ldr_device_ptr", "rt_set_ldr_target", "rt_get_owned_ldr_rows_device", "rt_get_launch_stats",
     "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_get_counters_device_ptr",
     "rt_launch_param_bytes", "rt_set_tuning", "rt_set_host_frame",
-    "rt_kernels_launched", "rt_octree_stats", "rt_octree_export", "rt_bvh_stats", "rt_bvh_export", "rt_bvh4_stats", "rt_bvh4_export", "rt_cwbvh_stats",
+    "rt_kernels_launched", "rt_get_ray_totals", "rt_octree_stats", "rt_octree_export", "rt_bvh_stats", "rt_bvh_export", "rt_bvh4_stats", "rt_bvh4_export", "rt_lbvh_build", "rt_lbvh_export", "rt_cwbvh_stats",
     "rt_cwbvh_export", "rt_stats_new",
     "rt_stats_free", "rt_stats_stats", "rt_stats_mean_stats", "rt_benchmark_new", "rt_benchmark_free",
     "rt_benchmark_start", "rt_benchmark_stop", "rt_benchmark_report", "rt_version",
@@ -168,6 +168,9 @@ def lib() -> C.CDLL:
         "rt_octree_export": (C.c_int, [vp, vp, vp, vp, vp, P(u64)]),
         "rt_bvh_stats": (C.c_int, [vp, vp]),
         "rt_bvh_export": (C.c_int, [vp, vp, vp, vp, vp]),
+        "rt_get_ray_totals": (C.c_int, [vp, vp]),
+        "rt_lbvh_build": (C.c_int, [vp, vp, P(f32)]),
+        "rt_lbvh_export": (C.c_int, [vp, vp, vp, vp, vp]),
         "rt_bvh4_stats": (C.c_int, [vp, vp]),
         "rt_bvh4_export": (C.c_int, [vp, vp, vp, vp, vp]),
         "rt_cwbvh_stats": (C.c_int, [vp, vp]),
@@ -508,6 +511,29 @@ class RayTracer:
         counts = np.zeros((n, 2), np.int32)
         order = np.zeros(max(1, self.num_triangles), np.uint32)
         self._check(lib().rt_bvh_export(self._h, _ptr(boxes), _ptr(children), _ptr(counts), _ptr(order)))
+        return boxes, children, counts, order[: self.num_triangles]
+
+    def ray_totals(self) -> dict:
+        """rays issued since creation (exact, over any number of asynchronous trace calls); synchronises the stream"""
+        raw = np.zeros(3, np.uint64)
+        self._check(lib().rt_get_ray_totals(self._h, _ptr(raw)))
+        return dict(zip(["primary", "shadow", "bounce"], (int(x) for x in raw)))
+
+    def lbvh_build(self) -> dict:
+        """(re)builds the BVH on the GPU; returns nodes, depth, triangles and the device time of the build (ms)"""
+        raw = np.zeros(3, np.uint64)
+        ms = C.c_float()
+        self._check(lib().rt_lbvh_build(self._h, _ptr(raw), C.byref(ms)))
+        return {"nodes": int(raw[0]), "depth": int(raw[1]), "triangles": int(raw[2]), "build_ms": float(ms.value)}
+
+    def lbvh_export(self):
+        """GPU-built tree in the layout of bvh_export"""
+        n = max(self.num_triangles - 1, 1)
+        boxes = np.zeros((n, 2, 2, 3), np.float32)
+        children = np.zeros((n, 2), np.int32)
+        counts = np.zeros((n, 2), np.int32)
+        order = np.zeros(max(1, self.num_triangles), np.uint32)
+        self._check(lib().rt_lbvh_export(self._h, _ptr(boxes), _ptr(children), _ptr(counts), _ptr(order)))
         return boxes, children, counts, order[: self.num_triangles]
 
     def bvh4_stats(self) -> dict:

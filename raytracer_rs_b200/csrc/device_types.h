@@ -31,7 +31,10 @@ constexpr int kBvhStack = 48;
 constexpr int kBvh4Stack = 64;  // up to three pushes per level
 constexpr int kCwStack = 32;  // node groups only: at most one per level plus slack
 
-enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3, CNT_TILE_QUEUE = 4, CNT_QUEUE_ITEMS = 5, CNT_SLOTS = 6 };
+// slots 0..4 are zeroed by every trace call; CNT_QUEUE_ITEMS survives between launches (tile schedule); the *_TOTAL
+// slots run since the handle was created (exact ray totals over many asynchronous calls, rt_get_ray_totals)
+enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3, CNT_TILE_QUEUE = 4, CNT_QUEUE_ITEMS = 5,
+                   CNT_SHADOW_TOTAL = 6, CNT_BOUNCE_TOTAL = 7, CNT_SLOTS = 8 };
 
 struct TraceParams {
     DevCamera cam;
@@ -64,6 +67,11 @@ struct TraceParams {
     // work: compact rows [0, n_rows) -> image row (first_row + c) % height, or row_list[c] when non-null
     const uint32_t* row_list;
     uint32_t first_row, n_rows;
+    // sample planes: with planes != null the launch covers n_planes samples of plane_rows compact rows each
+    // (n_rows = n_planes * plane_rows); radiance and primitive id go to planes[(plane * plane_rows + row) * width + col]
+    // instead of the film, and film_accumulate_kernel adds them in sample order afterwards
+    float4* planes;
+    uint32_t n_planes, plane_rows, magic_plane_rows;
     uint32_t jitter_mode, seed;
     int32_t recursions;          // RECURSIONS (mod.rs:81); 0 = primary + shadow only
     uint32_t sub_spread;         // SUB_SPREAD (mod.rs:82)

@@ -947,10 +947,16 @@ __device__ __forceinline__ void film_add_sample(const TraceParams& P, uint32_t i
 template <int ACCEL, int WW, int BOUNCE>
 __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, uint32_t crow, LaneCounters& cnt) {
     const uint32_t W = P.cam.width, H = P.cam.height;
-    const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % H;
+    // sample planes (several samples per pixel in one launch): compact row `crow` = plane * plane_rows + row of the pass
+    uint32_t plane = 0, prow = crow;
+    if (P.planes) {
+        plane = udiv_magic(crow, P.plane_rows, P.magic_plane_rows);
+        prow = crow - plane * P.plane_rows;
+    }
+    const uint32_t row = P.row_list ? P.row_list[prow] : (P.first_row + prow) % H;
     const uint32_t idx = row * W + col;
     const float4 fs_ = P.film_sum[idx];
-    const uint32_t nsamp = __float_as_uint(fs_.w);
+    const uint32_t nsamp = __float_as_uint(fs_.w) + plane;  // the number this sample will have in the film
     const V3 d = camera_ray_dir(P, idx, col, nsamp);
     const V3 o = {P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]};
 
@@ -967,6 +973,10 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, 
             shade_hit<ACCEL, WW>(P, o, d, hit, &nrm, &cr, &cg, &cb, cnt);
         }
     }
+    if (P.planes) {  // film_accumulate_kernel adds the planes to the film in sample order
+        P.planes[(size_t)crow * W + col] = make_float4(cr, cg, cb, __uint_as_float(id));
+        return;
+    }
     P.primary_ids[idx] = id;
     film_add_sample(P, idx, fs_, cr, cg, cb);
 }
@@ -978,8 +988,14 @@ __device__ __forceinline__ void flush_counters(const TraceParams& P, LaneCounter
     const uint32_t b = __reduce_add_sync(0xffffffffu, c.blocked);
     const uint32_t r = __reduce_add_sync(0xffffffffu, c.bounce_rays);
     if (lane == 0) {
-        if (r) atomicAdd(&P.counters[CNT_BOUNCE], (unsigned long long)r);
-        if (s) atomicAdd(&P.counters[CNT_SHADOW], (unsigned long long)s);
+        if (r) {
+            atomicAdd(&P.counters[CNT_BOUNCE], (unsigned long long)r);
+            atomicAdd(&P.counters[CNT_BOUNCE_TOTAL], (unsigned long long)r);
+        }
+        if (s) {
+            atomicAdd(&P.counters[CNT_SHADOW], (unsigned long long)s);
+            atomicAdd(&P.counters[CNT_SHADOW_TOTAL], (unsigned long long)s);
+        }
         if (h) atomicAdd(&P.counters[CNT_PRIMARY_HITS], (unsigned long long)h);
         if (b) atomicAdd(&P.counters[CNT_BLOCKED], (unsigned long long)b);
     }
@@ -1572,6 +1588,38 @@ __global__ void tonemap_pack_kernel(const float4* __restrict__ sum, uint32_t* __
     }
 }
 
+// Adds the sample planes of one launch to the film in sample order (PixelData::add_sample, film.rs:20-24, once per
+// plane), then mean, tonemap, pack of the final sums: exactly what `n_planes` consecutive single-sample launches leave.
+__global__ void __launch_bounds__(256) film_accumulate_kernel(const __grid_constant__ TraceParams P) {
+    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t prow = blockIdx.y;
+    const uint32_t W = P.cam.width, H = P.cam.height;
+    if (col >= W || prow >= P.plane_rows) return;
+    const uint32_t row = P.row_list ? P.row_list[prow] : (P.first_row + prow) % H;
+    const uint32_t idx = row * W + col;
+    float4 fs_ = P.film_sum[idx];
+    float4 sq = P.film_sq[idx];
+    uint32_t n = __float_as_uint(fs_.w), id = kNoHit;
+    for (uint32_t s = 0; s < P.n_planes; ++s) {
+        const float4 c = __ldcs(&P.planes[((size_t)s * P.plane_rows + prow) * W + col]);
+        fs_.x = fadd(fs_.x, c.x);
+        fs_.y = fadd(fs_.y, c.y);
+        fs_.z = fadd(fs_.z, c.z);
+        sq.x = fadd(sq.x, fmul(c.x, c.x));
+        sq.y = fadd(sq.y, fmul(c.y, c.y));
+        sq.z = fadd(sq.z, fmul(c.z, c.z));
+        n += 1u;
+        id = __float_as_uint(c.w);
+    }
+    fs_.w = __uint_as_float(n);
+    P.film_sum[idx] = fs_;
+    P.film_sq[idx] = sq;
+    P.primary_ids[idx] = id;
+    const uint32_t px = tonemap_pack(fs_.x, fs_.y, fs_.z, n);
+    P.ldr[idx] = px;
+    if (P.ldr_remote) P.ldr_remote[idx] = px;
+}
+
 __global__ void gather_rows_kernel(const uint32_t* __restrict__ ldr, const uint32_t* __restrict__ row_list, uint32_t n_rows, uint32_t width,
                                    uint32_t* __restrict__ out) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1584,7 +1632,7 @@ __global__ void gather_rows_kernel(const uint32_t* __restrict__ ldr, const uint3
 // ------------------------------------------------------------------------------------------------------
 template <int ACCEL, int BOUNCE>
 static void launch_trace_t(const TraceParams& p, int variant, uint32_t blocks, cudaStream_t stream) {
-    if (variant == 2 && ACCEL == 1 && BOUNCE == 0 && p.num_lights == 1) {
+    if (variant == 2 && ACCEL == 1 && BOUNCE == 0 && p.num_lights == 1 && !p.planes) {
         // > 48 KB of dynamic shared memory needs the opt-in (set per device by pool_blocks_per_sm, which every handle calls first)
         trace_shade_pool_kernel<<<blocks, 32 * kPoolWarps, kPoolSmemBytes, stream>>>(p);
         return;
@@ -1653,6 +1701,12 @@ cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* 
 cudaError_t launch_tonemap(const float4* sum, uint32_t* ldr, uint32_t n, cudaStream_t stream) {
     const uint32_t threads = (n + 3u) / 4u;
     tonemap_pack_kernel<<<(threads + 255u) / 256u, 256, 0, stream>>>(sum, ldr, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_film_accumulate(const TraceParams& p, cudaStream_t stream) {
+    if (p.plane_rows == 0 || p.n_planes == 0) return cudaSuccess;
+    dim3 grid((p.cam.width + 255u) / 256u, p.plane_rows);
+    film_accumulate_kernel<<<grid, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 cudaError_t launch_gather_rows(const uint32_t* ldr, const uint32_t* row_list, uint32_t n_rows, uint32_t width, uint32_t* out, cudaStream_t stream) {

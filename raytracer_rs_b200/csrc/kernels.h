@@ -21,7 +21,14 @@ cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, 
                              unsigned long long* counters, cudaStream_t stream);
 cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream);
 cudaError_t launch_tonemap(const float4* sum, uint32_t* ldr, uint32_t n, cudaStream_t stream);
+// adds the sample planes written by a multi-sample trace launch to the film, in sample order, and packs the LDR pixels
+cudaError_t launch_film_accumulate(const TraceParams& p, cudaStream_t stream);
 cudaError_t launch_gather_rows(const uint32_t* ldr, const uint32_t* row_list, uint32_t n_rows, uint32_t width, uint32_t* out,
                                cudaStream_t stream);
+
+// GPU build of the binary BVH (lbvh_build.cu): Morton codes, radix sort, Karras hierarchy, bottom-up refit
+size_t lbvh_scratch_bytes(uint32_t n);
+cudaError_t build_lbvh_device(const float* d_verts, uint32_t n, const float root_lo[3], const float root_hi[3], void* scratch, float4* d_nodes,
+                              float4* d_tris, uint32_t* d_tri_order, uint32_t* d_depth, cudaStream_t stream);
 
 }  // namespace rtb

@@ -86,6 +86,12 @@ struct rt_raytracer {
     bool cwbvh_built = false;
     FlatBvh4 bvh4;
     bool bvh4_built = false;
+    // GPU-built binary BVH (RT_ACCEL_LBVH)
+    DevBuf<float4> d_lbvh_nodes, d_lbvh_tris;
+    DevBuf<uint32_t> d_lbvh_order, d_lbvh_depth;
+    DevBuf<float> d_verts;
+    uint32_t lbvh_depth = 0, lbvh_nodes = 0;
+    float lbvh_build_ms = 0.f;
     std::string last_error;
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -95,7 +101,8 @@ struct rt_raytracer {
     DevBuf<CwWord> d_cw_nodes;
     std::vector<std::unique_ptr<DevBuf<float>>> d_tex_data;
     DevBuf<DevTexture> d_textures;
-    DevBuf<float4> d_film_sum, d_film_sq;
+    DevBuf<float4> d_film_sum, d_film_sq, d_planes;
+    bool multi_sample_launch = true;  // RT_TUNE_MULTI_SAMPLE_LAUNCH
     DevBuf<uint32_t> d_ldr, d_ids, d_row_list, d_owned_rows;
     DevBuf<unsigned long long> d_counters;
     unsigned long long* h_counters = nullptr;  // pinned
@@ -110,7 +117,7 @@ struct rt_raytracer {
     std::vector<uint32_t> owned_rows;       // all rows of this shard, ascending
     std::vector<uint32_t> row_list_cache;   // rows of the last sharded / wrapped launch
     uint32_t cached_first = ~0u, cached_n = ~0u;
-    uint64_t total_kernels = 0;
+    uint64_t total_kernels = 0, total_primary = 0;
     int variant = 1;            // RT_TUNE_KERNEL_VARIANT
     int pool_refill = 16;       // RT_TUNE_POOL_REFILL
     int pool_min_inner = 8;     // RT_TUNE_POOL_MIN_INNER
@@ -178,6 +185,7 @@ struct rt_raytracer {
         RT_CUDA(cudaEventCreate(&ev_stop));
         RT_CUDA(cudaHostAlloc((void**)&h_counters, CNT_SLOTS * sizeof(unsigned long long), cudaHostAllocDefault));
         d_counters.alloc(CNT_SLOTS);
+        RT_CUDA(cudaMemsetAsync(d_counters.p, 0, CNT_SLOTS * sizeof(unsigned long long), stream));
         upload_scene();
         ensure_accel(cfg.accel);
         d_film_sum.alloc(npix());
@@ -385,6 +393,9 @@ struct rt_raytracer {
             }
             d_bvh_nodes.upload(nodes, stream);
             d_bvh_tris.upload(tris, stream);
+        } else if (accel == RT_ACCEL_LBVH) {
+            if (d_lbvh_nodes.p) return;
+            build_lbvh();
         } else if (accel == RT_ACCEL_BVH4) {
             if (d_bvh4_nodes.p) return;
             ensure_bvh4_host();
@@ -427,6 +438,30 @@ struct rt_raytracer {
         }
     }
 
+    // the binary BVH built on the device (lbvh_build.cu); timed with CUDA events on the handle's stream
+    void build_lbvh() {
+        const uint32_t n = scene.num_triangles();
+        if (!d_verts.p) d_verts.upload(scene.vertices, stream);
+        DevBuf<char> scratch;
+        scratch.alloc(lbvh_scratch_bytes(n));
+        lbvh_nodes = n > 1 ? n - 1 : 1;
+        d_lbvh_nodes.alloc(4 * (size_t)lbvh_nodes);
+        d_lbvh_tris.alloc(3 * (size_t)std::max(n, 1u));
+        d_lbvh_order.alloc(std::max(n, 1u));
+        d_lbvh_depth.alloc(1);
+        RT_CUDA(cudaEventRecord(ev_start, stream));
+        RT_CUDA(build_lbvh_device(d_verts.p, n, root_lo, root_hi, scratch.p, d_lbvh_nodes.p, d_lbvh_tris.p, d_lbvh_order.p, d_lbvh_depth.p, stream));
+        RT_CUDA(cudaEventRecord(ev_stop, stream));
+        RT_CUDA(cudaMemcpyAsync(&lbvh_depth, d_lbvh_depth.p, 4, cudaMemcpyDeviceToHost, stream));
+        RT_CUDA(cudaStreamSynchronize(stream));
+        RT_CUDA(cudaEventElapsedTime(&lbvh_build_ms, ev_start, ev_stop));
+        total_kernels += n > 1 ? 16 : 3;
+        if (lbvh_depth + 2 > (uint32_t)kBvhStack) {
+            d_lbvh_nodes.release();
+            throw CudaFail{"GPU-built BVH is deeper than the traversal stack (degenerate triangle distribution); use RT_ACCEL_BVH"};
+        }
+    }
+
     void film_clear() {
         host_frame_stale = true;
         RT_CUDA(launch_film_clear(d_film_sum.p, d_film_sq.p, d_ldr.p, d_ids.p, npix(), stream));
@@ -446,8 +481,8 @@ struct rt_raytracer {
         p->cam.height = cfg.height;
         p->oct_nodes = d_oct_nodes.p;
         p->oct_tris = d_oct_tris.p;
-        p->bvh_nodes = d_bvh_nodes.p;
-        p->bvh_tris = d_bvh_tris.p;
+        p->bvh_nodes = cfg.accel == RT_ACCEL_LBVH ? d_lbvh_nodes.p : d_bvh_nodes.p;
+        p->bvh_tris = cfg.accel == RT_ACCEL_LBVH ? d_lbvh_tris.p : d_bvh_tris.p;
         p->bvh4_nodes = d_bvh4_nodes.p;
         p->bvh4_tris = d_bvh4_tris.p;
         p->cw_nodes = reinterpret_cast<const uint4*>(d_cw_nodes.p);
@@ -483,10 +518,10 @@ struct rt_raytracer {
 
     cudaError_t launch_one(const TraceParams& p_in) {
         TraceParams p = p_in;
-        const int a = cfg.accel == RT_ACCEL_OCTREE ? 0 : (cfg.accel == RT_ACCEL_CWBVH ? 2 : (cfg.accel == RT_ACCEL_BVH4 ? 3 : 1));
+        const int a = cfg.accel == RT_ACCEL_OCTREE ? 0 : (cfg.accel == RT_ACCEL_CWBVH ? 2 : (cfg.accel == RT_ACCEL_BVH4 ? 3 : 1));  // LBVH: same traversal as the SAH binary BVH
         const int b = cfg.recursions > 0 ? 1 : 0;
         // the ray-pool kernel covers the headline configuration; everything else runs the persistent tile kernel
-        const bool use_pool = variant == 2 && a == 1 && b == 0 && scene.lights.size() == 1;
+        const bool use_pool = variant == 2 && a == 1 && b == 0 && scene.lights.size() == 1 && !p.planes;
         if (use_pool && pool_blocks == 0) pool_blocks = pool_blocks_per_sm();
         if (!use_pool && variant != 0 && blocks_per_sm[a][b] == 0) blocks_per_sm[a][b] = persistent_blocks_per_sm(a, b);
         p.pool_refill = (uint32_t)pool_refill;
@@ -580,6 +615,23 @@ struct rt_raytracer {
                     RT_CUDA(launch_one(q));
                     ++launches;
                 }
+        } else if (spp > 1 && multi_sample_launch) {
+            // all samples of a pass in ONE launch (sample planes) + one ordered accumulation: same film as `spp`
+            // consecutive launches, but the GPU sees spp times as many work items (matters for small row ranges)
+            const size_t plane_px = (size_t)launch_rows * cfg.width;
+            const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(spp, (size_t(1) << 30) / std::max<size_t>(plane_px * sizeof(float4), 1)));
+            if (d_planes.n < plane_px * chunk) d_planes.alloc(plane_px * chunk);
+            for (uint32_t s0 = 0; s0 < spp; s0 += chunk) {
+                TraceParams q = p;
+                q.planes = d_planes.p;
+                q.n_planes = std::min(chunk, spp - s0);
+                q.plane_rows = launch_rows;
+                q.magic_plane_rows = udiv_magic_of(launch_rows);
+                q.n_rows = launch_rows * q.n_planes;
+                RT_CUDA(launch_one(q));
+                RT_CUDA(launch_film_accumulate(q, stream));
+                launches += 2;
+            }
         } else {
             p.n_rows = launch_rows;
             for (uint32_t s = 0; s < spp; ++s) {
@@ -592,6 +644,7 @@ struct rt_raytracer {
         total_kernels += launches;
         last.kernels_launched += launches;
         last.n_primary = (uint64_t)launch_rows * cfg.width * spp;
+        total_primary += last.n_primary;
         stats_pending = true;
     }
 
@@ -763,7 +816,7 @@ const char* rt_last_error(const rt_raytracer* rt) { return rt ? rt->last_error.c
 
 int rt_configure(rt_raytracer* rt, int32_t recursions, uint32_t sub_spread, int32_t jitter_mode, uint32_t seed, int32_t accel) {
     RT_GUARD_HOST(rt, {
-        if (accel != RT_ACCEL_OCTREE && accel != RT_ACCEL_BVH && accel != RT_ACCEL_CWBVH && accel != RT_ACCEL_BVH4) throw std::invalid_argument("unknown accel");
+        if (accel != RT_ACCEL_OCTREE && accel != RT_ACCEL_BVH && accel != RT_ACCEL_CWBVH && accel != RT_ACCEL_BVH4 && accel != RT_ACCEL_LBVH) throw std::invalid_argument("unknown accel");
         if (jitter_mode != RT_JITTER_FIXED_HALF && jitter_mode != RT_JITTER_HASHED) throw std::invalid_argument("unknown jitter mode");
         if (recursions < 0) throw std::invalid_argument("negative recursions");
         rt->cfg.recursions = recursions;
@@ -987,6 +1040,10 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
         rt->pool_refill = value;
         return RT_OK;
     }
+    if (key == RT_TUNE_MULTI_SAMPLE_LAUNCH && (value == 0 || value == 1)) {
+        rt->multi_sample_launch = value != 0;
+        return RT_OK;
+    }
     if (key == RT_TUNE_POOL_MIN_INNER && value >= 0 && value <= 32) {
         rt->pool_min_inner = value;
         return RT_OK;
@@ -1014,6 +1071,18 @@ int rt_get_launch_stats(const rt_raytracer* rt_c, rt_launch_stats* out) {
     });
 }
 uint64_t rt_kernels_launched(const rt_raytracer* rt) { return rt ? rt->total_kernels : 0; }
+
+int rt_get_ray_totals(rt_raytracer* rt, uint64_t* out3) {
+    RT_GUARD(rt, {
+        if (!out3) throw std::invalid_argument("null output");
+        unsigned long long tot[2];
+        RT_CUDA(cudaMemcpyAsync(tot, rt->d_counters.p + CNT_SHADOW_TOTAL, sizeof(tot), cudaMemcpyDeviceToHost, rt->stream));
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+        out3[0] = rt->total_primary;
+        out3[1] = tot[0];
+        out3[2] = tot[1];
+    });
+}
 
 int rt_octree_stats(const rt_raytracer* rt_c, uint64_t* out) {
     rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
@@ -1076,6 +1145,45 @@ int rt_bvh_export(const rt_raytracer* rt_c, float* boxes, int32_t* children, int
     }
     if (tri_order && !rt->bvh.tri_order.empty()) std::memcpy(tri_order, rt->bvh.tri_order.data(), rt->bvh.tri_order.size() * 4);
     return RT_OK;
+}
+int rt_lbvh_build(rt_raytracer* rt, uint64_t* out3, float* build_ms) {
+    RT_GUARD(rt, {
+        rt->d_lbvh_nodes.release();  // rebuild on every call: this entry point is also the build benchmark
+        rt->build_lbvh();
+        if (out3) {
+            out3[0] = rt->lbvh_nodes;
+            out3[1] = rt->lbvh_depth;
+            out3[2] = rt->scene.num_triangles();
+        }
+        if (build_ms) *build_ms = rt->lbvh_build_ms;
+    });
+}
+int rt_lbvh_export(rt_raytracer* rt, float* boxes, int32_t* children, int32_t* counts, uint32_t* tri_order) {
+    RT_GUARD(rt, {
+        if (!rt->d_lbvh_nodes.p) rt->build_lbvh();
+        const size_t nn = rt->lbvh_nodes;
+        std::vector<float4> nodes(4 * nn);
+        RT_CUDA(cudaMemcpyAsync(nodes.data(), rt->d_lbvh_nodes.p, nodes.size() * sizeof(float4), cudaMemcpyDeviceToHost, rt->stream));
+        if (tri_order && rt->scene.num_triangles())
+            RT_CUDA(cudaMemcpyAsync(tri_order, rt->d_lbvh_order.p, (size_t)rt->scene.num_triangles() * 4, cudaMemcpyDeviceToHost, rt->stream));
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+        for (size_t i = 0; i < nn; ++i) {
+            const float* f = reinterpret_cast<const float*>(&nodes[4 * i]);
+            if (boxes) std::memcpy(boxes + 12 * i, f, 48);
+            for (int k = 0; k < 2; ++k) {
+                int32_t ref;
+                std::memcpy(&ref, f + 12 + k, 4);
+                int32_t child = ref, count = 0;
+                if (ref < 0) {
+                    const uint32_t r = (uint32_t)~ref;
+                    child = ~(int32_t)(r >> 4);
+                    count = (int32_t)(r & 15u);
+                }
+                if (children) children[2 * i + k] = child;
+                if (counts) counts[2 * i + k] = count;
+            }
+        }
+    });
 }
 int rt_bvh4_stats(const rt_raytracer* rt_c, uint64_t* out) {
     rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);

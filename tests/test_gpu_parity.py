@@ -16,7 +16,7 @@ from oracle_lib import ISECT_BRUTE, JITTER_FIXED, JITTER_HASHED, Oracle
 
 pytestmark = pytest.mark.gpu
 
-ACCELS = [(rt.ACCEL_OCTREE, "octree"), (rt.ACCEL_BVH, "bvh"), (rt.ACCEL_CWBVH, "cwbvh"), (rt.ACCEL_BVH4, "bvh4")]
+ACCELS = [(rt.ACCEL_OCTREE, "octree"), (rt.ACCEL_BVH, "bvh"), (rt.ACCEL_CWBVH, "cwbvh"), (rt.ACCEL_BVH4, "bvh4"), (rt.ACCEL_LBVH, "lbvh")]
 ID_BAR = 0.9999  # north star
 LSB_BAR = 1
 
@@ -115,6 +115,51 @@ def test_hashed_jitter_multi_sample(scenes, accel, aname):
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
+def test_gpu_built_bvh_invariants(scenes, name):
+    """f-3: the tree built on the device (lbvh_build.cu: Morton codes, radix sort, Karras hierarchy, refit). Every
+    triangle sits in exactly one reachable leaf of at most 4 triangles, every stored child box strictly contains its
+    subtree, and the build is deterministic."""
+    s = scenes(name)
+    n_tri = s.vertices.shape[0]
+    t = rt.RayTracer.from_scene(s, rt.Config(64, 64, recursions=0, accel=rt.ACCEL_LBVH))
+    st = t.lbvh_build()
+    assert st["triangles"] == n_tri and st["nodes"] == n_tri - 1 and 0 < st["depth"] <= 46 and st["build_ms"] > 0
+    boxes, children, counts, order = t.lbvh_export()
+    st2 = t.lbvh_build()
+    again = t.lbvh_export()
+    assert st2["depth"] == st["depth"]
+    for a, b in zip((boxes, children, counts, order), again):
+        assert np.array_equal(a, b)
+    assert sorted(order.tolist()) == list(range(n_tri))
+    verts = s.vertices.reshape(n_tri, 3, 3)
+    seen = np.zeros(n_tri, bool)
+    depth_seen = [0]
+
+    def subtree_box(node, level):
+        depth_seen[0] = max(depth_seen[0], level)
+        lo_all, hi_all = np.full(3, np.inf), np.full(3, -np.inf)
+        for k in range(2):
+            c, cnt = int(children[node, k]), int(counts[node, k])
+            if c >= 0:
+                lo, hi = subtree_box(c, level + 1)
+            else:
+                assert 1 <= cnt <= 4
+                tri = order[~c:~c + cnt]
+                assert not seen[tri].any()
+                seen[tri] = True
+                lo, hi = verts[tri].reshape(-1, 3).min(0), verts[tri].reshape(-1, 3).max(0)
+            assert (boxes[node, k, 0] < lo).all() and (boxes[node, k, 1] > hi).all()
+            lo_all, hi_all = np.minimum(lo_all, lo), np.maximum(hi_all, hi)
+        return lo_all, hi_all
+
+    import sys
+    sys.setrecursionlimit(10000)
+    subtree_box(0, 1)
+    assert seen.all() and depth_seen[0] == st["depth"]
+    t.close()
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
 def test_kernel_variants_are_bit_identical(scenes, name):
     """The three schedules of the trace kernel (one thread per pixel / persistent tile warps / ray pool with
     shared-memory ray rings) evaluate the same f32 expressions per ray: ids, packed frame, HDR film and ray counts
@@ -133,6 +178,30 @@ def test_kernel_variants_are_bit_identical(scenes, name):
             for a, b in zip(got[:3], ref[:3]):
                 assert np.array_equal(a, b), variant
         t.close()
+
+
+@pytest.mark.parametrize("accel,aname", ACCELS)
+def test_multi_sample_launch_equals_one_launch_per_sample(scenes, accel, aname):
+    """rt_trace_rows with spp > 1 traces all samples in one launch (sample planes + ordered accumulation). The film,
+    frame, ids and ray counts must be bit-identical to one launch per sample — also for a shard of interleaved bands,
+    a wrapped row range, and when the film already holds samples."""
+    s = scenes("thai2")
+    w, h, spp = 640, 360, 5
+    for kw, first, rows in [({}, 0, h), ({}, 300, 100), ({"shard_index": 1, "shard_count": 3, "band_rows": 8}, 0, h)]:
+        got = []
+        for multi in (1, 0):
+            t = gpu_tracer(s, w, h, accel, jitter=rt.JITTER_HASHED, seed=9, **kw)
+            t.set_tuning(5, multi)
+            t.trace_rows(first, rows, 1)  # the film already holds one sample of these rows
+            n_primary, n_shadow = t.trace_rows(first, rows, spp)
+            got.append((n_primary, n_shadow, t.get_primary_ids(), t.get_tonemapped_pixels(), t.film.pixel_datas().view(np.uint32),
+                        t.launch_stats()["kernels_launched"]))
+            t.close()
+        a, b = got
+        assert a[0] == b[0] and a[1] == b[1]
+        for x, y in zip(a[2:5], b[2:5]):
+            assert np.array_equal(x, y)
+        assert a[5] < b[5]  # 1 trace + 1 accumulate launch instead of spp trace launches
 
 
 def test_4k_16spp_properties(scenes):
