@@ -229,7 +229,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="thai2_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--accel", default="bvh", choices=["bvh", "octree", "cwbvh", "bvh4", "lbvh"])
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N>1: how rank 0 receives the frame")
+    ap.add_argument("--gather", default="peer", choices=["peer", "peer_allreduce", "nccl"], help="N>1: how rank 0 receives the frame")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: samples per pixel per step = N (weak) or 1 (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--zero-copy", action="store_true",
@@ -290,9 +290,11 @@ def main():
         torch.cuda.synchronize(dev)
 
     def device_step():
+        if gather is not None:
+            gather.begin_frame()
         tracer.trace_rows(0, H, spp, want_shadow=False)
         if gather is not None:
-            gather.device_gather()
+            gather.device_gather(release=True)  # device-timed leg: the frame stays on rank 0
 
     def global_ray_totals():
         t = tracer.ray_totals()  # exact device counters since the handle was created (synchronises this rank's stream)
@@ -352,6 +354,8 @@ def main():
     def e2e_step(i):
         # per-step input: camera state from the host (travels to the device as the kernel's launch parameters)
         tracer.camera.set_state(0.0, 0.0, (0.0, 0.0, 0.0))
+        if gather is not None:
+            gather.begin_frame()
         tracer.trace_rows(0, H, spp, want_shadow=False)
         if gather is not None:
             gather.device_gather()

@@ -186,6 +186,16 @@ int rt_device_free(rt_raytracer* rt, void* dev_ptr);
 int rt_ipc_export(rt_raytracer* rt, void* dev_ptr, uint8_t* handle64);
 int rt_ipc_open(rt_raytracer* rt, const uint8_t* handle64, void** dev_ptr);
 int rt_ipc_close(rt_raytracer* rt, void* dev_ptr);
+/* Cross-GPU frame fence for the fused gather (all stream-ordered on the handle's stream, no host synchronisation):
+   rt_stream_signal_flag stores `value` into *dev_flag (system scope) once everything enqueued before it has finished;
+   rt_stream_wait_flags holds the stream until every one of dev_flags[0..n_flags) (uint32, n_flags <= 32, typically
+   peer-mapped memory of rank 0) has reached `target` (wrap-safe >=); in the same launch it can first store `target`
+   into dev_flags[signal_slot] and afterwards into dev_flags[release_slot] (-1 = none), which is rank 0's whole
+   per-frame fence. A wait gives up after ~2 s and counts a timeout (rt_sync_timeouts) instead of hanging the GPU. */
+int rt_stream_signal_flag(rt_raytracer* rt, void* dev_flag, uint32_t value);
+int rt_stream_wait_flags(rt_raytracer* rt, void* dev_flags, uint32_t n_flags, uint32_t target, int32_t signal_slot,
+                         int32_t release_slot);
+int rt_sync_timeouts(rt_raytracer* rt, uint32_t* count);
 /* Device pointer to the 4 uint64 ray counters of the last launch: shadow rays, primary hits, bounce rays, blocked
    shadow rays (zeroed at the start of every trace call). */
 int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr);

@@ -96,6 +96,7 @@ ABI_SYMBOLS = [
     "rt_camera_add_x_angle", "rt_camera_add_y_angle", "rt_camera_get", "rt_camera_set_state", "rt_set_stream",
     "rt_get_ldr_device_ptr", "rt_set_ldr_target", "rt_get_owned_ldr_rows_device", "rt_get_launch_stats",
     "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_get_counters_device_ptr",
+    "rt_stream_signal_flag", "rt_stream_wait_flags", "rt_sync_timeouts",
     "rt_launch_param_bytes", "rt_set_tuning", "rt_set_host_frame",
     "rt_kernels_launched", "rt_get_ray_totals", "rt_octree_stats", "rt_octree_export", "rt_bvh_stats", "rt_bvh_export", "rt_bvh4_stats", "rt_bvh4_export", "rt_lbvh_build", "rt_lbvh_export", "rt_cwbvh_stats",
     "rt_cwbvh_export", "rt_stats_new",
@@ -160,6 +161,9 @@ def lib() -> C.CDLL:
         "rt_ipc_open": (C.c_int, [vp, vp, P(vp)]),
         "rt_ipc_close": (C.c_int, [vp, vp]),
         "rt_get_counters_device_ptr": (C.c_int, [vp, P(vp)]),
+        "rt_stream_signal_flag": (C.c_int, [vp, vp, u32]),
+        "rt_stream_wait_flags": (C.c_int, [vp, vp, u32, u32, i32, i32]),
+        "rt_sync_timeouts": (C.c_int, [vp, P(u32)]),
         "rt_launch_param_bytes": (u32, []),
         "rt_set_tuning": (C.c_int, [vp, i32, i32]),
         "rt_set_host_frame": (C.c_int, [vp, vp]),
@@ -476,6 +480,17 @@ class RayTracer:
 
     def ipc_close(self, dev_ptr: int) -> None:
         self._check(lib().rt_ipc_close(self._h, C.c_void_p(dev_ptr)))
+
+    def signal_flag(self, dev_flag: int, value: int) -> None:
+        self._check(lib().rt_stream_signal_flag(self._h, dev_flag, value))
+
+    def wait_flags(self, dev_flags: int, n_flags: int, target: int, signal_slot: int = -1, release_slot: int = -1) -> None:
+        self._check(lib().rt_stream_wait_flags(self._h, dev_flags, n_flags, target, signal_slot, release_slot))
+
+    def sync_timeouts(self) -> int:
+        n = C.c_uint32()
+        self._check(lib().rt_sync_timeouts(self._h, C.byref(n)))
+        return int(n.value)
 
     def counters_device_ptr(self) -> int:
         p = C.c_void_p()

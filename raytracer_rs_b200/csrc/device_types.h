@@ -68,10 +68,10 @@ struct TraceParams {
     const uint32_t* row_list;
     uint32_t first_row, n_rows;
     // sample planes: with planes != null the launch covers n_planes samples of plane_rows compact rows each
-    // (n_rows = n_planes * plane_rows); radiance and primitive id go to planes[(plane * plane_rows + row) * width + col]
+    // (n_rows = n_planes * plane_rows_padded); radiance and primitive id go to planes[(plane * plane_rows_padded + row) * width + col]
     // instead of the film, and film_accumulate_kernel adds them in sample order afterwards
     float4* planes;
-    uint32_t n_planes, plane_rows, magic_plane_rows;
+    uint32_t n_planes, plane_rows, plane_rows_padded, magic_plane_rows;  // padded = plane_rows rounded up to 4
     uint32_t jitter_mode, seed;
     int32_t recursions;          // RECURSIONS (mod.rs:81); 0 = primary + shadow only
     uint32_t sub_spread;         // SUB_SPREAD (mod.rs:82)

@@ -949,9 +949,10 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, 
     const uint32_t W = P.cam.width, H = P.cam.height;
     // sample planes (several samples per pixel in one launch): compact row `crow` = plane * plane_rows + row of the pass
     uint32_t plane = 0, prow = crow;
-    if (P.planes) {
-        plane = udiv_magic(crow, P.plane_rows, P.magic_plane_rows);
-        prow = crow - plane * P.plane_rows;
+    if (P.planes) {  // planes are plane_rows_padded (a multiple of the tile height) rows apart; the padding rows are idle
+        plane = udiv_magic(crow, P.plane_rows_padded, P.magic_plane_rows);
+        prow = crow - plane * P.plane_rows_padded;
+        if (prow >= P.plane_rows) return;
     }
     const uint32_t row = P.row_list ? P.row_list[prow] : (P.first_row + prow) % H;
     const uint32_t idx = row * W + col;
@@ -1588,20 +1589,19 @@ __global__ void tonemap_pack_kernel(const float4* __restrict__ sum, uint32_t* __
     }
 }
 
-// Adds the sample planes of one launch to the film in sample order (PixelData::add_sample, film.rs:20-24, once per
-// plane), then mean, tonemap, pack of the final sums: exactly what `n_planes` consecutive single-sample launches leave.
-__global__ void __launch_bounds__(256) film_accumulate_kernel(const __grid_constant__ TraceParams P) {
-    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t prow = blockIdx.y;
+// Adds the sample planes of one launch to one pixel of the film in sample order (PixelData::add_sample,
+// film.rs:20-24, once per plane), then mean, tonemap, pack of the final sums: exactly what `n_planes` consecutive
+// single-sample launches leave. (Fusing this into the trace kernel — the warp that delivers a tile's last sample adds
+// them — was measured slower: the per-item __threadfence + atomic costs more than this 15 us pass.)
+__device__ __forceinline__ void accumulate_pixel(const TraceParams& P, uint32_t col, uint32_t prow) {
     const uint32_t W = P.cam.width, H = P.cam.height;
-    if (col >= W || prow >= P.plane_rows) return;
     const uint32_t row = P.row_list ? P.row_list[prow] : (P.first_row + prow) % H;
     const uint32_t idx = row * W + col;
     float4 fs_ = P.film_sum[idx];
     float4 sq = P.film_sq[idx];
     uint32_t n = __float_as_uint(fs_.w), id = kNoHit;
     for (uint32_t s = 0; s < P.n_planes; ++s) {
-        const float4 c = __ldcs(&P.planes[((size_t)s * P.plane_rows + prow) * W + col]);
+        const float4 c = __ldcg(&P.planes[((size_t)s * P.plane_rows_padded + prow) * W + col]);
         fs_.x = fadd(fs_.x, c.x);
         fs_.y = fadd(fs_.y, c.y);
         fs_.z = fadd(fs_.z, c.z);
@@ -1619,12 +1619,59 @@ __global__ void __launch_bounds__(256) film_accumulate_kernel(const __grid_const
     P.ldr[idx] = px;
     if (P.ldr_remote) P.ldr_remote[idx] = px;
 }
+__global__ void __launch_bounds__(256) film_accumulate_kernel(const __grid_constant__ TraceParams P) {
+    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t prow = blockIdx.y;
+    if (col >= P.cam.width || prow >= P.plane_rows) return;
+    accumulate_pixel(P, col, prow);
+}
 
 __global__ void gather_rows_kernel(const uint32_t* __restrict__ ldr, const uint32_t* __restrict__ row_list, uint32_t n_rows, uint32_t width,
                                    uint32_t* __restrict__ out) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t r = blockIdx.y;
     if (x < width && r < n_rows) out[(size_t)r * width + x] = ldr[(size_t)row_list[r] * width + x];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// cross-GPU frame fence for the fused peer-store gather (multi_gpu.py): every rank publishes "my stores of frame k
+// are done" by writing k+1 into its slot of a flag array that lives on rank 0 (peer-mapped), rank 0 waits for all
+// slots, and publishes "frame k has been read" the same way. Waits are bounded (~2 s): a lost peer turns into an
+// error count, never into a hung GPU.
+// ------------------------------------------------------------------------------------------------------
+__global__ void flag_signal_kernel(volatile uint32_t* flag, uint32_t value) {
+    __threadfence_system();  // everything this stream did before (kernel boundaries order it) is visible first
+    *flag = value;
+    __threadfence_system();
+}
+// optional signal (flags[signal_slot] = target) -> wait until flags[0..n) >= target -> optional release
+// (flags[release_slot] = target): rank 0's whole per-frame fence in one launch
+__global__ void flag_wait_kernel(volatile uint32_t* flags, uint32_t n, uint32_t target, int signal_slot, int release_slot,
+                                 unsigned long long timeout_ns, uint32_t* timeouts) {
+    const uint32_t i = threadIdx.x;
+    if (signal_slot >= 0 && i == 0) {
+        __threadfence_system();
+        flags[signal_slot] = target;
+    }
+    if (i < n) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        // wrap-safe "flags[i] >= target" for counters that only grow
+        while ((int32_t)(flags[i] - target) < 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {
+                atomicAdd(timeouts, 1u);
+                break;
+            }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (release_slot >= 0 && i == 0) {
+        flags[release_slot] = target;
+        __threadfence_system();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1701,6 +1748,16 @@ cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* 
 cudaError_t launch_tonemap(const float4* sum, uint32_t* ldr, uint32_t n, cudaStream_t stream) {
     const uint32_t threads = (n + 3u) / 4u;
     tonemap_pack_kernel<<<(threads + 255u) / 256u, 256, 0, stream>>>(sum, ldr, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream) {
+    flag_signal_kernel<<<1, 1, 0, stream>>>(flag, value);
+    return cudaGetLastError();
+}
+cudaError_t launch_flag_wait(uint32_t* flags, uint32_t n, uint32_t target, int signal_slot, int release_slot, uint32_t* timeouts,
+                             cudaStream_t stream) {
+    if (n == 0 || n > 32) return cudaErrorInvalidValue;
+    flag_wait_kernel<<<1, 32, 0, stream>>>(flags, n, target, signal_slot, release_slot, 2000000000ull, timeouts);
     return cudaGetLastError();
 }
 cudaError_t launch_film_accumulate(const TraceParams& p, cudaStream_t stream) {

@@ -26,6 +26,12 @@ cudaError_t launch_film_accumulate(const TraceParams& p, cudaStream_t stream);
 cudaError_t launch_gather_rows(const uint32_t* ldr, const uint32_t* row_list, uint32_t n_rows, uint32_t width, uint32_t* out,
                                cudaStream_t stream);
 
+// cross-GPU frame fence: *flag = value after everything earlier on the stream / wait until flags[0..n) >= target
+// (bounded: a timeout increments *timeouts instead of hanging)
+cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream);
+// signal_slot / release_slot (-1 = none): flags[signal_slot] = target before the wait, flags[release_slot] = target after it
+cudaError_t launch_flag_wait(uint32_t* flags, uint32_t n, uint32_t target, int signal_slot, int release_slot, uint32_t* timeouts,
+                             cudaStream_t stream);
 // GPU build of the binary BVH (lbvh_build.cu): Morton codes, radix sort, Karras hierarchy, bottom-up refit
 size_t lbvh_scratch_bytes(uint32_t n);
 cudaError_t build_lbvh_device(const float* d_verts, uint32_t n, const float root_lo[3], const float root_hi[3], void* scratch, float4* d_nodes,

@@ -105,6 +105,7 @@ struct rt_raytracer {
     bool multi_sample_launch = true;  // RT_TUNE_MULTI_SAMPLE_LAUNCH
     DevBuf<uint32_t> d_ldr, d_ids, d_row_list, d_owned_rows;
     DevBuf<unsigned long long> d_counters;
+    DevBuf<uint32_t> d_sync_timeouts;
     unsigned long long* h_counters = nullptr;  // pinned
     uint32_t* ldr_remote = nullptr;
     uint32_t* host_frame = nullptr;       // registered zero-copy frame (host address)
@@ -132,6 +133,7 @@ struct rt_raytracer {
     int num_sms = 0;
     rt_launch_stats last{};
     bool stats_pending = false;
+    bool queue_is_zero = false;  // the tile-queue counter was zeroed by the last memset and not used since
 
     ~rt_raytracer() {
         if (h_counters) cudaFreeHost(h_counters);
@@ -568,9 +570,13 @@ struct rt_raytracer {
             }
         }
         if (variant != 0) {
-            // the tile queue lives next to the ray counters; every launch starts it at zero
-            cudaError_t e = cudaMemsetAsync(d_counters.p + CNT_TILE_QUEUE, 0, sizeof(unsigned long long), stream);
-            if (e != cudaSuccess) return e;
+            // the tile queue lives next to the ray counters; every launch starts it at zero (the first launch of a
+            // call finds it already zeroed together with the ray counters)
+            if (!queue_is_zero) {
+                cudaError_t e = cudaMemsetAsync(d_counters.p + CNT_TILE_QUEUE, 0, sizeof(unsigned long long), stream);
+                if (e != cudaSuccess) return e;
+            }
+            queue_is_zero = false;
         }
         if (use_pool) return launch_trace(p, a, 2, pool_blocks * num_sms, stream);
         return launch_trace(p, a, variant == 0 ? 0 : 1, blocks_per_sm[a][b] * num_sms, stream);
@@ -602,6 +608,7 @@ struct rt_raytracer {
         }
         p.first_row = first_row;
         RT_CUDA(cudaMemsetAsync(d_counters.p, 0, CNT_QUEUE_ITEMS * sizeof(unsigned long long), stream));  // keeps the item count
+        queue_is_zero = true;
         last = rt_launch_stats{};
         RT_CUDA(cudaEventRecord(ev_start, stream));
         uint32_t launches = 0;
@@ -618,7 +625,8 @@ struct rt_raytracer {
         } else if (spp > 1 && multi_sample_launch) {
             // all samples of a pass in ONE launch (sample planes) + one ordered accumulation: same film as `spp`
             // consecutive launches, but the GPU sees spp times as many work items (matters for small row ranges)
-            const size_t plane_px = (size_t)launch_rows * cfg.width;
+            const uint32_t padded = (launch_rows + 3u) & ~3u;
+            const size_t plane_px = (size_t)padded * cfg.width;
             const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(spp, (size_t(1) << 30) / std::max<size_t>(plane_px * sizeof(float4), 1)));
             if (d_planes.n < plane_px * chunk) d_planes.alloc(plane_px * chunk);
             for (uint32_t s0 = 0; s0 < spp; s0 += chunk) {
@@ -626,10 +634,11 @@ struct rt_raytracer {
                 q.planes = d_planes.p;
                 q.n_planes = std::min(chunk, spp - s0);
                 q.plane_rows = launch_rows;
-                q.magic_plane_rows = udiv_magic_of(launch_rows);
-                q.n_rows = launch_rows * q.n_planes;
+                q.plane_rows_padded = padded;
+                q.magic_plane_rows = udiv_magic_of(padded);
+                q.n_rows = padded * q.n_planes;
                 RT_CUDA(launch_one(q));
-                RT_CUDA(launch_film_accumulate(q, stream));
+                RT_CUDA(launch_film_accumulate(q, stream));  // adds the planes to the film in sample order
                 launches += 2;
             }
         } else {
@@ -640,7 +649,7 @@ struct rt_raytracer {
             }
         }
         RT_CUDA(cudaEventRecord(ev_stop, stream));
-        RT_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, CNT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        // the ray counters are fetched only if somebody asks for them before the next trace call (finish_stats)
         total_kernels += launches;
         last.kernels_launched += launches;
         last.n_primary = (uint64_t)launch_rows * cfg.width * spp;
@@ -650,6 +659,7 @@ struct rt_raytracer {
 
     void finish_stats() {
         if (!stats_pending) return;
+        RT_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, CNT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         RT_CUDA(cudaStreamSynchronize(stream));
         float ms = 0.f;
         RT_CUDA(cudaEventElapsedTime(&ms, ev_start, ev_stop));
@@ -1021,6 +1031,34 @@ int rt_ipc_close(rt_raytracer* rt, void* dev_ptr) {
         RT_CUDA(cudaStreamSynchronize(rt->stream));
         if (rt->ldr_remote == dev_ptr) rt->ldr_remote = nullptr;
         RT_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    });
+}
+int rt_stream_signal_flag(rt_raytracer* rt, void* dev_flag, uint32_t value) {
+    RT_GUARD(rt, {
+        if (!dev_flag) throw std::invalid_argument("null flag");
+        RT_CUDA(launch_flag_signal((uint32_t*)dev_flag, value, rt->stream));
+        ++rt->total_kernels;
+    });
+}
+int rt_stream_wait_flags(rt_raytracer* rt, void* dev_flags, uint32_t n_flags, uint32_t target, int32_t signal_slot, int32_t release_slot) {
+    RT_GUARD(rt, {
+        if (!dev_flags) throw std::invalid_argument("null flags");
+        if (!rt->d_sync_timeouts.p) {
+            rt->d_sync_timeouts.alloc(1);
+            RT_CUDA(cudaMemsetAsync(rt->d_sync_timeouts.p, 0, 4, rt->stream));
+        }
+        RT_CUDA(launch_flag_wait((uint32_t*)dev_flags, n_flags, target, signal_slot, release_slot, rt->d_sync_timeouts.p, rt->stream));
+        ++rt->total_kernels;
+    });
+}
+int rt_sync_timeouts(rt_raytracer* rt, uint32_t* count) {
+    RT_GUARD(rt, {
+        if (!count) throw std::invalid_argument("null output");
+        *count = 0;
+        if (rt->d_sync_timeouts.p) {
+            RT_CUDA(cudaMemcpyAsync(count, rt->d_sync_timeouts.p, 4, cudaMemcpyDeviceToHost, rt->stream));
+            RT_CUDA(cudaStreamSynchronize(rt->stream));
+        }
     });
 }
 int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr) {

@@ -4,11 +4,17 @@ The image is partitioned into interleaved bands of `band_rows` rows (band b belo
 and camera are replicated; every rank owns the film entries of its bands. Rendering needs no exchange. What has to
 cross NVLink is the packed LDR frame, once per displayed frame, to rank 0:
 
-  mode "peer" (fused): rank 0 owns two frame buffers (plain cudaMalloc, exported over CUDA IPC); every rank maps
-      them, and the trace kernel's epilogue stores each packed pixel straight into rank 0's buffer (P2P store over
-      NVLink, raytracer_rs_b200/csrc/kernels.cu `ldr_remote`). One tiny all-reduce of the ray counters per frame is
-      both the global ray count and the completion fence: rank 0 reads the frame after it, on the same stream.
-      Frames alternate between the two buffers so that the next frame's stores never race with rank 0's readback.
+  mode "peer" (fused, default): rank 0 owns two frame buffers and a small flag array (plain cudaMalloc, exported over
+      CUDA IPC); every rank maps them, and the trace kernel's epilogue (or the sample-plane accumulation) stores each
+      packed pixel straight into rank 0's buffer (P2P store over NVLink, raytracer_rs_b200/csrc/kernels.cu `ldr_remote`).
+      The fence is device side and stream ordered, without NCCL or the host: after its kernels of frame k every rank
+      stores k+1 into its slot flags[rank]; rank 0's stream waits until all slots reached k+1 before it touches the
+      frame, then publishes flags[world] = k+1 ("frame k has been read"). Frames alternate between the two buffers and a
+      rank starts storing frame k only once frame k-2 (the previous user of that buffer) has been read, so stores never
+      race with rank 0's readback however far the other ranks run ahead. Waits are bounded (a lost peer becomes an
+      error count, rt_sync_timeouts, not a hung GPU).
+  mode "peer_allreduce": same stores, but one small NCCL all-reduce of the ray counters per frame is both the global
+      ray count and the completion fence (the previous design; kept for comparison).
   mode "nccl" (baseline): every rank compacts its rows (rt_get_owned_ldr_rows_device) and rank 0 gathers them with
       torch.distributed.gather, then scatters the rows into place.
 
@@ -58,23 +64,30 @@ class FrameGather:
         nbytes = self.W * self.H * 4
         cptr = tracer.counters_device_ptr()
         self.counters = torch.as_tensor(_DevPtr(cptr, 32), device=device).view(torch.int64)  # zero copy view of the library's counters
-        if mode == "peer":
-            handles = [None, None]
+        if mode in ("peer", "peer_allreduce"):
+            handles = [None, None, None]
             self.local_bufs = []
+            flag_bytes = 4 * (world + 1)
             if rank == 0:
-                self.local_bufs = [tracer.device_alloc(nbytes), tracer.device_alloc(nbytes)]
+                self.local_bufs = [tracer.device_alloc(nbytes), tracer.device_alloc(nbytes), tracer.device_alloc(256)]
+                torch.as_tensor(_DevPtr(self.local_bufs[2], 256), device=device).zero_()  # flags start at frame 0
+                torch.cuda.synchronize(device)
                 handles = [tracer.ipc_export(p) for p in self.local_bufs]
             box = [handles]
             dist.broadcast_object_list(box, src=0)
             handles = box[0]
             if rank == 0:
-                self.targets = list(self.local_bufs)
+                mapped = list(self.local_bufs)
             else:
-                self.targets = [tracer.ipc_open(h) for h in handles]
+                mapped = [tracer.ipc_open(h) for h in handles]
+            self.mapped = mapped
+            self.targets, self.flags = mapped[:2], mapped[2]
+            assert flag_bytes <= 256
             self.frames = None
             if rank == 0:
-                self.frames = [torch.as_tensor(_DevPtr(p, nbytes), device=device).view(torch.int32) for p in self.local_bufs]
+                self.frames = [torch.as_tensor(_DevPtr(p, nbytes), device=device).view(torch.int32) for p in self.local_bufs[:2]]
             tracer.set_ldr_target(self.targets[0])
+            self.consumed_signalled = 0
         elif mode == "nccl":
             self.max_rows = max(len(r) for r in self.partition)
             self.compact = torch.zeros(self.max_rows * self.W, dtype=torch.int32, device=device)
@@ -86,11 +99,33 @@ class FrameGather:
         torch.cuda.synchronize(device)
         dist.barrier()
 
-    def device_gather(self):
-        """Enqueue (on the tracer's stream) whatever makes the frame just traced complete on rank 0."""
+    def begin_frame(self):
+        """Call before tracing a frame (mode "peer"): holds this rank's stream until the buffer the frame will be stored
+        into has been read by rank 0 (frame k waits for "frame k-2 has been read")."""
+        # rank 0 publishes "read" itself, earlier on its own stream: only the other ranks have to wait
+        if self.mode == "peer" and self.rank != 0 and self.frame_no >= 2:
+            self.tracer.wait_flags(self.flags + 4 * self.world, 1, self.frame_no - 1)
+            self.kernels += 1
+
+    def device_gather(self, release: bool = False):
+        """Enqueue (on the tracer's stream) whatever makes the frame just traced complete on rank 0. release=True
+        (rank 0, mode "peer"): the frame is not going to be read, its buffer may be reused at once."""
         torch, dist = self.torch, self.dist
         with torch.cuda.stream(self.stream):
             if self.mode == "peer":
+                k = self.frame_no
+                if self.rank == 0:
+                    # one launch: my stores of frame k are done -> wait for everybody's -> (optionally) frame k is read
+                    self.tracer.wait_flags(self.flags, self.world, k + 1, 0, self.world if release else -1)
+                    if release:
+                        self.consumed_signalled = k + 1
+                else:
+                    self.tracer.signal_flag(self.flags + 4 * self.rank, k + 1)  # my stores of frame k are done
+                self.ready = k & 1
+                self.frame_no += 1
+                self.tracer.set_ldr_target(self.targets[self.frame_no & 1])
+                self.kernels += 1
+            elif self.mode == "peer_allreduce":
                 # global ray counters + completion fence: once this all-reduce has finished on rank 0, every rank's
                 # trace kernel (earlier on its stream) has completed, so its peer stores are visible
                 dist.all_reduce(self.counters)
@@ -106,21 +141,34 @@ class FrameGather:
                         n = len(self.partition[r])
                         self.frame.index_copy_(0, self.row_index[r], self.recv[r][: n * self.W].view(n, self.W))
 
+    def release_frame(self):
+        """rank 0, mode "peer": the completed frame is no longer needed on the device (it was copied out, or nobody wants
+        it): lets the other ranks overwrite its buffer. Stream ordered; idempotent per frame."""
+        if self.mode == "peer" and self.rank == 0 and self.consumed_signalled < self.frame_no:
+            self.tracer.signal_flag(self.flags + 4 * self.world, self.frame_no)
+            self.consumed_signalled = self.frame_no
+            self.kernels += 1
+
     def read_frame_into(self, host_tensor):
         """rank 0: device -> (pinned) host copy of the completed frame, synchronous."""
         torch = self.torch
         with torch.cuda.stream(self.stream):
-            src = self.frames[self.ready] if self.mode == "peer" else self.frame.view(-1)
+            src = self.frames[self.ready] if self.mode in ("peer", "peer_allreduce") else self.frame.view(-1)
             host_tensor.copy_(src, non_blocking=True)
+            self.release_frame()
         self.stream.synchronize()
 
     def global_counters(self):
-        """[shadow rays, primary hits, bounce rays, blocked] summed over ranks (valid after device_gather in peer mode)."""
+        """[shadow rays, primary hits, bounce rays, blocked] of the last frame summed over ranks (collective call)."""
+        with self.torch.cuda.stream(self.stream):
+            c = self.counters.clone()
+            if self.mode != "peer_allreduce":
+                self.dist.all_reduce(c)
         self.stream.synchronize()
-        return [int(x) for x in self.counters.cpu()]
+        return [int(x) for x in c.cpu()]
 
     def close(self):
-        if self.mode == "peer":
+        if self.mode in ("peer", "peer_allreduce"):
             self.tracer.set_ldr_target(None)
             self.torch.cuda.synchronize(self.device)
             self.dist.barrier()
@@ -128,5 +176,5 @@ class FrameGather:
                 for p in self.local_bufs:
                     self.tracer.device_free(p)
             else:
-                for p in self.targets:
+                for p in self.mapped:
                     self.tracer.ipc_close(p)

@@ -30,7 +30,8 @@ def _worker(rank, world, port, mode, result_path):
     g = FrameGather(t, rank, world, dev, stream, mode=mode)
     host = torch.empty(w * h, dtype=torch.int32).pin_memory()
     ok = True
-    for frame in range(3):  # alternates between the two peer buffers
+    for frame in range(5):  # alternates between the two peer buffers
+        g.begin_frame()
         t.trace_rows(0, h, 1, want_shadow=False)
         g.device_gather()
         if rank == 0:
@@ -41,9 +42,12 @@ def _worker(rank, world, port, mode, result_path):
                 ref = full.get_tonemapped_pixels()
                 full.close()
             ok = ok and bool(np.array_equal(host.numpy().view(np.uint32), ref))
-            if mode == "peer":
-                ok = ok and g.global_counters()[0] == n_shadow
+        if mode != "nccl":
+            shadow = g.global_counters()[0]  # collective
+            if rank == 0:
+                ok = ok and shadow == n_shadow
         dist.barrier()
+    ok = ok and t.sync_timeouts() == 0
     if rank == 0:
         open(result_path, "w").write(str(ok))
     g.close()
@@ -51,7 +55,7 @@ def _worker(rank, world, port, mode, result_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["peer", "nccl"])
+@pytest.mark.parametrize("mode", ["peer", "peer_allreduce", "nccl"])
 def test_two_rank_gather(tmp_path, mode):
     import torch
 

@@ -187,10 +187,12 @@ def test_multi_sample_launch_equals_one_launch_per_sample(scenes, accel, aname):
     a wrapped row range, and when the film already holds samples."""
     s = scenes("thai2")
     w, h, spp = 640, 360, 5
-    for kw, first, rows in [({}, 0, h), ({}, 300, 100), ({"shard_index": 1, "shard_count": 3, "band_rows": 8}, 0, h)]:
+    for kw, first, rows, variant in [({}, 0, h, 1), ({}, 300, 101, 1), ({"shard_index": 1, "shard_count": 3, "band_rows": 8}, 0, h, 1),
+                                     ({"shard_index": 0, "shard_count": 7, "band_rows": 3}, 5, 333, 1), ({}, 0, h, 0)]:
         got = []
         for multi in (1, 0):
             t = gpu_tracer(s, w, h, accel, jitter=rt.JITTER_HASHED, seed=9, **kw)
+            t.set_tuning(0, variant)
             t.set_tuning(5, multi)
             t.trace_rows(first, rows, 1)  # the film already holds one sample of these rows
             n_primary, n_shadow = t.trace_rows(first, rows, spp)
@@ -201,7 +203,7 @@ def test_multi_sample_launch_equals_one_launch_per_sample(scenes, accel, aname):
         assert a[0] == b[0] and a[1] == b[1]
         for x, y in zip(a[2:5], b[2:5]):
             assert np.array_equal(x, y)
-        assert a[5] < b[5]  # 1 trace + 1 accumulate launch instead of spp trace launches
+        assert a[5] < b[5]  # one trace launch instead of spp
 
 
 def test_4k_16spp_properties(scenes):
