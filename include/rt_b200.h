@@ -142,6 +142,13 @@ int rt_trace_rows(rt_raytracer* rt, uint32_t first_row, uint32_t n_rows, uint32_
                   uint64_t* n_shadow);
 /* RayTracer::get_tonemapped_pixels(&self) -> Vec<u32>   (mod.rs:120-128): width*height 0xAARRGGBB, caller-allocated. */
 int rt_get_tonemapped_pixels(rt_raytracer* rt, uint32_t* out);
+/* Pipelined form of the same readback, for a host that double-buffers frames the way the reference's render and GUI
+   threads do (raytracer/src/main.rs:200-209): takes a device-side snapshot of the packed frame on the render stream
+   (a few microseconds) and copies it to `pinned_out` (page-locked host memory) on a separate copy stream, so the
+   device -> host transfer overlaps the NEXT trace call. Returns at once; the pixels are valid after rt_wait_pixels.
+   One copy may be in flight per handle: a second call waits (on the device) for the first to leave the snapshot. */
+int rt_get_tonemapped_pixels_async(rt_raytracer* rt, uint32_t* pinned_out);
+int rt_wait_pixels(rt_raytracer* rt);
 /* Film::clear (film.rs:37-41) through the pub field `film` (raytracer/src/main.rs:126). */
 int rt_film_clear(rt_raytracer* rt);
 /* Film contents: width*height*7 floats per pixel: sum rgb, sum of squares rgb, num_samples (film.rs:3-7). */

@@ -92,7 +92,7 @@ ABI_SYMBOLS = [
     "rt_config_default", "rt_scene_load_file", "rt_scene_load_str", "rt_scene_get_desc", "rt_scene_free",
     "rt_create_raytracer", "rt_create_raytracer_from_file", "rt_create", "rt_destroy", "rt_last_error",
     "rt_configure", "rt_set_rows_per_call", "rt_trace_frame_additive", "rt_trace_rows",
-    "rt_get_tonemapped_pixels", "rt_film_clear", "rt_get_film", "rt_get_primary_ids", "rt_camera_move_rel",
+    "rt_get_tonemapped_pixels", "rt_get_tonemapped_pixels_async", "rt_wait_pixels", "rt_film_clear", "rt_get_film", "rt_get_primary_ids", "rt_camera_move_rel",
     "rt_camera_add_x_angle", "rt_camera_add_y_angle", "rt_camera_get", "rt_camera_set_state", "rt_set_stream",
     "rt_get_ldr_device_ptr", "rt_set_ldr_target", "rt_get_owned_ldr_rows_device", "rt_get_launch_stats",
     "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_get_counters_device_ptr",
@@ -142,6 +142,8 @@ def lib() -> C.CDLL:
         "rt_trace_frame_additive": (C.c_int, [vp, P(u32)]),
         "rt_trace_rows": (C.c_int, [vp, u32, u32, u32, P(u64), P(u64)]),
         "rt_get_tonemapped_pixels": (C.c_int, [vp, vp]),
+        "rt_get_tonemapped_pixels_async": (C.c_int, [vp, vp]),
+        "rt_wait_pixels": (C.c_int, [vp]),
         "rt_film_clear": (C.c_int, [vp]),
         "rt_get_film": (C.c_int, [vp, vp]),
         "rt_get_primary_ids": (C.c_int, [vp, vp]),
@@ -409,6 +411,14 @@ class RayTracer:
     def get_tonemapped_pixels_into(self, host_ptr: int) -> None:
         """Same, into a caller-owned (ideally pinned) host buffer given by address."""
         self._check(lib().rt_get_tonemapped_pixels(self._h, C.c_void_p(host_ptr)))
+
+    def get_tonemapped_pixels_async(self, pinned_host_ptr: int) -> None:
+        """Pipelined readback: snapshot now, device -> host copy on a second stream while the next trace call runs.
+        The pixels are valid after wait_pixels()."""
+        self._check(lib().rt_get_tonemapped_pixels_async(self._h, C.c_void_p(pinned_host_ptr)))
+
+    def wait_pixels(self) -> None:
+        self._check(lib().rt_wait_pixels(self._h))
 
     # -- extensions used by tests / bench --
     def configure(self, recursions=0, sub_spread=1, jitter_mode=JITTER_FIXED_HALF, seed=0, accel=ACCEL_BVH) -> None:

@@ -112,6 +112,11 @@ struct rt_raytracer {
     uint32_t* host_frame_dev = nullptr;   // its device-visible address
     bool host_frame_stale = true;         // rows traced before registration / film clear are not in it yet
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    // pipelined readback (rt_get_tonemapped_pixels_async): snapshot on the render stream, device -> host on a copy stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_snapshot = nullptr, ev_copied = nullptr;
+    DevBuf<uint32_t> d_ldr_snapshot;
+    bool copy_in_flight = false;
 
     // host state
     uint32_t current_row = 0;
@@ -139,6 +144,9 @@ struct rt_raytracer {
         if (h_counters) cudaFreeHost(h_counters);
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_stop) cudaEventDestroy(ev_stop);
+        if (ev_snapshot) cudaEventDestroy(ev_snapshot);
+        if (ev_copied) cudaEventDestroy(ev_copied);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 
     bool host_only = false;  // cfg.device == RT_DEVICE_NONE: construction, camera and accel introspection only
@@ -881,6 +889,34 @@ int rt_get_tonemapped_pixels(rt_raytracer* rt, uint32_t* out) {
     });
 }
 
+int rt_get_tonemapped_pixels_async(rt_raytracer* rt, uint32_t* pinned_out) {
+    RT_GUARD(rt, {
+        if (!pinned_out) throw std::invalid_argument("null output");
+        if (!rt->copy_stream) {
+            RT_CUDA(cudaStreamCreateWithFlags(&rt->copy_stream, cudaStreamNonBlocking));
+            RT_CUDA(cudaEventCreateWithFlags(&rt->ev_snapshot, cudaEventDisableTiming));
+            RT_CUDA(cudaEventCreateWithFlags(&rt->ev_copied, cudaEventDisableTiming));
+            rt->d_ldr_snapshot.alloc(rt->npix());
+        }
+        const size_t bytes = (size_t)rt->npix() * 4;
+        // the snapshot buffer is free again once the previous copy has left it
+        if (rt->copy_in_flight) RT_CUDA(cudaStreamWaitEvent(rt->stream, rt->ev_copied, 0));
+        RT_CUDA(cudaMemcpyAsync(rt->d_ldr_snapshot.p, rt->d_ldr.p, bytes, cudaMemcpyDeviceToDevice, rt->stream));
+        RT_CUDA(cudaEventRecord(rt->ev_snapshot, rt->stream));
+        RT_CUDA(cudaStreamWaitEvent(rt->copy_stream, rt->ev_snapshot, 0));
+        RT_CUDA(cudaMemcpyAsync(pinned_out, rt->d_ldr_snapshot.p, bytes, cudaMemcpyDeviceToHost, rt->copy_stream));
+        RT_CUDA(cudaEventRecord(rt->ev_copied, rt->copy_stream));
+        rt->copy_in_flight = true;
+    });
+}
+int rt_wait_pixels(rt_raytracer* rt) {
+    RT_GUARD(rt, {
+        if (rt->copy_in_flight) {
+            RT_CUDA(cudaEventSynchronize(rt->ev_copied));
+            rt->copy_in_flight = false;
+        }
+    });
+}
 int rt_set_host_frame(rt_raytracer* rt, uint32_t* pinned_host_frame) {
     RT_GUARD(rt, {
         if (rt->ldr_remote && rt->ldr_remote != rt->host_frame_dev) throw std::invalid_argument("an LDR target is already set (rt_set_ldr_target)");

@@ -256,6 +256,32 @@ def test_trace_frame_additive_call_pattern(scenes, accel, aname):
     t.close()
 
 
+def test_pipelined_readback_delivers_every_frame(scenes):
+    """rt_get_tonemapped_pixels_async / rt_wait_pixels: the copy of frame k overlaps the trace of frame k+1, and every
+    frame arrives intact (compared with the blocking readback of the same film state)."""
+    import torch
+
+    s = scenes("ico2")
+    w, h = 512, 384
+    t = gpu_tracer(s, w, h, rt.ACCEL_BVH, jitter=rt.JITTER_HASHED, seed=2)
+    ref = gpu_tracer(s, w, h, rt.ACCEL_BVH, jitter=rt.JITTER_HASHED, seed=2)
+    bufs = [torch.empty(w * h, dtype=torch.int32).pin_memory() for _ in range(2)]
+    expect = []
+    for k in range(6):
+        t.trace_rows(0, h, 1, want_shadow=False)
+        t.wait_pixels()  # frame k-1 is complete now
+        if k > 0:
+            assert np.array_equal(bufs[(k - 1) & 1].numpy().view(np.uint32), expect[k - 1]), k
+        t.get_tonemapped_pixels_async(bufs[k & 1].data_ptr())
+        ref.trace_rows(0, h, 1, want_shadow=False)
+        expect.append(ref.get_tonemapped_pixels())
+    t.wait_pixels()
+    assert np.array_equal(bufs[5 & 1].numpy().view(np.uint32), expect[5])
+    assert not np.array_equal(expect[0], expect[5])  # progressive accumulation changed the frame in between
+    t.close()
+    ref.close()
+
+
 def test_height_smaller_than_band(scenes):
     """height < 50: one call visits rows more than once, sequentially (mod.rs:87-114)."""
     w, h = 64, 20
