@@ -42,6 +42,13 @@ __device__ __forceinline__ V3 vunit(V3 v) {  // Vec3::normalized, vecmath.rs:23-
     return {fdiv(v.x, len), fdiv(v.y, len), fdiv(v.z, len)};
 }
 
+// MUFU.RCP (~1 ulp). Only for values that feed the conservative, padded box tests — never for anything that reaches a pixel.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 struct HitRec {
     float t, u, v;
     uint32_t tri;  // global triangle index
@@ -373,7 +380,7 @@ __device__ __forceinline__ bool octree_closest_hit_ww(const TraceParams& P, cons
 }
 
 __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V3& o, const V3& d, float t_limit, float early_t, HitRec* out) {
-    const float ix = fdiv(1.0f, d.x), iy = fdiv(1.0f, d.y), iz = fdiv(1.0f, d.z);
+    const float ix = rcp_approx(d.x), iy = rcp_approx(d.y), iz = rcp_approx(d.z);  // box tests only (padded boxes)
     const float ox = -o.x * ix, oy = -o.y * iy, oz = -o.z * iz;
     int stack_node[kBvhStack];
     float stack_t[kBvhStack];
@@ -1231,7 +1238,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, 3) trace_shade_pool_kernel(co
                 cr = fadd(0.0f, fmul(fadd(fmul(dr, ndl), spec), lc4.x));
                 cg = fadd(0.0f, fmul(fadd(fmul(dg, ndl), spec), lc4.y));
                 cb = fadd(0.0f, fmul(fadd(fmul(db, ndl), spec), lc4.z));
-                inv = V3{fdiv(1.0f, L.x), fdiv(1.0f, L.y), fdiv(1.0f, L.z)};
+                inv = V3{rcp_approx(L.x), rcp_approx(L.y), rcp_approx(L.z)};  // box tests only
             }
         }
         const uint32_t mask = __ballot_sync(full, to_shadow);
@@ -1260,6 +1267,9 @@ __global__ void __launch_bounds__(32 * kPoolWarps, 3) trace_shade_pool_kernel(co
             shade_stage(32u);
             while (final_cnt >= 32u) film_stage(32u);
         }
+        // once the tile queue is empty a hit must not wait for a full batch: its shadow ray is the end of the longest
+        // dependent chain of the launch (camera ray -> shade -> shadow ray)
+        if (queue_done && tile_px >= 32u && shade_cnt > 0u && shadow_cnt == 0u) shade_stage(shade_cnt < 32u ? shade_cnt : 32u);
         // ---- refill idle lanes: waiting shadow rays first, then camera rays of the next pixels ----
         const uint32_t idle_mask = __ballot_sync(full, !active);
         const uint32_t n_idle = (uint32_t)__popc(idle_mask);
@@ -1333,9 +1343,10 @@ __global__ void __launch_bounds__(32 * kPoolWarps, 3) trace_shade_pool_kernel(co
                     pix = row * W + col;
                     const uint32_t nsamp = P.jitter_mode == 1 ? __float_as_uint(P.film_sum[pix].w) : 0u;
                     d = camera_ray_dir(P, pix, col, nsamp);
-                    ix = fdiv(1.0f, d.x);
-                    iy = fdiv(1.0f, d.y);
-                    iz = fdiv(1.0f, d.z);
+                    // 1/d only feeds the (padded, conservative) box tests: the approximate reciprocal is enough
+                    ix = rcp_approx(d.x);
+                    iy = rcp_approx(d.y);
+                    iz = rcp_approx(d.z);
                     o = cam_o;
                     is_shadow = false;
                     ray_tile = my_tile;
@@ -1525,10 +1536,17 @@ __global__ void __launch_bounds__(1024) tile_sort_kernel(const uint32_t* __restr
         const int k = (int)(__log2f((float)c + 1.0f) * 64.0f);
         return (uint32_t)(kSortBuckets - 1 - min(max(k, 0), kSortBuckets - 1));
     };
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t c = cost[i];
-        if (c >= split_above) atomicAdd(&hist[bucket(c / 4u)], 4u);
-        else atomicAdd(&hist[bucket(c)], 1u);
+    // most tiles of a frame cost about the same (all-miss tiles): aggregate equal buckets inside a warp before the
+    // shared-memory atomic, otherwise tens of thousands of atomics serialise on one address
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const uint32_t n_round = (n + blockDim.x - 1u) / blockDim.x * blockDim.x;
+    for (uint32_t i = threadIdx.x; i < n_round; i += blockDim.x) {
+        const bool have = i < n;
+        const uint32_t c = have ? cost[i] : 0u;
+        const bool sp = have && c >= split_above;
+        const uint32_t b = have ? bucket(sp ? c / 4u : c) : 0xffffffffu, w = sp ? 4u : 1u;
+        const uint32_t same = __match_any_sync(0xffffffffu, (b << 1) | (sp ? 1u : 0u));  // same bucket and same weight
+        if (have && (same & lt) == 0u) atomicAdd(&hist[b], w * (uint32_t)__popc(same));
     }
     __syncthreads();
     // exclusive scan of 2048 buckets: each thread owns two adjacent buckets
@@ -1546,13 +1564,23 @@ __global__ void __launch_bounds__(1024) tile_sort_kernel(const uint32_t* __restr
     hist[2 * threadIdx.x] = base;
     hist[2 * threadIdx.x + 1] = base + a;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t c = cost[i];
-        if (c >= split_above) {
-            const uint32_t at = atomicAdd(&hist[bucket(c / 4u)], 4u);
-            for (uint32_t part = 0; part < 4u; ++part) order[at + part] = i | (part << kItemPartShift) | kItemSplitFlag;
-        } else {
-            order[atomicAdd(&hist[bucket(c)], 1u)] = i;
+    for (uint32_t i = threadIdx.x; i < n_round; i += blockDim.x) {
+        const bool have = i < n;
+        const uint32_t c = have ? cost[i] : 0u;
+        const bool sp = have && c >= split_above;
+        const uint32_t b = have ? bucket(sp ? c / 4u : c) : 0xffffffffu, w = sp ? 4u : 1u;
+        const uint32_t same = __match_any_sync(0xffffffffu, (b << 1) | (sp ? 1u : 0u));
+        const uint32_t leader = (uint32_t)__ffs((int)same) - 1u;
+        uint32_t base = 0u;
+        if (have && lane == leader) base = atomicAdd(&hist[b], w * (uint32_t)__popc(same));
+        base = __shfl_sync(0xffffffffu, base, (int)leader);
+        if (have) {
+            const uint32_t at = base + w * (uint32_t)__popc(same & lt);
+            if (sp) {
+                for (uint32_t part = 0; part < 4u; ++part) order[at + part] = i | (part << kItemPartShift) | kItemSplitFlag;
+            } else {
+                order[at] = i;
+            }
         }
     }
 }

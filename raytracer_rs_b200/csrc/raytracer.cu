@@ -524,6 +524,7 @@ struct rt_raytracer {
         sched_launches = 0;  // costs of the old view no longer predict the new one well: re-sort soon
     }
 
+    static constexpr uint32_t kResortEvery = 32;
     static uint32_t udiv_magic_of(uint32_t d) { return d <= 1u ? 0xffffffffu : (uint32_t)((1ull << 32) / d); }
 
     cudaError_t launch_one(const TraceParams& p_in) {
@@ -555,8 +556,9 @@ struct rt_raytracer {
                     RT_CUDA_RET(cudaMemsetAsync(d_tile_cost.p, 0, tiles * sizeof(uint32_t), stream));
                     sched_have_order = false;
                 }
-                // re-sort after the 1st and 2nd recorded launch of a view, then every 8th
-                if (sched_launches == 1 || sched_launches == 2 || (sched_launches > 2 && sched_launches % 8 == 0)) {
+                // re-sort after the 1st and 2nd recorded launch of a view, then every 32nd (the one-block sort costs
+                // ~0.1 ms for a 1080p frame; per-tile costs of an unchanged view move little between frames)
+                if (sched_launches == 1 || sched_launches == 2 || (sched_launches > 2 && sched_launches % kResortEvery == 0)) {
                     const uint32_t warps = (uint32_t)((use_pool ? pool_blocks : blocks_per_sm[a][b]) * num_sms * 8);
                     cudaError_t e = launch_tile_sort(d_tile_cost.p, d_tile_order.p, tiles, warps, a != 0 && !use_pool, d_counters.p, stream);
                     if (e != cudaSuccess) return e;
@@ -567,7 +569,7 @@ struct rt_raytracer {
                 if (use_pool) {
                     // the pool kernel ADDS every camera ray's steps to its tile's cost: record only the launches a sort
                     // will read (the one before each re-sort), starting from zero
-                    const bool record = sched_launches <= 1 || sched_launches % 8 == 7;
+                    const bool record = sched_launches <= 1 || sched_launches % kResortEvery == kResortEvery - 1;
                     if (record && sched_launches > 0) RT_CUDA_RET(cudaMemsetAsync(d_tile_cost.p, 0, tiles * sizeof(uint32_t), stream));
                     p.tile_cost = record ? d_tile_cost.p : nullptr;
                 } else {

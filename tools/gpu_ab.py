@@ -6,7 +6,7 @@ import numpy as np
 import raytracer_rs_b200 as rt
 scenes = [('4boxes',1920,1080),('ico2',1024,768),('ico3_tex',1920,1080),('thai2',1920,1080)]
 # (variant, lpt schedule, pool_refill, pool_min_inner, accel)
-variants = [(1,1,8,16,rt.ACCEL_BVH),(1,1,8,16,rt.ACCEL_BVH4),(1,0,8,16,rt.ACCEL_BVH4),(2,1,16,8,rt.ACCEL_BVH)]
+variants = [(1,1,8,16,rt.ACCEL_BVH),(2,1,16,8,rt.ACCEL_BVH),(2,1,8,8,rt.ACCEL_BVH),(2,1,24,8,rt.ACCEL_BVH)]
 if len(sys.argv) > 1:
     scenes = [s for s in scenes if s[0] in sys.argv[1].split(',')]
 for name,w,h in scenes:
