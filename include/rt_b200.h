@@ -226,6 +226,10 @@ uint32_t rt_launch_param_bytes(void);
 /* RT_TUNE_MULTI_SAMPLE_LAUNCH: 1 (default) rt_trace_rows with spp > 1 traces all samples of the pass in one launch
    (per-sample radiance planes + one ordered accumulation into the film); 0 one launch per sample. Same film either way. */
 #define RT_TUNE_MULTI_SAMPLE_LAUNCH 5
+/* RT_TUNE_BOUNCE_WAVEFRONT: 1 (default) bounce rays (recursions > 0) run as a wavefront — the hits of every level are
+   compacted into a dense list and the next level's rays fill whole warps; 0 every pixel walks its bounce tree depth
+   first inside the trace kernel. Same rays, same film. */
+#define RT_TUNE_BOUNCE_WAVEFRONT 6
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {

@@ -36,6 +36,15 @@ constexpr int kCwStack = 32;  // node groups only: at most one per level plus sl
 enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3, CNT_TILE_QUEUE = 4, CNT_QUEUE_ITEMS = 5,
                    CNT_SHADOW_TOTAL = 6, CNT_BOUNCE_TOTAL = 7, CNT_SLOTS = 8 };
 
+// one level of the bounce wavefront: dense list of shaded hits (3 float4 per node: hit point | pixel, normal | path,
+// shaded radiance | parent + child number) and, per node, the radiance its n_children bounce rays bring back
+struct WfLevel {
+    float4* rec;
+    float* child_r;  // cap * n_children * 3
+    uint32_t cap, n_children;
+};
+constexpr int kWfLevels = 5;  // recursions <= 4
+
 struct TraceParams {
     DevCamera cam;
     // acceleration structures (either may be null when not built)
@@ -76,6 +85,10 @@ struct TraceParams {
     int32_t recursions;          // RECURSIONS (mod.rs:81); 0 = primary + shadow only
     uint32_t sub_spread;         // SUB_SPREAD (mod.rs:82)
     const float* sample_table;   // 65 536 unit vectors (sample_generator.rs), 3 floats each
+    // bounce wavefront (null wf_counts = bounce rays are walked depth first inside the trace kernel)
+    unsigned int* wf_counts;     // [0, kWfLevels): nodes per level; [kWfLevels, 2 kWfLevels): ray-queue head per level
+    uint32_t wf_level;           // level processed by wf_bounce_kernel / wf_combine_kernel
+    WfLevel wf[kWfLevels];
     uint32_t pool_refill;        // ray-pool kernel: idle lanes of a warp that trigger a refill
     uint32_t pool_min_inner;     // ray-pool kernel: the inner-node loop yields when fewer lanes than this still descend
     uint32_t magic_w, magic_h, magic_tiles_x;  // floor(2^32 / d) for d = width, height, tiles per row (udiv_magic)

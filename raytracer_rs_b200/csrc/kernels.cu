@@ -951,6 +951,39 @@ __device__ __forceinline__ void film_add_sample(const TraceParams& P, uint32_t i
     if (P.ldr_remote) P.ldr_remote[idx] = px;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Bounce wavefront (compute_radiance with RECURSIONS > 0, mod.rs:132-196, level by level instead of depth first).
+// The hits of every level are COMPACTED into a dense node list (warp-aggregated atomic append = ballot/popc stream
+// compaction), so the incoherent bounce rays of the next level fill whole warps instead of running one after the
+// other in the few lanes of a pixel tile that hit something:
+//   trace kernel (BOUNCE = 2)   camera ray -> closest hit -> shade (shadow ray) -> level-0 node {hit point, normal, S, pixel}
+//   wf_bounce_kernel, level l   one thread per (node, k): bounce direction k of that node (same hash/table walk as the
+//                               depth-first code, so the rays are the same), closest hit, shade -> level-(l+1) node
+//   wf_combine_kernel, level l  bottom up: R = S + (sum over k of R_child_k) * (1 / n) with the children in k order
+//                               (a missing child is the +0 the reference adds for RGB::black), handed to the parent's
+//                               slot k; level 0 adds R to the film
+// Same float operations in the same order as radiance_with_bounces => same film.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t wf_append(unsigned int* counter) {
+    const uint32_t m = __activemask();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t leader = (uint32_t)__ffs((int)m) - 1u;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
+    base = __shfl_sync(m, base, (int)leader);
+    return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+__device__ __forceinline__ void wf_store_node(const TraceParams& P, uint32_t level, uint32_t slot, const V3& hp, uint32_t pixel, const V3& nrm,
+                                              uint32_t path, float sr, float sg, float sb, uint32_t parent, uint32_t k) {
+    const WfLevel& L = P.wf[level];
+    if (slot >= L.cap) return;  // cannot happen: capacities are worst case
+    float4* rec = L.rec + 3 * (size_t)slot;
+    rec[0] = make_float4(hp.x, hp.y, hp.z, __uint_as_float(pixel));
+    rec[1] = make_float4(nrm.x, nrm.y, nrm.z, __uint_as_float(path));
+    rec[2] = make_float4(sr, sg, sb, __uint_as_float(parent | (k << 28)));
+    for (uint32_t c = 0; c < 3u * L.n_children; ++c) L.child_r[(size_t)slot * 3u * L.n_children + c] = 0.0f;  // RGB::black
+}
+
 template <int ACCEL, int WW, int BOUNCE>
 __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, uint32_t crow, LaneCounters& cnt) {
     const uint32_t W = P.cam.width, H = P.cam.height;
@@ -974,7 +1007,14 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, 
     if (closest_hit<ACCEL, WW>(P, o, d, &hit)) {
         cnt.prim_hit += 1;
         id = hit.tri;
-        if (BOUNCE) {
+        if (BOUNCE == 2) {  // wavefront: this hit becomes a level-0 node, the film is updated by wf_combine_kernel
+            V3 nrm;
+            shade_hit<ACCEL, WW>(P, o, d, hit, &nrm, &cr, &cg, &cb, cnt);
+            const uint32_t slot = wf_append(&P.wf_counts[0]);
+            wf_store_node(P, 0u, slot, vadd(o, vscale(d, hit.t)), idx, nrm, 0u, cr, cg, cb, 0u, 0u);
+            P.primary_ids[idx] = id;
+            return;
+        } else if (BOUNCE == 1) {
             radiance_with_bounces<ACCEL, WW>(P, o, d, hit, idx, nsamp, &cr, &cg, &cb, cnt);
         } else {
             V3 nrm;
@@ -1703,6 +1743,86 @@ __global__ void flag_wait_kernel(volatile uint32_t* flags, uint32_t n, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// bounce wavefront kernels (see trace_pixel, BOUNCE = 2)
+// ------------------------------------------------------------------------------------------------------
+template <int ACCEL>
+__global__ void __launch_bounds__(256) wf_bounce_kernel(const __grid_constant__ TraceParams P) {
+    const uint32_t l = P.wf_level;
+    const WfLevel& L = P.wf[l];
+    const uint32_t n_nodes = min(P.wf_counts[l], L.cap), nch = L.n_children;
+    const uint32_t total = n_nodes * nch;
+    LaneCounters cnt;
+    const uint32_t lane = threadIdx.x & 31u;
+    // bounce rays differ a lot in cost: warps pull 32 rays at a time from a queue instead of owning a fixed slice
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&P.wf_counts[kWfLevels + l], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        const uint32_t j = base + lane;
+        if (j >= total) continue;
+        const uint32_t parent = j / nch, k = j - parent * nch;
+        const float4 r0 = L.rec[3 * (size_t)parent], r1 = L.rec[3 * (size_t)parent + 1];
+        const V3 hp0 = {r0.x, r0.y, r0.z}, normal = {r1.x, r1.y, r1.z};
+        const uint32_t pixel = __float_as_uint(r0.w), path = __float_as_uint(r1.w);
+        const uint32_t sample = __float_as_uint(P.film_sum[pixel].w);  // the film is not touched before the last combine
+        const uint32_t sub_path = path * 31u + k + 1u;
+        // normalized_vec_pseudo / normalized_vec_lookup, as in radiance_with_bounces
+        uint32_t idx = (uint32_t)(((unsigned long long)hash4(P.seed ^ 0xb0c0ffeeU, pixel, sample, sub_path) * 65535ull) >> 32);
+        V3 rd = {P.sample_table[3 * idx], P.sample_table[3 * idx + 1], P.sample_table[3 * idx + 2]};
+        while (vdot(rd, normal) <= 0.0f) {
+            idx = (idx + 1u) % 65535u;
+            rd = V3{P.sample_table[3 * idx], P.sample_table[3 * idx + 1], P.sample_table[3 * idx + 2]};
+        }
+        const V3 o2 = vadd(hp0, vscale(rd, 0.00001f));  // ray.pos + t * ray.dir + 0.00001 * random_dir (mod.rs:192-193)
+        cnt.bounce_rays += 1;
+        HitRec h;
+        if (closest_hit<ACCEL, 1>(P, o2, rd, &h)) {
+            V3 nrm;
+            float cr, cg, cb;
+            shade_hit<ACCEL, 1>(P, o2, rd, h, &nrm, &cr, &cg, &cb, cnt);
+            const uint32_t slot = wf_append(&P.wf_counts[l + 1u]);
+            wf_store_node(P, l + 1u, slot, vadd(o2, vscale(rd, h.t)), pixel, nrm, sub_path, cr, cg, cb, parent, k);
+        }
+    }
+    flush_counters(P, cnt, lane);
+}
+
+__global__ void __launch_bounds__(256) wf_combine_kernel(const __grid_constant__ TraceParams P) {
+    const uint32_t l = P.wf_level;
+    const WfLevel& L = P.wf[l];
+    const uint32_t n_nodes = min(P.wf_counts[l], L.cap), nch = L.n_children;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
+        const float4 r2 = L.rec[3 * (size_t)i + 2];
+        float rr = r2.x, rg = r2.y, rb = r2.z;
+        if (nch > 0u) {  // radiance + fold(sum) * (1.0 / num_sub_rays)   (mod.rs:154-175)
+            float sr = 0.f, sg = 0.f, sb = 0.f;
+            const float* c = L.child_r + (size_t)i * 3u * nch;
+            for (uint32_t k = 0; k < nch; ++k) {
+                sr = fadd(sr, c[3 * k]);
+                sg = fadd(sg, c[3 * k + 1]);
+                sb = fadd(sb, c[3 * k + 2]);
+            }
+            const float inv = fdiv(1.0f, (float)nch);
+            rr = fadd(rr, fmul(sr, inv));
+            rg = fadd(rg, fmul(sg, inv));
+            rb = fadd(rb, fmul(sb, inv));
+        }
+        if (l == 0u) {
+            const uint32_t pixel = __float_as_uint(L.rec[3 * (size_t)i].w);
+            film_add_sample(P, pixel, P.film_sum[pixel], rr, rg, rb);
+        } else {
+            const uint32_t pk = __float_as_uint(r2.w), parent = pk & 0x0fffffffu, k = pk >> 28;
+            const WfLevel& U = P.wf[l - 1u];
+            float* dst = U.child_r + ((size_t)parent * U.n_children + k) * 3u;
+            dst[0] = rr;
+            dst[1] = rg;
+            dst[2] = rb;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------
 template <int ACCEL, int BOUNCE>
@@ -1723,23 +1843,43 @@ static void launch_trace_t(const TraceParams& p, int variant, uint32_t blocks, c
 #endif
     }
 }
+// bounce_mode: 0 none, 1 depth first in the thread, 2 wavefront (the trace kernel only emits level-0 nodes)
 cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persistent_blocks, cudaStream_t stream) {
     if (p.n_rows == 0) return cudaSuccess;
     const uint32_t tiles = ((p.cam.width + 7u) / 8u) * ((p.n_rows + 3u) / 4u);
     uint32_t blocks = (uint32_t)persistent_blocks;
     if (blocks * 8u > tiles) blocks = (tiles + 7u) / 8u;
-    const bool bounce = p.recursions > 0;
-    switch (accel * 2 + (bounce ? 1 : 0)) {
+    const int bounce = p.recursions > 0 ? (p.wf_counts ? 2 : 1) : 0;
+    if (bounce == 2 && variant == 0) return cudaErrorInvalidValue;  // the wavefront trace kernel is the persistent one
+    switch (accel * 3 + bounce) {
         case 0: launch_trace_t<0, 0>(p, variant, blocks, stream); break;
         case 1: launch_trace_t<0, 1>(p, variant, blocks, stream); break;
-        case 2: launch_trace_t<1, 0>(p, variant, blocks, stream); break;
-        case 3: launch_trace_t<1, 1>(p, variant, blocks, stream); break;
-        case 4: launch_trace_t<2, 0>(p, variant, blocks, stream); break;
-        case 5: launch_trace_t<2, 1>(p, variant, blocks, stream); break;
-        case 6: launch_trace_t<3, 0>(p, variant, blocks, stream); break;
-        case 7: launch_trace_t<3, 1>(p, variant, blocks, stream); break;
+        case 2: trace_shade_persistent_kernel<0, 2><<<blocks, 256, 0, stream>>>(p); break;
+        case 3: launch_trace_t<1, 0>(p, variant, blocks, stream); break;
+        case 4: launch_trace_t<1, 1>(p, variant, blocks, stream); break;
+        case 5: trace_shade_persistent_kernel<1, 2><<<blocks, 256, 0, stream>>>(p); break;
+        case 6: launch_trace_t<2, 0>(p, variant, blocks, stream); break;
+        case 7: launch_trace_t<2, 1>(p, variant, blocks, stream); break;
+        case 8: trace_shade_persistent_kernel<2, 2><<<blocks, 256, 0, stream>>>(p); break;
+        case 9: launch_trace_t<3, 0>(p, variant, blocks, stream); break;
+        case 10: launch_trace_t<3, 1>(p, variant, blocks, stream); break;
+        case 11: trace_shade_persistent_kernel<3, 2><<<blocks, 256, 0, stream>>>(p); break;
         default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+cudaError_t launch_wf_bounce(const TraceParams& p, int accel, int blocks, cudaStream_t stream) {
+    switch (accel) {
+        case 0: wf_bounce_kernel<0><<<blocks, 256, 0, stream>>>(p); break;
+        case 1: wf_bounce_kernel<1><<<blocks, 256, 0, stream>>>(p); break;
+        case 2: wf_bounce_kernel<2><<<blocks, 256, 0, stream>>>(p); break;
+        case 3: wf_bounce_kernel<3><<<blocks, 256, 0, stream>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_wf_combine(const TraceParams& p, int blocks, cudaStream_t stream) {
+    wf_combine_kernel<<<blocks, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 int pool_blocks_per_sm() {

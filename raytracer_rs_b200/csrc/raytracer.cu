@@ -103,6 +103,10 @@ struct rt_raytracer {
     DevBuf<DevTexture> d_textures;
     DevBuf<float4> d_film_sum, d_film_sq, d_planes;
     bool multi_sample_launch = true;  // RT_TUNE_MULTI_SAMPLE_LAUNCH
+    bool bounce_wavefront = true;     // RT_TUNE_BOUNCE_WAVEFRONT
+    DevBuf<float4> d_wf_rec;
+    DevBuf<float> d_wf_child;
+    DevBuf<unsigned int> d_wf_counts;
     DevBuf<uint32_t> d_ldr, d_ids, d_row_list, d_owned_rows;
     DevBuf<unsigned long long> d_counters;
     DevBuf<uint32_t> d_sync_timeouts;
@@ -589,7 +593,71 @@ struct rt_raytracer {
             queue_is_zero = false;
         }
         if (use_pool) return launch_trace(p, a, 2, pool_blocks * num_sms, stream);
+        if (wavefront_applies(p)) return launch_wavefront(p, a);
         return launch_trace(p, a, variant == 0 ? 0 : 1, blocks_per_sm[a][b] * num_sms, stream);
+    }
+
+    // ---- bounce wavefront (kernels.cu: trace_pixel BOUNCE = 2, wf_bounce_kernel, wf_combine_kernel) ----
+    static constexpr size_t kWfMaxBytes = size_t(6) << 30;
+    // nodes of level l are at most pixels * prod_{i<l} n_i with n_i = sub_spread * (recursions - i) bounce rays per hit
+    bool wf_layout(const TraceParams& p, size_t cap[kWfLevels], uint32_t nch[kWfLevels], size_t* rec_total, size_t* child_total) const {
+        const int R = cfg.recursions;
+        if (R < 1 || R > kWfLevels - 1) return false;
+        size_t c = (size_t)p.n_rows * p.cam.width, recs = 0, childs = 0;
+        for (int l = 0; l <= R; ++l) {
+            cap[l] = c;
+            nch[l] = cfg.sub_spread * (uint32_t)(R - l);
+            if (cap[l] >= (size_t(1) << 28)) return false;  // parent index has 28 bits
+            recs += 3 * cap[l];
+            childs += 3 * cap[l] * nch[l];
+            if (nch[l] > 15u) return false;  // child number has 4 bits
+            c *= std::max<size_t>(nch[l], 1);
+            if (recs * 16 + childs * 4 > kWfMaxBytes) return false;
+        }
+        *rec_total = recs;
+        *child_total = childs;
+        return true;
+    }
+    bool wavefront_applies(const TraceParams& p) const {
+        if (!bounce_wavefront || cfg.recursions < 1 || variant == 0 || p.planes || cfg.sub_spread == 0) return false;
+        size_t cap[kWfLevels], rt_, ct_;
+        uint32_t nch[kWfLevels];
+        return wf_layout(p, cap, nch, &rt_, &ct_);
+    }
+    cudaError_t launch_wavefront(const TraceParams& p_in, int a) {
+        TraceParams p = p_in;
+        size_t cap[kWfLevels], rec_total = 0, child_total = 0;
+        uint32_t nch[kWfLevels];
+        wf_layout(p, cap, nch, &rec_total, &child_total);
+        if (d_wf_rec.n < rec_total) d_wf_rec.alloc(rec_total);
+        if (d_wf_child.n < std::max<size_t>(child_total, 1)) d_wf_child.alloc(std::max<size_t>(child_total, 1));
+        if (!d_wf_counts.p) d_wf_counts.alloc(2 * kWfLevels);  // nodes per level | ray-queue head per level
+        const int R = cfg.recursions;
+        size_t ro = 0, co = 0;
+        for (int l = 0; l <= R; ++l) {
+            p.wf[l].rec = d_wf_rec.p + ro;
+            p.wf[l].child_r = d_wf_child.p + co;
+            p.wf[l].cap = (uint32_t)cap[l];
+            p.wf[l].n_children = nch[l];
+            ro += 3 * cap[l];
+            co += 3 * cap[l] * nch[l];
+        }
+        p.wf_counts = d_wf_counts.p;
+        RT_CUDA_RET(cudaMemsetAsync(d_wf_counts.p, 0, 2 * kWfLevels * sizeof(unsigned int), stream));
+        if (blocks_per_sm[a][0] == 0) blocks_per_sm[a][0] = persistent_blocks_per_sm(a, 0);
+        RT_CUDA_RET(launch_trace(p, a, 1, blocks_per_sm[a][0] * num_sms, stream));
+        const int wf_blocks = num_sms * 3;  // 80 registers: three 256-thread blocks per SM
+        for (int l = 0; l < R; ++l) {  // level l -> l + 1
+            p.wf_level = (uint32_t)l;
+            RT_CUDA_RET(launch_wf_bounce(p, a, wf_blocks, stream));
+        }
+        for (int l = R; l >= 0; --l) {  // bottom up; level 0 adds the radiance to the film
+            p.wf_level = (uint32_t)l;
+            RT_CUDA_RET(launch_wf_combine(p, wf_blocks, stream));
+        }
+        total_kernels += (uint64_t)(2 * R + 1);
+        last.kernels_launched += (uint32_t)(2 * R + 1);
+        return cudaSuccess;
     }
 
     // rows [first_row, first_row + n_rows) modulo height, `spp` passes
@@ -632,7 +700,7 @@ struct rt_raytracer {
                     RT_CUDA(launch_one(q));
                     ++launches;
                 }
-        } else if (spp > 1 && multi_sample_launch) {
+        } else if (spp > 1 && multi_sample_launch && !(cfg.recursions > 0 && bounce_wavefront && variant != 0)) {
             // all samples of a pass in ONE launch (sample planes) + one ordered accumulation: same film as `spp`
             // consecutive launches, but the GPU sees spp times as many work items (matters for small row ranges)
             const uint32_t padded = (launch_rows + 3u) & ~3u;
@@ -1114,6 +1182,10 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     }
     if (key == RT_TUNE_POOL_REFILL && value >= 1 && value <= 32) {
         rt->pool_refill = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_BOUNCE_WAVEFRONT && (value == 0 || value == 1)) {
+        rt->bounce_wavefront = value != 0;
         return RT_OK;
     }
     if (key == RT_TUNE_MULTI_SAMPLE_LAUNCH && (value == 0 || value == 1)) {

@@ -430,6 +430,29 @@ def test_bounce_rays_reference_default_mode(scenes, name, w, h, accel, aname):
     t.close()
 
 
+@pytest.mark.parametrize("accel,aname", ACCELS)
+@pytest.mark.parametrize("rec,spread", [(2, 1), (1, 2), (3, 1)])
+def test_bounce_wavefront_equals_depth_first(scenes, accel, aname, rec, spread):
+    """f-2: the bounce wavefront (hits of every level compacted into a dense list, next level's rays one per thread,
+    bottom-up combine) traces the same rays and leaves the same film as the depth-first walk inside the trace kernel."""
+    if accel == rt.ACCEL_LBVH and rec == 3:
+        pytest.skip("same traversal kernel as bvh")
+    s = scenes("ico3_tex")
+    w, h = 384, 216
+    got = []
+    for wavefront in (1, 0):
+        t = rt.RayTracer.from_scene(s, rt.Config(w, h, recursions=rec, sub_spread=spread, jitter_mode=rt.JITTER_HASHED, seed=4, accel=accel))
+        t.set_tuning(6, wavefront)
+        n_primary, n_shadow = t.trace_rows(0, h, 2)
+        st = t.launch_stats()
+        got.append((n_shadow, st["n_bounce"], t.get_primary_ids(), t.get_tonemapped_pixels(), t.film.pixel_datas().view(np.uint32)))
+        t.close()
+    a, b = got
+    assert a[0] == b[0] and a[1] == b[1] and a[1] > 0
+    for x, y in zip(a[2:], b[2:]):
+        assert np.array_equal(x, y)
+
+
 def test_bounce_sample_table_matches_oracle(scenes):
     """sample_generator.rs:9-53 stand-in: host-generated table == oracle table, unit length, and recursion depth 1 and 3
     also agree with the oracle."""
