@@ -369,6 +369,10 @@ def main():
             # frame i to the copy stream
             tracer.wait_pixels()
             tracer.get_tonemapped_pixels_async(host_frames[i & 1].data_ptr())
+        elif gather is not None and not args.sync_readback:
+            if rank == 0:  # same pipelining on rank 0 of a multi-GPU run
+                gather.wait_frame()
+                gather.read_frame_async(host_frames[i & 1])
         elif rank == 0:
             tracer_or_gather_readback()
 
@@ -389,6 +393,8 @@ def main():
         e2e_step(i)
     if pipelined:
         tracer.wait_pixels()  # the last frame is delivered inside the timed region too
+    elif gather is not None and rank == 0:
+        gather.wait_frame()
     barrier()
     e2e_s = time.perf_counter() - t0
     rays1 = global_ray_totals()
@@ -474,7 +480,7 @@ def main():
         "frames_per_s": args.steps / (total_ms * 1e-3),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rt.lib().rt_launch_param_bytes()), "d2h_bytes_per_step": W * H * 4 + 32,
-                "ms_per_step": e2e_s / args.steps * 1e3, "readback": "nccl/peer gather + copy" if world > 1 else ("zero-copy stores from the trace kernel into the pinned frame" if args.zero_copy else ("pipelined: device snapshot + copy stream, the copy of frame k overlaps the trace of frame k+1, every frame delivered inside the timed region" if pipelined else "blocking cudaMemcpyAsync after the kernel")),
+                "ms_per_step": e2e_s / args.steps * 1e3, "readback": ("gather to rank 0 (%s) + %s copy to pinned host memory" % (args.gather, "blocking" if args.sync_readback else "pipelined (copy stream, overlaps the next frame)")) if world > 1 else ("zero-copy stores from the trace kernel into the pinned frame" if args.zero_copy else ("pipelined: device snapshot + copy stream, the copy of frame k overlaps the trace of frame k+1, every frame delivered inside the timed region" if pipelined else "blocking cudaMemcpyAsync after the kernel")),
                 "frame_matches_device": e2e_frame_ok,
                 "note": "camera state in (launch parameters), packed LDR frame out to pinned host memory, wall clock"},
         "gpu_launches": int(launches),

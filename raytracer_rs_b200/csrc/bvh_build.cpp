@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 
 #include "accel_build.h"
@@ -48,9 +49,11 @@ struct Builder {
     float pad_abs = 0.f;
 
     static constexpr float kTraversalCost = 1.0f;
-    static constexpr float kTriangleCost = 1.2f;
+    float kTriangleCost = 1.2f;  // developer override: RT_BVH_TRI_COST
 
-    Builder(const HostScene& s, uint32_t ml) : scene(s), max_leaf(ml) {}
+    Builder(const HostScene& s, uint32_t ml) : scene(s), max_leaf(ml) {
+        if (const char* e = std::getenv("RT_BVH_TRI_COST")) kTriangleCost = (float)std::atof(e);
+    }
 
     Aabb range_box(uint32_t b, uint32_t e) const {
         Aabb r;

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -327,7 +328,9 @@ struct rt_raytracer {
 
     void ensure_bvh_host() {
         if (bvh_built) return;
-        bvh = build_bvh(scene, 4);
+        uint32_t max_leaf = 4;
+        if (const char* e = std::getenv("RT_BVH_MAX_LEAF")) max_leaf = (uint32_t)std::min(15, std::max(1, std::atoi(e)));  // developer override
+        bvh = build_bvh(scene, max_leaf);
         bvh_built = true;
     }
 

@@ -48,8 +48,9 @@ class _DevPtr:
 
 
 class FrameGather:
-    """Delivers full frames to rank 0. Call order per frame: tracer.trace_rows(0, H, spp) -> device_gather()
-    -> (rank 0) read_frame_into(pinned_host_tensor)."""
+    """Delivers full frames to rank 0. Call order per frame: begin_frame() -> tracer.trace_rows(0, H, spp) ->
+    device_gather() -> (rank 0) read_frame_into(pinned_host_tensor), or the pipelined read_frame_async(pinned) ...
+    wait_frame(), or device_gather(release=True) when the frame stays on the device."""
 
     def __init__(self, tracer, rank: int, world: int, device, stream, mode: str = "peer", band_rows: int = 8):
         import torch
@@ -59,7 +60,8 @@ class FrameGather:
         self.tracer, self.rank, self.world, self.device, self.stream, self.mode = tracer, rank, world, device, stream, mode
         self.W, self.H = tracer.width, tracer.height
         self.partition = band_partition(self.H, world, band_rows)
-        self.kernels = 0  # kernels of OURS launched by this object (row compaction)
+        self.kernels = 0  # kernels of OURS launched by this object (row compaction, flag fence)
+        self.copy_stream, self.copy_done, self.copy_pending, self.flags_view = None, None, False, None
         self.frame_no = 0
         nbytes = self.W * self.H * 4
         cptr = tracer.counters_device_ptr()
@@ -148,6 +150,36 @@ class FrameGather:
             self.tracer.signal_flag(self.flags + 4 * self.world, self.frame_no)
             self.consumed_signalled = self.frame_no
             self.kernels += 1
+
+    def read_frame_async(self, host_tensor):
+        """rank 0: pipelined readback. The device -> (pinned) host copy of the completed frame runs on a copy stream
+        while the next frame is traced; in mode "peer" the "frame has been read" flag is published on that stream when
+        the copy is done, so the other ranks can never overwrite a buffer that is still being read. The pixels are valid
+        after wait_frame()."""
+        torch = self.torch
+        if self.mode != "peer":  # only the flag protocol protects a buffer that is still being copied
+            return self.read_frame_into(host_tensor)
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+            self.copy_done = torch.cuda.Event()
+            if self.mode == "peer":
+                self.flags_view = torch.as_tensor(_DevPtr(self.local_bufs[2], 256), device=self.device).view(torch.int32)
+        ready = torch.cuda.Event()
+        ready.record(self.stream)  # after the fence of the frame just gathered
+        self.copy_stream.wait_event(ready)
+        with torch.cuda.stream(self.copy_stream):
+            src = self.frames[self.ready] if self.mode in ("peer", "peer_allreduce") else self.frame.view(-1)
+            host_tensor.copy_(src, non_blocking=True)
+            if self.mode == "peer" and self.consumed_signalled < self.frame_no:
+                self.flags_view[self.world:self.world + 1].fill_(self.frame_no)  # frame k has been read (k + 1)
+                self.consumed_signalled = self.frame_no
+            self.copy_done.record(self.copy_stream)
+        self.copy_pending = True
+
+    def wait_frame(self):
+        if self.copy_pending:
+            self.copy_done.synchronize()
+            self.copy_pending = False
 
     def read_frame_into(self, host_tensor):
         """rank 0: device -> (pinned) host copy of the completed frame, synchronous."""

@@ -35,7 +35,11 @@ def _worker(rank, world, port, mode, result_path):
         t.trace_rows(0, h, 1, want_shadow=False)
         g.device_gather()
         if rank == 0:
-            g.read_frame_into(host)
+            if frame % 2 == 0:
+                g.read_frame_into(host)
+            else:  # pipelined form
+                g.read_frame_async(host)
+                g.wait_frame()
             if frame == 0:
                 full = rt.RayTracer.from_scene(scene, rt.Config(w, h, device=0, **cfg))
                 _, n_shadow = full.trace_rows(0, h, 1)
