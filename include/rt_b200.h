@@ -230,6 +230,9 @@ uint32_t rt_launch_param_bytes(void);
    compacted into a dense list and the next level's rays fill whole warps; 0 every pixel walks its bounce tree depth
    first inside the trace kernel. Same rays, same film. */
 #define RT_TUNE_BOUNCE_WAVEFRONT 6
+/* RT_TUNE_SPLIT_QUARTERS (variant 1, BVH kernels): tiles whose recorded cost exceeds (balanced launch time) * q / 4 are
+   handed out as four one-row items; 0 = never split (default 4). */
+#define RT_TUNE_SPLIT_QUARTERS 7
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {

@@ -18,9 +18,9 @@ cudaError_t launch_wf_combine(const TraceParams& p, int blocks, cudaStream_t str
 int pool_blocks_per_sm();
 // order[] = tile ids by descending cost (longest-processing-time-first schedule for the persistent kernel)
 // order must hold 4 * n entries (heavy tiles become four items); counters[CNT_QUEUE_ITEMS] receives the item count
-// allow_split: heavy tiles may become four quarter-tile items (pays off for the divergent BVH kernel, not for the octree's
-// long coherent leaf loops)
-cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, uint32_t n_warps, bool allow_split,
+// split_quarters: 0 = never split; q > 0 = tiles that cost more than (balanced launch time) * q / 4 become four one-row items
+// (pays off for the divergent BVH kernels, not for the octree's long coherent leaf loops)
+cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, uint32_t n_warps, uint32_t split_quarters,
                              unsigned long long* counters, cudaStream_t stream);
 cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream);
 cudaError_t launch_tonemap(const float4* sum, uint32_t* ldr, uint32_t n, cudaStream_t stream);

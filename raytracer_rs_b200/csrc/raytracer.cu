@@ -130,6 +130,7 @@ struct rt_raytracer {
     uint32_t cached_first = ~0u, cached_n = ~0u;
     uint64_t total_kernels = 0, total_primary = 0;
     int variant = 1;            // RT_TUNE_KERNEL_VARIANT
+    int split_quarters = 4;     // RT_TUNE_SPLIT_QUARTERS
     int pool_refill = 16;       // RT_TUNE_POOL_REFILL
     int pool_min_inner = 8;     // RT_TUNE_POOL_MIN_INNER
     int pool_blocks = 0;        // resident blocks per SM of the ray-pool kernel
@@ -567,7 +568,7 @@ struct rt_raytracer {
                 // ~0.1 ms for a 1080p frame; per-tile costs of an unchanged view move little between frames)
                 if (sched_launches == 1 || sched_launches == 2 || (sched_launches > 2 && sched_launches % kResortEvery == 0)) {
                     const uint32_t warps = (uint32_t)((use_pool ? pool_blocks : blocks_per_sm[a][b]) * num_sms * 8);
-                    cudaError_t e = launch_tile_sort(d_tile_cost.p, d_tile_order.p, tiles, warps, a != 0 && !use_pool, d_counters.p, stream);
+                    cudaError_t e = launch_tile_sort(d_tile_cost.p, d_tile_order.p, tiles, warps, (a != 0 && !use_pool) ? (uint32_t)split_quarters : 0u, d_counters.p, stream);
                     if (e != cudaSuccess) return e;
                     ++total_kernels;
                     ++last.kernels_launched;
@@ -1185,6 +1186,12 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     }
     if (key == RT_TUNE_POOL_REFILL && value >= 1 && value <= 32) {
         rt->pool_refill = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_SPLIT_QUARTERS && value >= 0 && value <= 64) {
+        rt->split_quarters = value;
+        rt->sched_have_order = false;
+        rt->sched_launches = 0;
         return RT_OK;
     }
     if (key == RT_TUNE_BOUNCE_WAVEFRONT && (value == 0 || value == 1)) {
