@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -26,8 +27,9 @@ struct Ref4 {
 
 struct Builder4 {
     static constexpr int kWidth = 4;
-    static constexpr uint32_t kMaxLeaf = 4;
-    static constexpr float kNodeCost = 1.0f, kPrimCost = 0.6f;
+    uint32_t kMaxLeaf = 4;                  // developer override: RT_BVH4_MAX_LEAF (<= 15)
+    static constexpr float kNodeCost = 1.0f;
+    float kPrimCost = 0.6f;                 // developer override: RT_BVH4_PRIM_COST
     enum : uint8_t { kLeaf = 0, kInternal = 1, kDistribute = 2, kFewer = 3 };
     struct Dp {
         float cost[kWidth];            // [1 .. kWidth-1]
@@ -39,7 +41,11 @@ struct Builder4 {
     std::vector<uint32_t> sub_first, sub_count;
     std::vector<Dp> dp;
 
-    explicit Builder4(const FlatBvh& b) : bvh(b), sub_first(b.nodes.size(), 0u), sub_count(b.nodes.size(), 0u), dp(b.nodes.size()) { solve(0); }
+    explicit Builder4(const FlatBvh& b) : bvh(b), sub_first(b.nodes.size(), 0u), sub_count(b.nodes.size(), 0u), dp(b.nodes.size()) {
+        if (const char* e = std::getenv("RT_BVH4_MAX_LEAF")) kMaxLeaf = (uint32_t)std::min(15, std::max(1, std::atoi(e)));
+        if (const char* e = std::getenv("RT_BVH4_PRIM_COST")) kPrimCost = (float)std::atof(e);
+        solve(0);
+    }
 
     static float box_area(const float* lo, const float* hi) {
         const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
@@ -178,7 +184,9 @@ struct Builder4 {
 }  // namespace
 
 FlatBvh4 build_bvh4(const HostScene& scene) {
-    const FlatBvh bvh = build_bvh(scene, 4);
+    uint32_t base_leaf = 4;
+    if (const char* e = std::getenv("RT_BVH4_BASE_LEAF")) base_leaf = (uint32_t)std::min(15, std::max(1, std::atoi(e)));  // developer override
+    const FlatBvh bvh = build_bvh(scene, base_leaf);
     Builder4 b(bvh);
     b.out.nodes.resize(1);
     b.out.tri_order.reserve(scene.num_triangles());
