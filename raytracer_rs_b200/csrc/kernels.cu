@@ -1731,24 +1731,33 @@ __device__ __forceinline__ void accumulate_pixel(const TraceParams& P, uint32_t 
     const uint32_t row = P.row_list ? P.row_list[prow] : (P.first_row + prow) % H;
     const uint32_t idx = row * W + col;
     float4 fs_ = P.film_sum[idx];
-    float4 sq = P.film_sq[idx];
     uint32_t n = __float_as_uint(fs_.w), id = kNoHit;
+    // sums of squares: a black sample adds +0 to sums that are never -0, so the Σrgb² record is only touched from the first
+    // non-black plane on (most pixels of a frame are black: no read, no write)
+    float4 sq = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool sq_loaded = false;
     for (uint32_t s = 0; s < P.n_planes; ++s) {
         const float4 c = __ldcg(&P.planes[((size_t)s * P.plane_rows_padded + prow) * W + col]);
         fs_.x = fadd(fs_.x, c.x);
         fs_.y = fadd(fs_.y, c.y);
         fs_.z = fadd(fs_.z, c.z);
-        sq.x = fadd(sq.x, fmul(c.x, c.x));
-        sq.y = fadd(sq.y, fmul(c.y, c.y));
-        sq.z = fadd(sq.z, fmul(c.z, c.z));
+        if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) {
+            if (!sq_loaded) {
+                sq = P.film_sq[idx];
+                sq_loaded = true;
+            }
+            sq.x = fadd(sq.x, fmul(c.x, c.x));
+            sq.y = fadd(sq.y, fmul(c.y, c.y));
+            sq.z = fadd(sq.z, fmul(c.z, c.z));
+        }
         n += 1u;
         id = __float_as_uint(c.w);
     }
     fs_.w = __uint_as_float(n);
     P.film_sum[idx] = fs_;
-    P.film_sq[idx] = sq;
+    if (sq_loaded) P.film_sq[idx] = sq;
     P.primary_ids[idx] = id;
-    const uint32_t px = tonemap_pack(fs_.x, fs_.y, fs_.z, n);
+    const uint32_t px = (fs_.x == 0.0f && fs_.y == 0.0f && fs_.z == 0.0f) ? 0xff000000u : tonemap_pack(fs_.x, fs_.y, fs_.z, n);
     P.ldr[idx] = px;
     if (P.ldr_remote) P.ldr_remote[idx] = px;
 }
