@@ -282,6 +282,60 @@ def test_pipelined_readback_delivers_every_frame(scenes):
     ref.close()
 
 
+def _subscene(scene, tri_index, lights=None):
+    """A scene made of some triangles of `scene` (same camera, materials and textures; optionally other lights)."""
+    from types import SimpleNamespace
+
+    idx = np.asarray(tri_index, dtype=np.int64)
+    return SimpleNamespace(vertices=scene.vertices[idx].copy(), tri_geom=scene.tri_geom[idx].copy(), materials=scene.materials,
+                           lights=scene.lights if lights is None else lights, textures=scene.textures,
+                           camera_orientation=scene.camera_orientation, camera_fov_deg=scene.camera_fov_deg)
+
+
+@pytest.mark.parametrize("accel,aname", ACCELS)
+def test_degenerate_scenes_and_ragged_image_sizes(scenes, accel, aname):
+    """Edge cases the tree builders and the tile schedule must survive: no triangle at all, one, two, a handful; image
+    sizes that are not multiples of the 8x4 tile; every structure against the oracle (ids exact except where a BVH may
+    resolve an exact tie differently, colour within 1 LSB)."""
+    full = scenes("ico2")
+    n = full.vertices.shape[0]
+    picks = [[], [n - 1], [n - 1, n - 2], list(range(n - 12, n)), list(range(0, n, 7))]
+    for tri in picks:
+        sub = _subscene(full, tri)
+        for w, h in [(101, 67), (64, 3)]:
+            o = Oracle(sub, w, h)
+            o.configure(recursions=0, jitter=JITTER_FIXED)
+            o.trace_rows(0, h, 1, threads=0)
+            t = gpu_tracer(sub, w, h, accel)
+            n_primary, n_shadow = t.trace_rows(0, h, 1)
+            assert n_primary == w * h and n_shadow == o.counters()["rays"]["shadow"], (len(tri), w, h)
+            check_frame(t, o, exact_ids=True)
+            t.close()
+
+
+@pytest.mark.parametrize("accel,aname", ACCELS)
+def test_several_lights_and_no_light(scenes, accel, aname):
+    """shade (mod.rs:214) loops over every light: two and three lights accumulate in light order; without a light every
+    hit is black. (The ray-pool kernel only takes single-light scenes; these run the tile kernel.)"""
+    full = scenes("ico2")
+    l0 = full.lights[0]
+    extra = [(np.array([-6.0, 9.0, 4.0], np.float32), np.array([3.0, 2.0, 1.0], np.float32)),
+             (np.array([2.0, 12.0, -7.0], np.float32), np.array([0.5, 4.0, 2.5], np.float32))]
+    w, h = 320, 240
+    for lights in ([l0, extra[0]], [l0] + extra, []):
+        sub = _subscene(full, range(full.vertices.shape[0]), lights=lights)
+        o = Oracle(sub, w, h)
+        o.configure(recursions=0, jitter=JITTER_FIXED)
+        o.trace_rows(0, h, 1, threads=0)
+        for variant in (1, 2):
+            t = gpu_tracer(sub, w, h, accel)
+            t.set_tuning(0, variant)
+            _, n_shadow = t.trace_rows(0, h, 1)
+            assert n_shadow == o.counters()["rays"]["shadow"]
+            check_frame(t, o, exact_ids=True)
+            t.close()
+
+
 def test_height_smaller_than_band(scenes):
     """height < 50: one call visits rows more than once, sequentially (mod.rs:87-114)."""
     w, h = 64, 20
