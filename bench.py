@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "peer_allreduce", "nccl"], help="N>1: how rank 0 receives the frame")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: samples per pixel per step = N (weak) or 1 (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tune", default="", help="developer: comma separated key=value pairs passed to rt_set_tuning")
     ap.add_argument("--sync-readback", action="store_true",
                     help="e2e leg (N=1): blocking rt_get_tonemapped_pixels after every trace call instead of the pipelined "
                          "rt_get_tonemapped_pixels_async (device->host copy of frame k overlapping the trace of frame k+1)")
@@ -276,6 +277,9 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     tracer = rt.RayTracer.from_scene(scene, cfg)
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        tracer.set_tuning(int(k), int(v))
     stream = torch.cuda.Stream(device=dev)
     tracer.set_stream(stream.cuda_stream)
 

@@ -1619,8 +1619,8 @@ constexpr int kSortBuckets = 2048;
 // the end of a launch is bounded by the slowest single item, and a warp that works on 8 instead of 32 divergent
 // rays has a much shorter serial chain. The extra items cost lanes, not time: they run while the GPU is full.
 __global__ void __launch_bounds__(1024) tile_sort_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n,
-                                                         uint32_t n_warps, uint32_t allow_split, unsigned long long* __restrict__ counters) {
-    // allow_split: 0 = never split; q > 0 = split tiles that cost more than (balanced launch time) * q / 4
+                                                         uint32_t n_warps, uint32_t split_quarters, unsigned long long* __restrict__ counters) {
+    // split_quarters: 0 = never split; q > 0 = split tiles that cost more than (balanced launch time) * q / 4
     __shared__ uint32_t hist[kSortBuckets];
     __shared__ uint32_t scan_tmp[1024];
     __shared__ unsigned long long total_cost;
@@ -1635,7 +1635,7 @@ __global__ void __launch_bounds__(1024) tile_sort_kernel(const uint32_t* __restr
     // stretch the tail, so only those are split (a launch of uniformly heavy tiles is left alone)
     const unsigned long long balanced = total_cost / (unsigned long long)max(n_warps, 1u);
     const uint32_t split_above =
-        allow_split ? (uint32_t)min((unsigned long long)0x7fffffffu, max(balanced * allow_split / 4ull, (unsigned long long)kSplitMinCycles)) : 0xffffffffu;
+        split_quarters ? (uint32_t)min((unsigned long long)0x7fffffffu, max(balanced * split_quarters / 4ull, (unsigned long long)kSplitMinCycles)) : 0xffffffffu;
     auto bucket = [](uint32_t c) {
         // 64 buckets per octave; reversed so that bucket 0 holds the most expensive items
         const int k = (int)(__log2f((float)c + 1.0f) * 64.0f);
