@@ -233,6 +233,10 @@ uint32_t rt_launch_param_bytes(void);
 /* RT_TUNE_SPLIT_QUARTERS (variant 1, BVH kernels): tiles whose recorded cost exceeds (balanced launch time) * q / 4 are
    handed out as four one-row items; 0 = never split (default 4). */
 #define RT_TUNE_SPLIT_QUARTERS 7
+/* RT_TUNE_QUEUE_BATCH / RT_TUNE_QUEUE_BATCH_FROM (variant 1): in the cheap tail of the cost-sorted tile queue — from
+   `from` percent of its length on — a warp claims `batch` slots with one atomic (defaults 4 and 33; batch 1 = off). */
+#define RT_TUNE_QUEUE_BATCH 8
+#define RT_TUNE_QUEUE_BATCH_FROM 9
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {

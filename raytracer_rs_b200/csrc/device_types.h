@@ -89,6 +89,7 @@ struct TraceParams {
     unsigned int* wf_counts;     // [0, kWfLevels): nodes per level; [kWfLevels, 2 kWfLevels): ray-queue head per level
     uint32_t wf_level;           // level processed by wf_bounce_kernel / wf_combine_kernel
     WfLevel wf[kWfLevels];
+    uint32_t queue_batch, queue_batch_from_pct;  // persistent kernel: slots claimed at a time in the cheap tail of the sorted queue
     uint32_t pool_refill;        // ray-pool kernel: idle lanes of a warp that trigger a refill
     uint32_t pool_min_inner;     // ray-pool kernel: the inner-node loop yields when fewer lanes than this still descend
     uint32_t magic_w, magic_h, magic_tiles_x;  // floor(2^32 / d) for d = width, height, tiles per row (udiv_magic)

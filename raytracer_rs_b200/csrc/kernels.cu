@@ -1137,22 +1137,32 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
     // The next queue slot is claimed when a tile's rays are done, before its film update: the atomic's round trip
     // (~1 us) overlaps the epilogue instead of sitting in front of the next tile, and the claim is early by so little
     // that the heaviest-first order is not disturbed (claiming a whole tile ahead was measured 10 % slower).
-    uint32_t slot = 0;
-    if (lane == 0) slot = (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], 1ull);
+    // In the cheap tail of the queue (with the cost-sorted order: the all-miss tiles, about a microsecond of work
+    // each) a warp claims kQueueBatch slots at a time, so the tail of the launch is not 3 552 warps queueing for one counter.
+    const uint32_t kQueueBatch = P.queue_batch;
+    const uint32_t batch_from = (P.tile_order && kQueueBatch > 1u) ? (uint32_t)((unsigned long long)n_items * P.queue_batch_from_pct / 100ull) : 0xffffffffu;
+    uint32_t slot = 0, slot_end = 0;  // this warp owns queue slots [slot, slot_end)
+    if (lane == 0) {
+        slot = (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], 1ull);
+        slot_end = slot + 1u;
+    }
     for (;;) {
         uint32_t item = 0;
+        bool last_of_batch = true;
         if (lane == 0) {
             // cost-feedback schedule: queue slot -> work item, heaviest tiles (by last frame's cycle count) first
             if (slot < n_items) item = P.tile_order ? P.tile_order[slot] : slot;
             else item = 0xffffffffu;
+            last_of_batch = slot + 1u >= slot_end;
         }
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item == 0xffffffffu) break;
         const uint32_t tile = item & kItemTileMask;
         const bool split = (item & kItemSplitFlag) != 0u;
         const uint32_t part = (item >> kItemPartShift) & 3u;
-        const uint32_t col = (tile % tiles_x) * 8u + (lane & 7u);
-        const uint32_t crow = (tile / tiles_x) * 4u + (lane >> 3);
+        const uint32_t tile_y = udiv_magic(tile, tiles_x, P.magic_tiles_x);
+        const uint32_t col = (tile - tile_y * tiles_x) * 8u + (lane & 7u);
+        const uint32_t crow = tile_y * 4u + (lane >> 3);
         const bool mine = col < P.cam.width && crow < P.n_rows && (!split || (lane >> 3) == part);
         const long long t0 = clock64();
 #ifdef RT_DEBUG_STEP_COUNTS
@@ -1163,7 +1173,15 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         pout.mode = 0u;
         if (mine) trace_pixel_radiance<ACCEL, 1, BOUNCE>(P, col, crow, cnt, pout);
         __syncwarp();
-        if (lane == 0) slot = (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], 1ull);
+        if (lane == 0) {
+            if (last_of_batch) {
+                const uint32_t k = slot >= batch_from ? kQueueBatch : 1u;
+                slot = (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], (unsigned long long)k);
+                slot_end = slot + k;
+            } else {
+                ++slot;
+            }
+        }
         if (mine) finish_pixel(P, pout);
         __syncwarp();
 #ifdef RT_DEBUG_STEP_COUNTS  // developer build only: (inner nodes visited | triangles tested << 16) instead of the primitive id

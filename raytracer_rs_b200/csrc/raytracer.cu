@@ -131,6 +131,7 @@ struct rt_raytracer {
     uint64_t total_kernels = 0, total_primary = 0;
     int variant = 1;            // RT_TUNE_KERNEL_VARIANT
     int split_quarters = 4;     // RT_TUNE_SPLIT_QUARTERS
+    int queue_batch = 4, queue_batch_from_pct = 33;  // RT_TUNE_QUEUE_BATCH, RT_TUNE_QUEUE_BATCH_FROM
     int pool_refill = 16;       // RT_TUNE_POOL_REFILL
     int pool_min_inner = 8;     // RT_TUNE_POOL_MIN_INNER
     int pool_blocks = 0;        // resident blocks per SM of the ray-pool kernel
@@ -543,6 +544,8 @@ struct rt_raytracer {
         const bool use_pool = variant == 2 && a == 1 && b == 0 && scene.lights.size() == 1 && !p.planes;
         if (use_pool && pool_blocks == 0) pool_blocks = pool_blocks_per_sm();
         if (!use_pool && variant != 0 && blocks_per_sm[a][b] == 0) blocks_per_sm[a][b] = persistent_blocks_per_sm(a, b);
+        p.queue_batch = (uint32_t)queue_batch;
+        p.queue_batch_from_pct = (uint32_t)queue_batch_from_pct;
         p.pool_refill = (uint32_t)pool_refill;
         p.pool_min_inner = (uint32_t)pool_min_inner;
         if (variant != 0 && lpt_schedule) {
@@ -1186,6 +1189,14 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     }
     if (key == RT_TUNE_POOL_REFILL && value >= 1 && value <= 32) {
         rt->pool_refill = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_QUEUE_BATCH && value >= 1 && value <= 64) {
+        rt->queue_batch = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_QUEUE_BATCH_FROM && value >= 0 && value <= 100) {
+        rt->queue_batch_from_pct = value;
         return RT_OK;
     }
     if (key == RT_TUNE_SPLIT_QUARTERS && value >= 0 && value <= 64) {
