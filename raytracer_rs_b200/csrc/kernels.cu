@@ -419,11 +419,12 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
             const float f1 = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), best.t));
             const bool h0 = n0 <= f0, h1 = n1 <= f1;
             const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-            // one branch instead of four: the far child is stored unconditionally and kept only if both children hit
             const bool go1 = h1 && (!h0 || n1 < n0);  // child 1 first (child 0 wins ties, as before)
-            stack_node[sp] = go1 ? c0 : c1;
-            stack_t[sp] = go1 ? n0 : n1;
-            sp += (h0 && h1) ? 1 : 0;
+            if (h0 && h1) {  // the far child waits on the stack (predicated stores: no local-memory traffic otherwise)
+                stack_node[sp] = go1 ? c0 : c1;
+                stack_t[sp] = go1 ? n0 : n1;
+                ++sp;
+            }
             if (h0 || h1) {
                 cur = go1 ? c1 : c0;
             } else {
@@ -539,15 +540,21 @@ __device__ __forceinline__ bool bvh4_closest_hit_ww(const TraceParams& P, const 
             cswap_near(d1, c1, d3, c3);
             cswap_near(d1, c1, d2, c2);
             // far to near; an entry is kept only if its child was entered (misses sort to the end as +inf)
-            stack_node[sp] = c3;
-            stack_t[sp] = d3;
-            sp += d3 < kMiss ? 1 : 0;
-            stack_node[sp] = c2;
-            stack_t[sp] = d2;
-            sp += d2 < kMiss ? 1 : 0;
-            stack_node[sp] = c1;
-            stack_t[sp] = d1;
-            sp += d1 < kMiss ? 1 : 0;
+            if (d1 < kMiss) {  // d1 <= d2 <= d3: nothing to push unless at least two children were entered
+                if (d3 < kMiss) {
+                    stack_node[sp] = c3;
+                    stack_t[sp] = d3;
+                    ++sp;
+                }
+                if (d2 < kMiss) {
+                    stack_node[sp] = c2;
+                    stack_t[sp] = d2;
+                    ++sp;
+                }
+                stack_node[sp] = c1;
+                stack_t[sp] = d1;
+                ++sp;
+            }
             if (d0 < kMiss) {
                 cur = c0;
             } else {
@@ -1528,9 +1535,11 @@ __global__ void __launch_bounds__(32 * kPoolWarps, 3) trace_shade_pool_kernel(co
                 const bool h0 = n0 <= f0, h1 = n1 <= f1;
                 const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
                 const bool go1 = h1 && (!h0 || n1 < n0);
-                stack_node[sp] = go1 ? c0 : c1;
-                stack_t[sp] = go1 ? n0 : n1;
-                sp += (h0 && h1) ? 1 : 0;
+                if (h0 && h1) {
+                    stack_node[sp] = go1 ? c0 : c1;
+                    stack_t[sp] = go1 ? n0 : n1;
+                    ++sp;
+                }
                 ++steps;
                 if (h0 || h1) {
                     cur = go1 ? c1 : c0;
