@@ -1640,23 +1640,37 @@ __global__ void __launch_bounds__(32 * kPoolWarps, 3) trace_shade_pool_kernel(co
 // cheap all-miss tiles fill the end of the launch, so no warp is still inside a 500k-cycle tile when the queue
 // runs dry. Only the schedule depends on it; pixel results do not.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kSortBuckets = 2048;
+constexpr int kSortBuckets = 256;  // 8 per octave of cost
+constexpr int kSortWarps = 32;
 // Items: bits 0..27 tile id, bits 28..29 part (pixel row of the 8x4 tile), bit 31 "split" flag.
 // A tile whose cost exceeds split_quarters/4 of the balanced launch time becomes four items (one pixel row each):
 // the end of a launch is bounded by the slowest single item, and a warp that works on 8 instead of 32 divergent
 // rays has a much shorter serial chain. The extra items cost lanes, not time: they run while the GPU is full.
-__global__ void __launch_bounds__(1024) tile_sort_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n,
-                                                         uint32_t n_warps, uint32_t split_quarters, unsigned long long* __restrict__ counters) {
+//
+// One block. Most tiles of a frame cost about the same (the all-miss tiles), so a shared histogram would see tens of
+// thousands of atomics on one address: every warp keeps a PRIVATE histogram (32 x 256 counters) and owns a contiguous
+// chunk of the tiles, which also keeps tiles of equal cost in image order (neighbouring tiles stay neighbours in the queue).
+__global__ void __launch_bounds__(32 * kSortWarps) tile_sort_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n,
+                                                                     uint32_t n_warps, uint32_t split_quarters,
+                                                                     unsigned long long* __restrict__ counters) {
     // split_quarters: 0 = never split; q > 0 = split tiles that cost more than (balanced launch time) * q / 4
-    __shared__ uint32_t hist[kSortBuckets];
-    __shared__ uint32_t scan_tmp[1024];
+    __shared__ uint32_t hist[kSortWarps][kSortBuckets];  // counts, then write cursors, per warp and bucket
+    __shared__ uint32_t bucket_base[kSortBuckets];
     __shared__ unsigned long long total_cost;
-    for (int b = threadIdx.x; b < kSortBuckets; b += blockDim.x) hist[b] = 0;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kSortWarps * kSortBuckets; i += blockDim.x) (&hist[0][0])[i] = 0u;
     if (threadIdx.x == 0) total_cost = 0;
     __syncthreads();
+    const uint32_t chunk = (n + kSortWarps - 1u) / kSortWarps;
+    const uint32_t begin = min(warp * chunk, n), end = min(begin + chunk, n);
     unsigned long long local_sum = 0;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) local_sum += cost[i];
-    atomicAdd(&total_cost, local_sum);
+    for (uint32_t i = begin + lane; i < end; i += 32u) local_sum += cost[i];
+    local_sum += __shfl_xor_sync(0xffffffffu, local_sum, 16);
+    local_sum += __shfl_xor_sync(0xffffffffu, local_sum, 8);
+    local_sum += __shfl_xor_sync(0xffffffffu, local_sum, 4);
+    local_sum += __shfl_xor_sync(0xffffffffu, local_sum, 2);
+    local_sum += __shfl_xor_sync(0xffffffffu, local_sum, 1);
+    if (lane == 0) atomicAdd(&total_cost, local_sum);
     __syncthreads();
     // a perfectly balanced launch would take total / n_warps; only tiles that alone exceed a fraction of that can
     // stretch the tail, so only those are split (a launch of uniformly heavy tiles is left alone)
@@ -1664,55 +1678,58 @@ __global__ void __launch_bounds__(1024) tile_sort_kernel(const uint32_t* __restr
     const uint32_t split_above =
         split_quarters ? (uint32_t)min((unsigned long long)0x7fffffffu, max(balanced * split_quarters / 4ull, (unsigned long long)kSplitMinCycles)) : 0xffffffffu;
     auto bucket = [](uint32_t c) {
-        // 64 buckets per octave; reversed so that bucket 0 holds the most expensive items
-        const int k = (int)(__log2f((float)c + 1.0f) * 64.0f);
+        // 8 buckets per octave; reversed so that bucket 0 holds the most expensive items
+        const int k = (int)(__log2f((float)c + 1.0f) * 8.0f);
         return (uint32_t)(kSortBuckets - 1 - min(max(k, 0), kSortBuckets - 1));
     };
-    // most tiles of a frame cost about the same (all-miss tiles): aggregate equal buckets inside a warp before the
-    // shared-memory atomic, otherwise tens of thousands of atomics serialise on one address
-    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    const uint32_t n_round = (n + blockDim.x - 1u) / blockDim.x * blockDim.x;
-    for (uint32_t i = threadIdx.x; i < n_round; i += blockDim.x) {
-        const bool have = i < n;
-        const uint32_t c = have ? cost[i] : 0u;
-        const bool sp = have && c >= split_above;
-        const uint32_t b = have ? bucket(sp ? c / 4u : c) : 0xffffffffu, w = sp ? 4u : 1u;
-        const uint32_t same = __match_any_sync(0xffffffffu, (b << 1) | (sp ? 1u : 0u));  // same bucket and same weight
-        if (have && (same & lt) == 0u) atomicAdd(&hist[b], w * (uint32_t)__popc(same));
+    for (uint32_t i = begin + lane; i < end; i += 32u) {
+        const uint32_t c = cost[i];
+        if (c >= split_above) atomicAdd(&hist[warp][bucket(c / 4u)], 4u);
+        else atomicAdd(&hist[warp][bucket(c)], 1u);
     }
     __syncthreads();
-    // exclusive scan of 2048 buckets: each thread owns two adjacent buckets
-    const uint32_t a = hist[2 * threadIdx.x], b2 = hist[2 * threadIdx.x + 1];
-    scan_tmp[threadIdx.x] = a + b2;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        const uint32_t v = threadIdx.x >= (unsigned)off ? scan_tmp[threadIdx.x - off] : 0u;
-        __syncthreads();
-        scan_tmp[threadIdx.x] += v;
-        __syncthreads();
+    // bucket totals -> exclusive scan over buckets -> per-warp write cursors (warp-major inside a bucket = image order)
+    if (threadIdx.x < kSortBuckets) {
+        uint32_t t = 0;
+        for (int w = 0; w < kSortWarps; ++w) t += hist[w][threadIdx.x];
+        bucket_base[threadIdx.x] = t;
     }
-    if (threadIdx.x == 1023) counters[CNT_QUEUE_ITEMS] = scan_tmp[1023];
-    const uint32_t base = scan_tmp[threadIdx.x] - (a + b2);
-    hist[2 * threadIdx.x] = base;
-    hist[2 * threadIdx.x + 1] = base + a;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n_round; i += blockDim.x) {
-        const bool have = i < n;
-        const uint32_t c = have ? cost[i] : 0u;
-        const bool sp = have && c >= split_above;
-        const uint32_t b = have ? bucket(sp ? c / 4u : c) : 0xffffffffu, w = sp ? 4u : 1u;
-        const uint32_t same = __match_any_sync(0xffffffffu, (b << 1) | (sp ? 1u : 0u));
-        const uint32_t leader = (uint32_t)__ffs((int)same) - 1u;
-        uint32_t base = 0u;
-        if (have && lane == leader) base = atomicAdd(&hist[b], w * (uint32_t)__popc(same));
-        base = __shfl_sync(0xffffffffu, base, (int)leader);
-        if (have) {
-            const uint32_t at = base + w * (uint32_t)__popc(same & lt);
-            if (sp) {
-                for (uint32_t part = 0; part < 4u; ++part) order[at + part] = i | (part << kItemPartShift) | kItemSplitFlag;
-            } else {
-                order[at] = i;
-            }
+    if (warp == 0) {  // 256 buckets: 8 per lane
+        uint32_t v[8], sum = 0;
+        for (int k = 0; k < 8; ++k) {
+            v[k] = bucket_base[lane * 8 + k];
+            sum += v[k];
+        }
+        uint32_t incl = sum;
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= (uint32_t)off) incl += o;
+        }
+        uint32_t run = incl - sum;
+        for (int k = 0; k < 8; ++k) {
+            bucket_base[lane * 8 + k] = run;
+            run += v[k];
+        }
+        if (lane == 31) counters[CNT_QUEUE_ITEMS] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x < kSortBuckets) {
+        uint32_t run = bucket_base[threadIdx.x];
+        for (int w = 0; w < kSortWarps; ++w) {
+            const uint32_t c = hist[w][threadIdx.x];
+            hist[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = begin + lane; i < end; i += 32u) {
+        const uint32_t c = cost[i];
+        if (c >= split_above) {
+            const uint32_t at = atomicAdd(&hist[warp][bucket(c / 4u)], 4u);
+            for (uint32_t part = 0; part < 4u; ++part) order[at + part] = i | (part << kItemPartShift) | kItemSplitFlag;
+        } else {
+            order[atomicAdd(&hist[warp][bucket(c)], 1u)] = i;
         }
     }
 }
@@ -2007,7 +2024,7 @@ int persistent_blocks_per_sm(int accel, int bounce) {
 }
 cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, uint32_t n_warps, uint32_t split_quarters,
                              unsigned long long* counters, cudaStream_t stream) {
-    tile_sort_kernel<<<1, 1024, 0, stream>>>(cost, order, n, n_warps, split_quarters, counters);
+    tile_sort_kernel<<<1, 32 * kSortWarps, 0, stream>>>(cost, order, n, n_warps, split_quarters, counters);
     return cudaGetLastError();
 }
 cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream) {
