@@ -464,6 +464,12 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic if world == 1 and spp == 1 else None,
                     "peak_source": peak_src, "kernel": "trace_shade_persistent_kernel<%s>" % args.accel, "kernel_ms": kms,
                     "algorithmic_bytes_per_launch": per_launch, "note": note}
+        if roofline["traffic"]:
+            # what actually crosses the HBM interface (ncu dram__bytes of one launch, profiles/traffic.json): the film
+            roofline["dram_achieved"] = roofline["traffic"] / (kms * 1e-3) / 1e9
+            roofline["dram_frac"] = roofline["dram_achieved"] / peak
+            roofline["bound_in_practice"] = ("instruction issue at partly filled warps + latency of dependent node loads "
+                                             "(ncu: issue slots 65 % busy, 22 of 32 lanes active; profiles/README.md)")
     line = {
         "metric": METRIC,
         "value": value,
