@@ -8,6 +8,17 @@
 // (__fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn/__fsqrt_rn). They are never contracted into FMAs, so the results are
 // bit-identical to the reference's Rust f32 arithmetic (and to oracle/rt_oracle.cpp) regardless of compiler flags.
 // BVH box tests are allowed to use FMAs because the boxes are padded and only decide which triangles get tested.
+//
+// Kernels in this file:
+//   trace_shade_persistent_kernel<ACCEL, BOUNCE>  the default: persistent warps, cost-sorted 8x4 tile queue (variant 1)
+//   trace_shade_kernel<ACCEL, BOUNCE>             one thread per pixel (variant 0, kept for A/B runs)
+//   trace_shade_pool_kernel                       ray pool with shared-memory ray rings (variant 2)
+//   wf_bounce_kernel<ACCEL>, wf_combine_kernel    bounce wavefront (RECURSIONS > 0)
+//   film_accumulate_kernel                        ordered accumulation of the sample planes of a multi-sample launch
+//   tile_sort_kernel                              heaviest-first order of the tile queue from last launch's tile costs
+//   flag_signal_kernel, flag_wait_kernel          cross-GPU frame fence of the fused peer-store gather
+//   film_clear_kernel, tonemap_pack_kernel, gather_rows_kernel
+// ACCEL: 0 exact octree, 1 binary BVH (host SAH or GPU LBVH), 2 compressed 8-wide BVH, 3 4-wide BVH.
 #include <cuda_runtime.h>
 
 #include <cfloat>
