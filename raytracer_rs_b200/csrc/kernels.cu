@@ -1032,7 +1032,6 @@ __device__ __forceinline__ void wf_store_node(const TraceParams& P, uint32_t lev
 
 // What trace_pixel_radiance leaves for finish_pixel: the radiance of one pixel sample and where it goes.
 struct PixelOut {
-    float4 fs_;            // the pixel's film sums before this sample
     float cr, cg, cb;
     uint32_t idx, id, plane_slot;
     uint32_t mode;         // 0 nothing left to do, 1 add to the film, 2 store to a sample plane
@@ -1052,8 +1051,9 @@ __device__ __forceinline__ void trace_pixel_radiance(const TraceParams& P, uint3
     }
     const uint32_t row = P.row_list ? P.row_list[prow] : (P.first_row + prow) % H;
     const uint32_t idx = row * W + col;
-    const float4 fs_ = P.film_sum[idx];
-    const uint32_t nsamp = __float_as_uint(fs_.w) + plane;  // the number this sample will have in the film
+    // the sample's number in the film only matters for the hashed sub-pixel offset and the bounce directions; the film
+    // record itself is read when the sample is added (finish_pixel), not kept in registers through the traversal
+    const uint32_t nsamp = (P.jitter_mode == 1 || BOUNCE != 0) ? __float_as_uint(P.film_sum[idx].w) + plane : 0u;
     const V3 d = camera_ray_dir(P, idx, col, nsamp);
     const V3 o = {P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]};
 
@@ -1077,7 +1077,6 @@ __device__ __forceinline__ void trace_pixel_radiance(const TraceParams& P, uint3
             shade_hit<ACCEL, WW>(P, o, d, hit, &nrm, &cr, &cg, &cb, cnt);
         }
     }
-    out.fs_ = fs_;
     out.cr = cr;
     out.cg = cg;
     out.cb = cb;
@@ -1092,7 +1091,7 @@ __device__ __forceinline__ void finish_pixel(const TraceParams& P, const PixelOu
         P.planes[out.plane_slot] = make_float4(out.cr, out.cg, out.cb, __uint_as_float(out.id));
     } else if (out.mode == 1u) {
         P.primary_ids[out.idx] = out.id;
-        film_add_sample(P, out.idx, out.fs_, out.cr, out.cg, out.cb);
+        film_add_sample(P, out.idx, P.film_sum[out.idx], out.cr, out.cg, out.cb);
     }
 }
 template <int ACCEL, int WW, int BOUNCE>
