@@ -399,10 +399,8 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
     const uint32_t mask = __activemask();
     const float ix = rcp_approx(d.x), iy = rcp_approx(d.y), iz = rcp_approx(d.z);  // box tests only (padded boxes)
     const float ox = -o.x * ix, oy = -o.y * iy, oz = -o.z * iz;
-    int stack_node[kBvhStack];
-    float stack_t[kBvhStack];
-    stack_node[0] = kSentinel;
-    stack_t[0] = -FLT_MAX;
+    int2 stack[kBvhStack];  // (node reference, entry distance as float bits): one 8-byte local store / load per entry
+    stack[0] = make_int2(kSentinel, __float_as_int(-FLT_MAX));
     int sp = 1;
     HitRec best;
     best.t = t_limit;
@@ -432,17 +430,17 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
             const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
             const bool go1 = h1 && (!h0 || n1 < n0);  // child 1 first (child 0 wins ties, as before)
             if (h0 && h1) {  // the far child waits on the stack (predicated stores: no local-memory traffic otherwise)
-                stack_node[sp] = go1 ? c0 : c1;
-                stack_t[sp] = go1 ? n0 : n1;
+                stack[sp] = make_int2(go1 ? c0 : c1, __float_as_int(go1 ? n0 : n1));
                 ++sp;
             }
             if (h0 || h1) {
                 cur = go1 ? c1 : c0;
             } else {
+                int2 e;
                 do {
-                    --sp;
-                    cur = stack_node[sp];
-                } while (stack_t[sp] > best.t);
+                    e = stack[--sp];
+                } while (__int_as_float(e.y) > best.t);
+                cur = e.x;
             }
         }
         if (cur != kSentinel) {  // leaf
@@ -471,10 +469,11 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
             if (early) {
                 cur = kSentinel;
             } else {
+                int2 e;
                 do {
-                    --sp;
-                    cur = stack_node[sp];
-                } while (stack_t[sp] > best.t);
+                    e = stack[--sp];
+                } while (__int_as_float(e.y) > best.t);
+                cur = e.x;
             }
         }
     }
