@@ -23,7 +23,7 @@
 namespace rtb {
 namespace {
 
-constexpr int kSortChunk = 1024;  // keys per (one-warp) block of the radix passes
+constexpr int kSortChunk = 256;  // keys per (one-warp) block of the radix passes
 constexpr uint32_t kLeafMax = 4;
 
 __device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {  // 10 bits -> every third bit
