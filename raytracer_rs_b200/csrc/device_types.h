@@ -36,14 +36,16 @@ constexpr int kCwStack = 32;  // node groups only: at most one per level plus sl
 enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3, CNT_TILE_QUEUE = 4, CNT_QUEUE_ITEMS = 5,
                    CNT_SHADOW_TOTAL = 6, CNT_BOUNCE_TOTAL = 7, CNT_SLOTS = 8 };
 
-// one level of the bounce wavefront: dense list of shaded hits (3 float4 per node: hit point | pixel, normal | path,
-// shaded radiance | parent + child number) and, per node, the radiance its n_children bounce rays bring back
+// one level of the bounce wavefront: dense list of shaded hits (node record: hit point | pixel, normal | path,
+// shaded radiance | parent + child number; before wf_shade_kernel: ray origin | pixel, direction | path, t u v | triangle,
+// parent + child number) and, per node, the radiance its n_children bounce rays bring back
 struct WfLevel {
     float4* rec;
     float* child_r;  // cap * n_children * 3
     uint32_t cap, n_children;
 };
-constexpr int kWfLevels = 5;  // recursions <= 4
+constexpr int kWfLevels = 5;    // recursions <= 4
+constexpr int kWfRecWords = 4;  // float4 per node record (the 4th holds parent + child number while a hit waits for shading)
 
 struct TraceParams {
     DevCamera cam;
@@ -86,7 +88,7 @@ struct TraceParams {
     uint32_t sub_spread;         // SUB_SPREAD (mod.rs:82)
     const float* sample_table;   // 65 536 unit vectors (sample_generator.rs), 3 floats each
     // bounce wavefront (null wf_counts = bounce rays are walked depth first inside the trace kernel)
-    unsigned int* wf_counts;     // [0, kWfLevels): nodes per level; [kWfLevels, 2 kWfLevels): ray-queue head per level
+    unsigned int* wf_counts;     // [0, L): nodes per level; [L, 2L): ray-queue head per level; [2L, 3L): shade-queue head (L = kWfLevels)
     uint32_t wf_level;           // level processed by wf_bounce_kernel / wf_combine_kernel
     WfLevel wf[kWfLevels];
     uint32_t queue_batch, queue_batch_from_pct;  // persistent kernel: slots claimed at a time in the cheap tail of the sorted queue

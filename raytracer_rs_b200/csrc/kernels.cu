@@ -13,7 +13,7 @@
 //   trace_shade_persistent_kernel<ACCEL, BOUNCE>  the default: persistent warps, cost-sorted 8x4 tile queue (variant 1)
 //   trace_shade_kernel<ACCEL, BOUNCE>             one thread per pixel (variant 0, kept for A/B runs)
 //   trace_shade_pool_kernel                       ray pool with shared-memory ray rings (variant 2)
-//   wf_bounce_kernel<ACCEL>, wf_combine_kernel    bounce wavefront (RECURSIONS > 0)
+//   wf_bounce_kernel<ACCEL>, wf_shade_kernel<ACCEL>, wf_combine_kernel    bounce wavefront (RECURSIONS > 0)
 //   film_accumulate_kernel                        ordered accumulation of the sample planes of a multi-sample launch
 //   tile_sort_kernel                              heaviest-first order of the tile queue from last launch's tile costs
 //   flag_signal_kernel, flag_wait_kernel          cross-GPU frame fence of the fused peer-store gather
@@ -1003,7 +1003,8 @@ __device__ __forceinline__ void film_add_sample(const TraceParams& P, uint32_t i
 // other in the few lanes of a pixel tile that hit something:
 //   trace kernel (BOUNCE = 2)   camera ray -> closest hit -> shade (shadow ray) -> level-0 node {hit point, normal, S, pixel}
 //   wf_bounce_kernel, level l   one thread per (node, k): bounce direction k of that node (same hash/table walk as the
-//                               depth-first code, so the rays are the same), closest hit, shade -> level-(l+1) node
+//                               depth-first code, so the rays are the same), closest hit -> compacted pending record
+//   wf_shade_kernel, level l+1  one thread per pending record: shade (shadow ray) -> level-(l+1) node
 //   wf_combine_kernel, level l  bottom up: R = S + (sum over k of R_child_k) * (1 / n) with the children in k order
 //                               (a missing child is the +0 the reference adds for RGB::black), handed to the parent's
 //                               slot k; level 0 adds R to the film
@@ -1022,7 +1023,7 @@ __device__ __forceinline__ void wf_store_node(const TraceParams& P, uint32_t lev
                                               uint32_t path, float sr, float sg, float sb, uint32_t parent, uint32_t k) {
     const WfLevel& L = P.wf[level];
     if (slot >= L.cap) return;  // cannot happen: capacities are worst case
-    float4* rec = L.rec + 3 * (size_t)slot;
+    float4* rec = L.rec + kWfRecWords * (size_t)slot;
     rec[0] = make_float4(hp.x, hp.y, hp.z, __uint_as_float(pixel));
     rec[1] = make_float4(nrm.x, nrm.y, nrm.z, __uint_as_float(path));
     rec[2] = make_float4(sr, sg, sb, __uint_as_float(parent | (k << 28)));
@@ -1889,7 +1890,7 @@ __global__ void __launch_bounds__(256) wf_bounce_kernel(const __grid_constant__ 
         const uint32_t j = base + lane;
         if (j >= total) continue;
         const uint32_t parent = j / nch, k = j - parent * nch;
-        const float4 r0 = L.rec[3 * (size_t)parent], r1 = L.rec[3 * (size_t)parent + 1];
+        const float4 r0 = L.rec[kWfRecWords * (size_t)parent], r1 = L.rec[kWfRecWords * (size_t)parent + 1];
         const V3 hp0 = {r0.x, r0.y, r0.z}, normal = {r1.x, r1.y, r1.z};
         const uint32_t pixel = __float_as_uint(r0.w), path = __float_as_uint(r1.w);
         const uint32_t sample = __float_as_uint(P.film_sum[pixel].w);  // the film is not touched before the last combine
@@ -1905,12 +1906,51 @@ __global__ void __launch_bounds__(256) wf_bounce_kernel(const __grid_constant__ 
         cnt.bounce_rays += 1;
         HitRec h;
         if (closest_hit<ACCEL, 1>(P, o2, rd, &h)) {
-            V3 nrm;
-            float cr, cg, cb;
-            shade_hit<ACCEL, 1>(P, o2, rd, h, &nrm, &cr, &cg, &cb, cnt);
+            // only ~30 % of the bounce rays hit something: the hits are compacted first and shaded (shadow ray) by
+            // wf_shade_kernel with full warps, instead of shading here in the few lanes that hit
             const uint32_t slot = wf_append(&P.wf_counts[l + 1u]);
-            wf_store_node(P, l + 1u, slot, vadd(o2, vscale(rd, h.t)), pixel, nrm, sub_path, cr, cg, cb, parent, k);
+            const WfLevel& N = P.wf[l + 1u];
+            if (slot < N.cap) {
+                float4* rec = N.rec + kWfRecWords * (size_t)slot;
+                rec[0] = make_float4(o2.x, o2.y, o2.z, __uint_as_float(pixel));
+                rec[1] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(sub_path));
+                rec[2] = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
+                rec[3] = make_float4(__uint_as_float(parent | (k << 28)), 0.f, 0.f, 0.f);
+            }
         }
+    }
+    flush_counters(P, cnt, lane);
+}
+
+// shades the compacted hits of level P.wf_level (shade, mod.rs:207-261, with its shadow ray) and turns the pending records
+// {ray, hit} into node records {hit point, normal, shaded radiance}
+template <int ACCEL>
+__global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ TraceParams P) {
+    const uint32_t l = P.wf_level;
+    const WfLevel& L = P.wf[l];
+    const uint32_t total = min(P.wf_counts[l], L.cap);
+    LaneCounters cnt;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&P.wf_counts[2 * kWfLevels + l], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        const uint32_t i = base + lane;
+        if (i >= total) continue;
+        const float4* rec = L.rec + kWfRecWords * (size_t)i;
+        const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+        const V3 o2 = {r0.x, r0.y, r0.z}, rd = {r1.x, r1.y, r1.z};
+        HitRec h;
+        h.t = r2.x;
+        h.u = r2.y;
+        h.v = r2.z;
+        h.tri = __float_as_uint(r2.w);
+        V3 nrm;
+        float cr, cg, cb;
+        shade_hit<ACCEL, 1>(P, o2, rd, h, &nrm, &cr, &cg, &cb, cnt);
+        const uint32_t pk = __float_as_uint(r3.x);
+        wf_store_node(P, l, i, vadd(o2, vscale(rd, h.t)), __float_as_uint(r0.w), nrm, __float_as_uint(r1.w), cr, cg, cb, pk & 0x0fffffffu, pk >> 28);
     }
     flush_counters(P, cnt, lane);
 }
@@ -1920,7 +1960,7 @@ __global__ void __launch_bounds__(256) wf_combine_kernel(const __grid_constant__
     const WfLevel& L = P.wf[l];
     const uint32_t n_nodes = min(P.wf_counts[l], L.cap), nch = L.n_children;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
-        const float4 r2 = L.rec[3 * (size_t)i + 2];
+        const float4 r2 = L.rec[kWfRecWords * (size_t)i + 2];
         float rr = r2.x, rg = r2.y, rb = r2.z;
         if (nch > 0u) {  // radiance + fold(sum) * (1.0 / num_sub_rays)   (mod.rs:154-175)
             float sr = 0.f, sg = 0.f, sb = 0.f;
@@ -1936,7 +1976,7 @@ __global__ void __launch_bounds__(256) wf_combine_kernel(const __grid_constant__
             rb = fadd(rb, fmul(sb, inv));
         }
         if (l == 0u) {
-            const uint32_t pixel = __float_as_uint(L.rec[3 * (size_t)i].w);
+            const uint32_t pixel = __float_as_uint(L.rec[kWfRecWords * (size_t)i].w);
             film_add_sample(P, pixel, P.film_sum[pixel], rr, rg, rb);
         } else {
             const uint32_t pk = __float_as_uint(r2.w), parent = pk & 0x0fffffffu, k = pk >> 28;
@@ -2001,6 +2041,16 @@ cudaError_t launch_wf_bounce(const TraceParams& p, int accel, int blocks, cudaSt
         case 1: wf_bounce_kernel<1><<<blocks, 256, 0, stream>>>(p); break;
         case 2: wf_bounce_kernel<2><<<blocks, 256, 0, stream>>>(p); break;
         case 3: wf_bounce_kernel<3><<<blocks, 256, 0, stream>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_wf_shade(const TraceParams& p, int accel, int blocks, cudaStream_t stream) {
+    switch (accel) {
+        case 0: wf_shade_kernel<0><<<blocks, 256, 0, stream>>>(p); break;
+        case 1: wf_shade_kernel<1><<<blocks, 256, 0, stream>>>(p); break;
+        case 2: wf_shade_kernel<2><<<blocks, 256, 0, stream>>>(p); break;
+        case 3: wf_shade_kernel<3><<<blocks, 256, 0, stream>>>(p); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -13,6 +13,7 @@ cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persi
 int persistent_blocks_per_sm(int accel, int bounce);
 // bounce wavefront: level p.wf_level -> level + 1 (one thread per (node, bounce ray)); bottom-up radiance combine
 cudaError_t launch_wf_bounce(const TraceParams& p, int accel, int blocks, cudaStream_t stream);
+cudaError_t launch_wf_shade(const TraceParams& p, int accel, int blocks, cudaStream_t stream);
 cudaError_t launch_wf_combine(const TraceParams& p, int blocks, cudaStream_t stream);
 // variant 2 (ray pool: binary BVH, recursions 0, one light; other configurations run variant 1)
 int pool_blocks_per_sm();

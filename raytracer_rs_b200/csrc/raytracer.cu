@@ -615,7 +615,7 @@ struct rt_raytracer {
             cap[l] = c;
             nch[l] = cfg.sub_spread * (uint32_t)(R - l);
             if (cap[l] >= (size_t(1) << 28)) return false;  // parent index has 28 bits
-            recs += 3 * cap[l];
+            recs += kWfRecWords * cap[l];
             childs += 3 * cap[l] * nch[l];
             if (nch[l] > 15u) return false;  // child number has 4 bits
             c *= std::max<size_t>(nch[l], 1);
@@ -638,7 +638,7 @@ struct rt_raytracer {
         wf_layout(p, cap, nch, &rec_total, &child_total);
         if (d_wf_rec.n < rec_total) d_wf_rec.alloc(rec_total);
         if (d_wf_child.n < std::max<size_t>(child_total, 1)) d_wf_child.alloc(std::max<size_t>(child_total, 1));
-        if (!d_wf_counts.p) d_wf_counts.alloc(2 * kWfLevels);  // nodes per level | ray-queue head per level
+        if (!d_wf_counts.p) d_wf_counts.alloc(3 * kWfLevels);  // nodes per level | ray-queue head | shade-queue head
         const int R = cfg.recursions;
         size_t ro = 0, co = 0;
         for (int l = 0; l <= R; ++l) {
@@ -646,24 +646,26 @@ struct rt_raytracer {
             p.wf[l].child_r = d_wf_child.p + co;
             p.wf[l].cap = (uint32_t)cap[l];
             p.wf[l].n_children = nch[l];
-            ro += 3 * cap[l];
+            ro += kWfRecWords * cap[l];
             co += 3 * cap[l] * nch[l];
         }
         p.wf_counts = d_wf_counts.p;
-        RT_CUDA_RET(cudaMemsetAsync(d_wf_counts.p, 0, 2 * kWfLevels * sizeof(unsigned int), stream));
+        RT_CUDA_RET(cudaMemsetAsync(d_wf_counts.p, 0, 3 * kWfLevels * sizeof(unsigned int), stream));
         if (blocks_per_sm[a][0] == 0) blocks_per_sm[a][0] = persistent_blocks_per_sm(a, 0);
         RT_CUDA_RET(launch_trace(p, a, 1, blocks_per_sm[a][0] * num_sms, stream));
         const int wf_blocks = num_sms * 3;  // 80 registers: three 256-thread blocks per SM
-        for (int l = 0; l < R; ++l) {  // level l -> l + 1
+        for (int l = 0; l < R; ++l) {  // level l -> l + 1: trace the bounce rays, then shade the compacted hits
             p.wf_level = (uint32_t)l;
             RT_CUDA_RET(launch_wf_bounce(p, a, wf_blocks, stream));
+            p.wf_level = (uint32_t)(l + 1);
+            RT_CUDA_RET(launch_wf_shade(p, a, wf_blocks, stream));
         }
         for (int l = R; l >= 0; --l) {  // bottom up; level 0 adds the radiance to the film
             p.wf_level = (uint32_t)l;
             RT_CUDA_RET(launch_wf_combine(p, wf_blocks, stream));
         }
-        total_kernels += (uint64_t)(2 * R + 1);
-        last.kernels_launched += (uint32_t)(2 * R + 1);
+        total_kernels += (uint64_t)(3 * R + 1);
+        last.kernels_launched += (uint32_t)(3 * R + 1);
         return cudaSuccess;
     }
 
