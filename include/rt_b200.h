@@ -223,8 +223,11 @@ uint32_t rt_launch_param_bytes(void);
 /* RT_TUNE_POOL_MIN_INNER: the ray-pool kernel leaves its inner-node loop when fewer lanes than this are still
    descending while other lanes wait at a leaf or with a finished ray (0..32, default 8; 0 = classic while-while). */
 #define RT_TUNE_POOL_MIN_INNER 4
-/* RT_TUNE_MULTI_SAMPLE_LAUNCH: 1 (default) rt_trace_rows with spp > 1 traces all samples of the pass in one launch
-   (per-sample radiance planes + one ordered accumulation into the film); 0 one launch per sample. Same film either way. */
+/* RT_TUNE_MULTI_SAMPLE_LAUNCH: how rt_trace_rows handles spp > 1. 1 (default): even spp on the persistent kernel use
+   sample lanes — the 32 lanes of a warp item trace 8, 4 or 2 samples of 4, 8 or 16 pixels and add them to the film in
+   sample order (spp/8, spp/4 or spp/2 launches, no intermediate buffer); everything else traces all samples in one launch
+   into per-sample radiance planes followed by one ordered accumulation pass. 2: always planes. 0: one launch per
+   sample. Same film in every mode. */
 #define RT_TUNE_MULTI_SAMPLE_LAUNCH 5
 /* RT_TUNE_BOUNCE_WAVEFRONT: 1 (default) bounce rays (recursions > 0) run as a wavefront — the hits of every level are
    compacted into a dense list and the next level's rays fill whole warps; 0 every pixel walks its bounce tree depth

@@ -94,7 +94,10 @@ struct TraceParams {
     uint32_t queue_batch, queue_batch_from_pct;  // persistent kernel: slots claimed at a time in the cheap tail of the sorted queue
     uint32_t pool_refill;        // ray-pool kernel: idle lanes of a warp that trigger a refill
     uint32_t pool_min_inner;     // ray-pool kernel: the inner-node loop yields when fewer lanes than this still descend
-    uint32_t magic_w, magic_h, magic_tiles_x;  // floor(2^32 / d) for d = width, height, tiles per row (udiv_magic)
+    uint32_t magic_w, magic_h, magic_tiles_x;  // floor(2^32 / d) for d = width, height, items per row (udiv_magic)
+    // warp items of the persistent kernel: 2^item_cols_log2 columns x item_rows rows x 2^lane_samples_log2 samples = 32 lanes,
+    // items_x * items_y items per launch (8 x 4 x 1 unless the lanes of an item share pixels, see finish_sample_lanes)
+    uint32_t lane_samples_log2, item_cols_log2, item_rows, items_x, items_y;
     float root_lo[3], root_hi[3];  // scene AABB = octree root cube (acceptance rule of the BVH path)
 };
 

@@ -10,7 +10,8 @@
 // BVH box tests are allowed to use FMAs because the boxes are padded and only decide which triangles get tested.
 //
 // Kernels in this file:
-//   trace_shade_persistent_kernel<ACCEL, BOUNCE>  the default: persistent warps, cost-sorted 8x4 tile queue (variant 1)
+//   trace_shade_persistent_kernel<ACCEL, BOUNCE>  the default: persistent warps, cost-sorted 8x4 tile queue (variant 1);
+//                                                 <ACCEL, 0, true>: multi-sample launches, the lanes of an item hold the samples of a pixel
 //   trace_shade_kernel<ACCEL, BOUNCE>             one thread per pixel (variant 0, kept for A/B runs)
 //   trace_shade_pool_kernel                       ray pool with shared-memory ray rings (variant 2)
 //   wf_bounce_kernel<ACCEL>, wf_shade_kernel<ACCEL>, wf_combine_kernel    bounce wavefront (RECURSIONS > 0)
@@ -1039,11 +1040,13 @@ struct PixelOut {
 
 // first half of a pixel sample: camera ray -> closest hit -> shading (shadow / bounce rays)
 template <int ACCEL, int WW, int BOUNCE>
-__device__ __forceinline__ void trace_pixel_radiance(const TraceParams& P, uint32_t col, uint32_t crow, LaneCounters& cnt, PixelOut& out) {
+__device__ __forceinline__ void trace_pixel_radiance(const TraceParams& P, uint32_t col, uint32_t crow, uint32_t lane_sample, LaneCounters& cnt,
+                                                     PixelOut& out) {
     const uint32_t W = P.cam.width, H = P.cam.height;
     out.mode = 0u;
-    // sample planes (several samples per pixel in one launch): compact row `crow` = plane * plane_rows + row of the pass
-    uint32_t plane = 0, prow = crow;
+    // sample planes (several samples per pixel in one launch): compact row `crow` = plane * plane_rows + row of the pass;
+    // sample lanes (persistent kernel): the lanes of a warp item hold `lane_sample` = 0 .. S-1 of the same pixel
+    uint32_t plane = lane_sample, prow = crow;
     if (P.planes) {  // planes are plane_rows_padded (a multiple of the tile height) rows apart; the padding rows are idle
         plane = udiv_magic(crow, P.plane_rows_padded, P.magic_plane_rows);
         prow = crow - plane * P.plane_rows_padded;
@@ -1094,10 +1097,54 @@ __device__ __forceinline__ void finish_pixel(const TraceParams& P, const PixelOu
         film_add_sample(P, out.idx, P.film_sum[out.idx], out.cr, out.cg, out.cb);
     }
 }
+// Sample lanes (multi-sample launches of the persistent kernel): lanes [g * S, (g + 1) * S) of a warp item traced samples
+// 0 .. S-1 of ONE pixel. The lane of sample 0 collects them with shuffles and adds them to the film in sample order —
+// PixelData::add_sample (film.rs:20-24) S times, then mean, tonemap, pack of the final sums: exactly what S consecutive
+// single-sample launches leave (their intermediate LDR / id stores are overwritten), with one film read-modify-write
+// per pixel and no sample planes. Called by all 32 lanes; `active` is uniform within a sample group.
+__device__ __forceinline__ void finish_sample_lanes(const TraceParams& P, const PixelOut& out, uint32_t lane, bool active) {
+    const uint32_t S = 1u << P.lane_samples_log2;
+    const uint32_t first = lane & ~(S - 1u);
+    const bool leader = active && lane == first && out.mode == 1u;
+    float4 fs_ = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool sq_loaded = false;
+    uint32_t id = kNoHit;
+    if (leader) fs_ = P.film_sum[out.idx];
+    for (uint32_t s = 0; s < S; ++s) {
+        const float cr = __shfl_sync(0xffffffffu, out.cr, (int)(first + s));
+        const float cg = __shfl_sync(0xffffffffu, out.cg, (int)(first + s));
+        const float cb = __shfl_sync(0xffffffffu, out.cb, (int)(first + s));
+        id = __shfl_sync(0xffffffffu, out.id, (int)(first + s));
+        if (leader) {
+            fs_.x = fadd(fs_.x, cr);
+            fs_.y = fadd(fs_.y, cg);
+            fs_.z = fadd(fs_.z, cb);
+            if (cr != 0.0f || cg != 0.0f || cb != 0.0f) {  // see film_add_sample: a black sample leaves the sums of squares alone
+                if (!sq_loaded) {
+                    sq = P.film_sq[out.idx];
+                    sq_loaded = true;
+                }
+                sq.x = fadd(sq.x, fmul(cr, cr));
+                sq.y = fadd(sq.y, fmul(cg, cg));
+                sq.z = fadd(sq.z, fmul(cb, cb));
+            }
+        }
+    }
+    if (leader) {
+        const uint32_t n_new = __float_as_uint(fs_.w) + S;
+        fs_.w = __uint_as_float(n_new);
+        P.film_sum[out.idx] = fs_;
+        if (sq_loaded) P.film_sq[out.idx] = sq;
+        P.primary_ids[out.idx] = id;  // the last sample's, as after S launches
+        const uint32_t px = (fs_.x == 0.0f && fs_.y == 0.0f && fs_.z == 0.0f) ? 0xff000000u : tonemap_pack(fs_.x, fs_.y, fs_.z, n_new);
+        P.ldr[out.idx] = px;
+        if (P.ldr_remote) P.ldr_remote[out.idx] = px;
+    }
+}
 template <int ACCEL, int WW, int BOUNCE>
 __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t col, uint32_t crow, LaneCounters& cnt) {
     PixelOut out;
-    trace_pixel_radiance<ACCEL, WW, BOUNCE>(P, col, crow, cnt, out);
+    trace_pixel_radiance<ACCEL, WW, BOUNCE>(P, col, crow, 0u, cnt, out);
     finish_pixel(P, out);
 }
 
@@ -1142,11 +1189,14 @@ __global__ void __launch_bounds__(256) trace_shade_kernel(const __grid_constant_
 #ifndef RT_PERSISTENT_MIN_BLOCKS
 #define RT_PERSISTENT_MIN_BLOCKS 3
 #endif
-template <int ACCEL, int BOUNCE>
+template <int ACCEL, int BOUNCE, bool SAMPLE_LANES = false>
 __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_persistent_kernel(const __grid_constant__ TraceParams P) {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t tiles_x = (P.cam.width + 7u) / 8u;
-    const uint32_t n_tiles = tiles_x * ((P.n_rows + 3u) / 4u);
+    // A warp item is 32 lanes = item_cols x item_rows pixels x S samples (sample innermost, then column, then row):
+    // 8 x 4 x 1 for single-sample launches; with SAMPLE_LANES 8 x 2 x 2, 8 x 1 x 4 or 4 x 1 x 8: the lanes of an item
+    // share pixels (finish_sample_lanes). Any 8 consecutive lanes hold whole pixels, which the heavy-item split relies on.
+    const uint32_t tiles_x = SAMPLE_LANES ? P.items_x : (P.cam.width + 7u) / 8u;
+    const uint32_t n_tiles = SAMPLE_LANES ? P.items_x * P.items_y : tiles_x * ((P.n_rows + 3u) / 4u);
     LaneCounters cnt;
     // queue length: n_tiles in image order, or the item count the last tile_sort_kernel produced (heavy tiles are
     // split into four 8-pixel items so that their serial divergent chain is spread over four warps)
@@ -1178,8 +1228,20 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         const bool split = (item & kItemSplitFlag) != 0u;
         const uint32_t part = (item >> kItemPartShift) & 3u;
         const uint32_t tile_y = udiv_magic(tile, tiles_x, P.magic_tiles_x);
-        const uint32_t col = (tile - tile_y * tiles_x) * 8u + (lane & 7u);
-        const uint32_t crow = tile_y * 4u + (lane >> 3);
+        uint32_t col, crow, lane_sample = 0u;
+        if (SAMPLE_LANES) {
+            // worked out per item from a fresh %laneid: more values kept live through the traversal would spill
+            uint32_t lane_now;
+            asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_now));
+            const uint32_t sl = P.lane_samples_log2, cl = P.item_cols_log2;
+            const uint32_t lane_px = lane_now >> sl;
+            lane_sample = lane_now & ((1u << sl) - 1u);
+            col = ((tile - tile_y * tiles_x) << cl) + (lane_px & ((1u << cl) - 1u));
+            crow = tile_y * P.item_rows + (lane_px >> cl);
+        } else {
+            col = (tile - tile_y * tiles_x) * 8u + (lane & 7u);
+            crow = tile_y * 4u + (lane >> 3);
+        }
         const bool mine = col < P.cam.width && crow < P.n_rows && (!split || (lane >> 3) == part);
         const long long t0 = clock64();
 #ifdef RT_DEBUG_STEP_COUNTS
@@ -1188,7 +1250,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
 #endif
         PixelOut pout;
         pout.mode = 0u;
-        if (mine) trace_pixel_radiance<ACCEL, 1, BOUNCE>(P, col, crow, cnt, pout);
+        if (mine) trace_pixel_radiance<ACCEL, 1, BOUNCE>(P, col, crow, lane_sample, cnt, pout);
         __syncwarp();
         if (lane == 0) {
             if (last_of_batch) {
@@ -1199,7 +1261,8 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
                 ++slot;
             }
         }
-        if (mine) finish_pixel(P, pout);
+        if (SAMPLE_LANES) finish_sample_lanes(P, pout, lane, mine);
+        else if (mine) finish_pixel(P, pout);
         __syncwarp();
 #ifdef RT_DEBUG_STEP_COUNTS  // developer build only: (inner nodes visited | triangles tested << 16) instead of the primitive id
         if (mine) {
@@ -2006,14 +2069,15 @@ static void launch_trace_t(const TraceParams& p, int variant, uint32_t blocks, c
 #ifdef RT_DEBUG_STEP_COUNTS
         trace_shade_persistent_kernel<ACCEL, BOUNCE><<<blocks, 256, 2048, stream>>>(p);
 #else
-        trace_shade_persistent_kernel<ACCEL, BOUNCE><<<blocks, 256, 0, stream>>>(p);
+        if (BOUNCE == 0 && p.lane_samples_log2 != 0u) trace_shade_persistent_kernel<ACCEL, 0, true><<<blocks, 256, 0, stream>>>(p);
+        else trace_shade_persistent_kernel<ACCEL, BOUNCE><<<blocks, 256, 0, stream>>>(p);
 #endif
     }
 }
 // bounce_mode: 0 none, 1 depth first in the thread, 2 wavefront (the trace kernel only emits level-0 nodes)
 cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persistent_blocks, cudaStream_t stream) {
     if (p.n_rows == 0) return cudaSuccess;
-    const uint32_t tiles = ((p.cam.width + 7u) / 8u) * ((p.n_rows + 3u) / 4u);
+    const uint32_t tiles = p.items_x * p.items_y;  // = 8x4 pixel tiles unless the launch uses sample lanes
     uint32_t blocks = (uint32_t)persistent_blocks;
     if (blocks * 8u > tiles) blocks = (tiles + 7u) / 8u;
     const int bounce = p.recursions > 0 ? (p.wf_counts ? 2 : 1) : 0;

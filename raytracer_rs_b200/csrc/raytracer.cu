@@ -103,7 +103,7 @@ struct rt_raytracer {
     std::vector<std::unique_ptr<DevBuf<float>>> d_tex_data;
     DevBuf<DevTexture> d_textures;
     DevBuf<float4> d_film_sum, d_film_sq, d_planes;
-    bool multi_sample_launch = true;  // RT_TUNE_MULTI_SAMPLE_LAUNCH
+    int multi_sample_launch = 1;      // RT_TUNE_MULTI_SAMPLE_LAUNCH: 0 one launch per sample, 1 sample lanes where they apply, else planes, 2 planes
     bool bounce_wavefront = true;     // RT_TUNE_BOUNCE_WAVEFRONT
     DevBuf<float4> d_wf_rec;
     DevBuf<float> d_wf_child;
@@ -138,7 +138,7 @@ struct rt_raytracer {
     int lpt_schedule = 1;       // RT_TUNE_TILE_SCHEDULE: 1 = heaviest tiles first (cost feedback), 0 = image order
     // cost-feedback schedule state, valid for one launch geometry (first_row, rows, row list)
     DevBuf<uint32_t> d_tile_cost, d_tile_order;
-    uint32_t sched_first = ~0u, sched_rows = ~0u, sched_tiles = 0;
+    uint32_t sched_first = ~0u, sched_rows = ~0u, sched_tiles = 0, sched_samples_log2 = 0;
     uint32_t sched_launches = 0;  // launches recorded since the schedule geometry / camera last changed
     bool sched_have_order = false;
     int blocks_per_sm[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [accel][bounce]
@@ -525,6 +525,11 @@ struct rt_raytracer {
         p->magic_w = udiv_magic_of(cfg.width);
         p->magic_h = udiv_magic_of(cfg.height);
         p->magic_tiles_x = udiv_magic_of((cfg.width + 7u) / 8u);
+        p->lane_samples_log2 = 0;  // item geometry: set_item_geometry() once n_rows is known
+        p->item_cols_log2 = 3;
+        p->item_rows = 4;
+        p->items_x = (cfg.width + 7u) / 8u;
+        p->items_y = 0;
         std::memcpy(p->root_lo, root_lo, 12);
         std::memcpy(p->root_hi, root_hi, 12);
     }
@@ -536,12 +541,24 @@ struct rt_raytracer {
     static constexpr uint32_t kResortEvery = 32;
     static uint32_t udiv_magic_of(uint32_t d) { return d <= 1u ? 0xffffffffu : (uint32_t)((1ull << 32) / d); }
 
+    // 32 lanes of a warp item = columns x rows x samples (kernels.cu, trace_shade_persistent_kernel)
+    static void set_item_geometry(TraceParams* p, uint32_t samples_log2) {
+        const uint32_t S = 1u << samples_log2, px = 32u / S;  // pixels per item
+        p->lane_samples_log2 = samples_log2;
+        p->item_cols_log2 = px >= 8u ? 3u : 2u;
+        p->item_rows = px >> p->item_cols_log2;
+        p->items_x = (p->cam.width + (1u << p->item_cols_log2) - 1u) >> p->item_cols_log2;
+        p->items_y = (p->n_rows + p->item_rows - 1u) / p->item_rows;
+        p->magic_tiles_x = udiv_magic_of(p->items_x);
+    }
+
     cudaError_t launch_one(const TraceParams& p_in) {
         TraceParams p = p_in;
+        set_item_geometry(&p, p.lane_samples_log2);
         const int a = cfg.accel == RT_ACCEL_OCTREE ? 0 : (cfg.accel == RT_ACCEL_CWBVH ? 2 : (cfg.accel == RT_ACCEL_BVH4 ? 3 : 1));  // LBVH: same traversal as the SAH binary BVH
         const int b = cfg.recursions > 0 ? 1 : 0;
         // the ray-pool kernel covers the headline configuration; everything else runs the persistent tile kernel
-        const bool use_pool = variant == 2 && a == 1 && b == 0 && scene.lights.size() == 1 && !p.planes;
+        const bool use_pool = variant == 2 && a == 1 && b == 0 && scene.lights.size() == 1 && !p.planes && p.lane_samples_log2 == 0;
         if (use_pool && pool_blocks == 0) pool_blocks = pool_blocks_per_sm();
         if (!use_pool && variant != 0 && blocks_per_sm[a][b] == 0) blocks_per_sm[a][b] = persistent_blocks_per_sm(a, b);
         p.queue_batch = (uint32_t)queue_batch;
@@ -549,9 +566,9 @@ struct rt_raytracer {
         p.pool_refill = (uint32_t)pool_refill;
         p.pool_min_inner = (uint32_t)pool_min_inner;
         if (variant != 0 && lpt_schedule) {
-            const uint32_t tiles = ((p.cam.width + 7u) / 8u) * ((p.n_rows + 3u) / 4u);
+            const uint32_t tiles = p.items_x * p.items_y;
             if (tiles >= 4096) {  // short launches are latency bound; keep them in image order
-                if (sched_first != p.first_row || sched_rows != p.n_rows || sched_tiles != tiles) {
+                if (sched_first != p.first_row || sched_rows != p.n_rows || sched_tiles != tiles || sched_samples_log2 != p.lane_samples_log2) {
                     if (d_tile_cost.n < tiles) {
                         d_tile_cost.alloc(tiles);
                         d_tile_order.alloc(4 * (size_t)tiles);
@@ -559,6 +576,7 @@ struct rt_raytracer {
                     sched_first = p.first_row;
                     sched_rows = p.n_rows;
                     sched_tiles = tiles;
+                    sched_samples_log2 = p.lane_samples_log2;
                     sched_launches = 0;
                     sched_have_order = false;
                     RT_CUDA_RET(cudaMemsetAsync(d_tile_cost.p, 0, tiles * sizeof(uint32_t), stream));
@@ -709,6 +727,16 @@ struct rt_raytracer {
                     RT_CUDA(launch_one(q));
                     ++launches;
                 }
+        } else if (spp > 1 && multi_sample_launch == 1 && variant == 1 && (spp & 1u) == 0u && cfg.recursions == 0) {
+            // sample lanes: the 32 lanes of a warp item hold S = 8, 4 or 2 samples of 4, 8 or 16 pixels and add them to the
+            // film in sample order themselves (finish_sample_lanes): spp / S launches, no sample planes, no second pass
+            const uint32_t s_log2 = (spp & 7u) == 0u ? 3u : ((spp & 3u) == 0u ? 2u : 1u);
+            p.n_rows = launch_rows;
+            p.lane_samples_log2 = s_log2;
+            for (uint32_t s = 0; s < spp; s += 1u << s_log2) {
+                RT_CUDA(launch_one(p));
+                ++launches;
+            }
         } else if (spp > 1 && multi_sample_launch && !(cfg.recursions > 0 && bounce_wavefront && variant != 0)) {
             // all samples of a pass in ONE launch (sample planes) + one ordered accumulation: same film as `spp`
             // consecutive launches, but the GPU sees spp times as many work items (matters for small row ranges)
@@ -1211,8 +1239,8 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
         rt->bounce_wavefront = value != 0;
         return RT_OK;
     }
-    if (key == RT_TUNE_MULTI_SAMPLE_LAUNCH && (value == 0 || value == 1)) {
-        rt->multi_sample_launch = value != 0;
+    if (key == RT_TUNE_MULTI_SAMPLE_LAUNCH && value >= 0 && value <= 2) {
+        rt->multi_sample_launch = value;
         return RT_OK;
     }
     if (key == RT_TUNE_POOL_MIN_INNER && value >= 0 && value <= 32) {

@@ -182,28 +182,40 @@ def test_kernel_variants_are_bit_identical(scenes, name):
 
 @pytest.mark.parametrize("accel,aname", ACCELS)
 def test_multi_sample_launch_equals_one_launch_per_sample(scenes, accel, aname):
-    """rt_trace_rows with spp > 1 traces all samples in one launch (sample planes + ordered accumulation). The film,
-    frame, ids and ray counts must be bit-identical to one launch per sample — also for a shard of interleaved bands,
-    a wrapped row range, and when the film already holds samples."""
+    """rt_trace_rows with spp > 1 has three forms (RT_TUNE_MULTI_SAMPLE_LAUNCH): sample lanes (even spp: the lanes of a warp
+    item hold 8, 4 or 2 samples of a pixel and add them to the film in order), sample planes + ordered accumulation pass
+    (one launch), one launch per sample. Film, frame, ids and ray counts must be bit-identical in all three — also for a
+    shard of interleaved bands, a wrapped row range, and when the film already holds samples."""
     s = scenes("thai2")
-    w, h, spp = 640, 360, 5
-    for kw, first, rows, variant in [({}, 0, h, 1), ({}, 300, 101, 1), ({"shard_index": 1, "shard_count": 3, "band_rows": 8}, 0, h, 1),
-                                     ({"shard_index": 0, "shard_count": 7, "band_rows": 3}, 5, 333, 1), ({}, 0, h, 0)]:
-        got = []
-        for multi in (1, 0):
+    w, h = 640, 360
+    cases = [({}, 0, h, 1, (5, 8, 6)), ({}, 300, 101, 1, (4, 16)), ({"shard_index": 1, "shard_count": 3, "band_rows": 8}, 0, h, 1, (2, 8)),
+             ({"shard_index": 0, "shard_count": 7, "band_rows": 3}, 5, 333, 1, (5, 12)), ({}, 0, h, 0, (5, 4))]
+    for kw, first, rows, variant, spps in cases:
+        tracers = []
+        for multi in (1, 2, 0):
             t = gpu_tracer(s, w, h, accel, jitter=rt.JITTER_HASHED, seed=9, **kw)
             t.set_tuning(0, variant)
             t.set_tuning(5, multi)
-            t.trace_rows(first, rows, 1)  # the film already holds one sample of these rows
-            n_primary, n_shadow = t.trace_rows(first, rows, spp)
-            got.append((n_primary, n_shadow, t.get_primary_ids(), t.get_tonemapped_pixels(), t.film.pixel_datas().view(np.uint32),
-                        t.launch_stats()["kernels_launched"]))
+            tracers.append(t)
+        for spp in spps:
+            got = []
+            for t in tracers:
+                t.film.clear()
+                t.trace_rows(first, rows, 1)  # the film already holds one sample of these rows
+                n_primary, n_shadow = t.trace_rows(first, rows, spp)
+                got.append((n_primary, n_shadow, t.get_primary_ids(), t.get_tonemapped_pixels(), t.film.pixel_datas().view(np.uint32),
+                            t.launch_stats()["kernels_launched"]))
+            lanes, planes, single = got
+            for other in (planes, single):
+                assert lanes[0] == other[0] and lanes[1] == other[1], (kw, spp)
+                for x, y in zip(lanes[2:5], other[2:5]):
+                    assert np.array_equal(x, y), (kw, spp)
+            if spp > 2:
+                assert planes[5] < single[5]  # one trace launch (+ accumulation) instead of spp
+            if variant == 1 and spp % 2 == 0 and spp >= 4:  # sample lanes: spp / 8, spp / 4 or spp / 2 launches
+                assert lanes[5] < single[5], (kw, spp)
+        for t in tracers:
             t.close()
-        a, b = got
-        assert a[0] == b[0] and a[1] == b[1]
-        for x, y in zip(a[2:5], b[2:5]):
-            assert np.array_equal(x, y)
-        assert a[5] < b[5]  # one trace launch instead of spp
 
 
 def test_4k_16spp_properties(scenes):
