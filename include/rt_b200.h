@@ -198,8 +198,12 @@ int rt_ipc_close(rt_raytracer* rt, void* dev_ptr);
    rt_stream_wait_flags holds the stream until every one of dev_flags[0..n_flags) (uint32, n_flags <= 32, typically
    peer-mapped memory of rank 0) has reached `target` (wrap-safe >=); in the same launch it can first store `target`
    into dev_flags[signal_slot] and afterwards into dev_flags[release_slot] (-1 = none), which is rank 0's whole
-   per-frame fence. A wait gives up after ~2 s and counts a timeout (rt_sync_timeouts) instead of hanging the GPU. */
+   per-frame fence. rt_stream_signal_then_wait is the per-frame fence of every other rank in one launch: store `value`
+   into *dev_signal_flag ("my stores of this frame are done"), then hold the stream until *dev_wait_flag has reached
+   `target` ("the frame that last used the next buffer has been read"). A wait gives up after ~2 s and counts a timeout
+   (rt_sync_timeouts) instead of hanging the GPU. */
 int rt_stream_signal_flag(rt_raytracer* rt, void* dev_flag, uint32_t value);
+int rt_stream_signal_then_wait(rt_raytracer* rt, void* dev_signal_flag, uint32_t value, void* dev_wait_flag, uint32_t target);
 int rt_stream_wait_flags(rt_raytracer* rt, void* dev_flags, uint32_t n_flags, uint32_t target, int32_t signal_slot,
                          int32_t release_slot);
 int rt_sync_timeouts(rt_raytracer* rt, uint32_t* count);

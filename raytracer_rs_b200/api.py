@@ -96,7 +96,7 @@ ABI_SYMBOLS = [
     "rt_camera_add_x_angle", "rt_camera_add_y_angle", "rt_camera_get", "rt_camera_set_state", "rt_set_stream",
     "rt_get_ldr_device_ptr", "rt_set_ldr_target", "rt_get_owned_ldr_rows_device", "rt_get_launch_stats",
     "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_get_counters_device_ptr",
-    "rt_stream_signal_flag", "rt_stream_wait_flags", "rt_sync_timeouts",
+    "rt_stream_signal_flag", "rt_stream_signal_then_wait", "rt_stream_wait_flags", "rt_sync_timeouts",
     "rt_launch_param_bytes", "rt_set_tuning", "rt_set_host_frame",
     "rt_kernels_launched", "rt_get_ray_totals", "rt_octree_stats", "rt_octree_export", "rt_bvh_stats", "rt_bvh_export", "rt_bvh4_stats", "rt_bvh4_export", "rt_lbvh_build", "rt_lbvh_export", "rt_cwbvh_stats",
     "rt_cwbvh_export", "rt_stats_new",
@@ -164,6 +164,7 @@ def lib() -> C.CDLL:
         "rt_ipc_close": (C.c_int, [vp, vp]),
         "rt_get_counters_device_ptr": (C.c_int, [vp, P(vp)]),
         "rt_stream_signal_flag": (C.c_int, [vp, vp, u32]),
+        "rt_stream_signal_then_wait": (C.c_int, [vp, vp, u32, vp, u32]),
         "rt_stream_wait_flags": (C.c_int, [vp, vp, u32, u32, i32, i32]),
         "rt_sync_timeouts": (C.c_int, [vp, P(u32)]),
         "rt_launch_param_bytes": (u32, []),
@@ -493,6 +494,9 @@ class RayTracer:
 
     def signal_flag(self, dev_flag: int, value: int) -> None:
         self._check(lib().rt_stream_signal_flag(self._h, dev_flag, value))
+
+    def signal_then_wait(self, dev_signal_flag: int, value: int, dev_wait_flag: int, target: int) -> None:
+        self._check(lib().rt_stream_signal_then_wait(self._h, dev_signal_flag, value, dev_wait_flag, target))
 
     def wait_flags(self, dev_flags: int, n_flags: int, target: int, signal_slot: int = -1, release_slot: int = -1) -> None:
         self._check(lib().rt_stream_wait_flags(self._h, dev_flags, n_flags, target, signal_slot, release_slot))

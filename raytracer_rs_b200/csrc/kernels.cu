@@ -1903,6 +1903,25 @@ __global__ void flag_signal_kernel(volatile uint32_t* flag, uint32_t value) {
     *flag = value;
     __threadfence_system();
 }
+// the per-frame fence of a rank other than 0 in one launch: "my stores of frame k are done" (*signal = value), then hold the
+// stream until *wait_flag >= target ("the frame that used the next buffer has been read")
+__global__ void flag_signal_wait_kernel(volatile uint32_t* signal, uint32_t value, volatile uint32_t* wait_flag, uint32_t target,
+                                        unsigned long long timeout_ns, uint32_t* timeouts) {
+    __threadfence_system();
+    *signal = value;
+    __threadfence_system();
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int32_t)(*wait_flag - target) < 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {
+            atomicAdd(timeouts, 1u);
+            break;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
 // optional signal (flags[signal_slot] = target) -> wait until flags[0..n) >= target -> optional release
 // (flags[release_slot] = target): rank 0's whole per-frame fence in one launch
 __global__ void flag_wait_kernel(volatile uint32_t* flags, uint32_t n, uint32_t target, int signal_slot, int release_slot,
@@ -2161,6 +2180,10 @@ cudaError_t launch_tonemap(const float4* sum, uint32_t* ldr, uint32_t n, cudaStr
 }
 cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream) {
     flag_signal_kernel<<<1, 1, 0, stream>>>(flag, value);
+    return cudaGetLastError();
+}
+cudaError_t launch_flag_signal_wait(uint32_t* signal, uint32_t value, uint32_t* wait_flag, uint32_t target, uint32_t* timeouts, cudaStream_t stream) {
+    flag_signal_wait_kernel<<<1, 1, 0, stream>>>(signal, value, wait_flag, target, 2000000000ull, timeouts);
     return cudaGetLastError();
 }
 cudaError_t launch_flag_wait(uint32_t* flags, uint32_t n, uint32_t target, int signal_slot, int release_slot, uint32_t* timeouts,

@@ -33,6 +33,8 @@ cudaError_t launch_gather_rows(const uint32_t* ldr, const uint32_t* row_list, ui
 // cross-GPU frame fence: *flag = value after everything earlier on the stream / wait until flags[0..n) >= target
 // (bounded: a timeout increments *timeouts instead of hanging)
 cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream);
+// *signal = value, then wait until *wait_flag >= target, in one launch
+cudaError_t launch_flag_signal_wait(uint32_t* signal, uint32_t value, uint32_t* wait_flag, uint32_t target, uint32_t* timeouts, cudaStream_t stream);
 // signal_slot / release_slot (-1 = none): flags[signal_slot] = target before the wait, flags[release_slot] = target after it
 cudaError_t launch_flag_wait(uint32_t* flags, uint32_t n, uint32_t target, int signal_slot, int release_slot, uint32_t* timeouts,
                              cudaStream_t stream);

@@ -1194,6 +1194,17 @@ int rt_stream_wait_flags(rt_raytracer* rt, void* dev_flags, uint32_t n_flags, ui
         ++rt->total_kernels;
     });
 }
+int rt_stream_signal_then_wait(rt_raytracer* rt, void* dev_signal_flag, uint32_t value, void* dev_wait_flag, uint32_t target) {
+    RT_GUARD(rt, {
+        if (!dev_signal_flag || !dev_wait_flag) throw std::invalid_argument("null flag");
+        if (!rt->d_sync_timeouts.p) {
+            rt->d_sync_timeouts.alloc(1);
+            RT_CUDA(cudaMemsetAsync(rt->d_sync_timeouts.p, 0, 4, rt->stream));
+        }
+        RT_CUDA(launch_flag_signal_wait((uint32_t*)dev_signal_flag, value, (uint32_t*)dev_wait_flag, target, rt->d_sync_timeouts.p, rt->stream));
+        ++rt->total_kernels;
+    });
+}
 int rt_sync_timeouts(rt_raytracer* rt, uint32_t* count) {
     RT_GUARD(rt, {
         if (!count) throw std::invalid_argument("null output");

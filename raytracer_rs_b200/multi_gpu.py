@@ -11,7 +11,8 @@ cross NVLink is the packed LDR frame, once per displayed frame, to rank 0:
       stores k+1 into its slot flags[rank]; rank 0's stream waits until all slots reached k+1 before it touches the
       frame, then publishes flags[world] = k+1 ("frame k has been read"). Frames alternate between the two buffers and a
       rank starts storing frame k only once frame k-2 (the previous user of that buffer) has been read, so stores never
-      race with rank 0's readback however far the other ranks run ahead. Waits are bounded (a lost peer becomes an
+      race with rank 0's readback however far the other ranks run ahead; that wait sits in the same launch as the
+      rank's "frame k-1 is done" signal (rt_stream_signal_then_wait), so a frame costs every rank one fence launch. Waits are bounded (a lost peer becomes an
       error count, rt_sync_timeouts, not a hung GPU).
   mode "peer_allreduce": same stores, but one small NCCL all-reduce of the ray counters per frame is both the global
       ray count and the completion fence (the previous design; kept for comparison).
@@ -102,12 +103,9 @@ class FrameGather:
         dist.barrier()
 
     def begin_frame(self):
-        """Call before tracing a frame (mode "peer"): holds this rank's stream until the buffer the frame will be stored
-        into has been read by rank 0 (frame k waits for "frame k-2 has been read")."""
-        # rank 0 publishes "read" itself, earlier on its own stream: only the other ranks have to wait
-        if self.mode == "peer" and self.rank != 0 and self.frame_no >= 2:
-            self.tracer.wait_flags(self.flags + 4 * self.world, 1, self.frame_no - 1)
-            self.kernels += 1
+        """Call before tracing a frame. Nothing is enqueued any more: in mode "peer" the wait for the buffer the frame
+        will be stored into ("frame k-2 has been read") sits in the fence launch at the end of frame k-1
+        (device_gather), which saves one launch per frame on every rank but 0. Kept for the call order of the API."""
 
     def device_gather(self, release: bool = False):
         """Enqueue (on the tracer's stream) whatever makes the frame just traced complete on rank 0. release=True
@@ -121,8 +119,12 @@ class FrameGather:
                     self.tracer.wait_flags(self.flags, self.world, k + 1, 0, self.world if release else -1)
                     if release:
                         self.consumed_signalled = k + 1
+                elif k >= 1:
+                    # one launch: my stores of frame k are done -> frame k+1 (same buffer as frame k-1) may be stored once
+                    # rank 0 has read frame k-1, which it publishes as flags[world] = k
+                    self.tracer.signal_then_wait(self.flags + 4 * self.rank, k + 1, self.flags + 4 * self.world, k)
                 else:
-                    self.tracer.signal_flag(self.flags + 4 * self.rank, k + 1)  # my stores of frame k are done
+                    self.tracer.signal_flag(self.flags + 4 * self.rank, k + 1)  # my stores of frame 0 are done
                 self.ready = k & 1
                 self.frame_no += 1
                 self.tracer.set_ldr_target(self.targets[self.frame_no & 1])
