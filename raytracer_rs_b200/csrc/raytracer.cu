@@ -890,9 +890,20 @@ static int create_from_host_scene(const HostScene& sc, const rt_config& cfg, rt_
 
 int rt_create(const rt_scene_desc* scene, const rt_config* cfg, rt_raytracer** out, char* err, size_t err_len) {
     if (!scene || !cfg || !out) return RT_ERR_INVALID;
+    // a null array with a non-zero count would be read out of bounds below and in HostScene::from_desc
+    if ((scene->num_triangles && (!scene->vertices || !scene->tri_geom)) || (scene->num_geometries && !scene->materials) ||
+        (scene->num_lights && !scene->lights) || (scene->num_textures && !scene->textures)) {
+        copy_err("scene description has a null array with a non-zero count", err, err_len);
+        return RT_ERR_INVALID;
+    }
     for (uint32_t t = 0; t < scene->num_triangles; ++t)
         if (scene->tri_geom[t] >= scene->num_geometries) {
             copy_err("tri_geom entry out of range", err, err_len);
+            return RT_ERR_INVALID;
+        }
+    for (uint32_t k = 0; k < scene->num_textures; ++k)
+        if (!scene->textures[k].rgb || scene->textures[k].width == 0 || scene->textures[k].height == 0) {
+            copy_err("texture without texels", err, err_len);
             return RT_ERR_INVALID;
         }
     return create_from_host_scene(HostScene::from_desc(*scene), *cfg, out, err, err_len);
@@ -968,7 +979,8 @@ int rt_trace_frame_additive(rt_raytracer* rt, uint32_t* num_primary_rays) {
         const uint32_t rows = rt->cfg.rows_per_call;
         rt->trace_rows(rt->current_row, rows, 1);
         rt->current_row = (rt->current_row + rows) % rt->cfg.height;
-        if (num_primary_rays) *num_primary_rays = rows * rt->cfg.width;  // mod.rs:113-116
+        // mod.rs:113-116 returns rows * width; a sharded handle traces (and reports) only the rows it owns
+        if (num_primary_rays) *num_primary_rays = (uint32_t)rt->last.n_primary;
     });
 }
 

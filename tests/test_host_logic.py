@@ -295,6 +295,61 @@ def test_render_calls_fail_loudly_without_a_device(scenes):
         assert e.value.code == -3
 
 
+def test_rt_create_rejects_malformed_scene_descriptions():
+    """The C ABI takes raw pointers: a non-zero count with a null array, a texture without texels or a triangle that
+    names a geometry that does not exist must come back as RT_ERR_INVALID with a message, not as a crash."""
+    import ctypes as C
+
+    from raytracer_rs_b200 import api
+
+    lib = rt.lib()
+    cfg = rt.Config(16, 16, device=api.DEVICE_NONE).to_c()
+    verts = (C.c_float * 9)(0, 0, 0, 1, 0, 0, 0, 1, 0)
+    geom = (C.c_uint32 * 1)(0)
+    mats = (api.CMaterial * 1)()
+    lights = (api.CLight * 1)()
+    texels = (C.c_float * 3)(0.5, 0.5, 0.5)
+
+    def desc():
+        d = api.CSceneDesc()
+        d.num_triangles, d.vertices, d.tri_geom = 1, verts, geom
+        d.num_geometries, d.materials = 1, mats
+        d.num_lights, d.lights = 1, lights
+        d.camera_orientation[:] = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]
+        d.camera_fov_deg = 40.0
+        return d
+
+    def create(d):
+        h, err = C.c_void_p(), C.create_string_buffer(256)
+        rc = lib.rt_create(C.byref(d), C.byref(cfg), C.byref(h), err, len(err))
+        if rc == 0:
+            lib.rt_destroy(h)
+        return rc, err.value.decode()
+
+    assert create(desc())[0] == 0
+    for field in ("vertices", "tri_geom", "materials", "lights"):
+        d = desc()
+        setattr(d, field, None)
+        rc, msg = create(d)
+        assert rc == -1 and "null array" in msg, field
+    d = desc()
+    d.num_textures, d.textures = 1, None
+    assert create(d)[0] == -1
+    d = desc()
+    tex = (api.CTexture * 1)()
+    tex[0].width, tex[0].height = 1, 1  # rgb stays null
+    d.num_textures, d.textures = 1, tex
+    rc, msg = create(d)
+    assert rc == -1 and "texels" in msg
+    tex[0].rgb = texels
+    assert create(d)[0] == 0
+    d = desc()
+    geom_bad = (C.c_uint32 * 1)(3)
+    d.tri_geom = geom_bad
+    rc, msg = create(d)
+    assert rc == -1 and "out of range" in msg
+
+
 # ---- stats.rs / timing crate ---------------------------------------------------------------------------------------------
 
 
