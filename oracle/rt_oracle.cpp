@@ -13,7 +13,10 @@
 // tests/test_oracle_golden.py. Everything else on the path (Moller-Trumbore, octree
 // build/traversal, shading, tonemap, packing, pixel->ray mapping) is "parity unpinned":
 // no reference vector or reference run exists for it; this restatement follows the source
-// line by line and is the only arbiter.
+// line by line. It is cross-checked bit for bit against a second restatement written
+// independently from the Rust sources in numpy float32 (tests/render_ref.py,
+// tests/test_oracle_golden.py::test_oracle_matches_independent_numpy_restatement), which guards
+// against transcription slips but is not a run of the reference: the status stays "unpinned".
 //
 // Arithmetic rules: IEEE binary32 everywhere, no FMA contraction (-ffp-contract=off), sums
 // left to right exactly as the Rust source writes them, glibc tanf/sinf/cosf/powf/sqrtf (what
