@@ -10,7 +10,7 @@ import pytest
 import raytracer_rs_b200 as rt
 from collada_ref import load_collada
 from conftest import CONFIGS, DATA
-from oracle_lib import Oracle
+from oracle_lib import JITTER_FIXED, Oracle
 from raytracer_rs_b200.api import DEVICE_NONE
 
 F = np.float32
@@ -379,3 +379,28 @@ def test_benchmark_report_shape():
     assert m and abs(float(m.group(1)) / 3 - float(m.group(2))) < 0.01
     with pytest.raises(KeyError):
         bm.stop("never started")
+
+
+# ---- bench.py: the roofline's numerator ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("workload", ["thai2_1080p", "ico2_1024x768", "4boxes_1080p", "ico3_tex_1080p"])
+def test_bench_reference_work_constants_are_the_oracles_counters(scenes, workload):
+    """bench.py's `roofline.achieved` = algorithmic bytes of the REFERENCE algorithm per pinned frame / kernel time, with
+    the bytes computed from constants (rays, cube tests, triangle tests per frame). They must be what the oracle counts
+    when it renders that frame at full size (24 B per cube test + 36 B per triangle test + 4 B per pixel)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(os.path.dirname(DATA), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    fname, w, h, spp = bench.WORKLOADS[workload]
+    assert spp == 1
+    o = Oracle(scenes(fname.split(".")[0]), w, h)
+    o.configure(recursions=0, jitter=JITTER_FIXED)
+    o.trace_rows(0, h, 1, threads=0)
+    c = o.counters()
+    got = (c["rays"]["primary"], c["rays"]["shadow"], c["cube_tests"]["primary"] + c["cube_tests"]["shadow"],
+           c["tri_tests"]["primary"] + c["tri_tests"]["shadow"])
+    assert got == bench.REFERENCE_WORK[workload]
+    assert bench.algorithmic_bytes(workload) == 24 * got[2] + 36 * got[3] + 4 * got[0]
