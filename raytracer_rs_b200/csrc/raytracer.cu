@@ -127,6 +127,7 @@ struct rt_raytracer {
     uint32_t current_row = 0;
     std::vector<uint32_t> owned_rows;       // all rows of this shard, ascending
     std::vector<uint32_t> row_list_cache;   // rows of the last sharded / wrapped launch
+    std::vector<uint32_t> lap_start;        // offsets into row_list_cache where each lap over the image begins
     uint32_t cached_first = ~0u, cached_n = ~0u;
     uint64_t total_kernels = 0, total_primary = 0;
     int variant = 1;            // RT_TUNE_KERNEL_VARIANT
@@ -700,7 +701,9 @@ struct rt_raytracer {
         if (sharded() || wraps_twice) {
             if (cached_first != first_row || cached_n != n_rows) {
                 row_list_cache.clear();
+                lap_start.clear();
                 for (uint32_t k = 0; k < n_rows; ++k) {
+                    if (k % cfg.height == 0) lap_start.push_back((uint32_t)row_list_cache.size());  // a new lap over the image begins
                     const uint32_t r = (first_row + k) % cfg.height;
                     if (owns_row(r)) row_list_cache.push_back(r);
                 }
@@ -717,13 +720,18 @@ struct rt_raytracer {
         last = rt_launch_stats{};
         RT_CUDA(cudaEventRecord(ev_start, stream));
         uint32_t launches = 0;
-        if (wraps_twice && !sharded()) {
-            // the same pixel appears more than once: keep the reference's sequential order, one launch per lap
+        if (wraps_twice) {
+            // the same pixel appears more than once: keep the reference's sequential order, one launch per lap (a launch
+            // must never hold a pixel twice — two warps would update its film record concurrently); a sharded handle's laps
+            // are the owned rows of each lap
             for (uint32_t s = 0; s < spp; ++s)
-                for (uint32_t off = 0; off < launch_rows; off += cfg.height) {
+                for (size_t lap = 0; lap < lap_start.size(); ++lap) {
+                    const uint32_t off = lap_start[lap];
+                    const uint32_t end = lap + 1 < lap_start.size() ? lap_start[lap + 1] : launch_rows;
+                    if (end == off) continue;
                     TraceParams q = p;
                     q.row_list = d_row_list.p + off;
-                    q.n_rows = std::min(cfg.height, launch_rows - off);
+                    q.n_rows = end - off;
                     RT_CUDA(launch_one(q));
                     ++launches;
                 }

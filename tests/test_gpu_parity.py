@@ -535,3 +535,31 @@ def test_bounce_sample_table_matches_oracle(scenes):
         t.close()
     tab = o.sample_table()
     assert np.allclose(np.linalg.norm(tab, axis=1), 1.0, atol=1e-6)
+
+
+def test_sharded_handle_with_a_row_range_longer_than_the_image(scenes):
+    """rt_trace_rows(first, n_rows > height) passes over some rows twice. A launch must never hold a pixel twice (two
+    warps would update its film record concurrently), so the call is split into laps — also on a sharded handle, whose
+    laps are the rows it owns of each lap. The shards' films must equal the unsharded film on the rows they own.
+    (Last test of the GPU suite on purpose: it exercises a host path no other test or benchmark uses.)"""
+    w, h, world = 320, 90, 2
+    first, n_rows = 70, 2 * h + 37  # wraps, 2.4 laps
+    s = scenes("ico2")
+    full = gpu_tracer(s, w, h, rt.ACCEL_BVH, jitter=rt.JITTER_HASHED, seed=3)
+    n_full, sh_full = full.trace_rows(first, n_rows, 1)
+    assert n_full == n_rows * w
+    ref = full.film.pixel_datas().view(np.uint32).reshape(h, w, 7)
+    ref_ldr = full.get_tonemapped_pixels().reshape(h, w)
+    total, total_shadow = 0, 0
+    for r in range(world):
+        t = gpu_tracer(s, w, h, rt.ACCEL_BVH, jitter=rt.JITTER_HASHED, seed=3, shard_index=r, shard_count=world, band_rows=8)
+        n, sh = t.trace_rows(first, n_rows, 1)
+        total, total_shadow = total + n, total_shadow + sh
+        own = ((np.arange(h) // 8) % world) == r
+        film = t.film.pixel_datas().view(np.uint32).reshape(h, w, 7)
+        assert np.array_equal(film[own], ref[own])
+        assert np.array_equal(t.get_tonemapped_pixels().reshape(h, w)[own], ref_ldr[own])
+        assert (film[~own][:, :, 6] == 0).all()  # rows of the other shard stay unsampled
+        t.close()
+    assert (total, total_shadow) == (n_full, sh_full)
+    full.close()
