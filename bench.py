@@ -444,10 +444,12 @@ def main():
 
     peak, peak_src = measured_hbm_peak()
     alg = algorithmic_bytes(args.workload)
-    traffic = None
+    traffic, warp_inst = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("%s/%s" % (args.workload, args.accel))
+            prof = json.load(f)
+        traffic = prof.get("%s/%s" % (args.workload, args.accel))
+        warp_inst = prof.get("warp_instructions", {}).get("%s/%s" % (args.workload, args.accel))
     except Exception:
         pass
     roofline = None
@@ -470,6 +472,14 @@ def main():
             roofline["dram_frac"] = roofline["dram_achieved"] / peak
             roofline["bound_in_practice"] = ("instruction issue at partly filled warps + latency of dependent node loads "
                                              "(ncu: issue slots 65 % busy, 22 of 32 lanes active; profiles/README.md)")
+        if warp_inst and world == 1 and spp == 1 and clocks.get("sm_mhz"):
+            # the resource that actually binds: warp instructions issued (ncu smsp__inst_executed.sum of one launch,
+            # profiles/traffic.json) / measured kernel time, against 4 schedulers x SMs x the SM clock measured during the run
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_issue = 4.0 * sms * clocks["sm_mhz"] * 1e6
+            roofline["issue_slots"] = {"warp_instructions_per_launch": warp_inst, "achieved_ginst_s": warp_inst / (kms * 1e-3) / 1e9,
+                                       "peak_ginst_s": peak_issue / 1e9, "frac": warp_inst / (kms * 1e-3) / peak_issue,
+                                       "note": "one warp instruction per scheduler and cycle; 22 of 32 lanes active on average"}
     line = {
         "metric": METRIC,
         "value": value,
