@@ -60,3 +60,45 @@ def test_product_does_not_link_or_import_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle_lib" not in text and "liboracle" not in text and "orc_" not in text, (dirpath, f)
+
+
+def build_c_client(tmp_path):
+    """Compiles tests/c_client/host_client.c as strict C99 against include/rt_b200.h and links librt_b200.so."""
+    exe = str(tmp_path / "host_client")
+    libdir = os.path.dirname(rt.lib_path())
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_client", "host_client.c"), "-o", exe, "-L", libdir, "-l:" + os.path.basename(rt.lib_path()),
+                    "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+    return exe
+
+
+def run_c_client(exe, *args):
+    out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    return dict(line.split(" ", 1) for line in out.stdout.splitlines() if " " in line)
+
+
+def test_plain_c_client_drives_the_host_side_of_the_abi(tmp_path):
+    """The boundary is a C ABI for a non-C++ host (the reference is Rust): the header compiles as strict C99 and a C
+    program gets the same scene, tree and camera as the Python binding; a host-only handle refuses to render."""
+    import numpy as np
+
+    got = run_c_client(build_c_client(tmp_path), os.path.join(ROOT, "data", "thai2.dae"))
+    assert got["version"] == rt.version()
+    scene = rt.load_scene(os.path.join(ROOT, "data", "thai2.dae"))
+    assert int(got["triangles"]) == scene.vertices.shape[0] == 20049 and int(got["lights"]) == len(scene.lights)
+    assert np.float32(got["fov"]) == scene.camera_fov_deg
+    t = rt.RayTracer.from_scene(scene, rt.Config(96, 54, recursions=0, jitter_mode=rt.JITTER_FIXED_HALF, accel=rt.ACCEL_OCTREE,
+                                                 device=api.DEVICE_NONE))
+    st = t.octree_stats()
+    assert (int(got["octree_nodes"]), int(got["octree_refs"]), int(got["octree_depth"])) == (st["nodes"], st["tri_refs"], st["depth"])
+    t.camera.move_rel(0.25, 0.0, -0.5)
+    t.camera.add_x_angle(0.125)
+    t.camera.add_y_angle(-0.0625)
+    cam = t.camera.matrices()
+    assert np.float32(got["camera_rot0"]) == cam[0] and np.float32(got["camera_max_x"]) == cam[32]
+    assert [np.float32(x) for x in got["camera_pos"].split()] == [cam[28], cam[29], cam[30]]
+    assert int(got["trace_rc"]) == -3 and "RT_DEVICE_NONE" in got["trace_error"]  # no CPU fallback
+    assert got["stats_prefix"].startswith("fps:") and got["mean_stats_prefix"].startswith("mean fps")
+    assert int(got["benchmark_unknown_rc"]) == -1 and got["benchmark_report"].startswith("frame total:")
+    t.close()
