@@ -374,9 +374,10 @@ def main():
             tracer.wait_pixels()
             tracer.get_tonemapped_pixels_async(host_frames[i & 1].data_ptr())
         elif gather is not None and not args.sync_readback:
-            if rank == 0:  # same pipelining on rank 0 of a multi-GPU run
-                gather.wait_frame()
+            if rank == 0:  # same pipelining on rank 0 of a multi-GPU run: hand frame i to the copy stream, then make sure
+                # frame i-1 (the other host buffer) has arrived
                 gather.read_frame_async(host_frames[i & 1])
+                gather.wait_frame(keep=1)
         elif rank == 0:
             tracer_or_gather_readback()
 

@@ -62,7 +62,8 @@ class FrameGather:
         self.W, self.H = tracer.width, tracer.height
         self.partition = band_partition(self.H, world, band_rows)
         self.kernels = 0  # kernels of OURS launched by this object (row compaction, flag fence)
-        self.copy_stream, self.copy_done, self.copy_pending, self.flags_view = None, None, False, None
+        # pipelined readback: copies enqueued on the copy stream and not yet waited for (their completion events, oldest first)
+        self.copy_stream, self.copy_events, self.copy_pending, self.copy_seq, self.flags_view = None, None, [], 0, None
         self.frame_no = 0
         nbytes = self.W * self.H * 4
         cptr = tracer.counters_device_ptr()
@@ -157,31 +158,32 @@ class FrameGather:
         """rank 0: pipelined readback. The device -> (pinned) host copy of the completed frame runs on a copy stream
         while the next frame is traced; in mode "peer" the "frame has been read" flag is published on that stream when
         the copy is done, so the other ranks can never overwrite a buffer that is still being read. The pixels are valid
-        after wait_frame()."""
+        after wait_frame(). Enqueue the copy of frame k BEFORE waiting for the copy of frame k-1 (wait_frame(keep=1)
+        with two alternating host buffers): the PCIe link then never idles while the host gets around to the next call."""
         torch = self.torch
         if self.mode != "peer":  # only the flag protocol protects a buffer that is still being copied
             return self.read_frame_into(host_tensor)
         if self.copy_stream is None:
             self.copy_stream = torch.cuda.Stream(device=self.device)
-            self.copy_done = torch.cuda.Event()
-            if self.mode == "peer":
-                self.flags_view = torch.as_tensor(_DevPtr(self.local_bufs[2], 256), device=self.device).view(torch.int32)
+            self.copy_events = [torch.cuda.Event(), torch.cuda.Event()]
+            self.flags_view = torch.as_tensor(_DevPtr(self.local_bufs[2], 256), device=self.device).view(torch.int32)
         ready = torch.cuda.Event()
         ready.record(self.stream)  # after the fence of the frame just gathered
         self.copy_stream.wait_event(ready)
+        done = self.copy_events[self.copy_seq & 1]
+        self.copy_seq += 1
         with torch.cuda.stream(self.copy_stream):
-            src = self.frames[self.ready] if self.mode in ("peer", "peer_allreduce") else self.frame.view(-1)
-            host_tensor.copy_(src, non_blocking=True)
-            if self.mode == "peer" and self.consumed_signalled < self.frame_no:
+            host_tensor.copy_(self.frames[self.ready], non_blocking=True)
+            if self.consumed_signalled < self.frame_no:
                 self.flags_view[self.world:self.world + 1].fill_(self.frame_no)  # frame k has been read (k + 1)
                 self.consumed_signalled = self.frame_no
-            self.copy_done.record(self.copy_stream)
-        self.copy_pending = True
+            done.record(self.copy_stream)
+        self.copy_pending.append(done)
 
-    def wait_frame(self):
-        if self.copy_pending:
-            self.copy_done.synchronize()
-            self.copy_pending = False
+    def wait_frame(self, keep: int = 0):
+        """Blocks until at most `keep` of the copies enqueued by read_frame_async are still in flight (oldest first)."""
+        while len(self.copy_pending) > keep:
+            self.copy_pending.pop(0).synchronize()
 
     def read_frame_into(self, host_tensor):
         """rank 0: device -> (pinned) host copy of the completed frame, synchronous."""

@@ -79,3 +79,72 @@ def test_sharded_render_gathers_to_rank0(tmp_path, world):
     result = tmp_path / "result.txt"
     mp.spawn(_worker, args=(world, port, 96, 70, str(result)), nprocs=world, join=True)
     assert result.read_text() == "True True"
+
+
+def test_pipelined_readback_keeps_one_copy_in_flight():
+    """FrameGather.read_frame_async / wait_frame(keep) with stand-ins for the CUDA objects (no GPU here): the copy of
+    frame k is enqueued before the host waits for the copy of frame k-1, events alternate so that a pending copy's
+    event is never re-recorded, and every frame publishes its "has been read" flag on the copy stream."""
+    import contextlib
+    import types
+
+    from raytracer_rs_b200.multi_gpu import FrameGather
+
+    log = []
+
+    class Event:
+        n = 0
+
+        def __init__(self):
+            Event.n += 1
+            self.id, self.recorded, self.synced = Event.n, 0, 0
+
+        def record(self, stream):
+            self.recorded += 1
+            log.append(("record", self.id, stream.name))
+
+        def synchronize(self):
+            self.synced += 1
+            log.append(("sync", self.id))
+
+    class Stream:
+        def __init__(self, device=None, name="copy"):
+            self.name = name
+
+        def wait_event(self, ev):
+            log.append(("wait_event", self.name, ev.id))
+
+    class Flags:
+        def __getitem__(self, sl):
+            return self
+
+        def fill_(self, v):
+            log.append(("read_flag", v))
+
+    class Host:
+        def copy_(self, src, non_blocking=False):
+            log.append(("copy", src))
+
+    cuda = types.SimpleNamespace(Stream=Stream, Event=Event, stream=lambda s: contextlib.nullcontext())
+    g = FrameGather.__new__(FrameGather)
+    g.torch = types.SimpleNamespace(cuda=cuda, as_tensor=lambda *a, **k: types.SimpleNamespace(view=lambda dt: Flags()), int32=None)
+    g.mode, g.device, g.stream, g.world = "peer", None, Stream(name="render"), 4
+    g.copy_stream, g.copy_events, g.copy_pending, g.copy_seq, g.flags_view = None, None, [], 0, None
+    g.local_bufs, g.frames, g.consumed_signalled = [0, 0, 0], ["buffer0", "buffer1"], 0
+    hosts = [Host(), Host()]
+    for k in range(5):
+        g.ready, g.frame_no = k & 1, k + 1  # what device_gather leaves behind for frame k
+        g.read_frame_async(hosts[k & 1])
+        assert len(g.copy_pending) == min(k + 1, 2)
+        g.wait_frame(keep=1)
+        assert len(g.copy_pending) == 1
+    g.wait_frame()
+    assert g.copy_pending == []
+    copies = [e for e in log if e[0] == "copy"]
+    assert copies == [("copy", "buffer%d" % (k & 1)) for k in range(5)]
+    assert [e[1] for e in log if e[0] == "read_flag"] == [1, 2, 3, 4, 5]
+    syncs = [e[1] for e in log if e[0] == "sync"]
+    assert len(syncs) == 5 and len(set(syncs)) == 2  # two alternating completion events, each copy waited for once
+    # the host never waits for copy k before copy k+1 has been enqueued (except for the last one)
+    order = [e for e in log if e[0] in ("copy", "sync")]
+    assert [e[0] for e in order] == ["copy", "copy", "sync", "copy", "sync", "copy", "sync", "copy", "sync", "sync"]
