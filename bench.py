@@ -232,6 +232,9 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "peer_allreduce", "nccl"], help="N>1: how rank 0 receives the frame")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: samples per pixel per step = N (weak) or 1 (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-launch-timing", action="store_true",
+                    help="developer: RT_TUNE_TIME_LAUNCHES = 0 in the device-timed and end-to-end legs (the library then skips the two CUDA "
+                         "events behind launch_stats().trace_kernel_ms); the roofline leg, which needs that figure, switches them back on")
     ap.add_argument("--tune", default="", help="developer: comma separated key=value pairs passed to rt_set_tuning")
     ap.add_argument("--sync-readback", action="store_true",
                     help="e2e leg (N=1): blocking rt_get_tonemapped_pixels after every trace call instead of the pipelined "
@@ -280,6 +283,8 @@ def main():
     for kv in filter(None, args.tune.split(",")):
         k, v = kv.split("=")
         tracer.set_tuning(int(k), int(v))
+    if args.no_launch_timing:
+        tracer.set_tuning(10, 0)
     stream = torch.cuda.Stream(device=dev)
     tracer.set_stream(stream.cuda_stream)
 
@@ -348,11 +353,14 @@ def main():
     value = rays_per_step * args.steps / (total_ms * 1e-3) / 1e6
 
     # ---- trace-kernel duration for the roofline (library's own CUDA events around the kernel, same stream) ----
+    tracer.set_tuning(10, 1)
     with torch.cuda.stream(stream):
         for _ in range(20):
             flush.zero_()
             tracer.trace_rows(0, H, spp, want_shadow=False)
             kernel_ms.append(tracer.launch_stats()["trace_kernel_ms"])
+    if args.no_launch_timing:
+        tracer.set_tuning(10, 0)
     kms = float(np.mean(kernel_ms))
     kms_t = torch.tensor([kms], dtype=torch.float64, device=dev)
     if world > 1:

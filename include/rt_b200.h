@@ -244,6 +244,10 @@ uint32_t rt_launch_param_bytes(void);
    `from` percent of its length on — a warp claims `batch` slots with one atomic (defaults 4 and 33; batch 1 = off). */
 #define RT_TUNE_QUEUE_BATCH 8
 #define RT_TUNE_QUEUE_BATCH_FROM 9
+/* RT_TUNE_TIME_LAUNCHES: 1 (default) every trace call records two CUDA events around its kernels so that
+   rt_launch_stats.trace_kernel_ms is available; 0 skips them (trace_kernel_ms reads 0) — two stream operations less per
+   call for hosts that time frames themselves. */
+#define RT_TUNE_TIME_LAUNCHES 10
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {

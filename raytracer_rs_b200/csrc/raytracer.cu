@@ -136,6 +136,8 @@ struct rt_raytracer {
     int pool_refill = 16;       // RT_TUNE_POOL_REFILL
     int pool_min_inner = 8;     // RT_TUNE_POOL_MIN_INNER
     int pool_blocks = 0;        // resident blocks per SM of the ray-pool kernel
+    int time_launches = 1;      // RT_TUNE_TIME_LAUNCHES: record the two CUDA events behind rt_launch_stats.trace_kernel_ms
+    bool last_timed = false;    // the last trace call recorded them
     int lpt_schedule = 1;       // RT_TUNE_TILE_SCHEDULE: 1 = heaviest tiles first (cost feedback), 0 = image order
     // cost-feedback schedule state, valid for one launch geometry (first_row, rows, row list)
     DevBuf<uint32_t> d_tile_cost, d_tile_order;
@@ -718,7 +720,8 @@ struct rt_raytracer {
         RT_CUDA(cudaMemsetAsync(d_counters.p, 0, CNT_QUEUE_ITEMS * sizeof(unsigned long long), stream));  // keeps the item count
         queue_is_zero = true;
         last = rt_launch_stats{};
-        RT_CUDA(cudaEventRecord(ev_start, stream));
+        last_timed = time_launches != 0;
+        if (last_timed) RT_CUDA(cudaEventRecord(ev_start, stream));
         uint32_t launches = 0;
         if (wraps_twice) {
             // the same pixel appears more than once: keep the reference's sequential order, one launch per lap (a launch
@@ -771,7 +774,7 @@ struct rt_raytracer {
                 ++launches;
             }
         }
-        RT_CUDA(cudaEventRecord(ev_stop, stream));
+        if (last_timed) RT_CUDA(cudaEventRecord(ev_stop, stream));
         // the ray counters are fetched only if somebody asks for them before the next trace call (finish_stats)
         total_kernels += launches;
         last.kernels_launched += launches;
@@ -785,7 +788,7 @@ struct rt_raytracer {
         RT_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, CNT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         RT_CUDA(cudaStreamSynchronize(stream));
         float ms = 0.f;
-        RT_CUDA(cudaEventElapsedTime(&ms, ev_start, ev_stop));
+        if (last_timed) RT_CUDA(cudaEventElapsedTime(&ms, ev_start, ev_stop));
         last.trace_kernel_ms = ms;
         last.n_shadow = h_counters[CNT_SHADOW];
         last.n_bounce = h_counters[CNT_BOUNCE];
@@ -1280,6 +1283,10 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     }
     if (key == RT_TUNE_POOL_BLOCKS && value >= 0 && value <= 8) {
         rt->pool_blocks = value;  // 0 = as many as fit
+        return RT_OK;
+    }
+    if (key == RT_TUNE_TIME_LAUNCHES && (value == 0 || value == 1)) {
+        rt->time_launches = value;
         return RT_OK;
     }
     if (key == RT_TUNE_TILE_SCHEDULE && (value == 0 || value == 1)) {

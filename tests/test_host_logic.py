@@ -404,3 +404,17 @@ def test_bench_reference_work_constants_are_the_oracles_counters(scenes, workloa
            c["tri_tests"]["primary"] + c["tri_tests"]["shadow"])
     assert got == bench.REFERENCE_WORK[workload]
     assert bench.algorithmic_bytes(workload) == 24 * got[2] + 36 * got[3] + 4 * got[0]
+
+
+def test_tuning_knobs_accept_their_documented_ranges(scenes):
+    """rt_set_tuning (include/rt_b200.h): every knob takes its documented values and rejects the first value outside."""
+    r = host_tracer(scenes("4boxes"))
+    ranges = {0: (0, 2), 1: (0, 1), 2: (1, 32), 3: (0, 8), 4: (0, 32), 5: (0, 2), 6: (0, 1), 7: (0, 64), 8: (1, 64), 9: (0, 100), 10: (0, 1)}
+    for key, (lo, hi) in ranges.items():
+        r.set_tuning(key, lo)
+        r.set_tuning(key, hi)
+        for bad in (lo - 1, hi + 1):
+            with pytest.raises(rt.RtError):
+                r.set_tuning(key, bad)
+    with pytest.raises(rt.RtError):
+        r.set_tuning(11, 0)
