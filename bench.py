@@ -131,14 +131,27 @@ def run_reference(args):
     orc = Oracle(scene, w, h, rt.DEFAULT_TRIANGLES_PER_LEAF)
     orc.configure(recursions=0, jitter=JITTER_FIXED)
     threads = orc_lib().orc_max_threads()
-    for _ in range(args.warmup):
-        orc.trace_rows(0, h, spp, threads=threads)
+    # Bounded sample: a step is the whole frame unless steps + warmup whole frames would take longer than --reference-budget
+    # seconds on this host; then a step is one of `parts` equal row ranges, rotating over the frame from step to step, so
+    # that any `parts` consecutive steps cover the frame once (rays are counted exactly either way).
+    t1 = time.perf_counter()
+    orc.trace_rows(0, h, spp, threads=threads)
+    orc.get_tonemapped_pixels()
+    t_frame = time.perf_counter() - t1
+    parts = max(1, min(h // 8, int(-(-t_frame * (args.steps + args.warmup) // args.reference_budget))))
+    rows = -(-h // parts)
+
+    def step(i):
+        first = (i % parts) * rows
+        orc.trace_rows(first, min(rows, h - first), spp, threads=threads)
         orc.get_tonemapped_pixels()
+
+    for i in range(args.warmup):
+        step(i)
     orc.counters(reset=True)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.trace_rows(0, h, spp, threads=threads)
-        orc.get_tonemapped_pixels()
+    for i in range(args.steps):
+        step(i)
     dt = time.perf_counter() - t0
     c = orc.counters()
     rays = c["rays"]["primary"] + c["rays"]["shadow"]
@@ -158,9 +171,12 @@ def run_reference(args):
         "dtype": "f32",
         "data": "reference scene fixture data/%s (the upstream repository's own scene), pinned camera" % fname,
         "config": {"workload": args.workload, "width": w, "height": h, "spp": spp, "recursions": 0, "jitter": "fixed 0.5",
-                   "accel": "reference octree, triangles_per_leaf 70", "step": "one full frame + get_tonemapped_pixels"},
+                   "accel": "reference octree, triangles_per_leaf 70",
+                   "step": ("one full frame" if parts == 1 else "%d rows (1/%d of the frame, rotating)" % (rows, parts)) + " + get_tonemapped_pixels"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d full frames (%d rays) of the same workload, OpenMP over rows" % (args.steps, rays)},
+                         "sample": ("%d full frames" % args.steps if parts == 1 else
+                                    "%d steps of %d rows each (1/%d of the frame, rotating over it)" % (args.steps, rows, parts))
+                                   + " (%d rays) of the same workload, OpenMP over rows" % rays},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -232,6 +248,8 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "peer_allreduce", "nccl"], help="N>1: how rank 0 receives the frame")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: samples per pixel per step = N (weak) or 1 (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-budget", type=float, default=150.0,
+                    help="--impl reference: seconds the whole run may take; longer runs trace a rotating part of the frame per step")
     ap.add_argument("--no-launch-timing", action="store_true",
                     help="developer: RT_TUNE_TIME_LAUNCHES = 0 in the device-timed and end-to-end legs (the library then skips the two CUDA "
                          "events behind launch_stats().trace_kernel_ms); the roofline leg, which needs that figure, switches them back on")
