@@ -15,9 +15,9 @@
 //   trace_shade_kernel<ACCEL, BOUNCE>             one thread per pixel (variant 0, kept for A/B runs)
 //   trace_shade_pool_kernel                       ray pool with shared-memory ray rings (variant 2)
 //   wf_bounce_kernel<ACCEL>, wf_shade_kernel<ACCEL>, wf_combine_kernel    bounce wavefront (RECURSIONS > 0)
-//   film_accumulate_kernel                        ordered accumulation of the sample planes of a multi-sample launch
+//   film_accumulate_kernel                        ordered accumulation of the sample planes of a multi-sample launch (odd spp)
 //   tile_sort_kernel                              heaviest-first order of the tile queue from last launch's tile costs
-//   flag_signal_kernel, flag_wait_kernel          cross-GPU frame fence of the fused peer-store gather
+//   flag_signal_kernel, flag_signal_wait_kernel, flag_wait_kernel    cross-GPU frame fence of the fused peer-store gather
 //   film_clear_kernel, tonemap_pack_kernel, gather_rows_kernel
 // ACCEL: 0 exact octree, 1 binary BVH (host SAH or GPU LBVH), 2 compressed 8-wide BVH, 3 4-wide BVH.
 #include <cuda_runtime.h>
