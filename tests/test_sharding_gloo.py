@@ -148,3 +148,44 @@ def test_pipelined_readback_keeps_one_copy_in_flight():
     # the host never waits for copy k before copy k+1 has been enqueued (except for the last one)
     order = [e for e in log if e[0] in ("copy", "sync")]
     assert [e[0] for e in order] == ["copy", "copy", "sync", "copy", "sync", "copy", "sync", "copy", "sync", "sync"]
+
+
+def test_peer_fence_protocol_calls():
+    """FrameGather.device_gather in mode "peer" with a recording stand-in for the tracer: every rank issues exactly one
+    fence launch per frame. Rank r != 0 signals "frame k done" as flags[r] = k + 1 and, from frame 1 on, waits in the
+    same launch for flags[world] >= k ("frame k-1 has been read": frame k+1 reuses its buffer); rank 0 signals its own
+    slot, waits for all slots and, when the frame stays on the device, publishes "read" in that launch too. The store
+    target alternates between the two frame buffers."""
+    import contextlib
+    import types
+
+    from raytracer_rs_b200.multi_gpu import FrameGather
+
+    def gather(rank, world):
+        calls = []
+        tracer = types.SimpleNamespace(
+            signal_flag=lambda p, v: calls.append(("signal", p, v)),
+            signal_then_wait=lambda p, v, q, t: calls.append(("signal_then_wait", p, v, q, t)),
+            wait_flags=lambda p, n, t, s=-1, r=-1: calls.append(("wait", p, n, t, s, r)),
+            set_ldr_target=lambda p: calls.append(("target", p)))
+        g = FrameGather.__new__(FrameGather)
+        g.torch = types.SimpleNamespace(cuda=types.SimpleNamespace(stream=lambda s: contextlib.nullcontext()))
+        g.dist, g.tracer, g.rank, g.world, g.mode, g.stream = None, tracer, rank, world, "peer", None
+        g.flags, g.targets, g.frame_no, g.kernels, g.consumed_signalled = 1000, [0xA000, 0xB000], 0, 0, 0
+        return g, calls
+
+    g, calls = gather(rank=2, world=4)
+    for _ in range(4):
+        g.begin_frame()  # enqueues nothing any more
+        g.device_gather()
+    assert calls == [("signal", 1008, 1), ("target", 0xB000),
+                     ("signal_then_wait", 1008, 2, 1016, 1), ("target", 0xA000),
+                     ("signal_then_wait", 1008, 3, 1016, 2), ("target", 0xB000),
+                     ("signal_then_wait", 1008, 4, 1016, 3), ("target", 0xA000)]
+    assert g.kernels == 4 and g.frame_no == 4
+
+    g, calls = gather(rank=0, world=4)
+    g.device_gather(release=True)
+    g.device_gather()
+    assert calls == [("wait", 1000, 4, 1, 0, 4), ("target", 0xB000), ("wait", 1000, 4, 2, 0, -1), ("target", 0xA000)]
+    assert g.consumed_signalled == 1 and g.ready == 1 and g.kernels == 2
