@@ -10,4 +10,4 @@ ms = []
 for i in range(12):
     t.trace_rows(0, h, n, want_shadow=False)
     ms.append(round(t.launch_stats()["trace_kernel_ms"], 4))
-print("shard 0 of", n, "kernel ms (trace + accumulate)", ms)
+print("shard 0 of", n, "pass ms (sample lanes: one trace launch; odd sample counts: trace + accumulate)", ms)
