@@ -68,6 +68,15 @@ typedef struct rt_scene_desc {
     const rt_texture* textures;
     float camera_orientation[16]; /* cameras[0]: ColladaMatrix::to_vecmath_matrix of its node (row-vector convention) */
     float camera_fov_deg;         /* xfov */
+    /* Reserved per-vertex attributes, both may be NULL. The reference parses the NORMAL and TEXCOORD inputs of a
+       <triangles> element but consumes only the positions (scene/loaders/colladaloader.rs:587-593): normals are
+       recomputed per hit from the vertices (raytracer/mod.rs:198-205) and texture lookups use the hit's barycentrics
+       (raytracer/mod.rs:246). The path therefore IGNORES these arrays, exactly as the reference does; they are part of
+       the structure so that a host which keeps them (the Rust loader does, in its Collada DOM) has a slot to pass them
+       and a future shading model needs no ABI change. Layout when present: normals num_triangles*9 (one xyz per
+       vertex, same order as `vertices`), uvs num_triangles*6 (one uv per vertex). */
+    const float* normals;
+    const float* uvs;
 } rt_scene_desc;
 
 /* ---- configuration ------------------------------------------------------------------------------------ */
@@ -142,6 +151,15 @@ int rt_trace_rows(rt_raytracer* rt, uint32_t first_row, uint32_t n_rows, uint32_
                   uint64_t* n_shadow);
 /* RayTracer::get_tonemapped_pixels(&self) -> Vec<u32>   (mod.rs:120-128): width*height 0xAARRGGBB, caller-allocated. */
 int rt_get_tonemapped_pixels(rt_raytracer* rt, uint32_t* out);
+/* Incremental form of the same readback for a host that keeps ONE frame buffer across calls, which is what the reference's
+   render loop amounts to (trace_frame_additive traces 50 rows, get_tonemapped_pixels converts the whole frame,
+   raytracer/src/main.rs:200-201: 2.07 M pixel conversions and 8.3 MB for 96 000 traced pixels at 1080p). `out` must be the
+   buffer passed to the previous rt_get_tonemapped_pixels_delta call on this handle, unmodified since; then only the rows
+   whose pixels can have changed since that call (rows traced, film cleared or replaced) are copied — 384 KB instead of
+   8.3 MB after a 50-row call — and the buffer again equals what rt_get_tonemapped_pixels would deliver. A different (or
+   first) buffer receives the whole frame. The contract is the caller's: a buffer that was freed and reallocated at the
+   same address, or scribbled over, keeps its stale rows. */
+int rt_get_tonemapped_pixels_delta(rt_raytracer* rt, uint32_t* out);
 /* Pipelined form of the same readback, for a host that double-buffers frames the way the reference's render and GUI
    threads do (raytracer/src/main.rs:200-209): takes a device-side snapshot of the packed frame on the render stream
    (a few microseconds) and copies it to `pinned_out` (page-locked host memory) on a separate copy stream, so the
@@ -153,6 +171,13 @@ int rt_wait_pixels(rt_raytracer* rt);
 int rt_film_clear(rt_raytracer* rt);
 /* Film contents: width*height*7 floats per pixel: sum rgb, sum of squares rgb, num_samples (film.rs:3-7). */
 int rt_get_film(rt_raytracer* rt, float* out);
+/* Overwrites the film (`pub film: Film` with `pub pixel_datas`, film.rs:27-29, is writable in the reference too) from the
+   layout rt_get_film returns; the packed frame is recomputed from it. num_samples must be an integer in [0, 2^32). */
+int rt_set_film(rt_raytracer* rt, const float* in);
+/* Film::get_estimated_variances(&self) -> Vec<RGB>   (film.rs:50-67): width*height*3 floats, per pixel and channel
+   (sum_sq / (n (n-1)) - sum^2 / (n * n (n-1))) * 50, with n (n-1) evaluated in wrapping u32 arithmetic before the
+   conversion to f32 as the reference's release build does. Pixels with n <= 1 are NaN (x/0 - y/0), as in the reference. */
+int rt_get_estimated_variances(rt_raytracer* rt, float* out);
 /* Parity hook: global triangle index (geometry order, then triangle order) of the last primary hit per pixel,
    0xFFFFFFFF for a miss. */
 int rt_get_primary_ids(rt_raytracer* rt, uint32_t* out);
@@ -195,7 +220,7 @@ int rt_ipc_open(rt_raytracer* rt, const uint8_t* handle64, void** dev_ptr);
 int rt_ipc_close(rt_raytracer* rt, void* dev_ptr);
 /* Cross-GPU frame fence for the fused gather (all stream-ordered on the handle's stream, no host synchronisation):
    rt_stream_signal_flag stores `value` into *dev_flag (system scope) once everything enqueued before it has finished;
-   rt_stream_wait_flags holds the stream until every one of dev_flags[0..n_flags) (uint32, n_flags <= 32, typically
+   rt_stream_wait_flags holds the stream until every one of dev_flags[0..n_flags) (uint32, typically
    peer-mapped memory of rank 0) has reached `target` (wrap-safe >=); in the same launch it can first store `target`
    into dev_flags[signal_slot] and afterwards into dev_flags[release_slot] (-1 = none), which is rank 0's whole
    per-frame fence. rt_stream_signal_then_wait is the per-frame fence of every other rank in one launch: store `value`
@@ -207,8 +232,15 @@ int rt_stream_signal_then_wait(rt_raytracer* rt, void* dev_signal_flag, uint32_t
 int rt_stream_wait_flags(rt_raytracer* rt, void* dev_flags, uint32_t n_flags, uint32_t target, int32_t signal_slot,
                          int32_t release_slot);
 int rt_sync_timeouts(rt_raytracer* rt, uint32_t* count);
-/* Device pointer to the 4 uint64 ray counters of the last launch: shadow rays, primary hits, bounce rays, blocked
-   shadow rays (zeroed at the start of every trace call). */
+/* Fuses the "my stores of this frame are done" half of that fence into the NEXT trace call (one-shot): the last warp out of
+   the call's last kernel stores `value` into *dev_flag at system scope, after every warp has fenced its own stores into
+   the peer-mapped frame — no separate signal launch, and the flag is on its way while the launch drains. Calls whose last
+   kernel does not finish the pixels itself (sample planes, bounce wavefront, the one-thread-per-pixel variant) append
+   the signal as a launch of its own; either way the flag is published exactly once per armed call. */
+int rt_set_done_signal(rt_raytracer* rt, void* dev_flag, uint32_t value);
+/* Device pointer to the 4 uint64 ray counters of the LAST trace call: shadow rays, primary hits, bounce rays, blocked
+   shadow rays. Two sets alternate from call to call (the kernel of one call zeroes the set of the next, so a call needs no
+   memset): ask again after every trace call. */
 int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr);
 /* Bytes of per-launch parameters (camera + pointers) that travel host -> device with every trace launch. */
 uint32_t rt_launch_param_bytes(void);
@@ -237,8 +269,8 @@ uint32_t rt_launch_param_bytes(void);
    compacted into a dense list and the next level's rays fill whole warps; 0 every pixel walks its bounce tree depth
    first inside the trace kernel. Same rays, same film. */
 #define RT_TUNE_BOUNCE_WAVEFRONT 6
-/* RT_TUNE_SPLIT_QUARTERS (variant 1, BVH kernels): tiles whose recorded cost exceeds (balanced launch time) * q / 4 are
-   handed out as four one-row items; 0 = never split (default 4). */
+/* RT_TUNE_SPLIT_QUARTERS (variant 1, BVH kernels): tiles whose recorded cost exceeds T = (balanced launch time) * q / 4 are
+   handed out as 4 (cost <= 4T), 8 (<= 8T) or 16 items; 0 = never split (default 4). */
 #define RT_TUNE_SPLIT_QUARTERS 7
 /* RT_TUNE_QUEUE_BATCH / RT_TUNE_QUEUE_BATCH_FROM (variant 1): in the cheap tail of the cost-sorted tile queue — from
    `from` percent of its length on — a warp claims `batch` slots with one atomic (defaults 4 and 33; batch 1 = off). */
@@ -248,6 +280,12 @@ uint32_t rt_launch_param_bytes(void);
    rt_launch_stats.trace_kernel_ms is available; 0 skips them (trace_kernel_ms reads 0) — two stream operations less per
    call for hosts that time frames themselves. */
 #define RT_TUNE_TIME_LAUNCHES 10
+/* RT_TUNE_MIN_SCHEDULE_TILES: launches with fewer 32-lane tiles than this run in image order without cost feedback
+   (default 1024: a 50-row band of a 1024-wide frame has 1664). RT_TUNE_MAX_SPLIT_LEVEL: finest split of a heavy tile,
+   0 never, 1 / 2 / 3 = up to 4 / 8 / 16 items of 8 / 4 / 2 pixels (default 3; the finer levels only engage when a tile
+   alone costs more than 4x / 8x the balanced launch time, i.e. when the launch cannot fill the GPU). */
+#define RT_TUNE_MIN_SCHEDULE_TILES 11
+#define RT_TUNE_MAX_SPLIT_LEVEL 12
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {

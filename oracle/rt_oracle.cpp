@@ -774,6 +774,22 @@ struct RayTracer {
     void film_clear() {  // film.rs:37-41
         for (PixelData& p : film) p = PixelData();
     }
+    // Film::get_estimated_variances, film.rs:50-67 (dead code in the reference, restated for completeness of the film API).
+    // `num_samples * (num_samples - 1)` is u32 arithmetic: the release build the reference ships (ci.yaml:35-39) wraps, so
+    // n = 0 gives 0 * 0xffffffff = 0 (a debug build would panic); n <= 1 therefore yields x/0 - y/0 = NaN in every channel.
+    void get_estimated_variances(float* out) const {
+        for (size_t i = 0; i < film.size(); ++i) {
+            const PixelData& pd = film[i];
+            const float n_times_n_minus_1 = (float)(uint32_t)(pd.n * (pd.n - 1u));
+            const float n_squared_times_n_minus_1 = (float)pd.n * n_times_n_minus_1;
+            const float vr = pd.sum_sq.r / n_times_n_minus_1 - pd.sum.r * pd.sum.r / n_squared_times_n_minus_1;
+            const float vg = pd.sum_sq.g / n_times_n_minus_1 - pd.sum.g * pd.sum.g / n_squared_times_n_minus_1;
+            const float vb = pd.sum_sq.b / n_times_n_minus_1 - pd.sum.b * pd.sum.b / n_squared_times_n_minus_1;
+            out[3 * i] = vr * 50.0f;
+            out[3 * i + 1] = vg * 50.0f;
+            out[3 * i + 2] = vb * 50.0f;
+        }
+    }
 };
 
 }  // namespace orc
@@ -898,6 +914,20 @@ void orc_trace_rows(void* h, uint32_t first_row, uint32_t n_rows, uint32_t spp, 
     ((orc::RayTracer*)h)->trace_rows(first_row, n_rows, spp, threads);
 }
 void orc_get_tonemapped_pixels(void* h, uint32_t* out) { ((orc::RayTracer*)h)->get_tonemapped_pixels(out); }
+// out: width*height*3 floats (film.rs:50-67)
+void orc_get_estimated_variances(void* h, float* out) { ((orc::RayTracer*)h)->get_estimated_variances(out); }
+// test hook: overwrite the film (layout of orc_get_film: sum rgb, sum_sq rgb, n) so that edge cases of the film functions
+// (n = 0, n = 1, wrapping n * (n - 1)) can be pinned and a film produced elsewhere can be run through the oracle's readers
+void orc_set_film(void* h, const float* in, const uint32_t* n) {
+    orc::RayTracer* rt = (orc::RayTracer*)h;
+    for (size_t i = 0; i < rt->film.size(); ++i) {
+        orc::PixelData& p = rt->film[i];
+        const float* o = in + 7 * i;
+        p.sum = orc::RGB{o[0], o[1], o[2]};
+        p.sum_sq = orc::RGB{o[3], o[4], o[5]};
+        p.n = n ? n[i] : (uint32_t)o[6];
+    }
+}
 void orc_get_primary_ids(void* h, uint32_t* out) {
     orc::RayTracer* rt = (orc::RayTracer*)h;
     memcpy(out, rt->primary_ids.data(), rt->primary_ids.size() * 4);

@@ -56,6 +56,8 @@ class CSceneDesc(C.Structure):
         ("textures", C.POINTER(CTexture)),
         ("camera_orientation", C.c_float * 16),
         ("camera_fov_deg", C.c_float),
+        ("normals", C.POINTER(C.c_float)),  # reserved, may be NULL: ignored as the reference ignores them (colladaloader.rs:587-593)
+        ("uvs", C.POINTER(C.c_float)),
     ]
 
 
@@ -92,11 +94,12 @@ ABI_SYMBOLS = [
     "rt_config_default", "rt_scene_load_file", "rt_scene_load_str", "rt_scene_get_desc", "rt_scene_free",
     "rt_create_raytracer", "rt_create_raytracer_from_file", "rt_create", "rt_destroy", "rt_last_error",
     "rt_configure", "rt_set_rows_per_call", "rt_trace_frame_additive", "rt_trace_rows",
-    "rt_get_tonemapped_pixels", "rt_get_tonemapped_pixels_async", "rt_wait_pixels", "rt_film_clear", "rt_get_film", "rt_get_primary_ids", "rt_camera_move_rel",
+    "rt_get_tonemapped_pixels", "rt_get_tonemapped_pixels_delta", "rt_get_tonemapped_pixels_async", "rt_wait_pixels", "rt_film_clear", "rt_get_film",
+    "rt_set_film", "rt_get_estimated_variances", "rt_get_primary_ids", "rt_camera_move_rel",
     "rt_camera_add_x_angle", "rt_camera_add_y_angle", "rt_camera_get", "rt_camera_set_state", "rt_set_stream",
     "rt_get_ldr_device_ptr", "rt_set_ldr_target", "rt_get_owned_ldr_rows_device", "rt_get_launch_stats",
     "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_get_counters_device_ptr",
-    "rt_stream_signal_flag", "rt_stream_signal_then_wait", "rt_stream_wait_flags", "rt_sync_timeouts",
+    "rt_stream_signal_flag", "rt_stream_signal_then_wait", "rt_stream_wait_flags", "rt_sync_timeouts", "rt_set_done_signal",
     "rt_launch_param_bytes", "rt_set_tuning", "rt_set_host_frame",
     "rt_kernels_launched", "rt_get_ray_totals", "rt_octree_stats", "rt_octree_export", "rt_bvh_stats", "rt_bvh_export", "rt_bvh4_stats", "rt_bvh4_export", "rt_lbvh_build", "rt_lbvh_export", "rt_cwbvh_stats",
     "rt_cwbvh_export", "rt_stats_new",
@@ -142,10 +145,13 @@ def lib() -> C.CDLL:
         "rt_trace_frame_additive": (C.c_int, [vp, P(u32)]),
         "rt_trace_rows": (C.c_int, [vp, u32, u32, u32, P(u64), P(u64)]),
         "rt_get_tonemapped_pixels": (C.c_int, [vp, vp]),
+        "rt_get_tonemapped_pixels_delta": (C.c_int, [vp, vp]),
         "rt_get_tonemapped_pixels_async": (C.c_int, [vp, vp]),
         "rt_wait_pixels": (C.c_int, [vp]),
         "rt_film_clear": (C.c_int, [vp]),
         "rt_get_film": (C.c_int, [vp, vp]),
+        "rt_set_film": (C.c_int, [vp, vp]),
+        "rt_get_estimated_variances": (C.c_int, [vp, vp]),
         "rt_get_primary_ids": (C.c_int, [vp, vp]),
         "rt_camera_move_rel": (C.c_int, [vp, f32, f32, f32]),
         "rt_camera_add_x_angle": (C.c_int, [vp, f32]),
@@ -167,6 +173,7 @@ def lib() -> C.CDLL:
         "rt_stream_signal_then_wait": (C.c_int, [vp, vp, u32, vp, u32]),
         "rt_stream_wait_flags": (C.c_int, [vp, vp, u32, u32, i32, i32]),
         "rt_sync_timeouts": (C.c_int, [vp, P(u32)]),
+        "rt_set_done_signal": (C.c_int, [vp, vp, u32]),
         "rt_launch_param_bytes": (u32, []),
         "rt_set_tuning": (C.c_int, [vp, i32, i32]),
         "rt_set_host_frame": (C.c_int, [vp, vp]),
@@ -328,6 +335,18 @@ class _Film:
         self._rt._check(lib().rt_get_film(self._rt._h, _ptr(out)))
         return out
 
+    def set_pixel_datas(self, film7: np.ndarray) -> None:
+        """overwrite the film (`pub pixel_datas`, film.rs:27-29) from the layout pixel_datas() returns"""
+        a = np.ascontiguousarray(film7, np.float32)
+        assert a.shape == (self._rt.width * self._rt.height, 7)
+        self._rt._check(lib().rt_set_film(self._rt._h, _ptr(a)))
+
+    def get_estimated_variances(self) -> np.ndarray:
+        """Film::get_estimated_variances (film.rs:50-67): [W*H, 3]"""
+        out = np.zeros((self._rt.width * self._rt.height, 3), np.float32)
+        self._rt._check(lib().rt_get_estimated_variances(self._rt._h, _ptr(out)))
+        return out
+
 
 class RayTracer:
     """Device-resident `RayTracer` (raytracer/mod.rs:32-128)."""
@@ -374,6 +393,12 @@ class RayTracer:
         d.textures = texs
         d.camera_orientation[:] = [float(x) for x in scene.camera_orientation]
         d.camera_fov_deg = float(scene.camera_fov_deg)
+        for name in ("normals", "uvs"):  # reserved attributes: passed through when the scene object has them, ignored by the path
+            arr = getattr(scene, name, None)
+            if arr is not None:
+                arr = np.ascontiguousarray(arr, dtype=np.float32)
+                keep.append(arr)
+                setattr(d, name, arr.ctypes.data_as(C.POINTER(C.c_float)))
         cfg = config.to_c()
         h = C.c_void_p()
         err = C.create_string_buffer(1024)
@@ -412,6 +437,11 @@ class RayTracer:
     def get_tonemapped_pixels_into(self, host_ptr: int) -> None:
         """Same, into a caller-owned (ideally pinned) host buffer given by address."""
         self._check(lib().rt_get_tonemapped_pixels(self._h, C.c_void_p(host_ptr)))
+
+    def get_tonemapped_pixels_delta_into(self, host_ptr: int) -> None:
+        """Incremental readback into a buffer the caller keeps across calls: only the rows that changed since the previous
+        call with the same buffer are copied (rt_get_tonemapped_pixels_delta)."""
+        self._check(lib().rt_get_tonemapped_pixels_delta(self._h, C.c_void_p(host_ptr)))
 
     def get_tonemapped_pixels_async(self, pinned_host_ptr: int) -> None:
         """Pipelined readback: snapshot now, device -> host copy on a second stream while the next trace call runs.
@@ -500,6 +530,10 @@ class RayTracer:
 
     def wait_flags(self, dev_flags: int, n_flags: int, target: int, signal_slot: int = -1, release_slot: int = -1) -> None:
         self._check(lib().rt_stream_wait_flags(self._h, dev_flags, n_flags, target, signal_slot, release_slot))
+
+    def set_done_signal(self, dev_flag: int | None, value: int) -> None:
+        """the next trace call publishes `value` at *dev_flag when its last pixel is stored (rt_set_done_signal)"""
+        self._check(lib().rt_set_done_signal(self._h, C.c_void_p(dev_flag or 0), value))
 
     def sync_timeouts(self) -> int:
         n = C.c_uint32()

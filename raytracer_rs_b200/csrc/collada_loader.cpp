@@ -580,6 +580,9 @@ void HostScene::make_desc(rt_scene_desc* d) {
     d->textures = texture_views.data();
     for (int i = 0; i < 16; ++i) d->camera_orientation[i] = camera_orientation[i];
     d->camera_fov_deg = camera_fov_deg;
+    // the NORMAL / TEXCOORD inputs are parsed past, not kept, as in the reference (colladaloader.rs:587-593)
+    d->normals = nullptr;
+    d->uvs = nullptr;
 }
 
 HostScene HostScene::from_desc(const rt_scene_desc& d) {

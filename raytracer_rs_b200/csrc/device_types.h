@@ -31,10 +31,13 @@ constexpr int kBvhStack = 48;
 constexpr int kBvh4Stack = 64;  // up to three pushes per level
 constexpr int kCwStack = 32;  // node groups only: at most one per level plus slack
 
-// slots 0..4 are zeroed by every trace call; CNT_QUEUE_ITEMS survives between launches (tile schedule); the *_TOTAL
-// slots run since the handle was created (exact ray totals over many asynchronous calls, rt_get_ray_totals)
-enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3, CNT_TILE_QUEUE = 4, CNT_QUEUE_ITEMS = 5,
-                   CNT_SHADOW_TOTAL = 6, CNT_BOUNCE_TOTAL = 7, CNT_SLOTS = 8 };
+// Ray counters (u64 slots). Per-call counters exist twice (sets A and B): a trace call counts into the set its launch
+// parameters name (TraceParams::counter_set) while the last warp out of every queue-driven launch zeroes the other set for the
+// next call and puts the tile queue back to zero (warp_checkout, kernels.cu), so a call needs no memset. The *_TOTAL slots run
+// since the handle was created (exact ray totals over many asynchronous calls, rt_get_ray_totals).
+enum CounterSlot { CNT_SHADOW = 0, CNT_PRIMARY_HITS = 1, CNT_BOUNCE = 2, CNT_BLOCKED = 3,  // offsets inside a per-call set
+                   CNT_SET_A = 0, CNT_TILE_QUEUE = 4, CNT_WARPS_DONE = 5, CNT_SHADOW_TOTAL = 6, CNT_BOUNCE_TOTAL = 7, CNT_SET_B = 8,
+                   CNT_SLOTS = 12 };
 
 // one level of the bounce wavefront: dense list of shaded hits (node record: hit point | pixel, normal | path,
 // shaded radiance | parent + child number; before wf_shade_kernel: ray origin | pixel, direction | path, t u v | triangle,
@@ -71,6 +74,12 @@ struct TraceParams {
     uint32_t* ldr_remote;  // optional second target (peer-mapped framebuffer of rank 0), may be null
     uint32_t* primary_ids;
     unsigned long long* counters;
+    uint32_t counter_set;        // CNT_SET_A or CNT_SET_B: where this call's per-call ray counters live
+    // multi-GPU fused gather: when non-null, the last warp out of the launch stores done_value here at system scope after
+    // every warp's peer stores ("my stores of this frame are done", the signal half of the frame fence)
+    uint32_t* done_flag;
+    uint32_t done_value;
+    const uint32_t* queue_items;  // number of entries of tile_order (written by tile_sort_kernel); unused when tile_order is null
     // cost-feedback tile schedule of the persistent kernel (either may be null): cycles spent per 8x4 tile in this
     // launch (written), queue slot -> tile id (read)
     uint32_t* tile_cost;

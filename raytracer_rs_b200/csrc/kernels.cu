@@ -298,10 +298,10 @@ done:
 // made only ~11 of 32 lanes useful per instruction in the first version (profiles/r1_v1_*.csv).
 // ------------------------------------------------------------------------------------------------------
 constexpr int kSentinel = 0x7fffffff;
-constexpr uint32_t kItemTileMask = 0x0fffffffu, kItemSplitFlag = 0x80000000u;
-constexpr int kItemPartShift = 28;
-// tiles costing more than (sum of costs / resident warps) * split_quarters / 4 (a launch parameter of tile_sort_kernel) ...
-constexpr uint32_t kSplitMinCycles = 40000u;  // ... and at least this many cycles
+// queue item = tile id (bits 0..23) | part (bits 24..27) | split level (bits 28..29): level 0 = the whole 32-lane tile,
+// level L > 0 = one of 2^(L+1) parts (4, 8 or 16) of 2^(4-L) consecutive lanes (8, 4 or 2 pixels of a single-sample tile)
+constexpr uint32_t kItemTileMask = 0x00ffffffu;
+constexpr int kItemPartShift = 24, kItemLevelShift = 28;
 #ifdef RT_DEBUG_STEP_COUNTS
 #define g_dbg_nodes (*dbg_nodes_ptr())
 #define g_dbg_tris (*dbg_tris_ptr())
@@ -1155,16 +1155,43 @@ __device__ __forceinline__ void flush_counters(const TraceParams& P, LaneCounter
     const uint32_t b = __reduce_add_sync(0xffffffffu, c.blocked);
     const uint32_t r = __reduce_add_sync(0xffffffffu, c.bounce_rays);
     if (lane == 0) {
+        unsigned long long* set = P.counters + P.counter_set;  // the per-call counters of this call (device_types.h)
         if (r) {
-            atomicAdd(&P.counters[CNT_BOUNCE], (unsigned long long)r);
+            atomicAdd(&set[CNT_BOUNCE], (unsigned long long)r);
             atomicAdd(&P.counters[CNT_BOUNCE_TOTAL], (unsigned long long)r);
         }
         if (s) {
-            atomicAdd(&P.counters[CNT_SHADOW], (unsigned long long)s);
+            atomicAdd(&set[CNT_SHADOW], (unsigned long long)s);
             atomicAdd(&P.counters[CNT_SHADOW_TOTAL], (unsigned long long)s);
         }
-        if (h) atomicAdd(&P.counters[CNT_PRIMARY_HITS], (unsigned long long)h);
-        if (b) atomicAdd(&P.counters[CNT_BLOCKED], (unsigned long long)b);
+        if (h) atomicAdd(&set[CNT_PRIMARY_HITS], (unsigned long long)h);
+        if (b) atomicAdd(&set[CNT_BLOCKED], (unsigned long long)b);
+    }
+}
+// Last warp out of a queue-driven launch (persistent and ray-pool kernels): leaves the device state the NEXT launch needs, so
+// that a trace call is one kernel launch and no memset — the tile queue back at zero, the other set of per-call ray counters
+// zeroed (the next call counts into it), and, on a multi-GPU run, this rank's "my stores of this frame are done" flag
+// published at system scope (every warp fenced its own peer stores before it checked out).
+__device__ __forceinline__ void warp_checkout(const TraceParams& P, uint32_t lane, uint32_t total_warps) {
+    __syncwarp();
+    if (lane == 0) {
+        if (P.done_flag) __threadfence_system();  // this warp's stores into rank 0's frame are visible before the count below
+        else __threadfence();
+        const unsigned long long done = atomicAdd(&P.counters[CNT_WARPS_DONE], 1ull) + 1ull;
+        if (done == (unsigned long long)total_warps) {
+            P.counters[CNT_TILE_QUEUE] = 0ull;
+            P.counters[CNT_WARPS_DONE] = 0ull;
+            unsigned long long* other = P.counters + (P.counter_set ^ (CNT_SET_B ^ CNT_SET_A));
+            other[CNT_SHADOW] = 0ull;
+            other[CNT_PRIMARY_HITS] = 0ull;
+            other[CNT_BOUNCE] = 0ull;
+            other[CNT_BLOCKED] = 0ull;
+            if (P.done_flag) {
+                __threadfence_system();
+                *(volatile uint32_t*)P.done_flag = P.done_value;
+                __threadfence_system();
+            }
+        }
     }
 }
 
@@ -1200,7 +1227,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
     LaneCounters cnt;
     // queue length: n_tiles in image order, or the item count the last tile_sort_kernel produced (heavy tiles are
     // split into four 8-pixel items so that their serial divergent chain is spread over four warps)
-    const uint32_t n_items = P.tile_order ? (uint32_t)P.counters[CNT_QUEUE_ITEMS] : n_tiles;
+    const uint32_t n_items = P.tile_order ? *P.queue_items : n_tiles;
     // The next queue slot is claimed when a tile's rays are done, before its film update: the atomic's round trip
     // (~1 us) overlaps the epilogue instead of sitting in front of the next tile, and the claim is early by so little
     // that the heaviest-first order is not disturbed (claiming a whole tile ahead was measured 10 % slower).
@@ -1225,8 +1252,8 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item == 0xffffffffu) break;
         const uint32_t tile = item & kItemTileMask;
-        const bool split = (item & kItemSplitFlag) != 0u;
-        const uint32_t part = (item >> kItemPartShift) & 3u;
+        const uint32_t level = (item >> kItemLevelShift) & 3u;
+        const uint32_t part = (item >> kItemPartShift) & 15u;
         const uint32_t tile_y = udiv_magic(tile, tiles_x, P.magic_tiles_x);
         uint32_t col, crow, lane_sample = 0u;
         if (SAMPLE_LANES) {
@@ -1242,7 +1269,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
             col = (tile - tile_y * tiles_x) * 8u + (lane & 7u);
             crow = tile_y * 4u + (lane >> 3);
         }
-        const bool mine = col < P.cam.width && crow < P.n_rows && (!split || (lane >> 3) == part);
+        const bool mine = col < P.cam.width && crow < P.n_rows && (level == 0u || (lane >> (4u - level)) == part);
         const long long t0 = clock64();
 #ifdef RT_DEBUG_STEP_COUNTS
         g_dbg_nodes = 0;
@@ -1273,8 +1300,8 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         const long long dt = clock64() - t0;
         if (lane == 0 && P.tile_cost) {
             const uint32_t c = dt > 0x3fffffffll ? 0x3fffffffu : (uint32_t)dt;
-            // a split tile keeps the largest 4 x part cost seen (sticky, so it stays split while the view lasts)
-            if (split) atomicMax(&P.tile_cost[tile], 4u * c);
+            // a split tile keeps the largest (parts x part cost) seen (sticky, so it stays split while the view lasts)
+            if (level) atomicMax(&P.tile_cost[tile], min(c, 0x3fffffffu >> (level + 1u)) << (level + 1u));
             else P.tile_cost[tile] = c;
         }
 #ifdef RT_DEBUG_TILE_CLOCKS  // developer build only (tools/): per-item cycle count instead of the primitive id
@@ -1285,6 +1312,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
 #endif
     }
     flush_counters(P, cnt, lane);
+    warp_checkout(P, lane, gridDim.x * (blockDim.x >> 5));
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1328,7 +1356,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, 3) trace_shade_pool_kernel(co
     const uint32_t W = P.cam.width, H = P.cam.height;
     const uint32_t tiles_x = (W + 7u) / 8u;
     const uint32_t n_tiles = tiles_x * ((P.n_rows + 3u) / 4u);
-    const uint32_t n_items = P.tile_order ? (uint32_t)P.counters[CNT_QUEUE_ITEMS] : n_tiles;
+    const uint32_t n_items = P.tile_order ? *P.queue_items : n_tiles;
     const uint32_t refill_at = P.pool_refill, min_inner = P.pool_min_inner;
     bool queue_done = false;
     uint32_t tile_id = 0, tile_px = 32u;  // the warp's current tile and its next unassigned pixel (32 = used up)
@@ -1510,7 +1538,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, 3) trace_shade_pool_kernel(co
                     uint32_t item = 0;
                     if (lane == 0) {
                         item = (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], 1ull);
-                        if (item < n_items) item = P.tile_order ? (P.tile_order[item] & kItemTileMask) : item;
+                        if (item < n_items) item = P.tile_order ? P.tile_order[item] : item;
                         else item = 0xffffffffu;
                     }
                     item = __shfl_sync(full, item, 0);
@@ -1518,7 +1546,10 @@ __global__ void __launch_bounds__(32 * kPoolWarps, 3) trace_shade_pool_kernel(co
                         queue_done = true;
                         break;
                     }
-                    tile_id = item;
+                    // an order written for the persistent kernel may hold split tiles (one item per part): this kernel
+                    // always takes whole tiles, so part 0 stands for the tile and the other parts are skipped
+                    if (((item >> kItemPartShift) & 15u) != 0u) continue;
+                    tile_id = item & kItemTileMask;
                     tile_px = 0u;
                 }
                 const uint32_t n = min(32u - tile_px, need - given);
@@ -1705,6 +1736,7 @@ __global__ void __launch_bounds__(32 * kPoolWarps, 3) trace_shade_pool_kernel(co
     }
 #endif
     flush_counters(P, cnt, lane);
+    warp_checkout(P, lane, gridDim.x * kPoolWarps);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1715,17 +1747,18 @@ __global__ void __launch_bounds__(32 * kPoolWarps, 3) trace_shade_pool_kernel(co
 // ------------------------------------------------------------------------------------------------------
 constexpr int kSortBuckets = 256;  // 8 per octave of cost
 constexpr int kSortWarps = 32;
-// Items: bits 0..27 tile id, bits 28..29 part (pixel row of the 8x4 tile), bit 31 "split" flag.
-// A tile whose cost exceeds split_quarters/4 of the balanced launch time becomes four items (one pixel row each):
-// the end of a launch is bounded by the slowest single item, and a warp that works on 8 instead of 32 divergent
-// rays has a much shorter serial chain. The extra items cost lanes, not time: they run while the GPU is full.
+// A tile whose cost exceeds the split threshold T = (balanced launch time) * split_quarters / 4 becomes 4, 8 or 16 items
+// (the smallest count p with cost / p <= T, limited by max_level): the end of a launch is bounded by the slowest single
+// item, and a warp that works on 8, 4 or 2 instead of 32 divergent rays has a much shorter serial chain. The extra items cost
+// lanes, not time: on a full GPU only the few heaviest tiles qualify (p = 4), and a launch that cannot fill the GPU — the
+// shard of one rank when a frame is split over 8 GPUs, a 50-row band — has the issue slots to spare.
 //
 // One block. Most tiles of a frame cost about the same (the all-miss tiles), so a shared histogram would see tens of
 // thousands of atomics on one address: every warp keeps a PRIVATE histogram (32 x 256 counters) and owns a contiguous
 // chunk of the tiles, which also keeps tiles of equal cost in image order (neighbouring tiles stay neighbours in the queue).
 __global__ void __launch_bounds__(32 * kSortWarps) tile_sort_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t n,
-                                                                     uint32_t n_warps, uint32_t split_quarters,
-                                                                     unsigned long long* __restrict__ counters) {
+                                                                     uint32_t n_warps, uint32_t split_quarters, uint32_t max_level,
+                                                                     uint32_t min_split_cycles, uint32_t* __restrict__ queue_items) {
     // split_quarters: 0 = never split; q > 0 = split tiles that cost more than (balanced launch time) * q / 4
     __shared__ uint32_t hist[kSortWarps][kSortBuckets];  // counts, then write cursors, per warp and bucket
     __shared__ uint32_t bucket_base[kSortBuckets];
@@ -1749,15 +1782,20 @@ __global__ void __launch_bounds__(32 * kSortWarps) tile_sort_kernel(const uint32
     // stretch the tail, so only those are split (a launch of uniformly heavy tiles is left alone)
     const unsigned long long balanced = total_cost / (unsigned long long)max(n_warps, 1u);
     const uint32_t split_above =
-        split_quarters ? (uint32_t)min((unsigned long long)0x7fffffffu, max(balanced * split_quarters / 4ull, (unsigned long long)kSplitMinCycles)) : 0xffffffffu;
+        split_quarters ? (uint32_t)min((unsigned long long)0x0fffffffu, max(balanced * split_quarters / 4ull, (unsigned long long)min_split_cycles)) : 0xffffffffu;
+    auto split_level = [&](uint32_t c) -> uint32_t {  // 0 whole tile, 1 / 2 / 3 = 4 / 8 / 16 parts
+        if (c < split_above || max_level == 0u) return 0u;
+        const uint32_t lv = c <= 4u * split_above ? 1u : (c <= 8u * split_above ? 2u : 3u);
+        return min(lv, max_level);
+    };
     auto bucket = [](uint32_t c) {
         // 8 buckets per octave; reversed so that bucket 0 holds the most expensive items
         const int k = (int)(__log2f((float)c + 1.0f) * 8.0f);
         return (uint32_t)(kSortBuckets - 1 - min(max(k, 0), kSortBuckets - 1));
     };
     for (uint32_t i = begin + lane; i < end; i += 32u) {
-        const uint32_t c = cost[i];
-        if (c >= split_above) atomicAdd(&hist[warp][bucket(c / 4u)], 4u);
+        const uint32_t c = cost[i], lv = split_level(c);
+        if (lv) atomicAdd(&hist[warp][bucket(c >> (lv + 1u))], 2u << lv);
         else atomicAdd(&hist[warp][bucket(c)], 1u);
     }
     __syncthreads();
@@ -1784,7 +1822,7 @@ __global__ void __launch_bounds__(32 * kSortWarps) tile_sort_kernel(const uint32
             bucket_base[lane * 8 + k] = run;
             run += v[k];
         }
-        if (lane == 31) counters[CNT_QUEUE_ITEMS] = incl;
+        if (lane == 31) *queue_items = incl;
     }
     __syncthreads();
     if (threadIdx.x < kSortBuckets) {
@@ -1797,10 +1835,11 @@ __global__ void __launch_bounds__(32 * kSortWarps) tile_sort_kernel(const uint32
     }
     __syncthreads();
     for (uint32_t i = begin + lane; i < end; i += 32u) {
-        const uint32_t c = cost[i];
-        if (c >= split_above) {
-            const uint32_t at = atomicAdd(&hist[warp][bucket(c / 4u)], 4u);
-            for (uint32_t part = 0; part < 4u; ++part) order[at + part] = i | (part << kItemPartShift) | kItemSplitFlag;
+        const uint32_t c = cost[i], lv = split_level(c);
+        if (lv) {
+            const uint32_t parts = 2u << lv;
+            const uint32_t at = atomicAdd(&hist[warp][bucket(c >> (lv + 1u))], parts);
+            for (uint32_t part = 0; part < parts; ++part) order[at + part] = i | (part << kItemPartShift) | (lv << kItemLevelShift);
         } else {
             order[atomicAdd(&hist[warp][bucket(c)], 1u)] = i;
         }
@@ -1837,6 +1876,21 @@ __global__ void tonemap_pack_kernel(const float4* __restrict__ sum, uint32_t* __
     } else {
         for (int k = 0; k < 4 && i4 + k < n; ++k) ldr[i4 + k] = px[k];
     }
+}
+
+// Film::get_estimated_variances (film.rs:50-67): per pixel and channel (sum_sq / (n (n-1)) - sum * sum / (n * n (n-1))) * 50 with
+// `n * (n - 1)` evaluated in u32 (wrapping, as the reference's release build does) before the conversion to f32. n <= 1 gives
+// x/0 - y/0 = NaN in every channel, exactly as the reference's arithmetic does. One thread per pixel, same f32 operation order.
+__global__ void film_variance_kernel(const float4* __restrict__ sum, const float4* __restrict__ sq, float* __restrict__ out, uint32_t n_px) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    const float4 s = sum[i], q = sq[i];
+    const uint32_t n = __float_as_uint(s.w);
+    const float nn1 = __uint2float_rn(n * (n - 1u));
+    const float n2n1 = fmul(__uint2float_rn(n), nn1);
+    out[3 * i] = fmul(fsub(fdiv(q.x, nn1), fdiv(fmul(s.x, s.x), n2n1)), 50.0f);
+    out[3 * i + 1] = fmul(fsub(fdiv(q.y, nn1), fdiv(fmul(s.y, s.y), n2n1)), 50.0f);
+    out[3 * i + 2] = fmul(fsub(fdiv(q.z, nn1), fdiv(fmul(s.z, s.z), n2n1)), 50.0f);
 }
 
 // Adds the sample planes of one launch to one pixel of the film in sample order (PixelData::add_sample,
@@ -1931,11 +1985,11 @@ __global__ void flag_wait_kernel(volatile uint32_t* flags, uint32_t n, uint32_t 
         __threadfence_system();
         flags[signal_slot] = target;
     }
-    if (i < n) {
+    for (uint32_t f = i; f < n; f += blockDim.x) {  // one lane per flag (lanes take several when there are more flags than lanes)
         unsigned long long t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        // wrap-safe "flags[i] >= target" for counters that only grow
-        while ((int32_t)(flags[i] - target) < 0) {
+        // wrap-safe "flags[f] >= target" for counters that only grow
+        while ((int32_t)(flags[f] - target) < 0) {
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             if (t1 - t0 > timeout_ns) {
                 atomicAdd(timeouts, 1u);
@@ -2164,13 +2218,17 @@ int persistent_blocks_per_sm(int accel, int bounce) {
     }
     return n > 0 ? n : 1;
 }
-cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, uint32_t n_warps, uint32_t split_quarters,
-                             unsigned long long* counters, cudaStream_t stream) {
-    tile_sort_kernel<<<1, 32 * kSortWarps, 0, stream>>>(cost, order, n, n_warps, split_quarters, counters);
+cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, uint32_t n_warps, uint32_t split_quarters, uint32_t max_level,
+                             uint32_t min_split_cycles, uint32_t* queue_items, cudaStream_t stream) {
+    tile_sort_kernel<<<1, 32 * kSortWarps, 0, stream>>>(cost, order, n, n_warps, split_quarters, max_level, min_split_cycles, queue_items);
     return cudaGetLastError();
 }
 cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream) {
     film_clear_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(sum, sq, ldr, ids, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_film_variance(const float4* sum, const float4* sq, float* out, uint32_t n, cudaStream_t stream) {
+    film_variance_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(sum, sq, out, n);
     return cudaGetLastError();
 }
 cudaError_t launch_tonemap(const float4* sum, uint32_t* ldr, uint32_t n, cudaStream_t stream) {
@@ -2188,7 +2246,7 @@ cudaError_t launch_flag_signal_wait(uint32_t* signal, uint32_t value, uint32_t* 
 }
 cudaError_t launch_flag_wait(uint32_t* flags, uint32_t n, uint32_t target, int signal_slot, int release_slot, uint32_t* timeouts,
                              cudaStream_t stream) {
-    if (n == 0 || n > 32) return cudaErrorInvalidValue;
+    if (n == 0) return cudaErrorInvalidValue;
     flag_wait_kernel<<<1, 32, 0, stream>>>(flags, n, target, signal_slot, release_slot, 2000000000ull, timeouts);
     return cudaGetLastError();
 }

@@ -17,13 +17,16 @@ cudaError_t launch_wf_shade(const TraceParams& p, int accel, int blocks, cudaStr
 cudaError_t launch_wf_combine(const TraceParams& p, int blocks, cudaStream_t stream);
 // variant 2 (ray pool: binary BVH, recursions 0, one light; other configurations run variant 1)
 int pool_blocks_per_sm();
-// order[] = tile ids by descending cost (longest-processing-time-first schedule for the persistent kernel)
-// order must hold 4 * n entries (heavy tiles become four items); counters[CNT_QUEUE_ITEMS] receives the item count
-// split_quarters: 0 = never split; q > 0 = tiles that cost more than (balanced launch time) * q / 4 become four one-row items
-// (pays off for the divergent BVH kernels, not for the octree's long coherent leaf loops)
-cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, uint32_t n_warps, uint32_t split_quarters,
-                             unsigned long long* counters, cudaStream_t stream);
+// order[] = queue items by descending cost (longest-processing-time-first schedule for the persistent kernel). A tile that costs
+// more than T = (balanced launch time) * split_quarters / 4 (and at least min_split_cycles) becomes 4, 8 or 16 items, the smallest
+// count p with cost / p <= T, at most 2^(max_level + 1) (max_level 0 = never split): order must hold n * 2^(max_level + 1) entries
+// (n when max_level = 0); *queue_items receives the item count. split_quarters 0 = never split (the octree's long coherent leaf
+// loops do not profit).
+cudaError_t launch_tile_sort(const uint32_t* cost, uint32_t* order, uint32_t n, uint32_t n_warps, uint32_t split_quarters, uint32_t max_level,
+                             uint32_t min_split_cycles, uint32_t* queue_items, cudaStream_t stream);
 cudaError_t launch_film_clear(float4* sum, float4* sq, uint32_t* ldr, uint32_t* ids, uint32_t n, cudaStream_t stream);
+// Film::get_estimated_variances (film.rs:50-67): out = n * 3 floats
+cudaError_t launch_film_variance(const float4* sum, const float4* sq, float* out, uint32_t n, cudaStream_t stream);
 cudaError_t launch_tonemap(const float4* sum, uint32_t* ldr, uint32_t n, cudaStream_t stream);
 // adds the sample planes written by a multi-sample trace launch to the film, in sample order, and packs the LDR pixels
 cudaError_t launch_film_accumulate(const TraceParams& p, cudaStream_t stream);

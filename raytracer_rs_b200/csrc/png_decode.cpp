@@ -77,6 +77,11 @@ bool decode_png_rgb8(const std::string& path, uint32_t* width, uint32_t* height,
         *err = "Format error decoding Png: invalid colour type";
         return false;
     }
+    // the IHDR is untrusted input: bound the dimensions so that none of the size products below can wrap or ask for terabytes
+    if (w > (1u << 15) || h > (1u << 15)) {
+        *err = "The decoder for Png does not support the format features: image larger than 32768 x 32768";
+        return false;
+    }
     const size_t bpp = (size_t)channels * (depth / 8);
     const size_t stride = (size_t)w * bpp;
     std::vector<uint8_t> raw((stride + 1) * (size_t)h);
@@ -113,6 +118,13 @@ bool decode_png_rgb8(const std::string& path, uint32_t* width, uint32_t* height,
     }
     rgb->resize((size_t)w * h * 3);
     const size_t step = depth / 8;  // for 16-bit samples the high byte comes first
+    // 16-bit samples -> 8 bit the way `image` 0.25's to_rgb8 does (FromPrimitive<u16> for u8: (c + 128) / 257, i.e.
+    // round(c * 255 / 65535)); the crate is not vendored under /root/reference, so this is its published rule, unpinned
+    auto sample8 = [&](const uint8_t* sp) -> uint8_t {
+        if (step == 1) return sp[0];
+        const uint32_t c = ((uint32_t)sp[0] << 8) | sp[1];
+        return (uint8_t)((c + 128u) / 257u);
+    };
     for (size_t i = 0; i < (size_t)w * h; ++i) {
         const uint8_t* px = &img[i * bpp];
         uint8_t r, g, b;
@@ -126,11 +138,11 @@ bool decode_png_rgb8(const std::string& path, uint32_t* width, uint32_t* height,
             g = palette[k + 1];
             b = palette[k + 2];
         } else if (ctype == 0 || ctype == 4) {
-            r = g = b = px[0];
+            r = g = b = sample8(px);
         } else {
-            r = px[0];
-            g = px[step];
-            b = px[2 * step];
+            r = sample8(px);
+            g = sample8(px + step);
+            b = sample8(px + 2 * step);
         }
         (*rgb)[3 * i] = r;
         (*rgb)[3 * i + 1] = g;

@@ -67,6 +67,19 @@ struct DevBuf {
     }
 };
 
+// No C++ exception may cross the extern "C" boundary (std::bad_alloc from a huge texture, a parser fault): it becomes a load error.
+template <typename F>
+bool load_guarded(F&& f, std::string* err) {
+    try {
+        return f();
+    } catch (std::exception& ex) {
+        *err = std::string("scene loading failed: ") + ex.what();
+    } catch (...) {
+        *err = "scene loading failed";
+    }
+    return false;
+}
+
 void copy_err(const std::string& msg, char* err, size_t err_len) {
     if (err && err_len) {
         std::snprintf(err, err_len, "%s", msg.c_str());
@@ -103,6 +116,7 @@ struct rt_raytracer {
     std::vector<std::unique_ptr<DevBuf<float>>> d_tex_data;
     DevBuf<DevTexture> d_textures;
     DevBuf<float4> d_film_sum, d_film_sq, d_planes;
+    DevBuf<float> d_variance;  // rt_get_estimated_variances staging (allocated on first use)
     int multi_sample_launch = 1;      // RT_TUNE_MULTI_SAMPLE_LAUNCH: 0 one launch per sample, 1 sample lanes where they apply, else planes, 2 planes
     bool bounce_wavefront = true;     // RT_TUNE_BOUNCE_WAVEFRONT
     DevBuf<float4> d_wf_rec;
@@ -139,16 +153,30 @@ struct rt_raytracer {
     int time_launches = 1;      // RT_TUNE_TIME_LAUNCHES: record the two CUDA events behind rt_launch_stats.trace_kernel_ms
     bool last_timed = false;    // the last trace call recorded them
     int lpt_schedule = 1;       // RT_TUNE_TILE_SCHEDULE: 1 = heaviest tiles first (cost feedback), 0 = image order
-    // cost-feedback schedule state, valid for one launch geometry (first_row, rows, row list)
-    DevBuf<uint32_t> d_tile_cost, d_tile_order;
-    uint32_t sched_first = ~0u, sched_rows = ~0u, sched_tiles = 0, sched_samples_log2 = 0;
-    uint32_t sched_launches = 0;  // launches recorded since the schedule geometry / camera last changed
-    bool sched_have_order = false;
+    // cost-feedback schedules, one per launch geometry (first row, rows, item shape): a host that walks over the image in 50-row
+    // bands (trace_frame_additive, mod.rs:87) retraces the same 22 geometries frame after frame and finds each band's schedule again
+    struct TileSchedule {
+        uint32_t first = ~0u, rows = ~0u, tiles = 0, samples_log2 = 0;
+        uint32_t launches = 0;      // launches recorded since the schedule was created / the view last changed
+        bool have_order = false;    // `order` holds a queue
+        bool restart_costs = true;  // the next launch starts from zeroed costs (new schedule, or the view changed)
+        uint32_t max_level = 0;     // finest split the order buffer has room for (kernels.cu, tile_sort_kernel)
+        uint64_t last_use = 0;
+        DevBuf<uint32_t> cost, order;  // order: tiles << (max_level + 1) items, then the item count
+    };
+    std::vector<std::unique_ptr<TileSchedule>> schedules;
+    uint64_t schedule_clock = 0;
+    int min_schedule_tiles = 1024;   // RT_TUNE_MIN_SCHEDULE_TILES: launches with fewer tiles run in image order, unsplit
+    int max_split_level = 3;         // RT_TUNE_MAX_SPLIT_LEVEL: 0 never split, 1 / 2 / 3 = up to 4 / 8 / 16 items per tile
+    int call_parity = 0;             // which per-call counter set the current trace call counts into (device_types.h)
+    uint32_t* done_flag = nullptr;   // multi-GPU: the trace kernel's last warp publishes done_value here (rt_set_done_signal)
+    uint32_t done_value = 0;
+    bool arm_done = false;           // the launch being issued is the last one of its trace call
+    bool done_published = false;     // ... and carried the signal
     int blocks_per_sm[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [accel][bounce]
     int num_sms = 0;
     rt_launch_stats last{};
     bool stats_pending = false;
-    bool queue_is_zero = false;  // the tile-queue counter was zeroed by the last memset and not used since
 
     ~rt_raytracer() {
         if (h_counters) cudaFreeHost(h_counters);
@@ -180,6 +208,7 @@ struct rt_raytracer {
         if (cfg.shard_count == 0) cfg.shard_count = 1;
         if (cfg.shard_index >= cfg.shard_count) throw CudaFail{"shard_index out of range"};
         scene = sc;
+        dirty_rows.assign(cfg.height, 1);
         camera.init(cfg.width, cfg.height, scene.camera_orientation, scene.camera_fov_deg);
         for (uint32_t r = 0; r < cfg.height; ++r)
             if (owns_row(r)) owned_rows.push_back(r);
@@ -484,8 +513,18 @@ struct rt_raytracer {
         }
     }
 
+    // rows of the packed frame that changed since the last rt_get_tonemapped_pixels_delta (see there)
+    std::vector<uint8_t> dirty_rows;
+    const void* delta_host = nullptr;  // host buffer that equals the device frame except for the dirty rows
+    void mark_frame_dirty_all() { std::fill(dirty_rows.begin(), dirty_rows.end(), (uint8_t)1); }
+    void mark_rows_dirty(uint32_t first_row, uint32_t n_rows) {
+        if (n_rows >= cfg.height) return mark_frame_dirty_all();
+        for (uint32_t k = 0; k < n_rows; ++k) dirty_rows[(first_row + k) % cfg.height] = 1;
+    }
+
     void film_clear() {
         host_frame_stale = true;
+        mark_frame_dirty_all();
         RT_CUDA(launch_film_clear(d_film_sum.p, d_film_sq.p, d_ldr.p, d_ids.p, npix(), stream));
         ++total_kernels;
     }
@@ -537,8 +576,23 @@ struct rt_raytracer {
         std::memcpy(p->root_hi, root_hi, 12);
     }
 
+    // The camera moved: the recorded costs no longer describe the view, but they still predict it far better than image order
+    // does (a key press moves the camera by a fraction of the scene, main.rs:124-162), so every schedule keeps its order for the
+    // next launch, restarts its cost record from zero and re-sorts after that launch and the one after it.
     void invalidate_schedule() {
-        sched_launches = 0;  // costs of the old view no longer predict the new one well: re-sort soon
+        for (auto& sc : schedules) {
+            sc->launches = 0;
+            sc->restart_costs = true;
+        }
+    }
+    // The kernel variant / structure / split policy changed: an order written for one kernel must not reach another (the ray-pool
+    // kernel takes whole tiles, the persistent kernel takes the split items), and its costs are in different units.
+    void reset_schedules() {
+        if (!schedules.empty() && !host_only) {  // a launch in flight may still read an order
+            cudaSetDevice(device);
+            cudaStreamSynchronize(stream);
+        }
+        schedules.clear();
     }
 
     static constexpr uint32_t kResortEvery = 32;
@@ -555,6 +609,33 @@ struct rt_raytracer {
         p->magic_tiles_x = udiv_magic_of(p->items_x);
     }
 
+    TileSchedule* find_schedule(const TraceParams& p, uint32_t tiles) {
+        for (auto& sc : schedules)
+            if (sc->first == p.first_row && sc->rows == p.n_rows && sc->tiles == tiles && sc->samples_log2 == p.lane_samples_log2) return sc.get();
+        if (schedules.size() >= 64) {  // drop the least recently used geometry
+            size_t lru = 0;
+            for (size_t i = 1; i < schedules.size(); ++i)
+                if (schedules[i]->last_use < schedules[lru]->last_use) lru = i;
+            RT_CUDA(cudaStreamSynchronize(stream));  // a launch may still read its buffers
+            schedules.erase(schedules.begin() + (long)lru);
+        }
+        auto sc = std::make_unique<TileSchedule>();
+        sc->first = p.first_row;
+        sc->rows = p.n_rows;
+        sc->tiles = tiles;
+        sc->samples_log2 = p.lane_samples_log2;
+        // a part must hold whole pixels (32 >> (level + 1) lanes >= the samples of a pixel); big launches fill the GPU with
+        // whole tiles and four-way splits, so their order buffer is not sized for the finer levels
+        uint32_t lv = (uint32_t)std::max(0, std::min(max_split_level, 3));
+        while (lv > 0 && (32u >> (lv + 1u)) < (1u << p.lane_samples_log2)) --lv;
+        if (tiles > (1u << 16)) lv = std::min(lv, 1u);
+        sc->max_level = lv;
+        sc->cost.alloc(tiles);
+        sc->order.alloc(((size_t)tiles << (lv ? lv + 1u : 0u)) + 1);
+        schedules.push_back(std::move(sc));
+        return schedules.back().get();
+    }
+
     cudaError_t launch_one(const TraceParams& p_in) {
         TraceParams p = p_in;
         set_item_geometry(&p, p.lane_samples_log2);
@@ -568,61 +649,64 @@ struct rt_raytracer {
         p.queue_batch_from_pct = (uint32_t)queue_batch_from_pct;
         p.pool_refill = (uint32_t)pool_refill;
         p.pool_min_inner = (uint32_t)pool_min_inner;
-        if (variant != 0 && lpt_schedule) {
-            const uint32_t tiles = p.items_x * p.items_y;
-            if (tiles >= 4096) {  // short launches are latency bound; keep them in image order
-                if (sched_first != p.first_row || sched_rows != p.n_rows || sched_tiles != tiles || sched_samples_log2 != p.lane_samples_log2) {
-                    if (d_tile_cost.n < tiles) {
-                        d_tile_cost.alloc(tiles);
-                        d_tile_order.alloc(4 * (size_t)tiles);
-                    }
-                    sched_first = p.first_row;
-                    sched_rows = p.n_rows;
-                    sched_tiles = tiles;
-                    sched_samples_log2 = p.lane_samples_log2;
-                    sched_launches = 0;
-                    sched_have_order = false;
-                    RT_CUDA_RET(cudaMemsetAsync(d_tile_cost.p, 0, tiles * sizeof(uint32_t), stream));
-                }
-                if (sched_launches == 0 && sched_have_order) {  // the view changed: forget the old costs and order
-                    RT_CUDA_RET(cudaMemsetAsync(d_tile_cost.p, 0, tiles * sizeof(uint32_t), stream));
-                    sched_have_order = false;
-                }
-                // re-sort after the 1st and 2nd recorded launch of a view, then every 32nd (the one-block sort costs
-                // ~0.1 ms for a 1080p frame; per-tile costs of an unchanged view move little between frames)
-                if (sched_launches == 1 || sched_launches == 2 || (sched_launches > 2 && sched_launches % kResortEvery == 0)) {
-                    const uint32_t warps = (uint32_t)((use_pool ? pool_blocks : blocks_per_sm[a][b]) * num_sms * 8);
-                    cudaError_t e = launch_tile_sort(d_tile_cost.p, d_tile_order.p, tiles, warps, (a != 0 && !use_pool) ? (uint32_t)split_quarters : 0u, d_counters.p, stream);
-                    if (e != cudaSuccess) return e;
-                    ++total_kernels;
-                    ++last.kernels_launched;
-                    sched_have_order = true;
-                }
-                if (use_pool) {
-                    // the pool kernel ADDS every camera ray's steps to its tile's cost: record only the launches a sort
-                    // will read (the one before each re-sort), starting from zero
-                    const bool record = sched_launches <= 1 || sched_launches % kResortEvery == kResortEvery - 1;
-                    if (record && sched_launches > 0) RT_CUDA_RET(cudaMemsetAsync(d_tile_cost.p, 0, tiles * sizeof(uint32_t), stream));
-                    p.tile_cost = record ? d_tile_cost.p : nullptr;
-                } else {
-                    p.tile_cost = d_tile_cost.p;
-                }
-                p.tile_order = sched_have_order ? d_tile_order.p : nullptr;
-                ++sched_launches;
+        p.counter_set = call_parity ? CNT_SET_B : CNT_SET_A;
+        // the frame-done signal of a multi-GPU run rides on the last launch of the call when that launch is the one that finishes
+        // the pixels (persistent / ray-pool kernel writing the film itself); otherwise trace_rows appends a signal launch
+        const bool finishes_pixels = variant != 0 && !p.planes && !wavefront_applies(p);
+        p.done_flag = (arm_done && finishes_pixels) ? done_flag : nullptr;
+        p.done_value = done_value;
+        if (p.done_flag) done_published = true;
+        const uint32_t tiles = p.items_x * p.items_y;
+        if (variant != 0 && lpt_schedule && tiles >= (uint32_t)min_schedule_tiles) {  // tiny launches are latency bound: image order
+            TileSchedule* sc = nullptr;
+            try {
+                sc = find_schedule(p, tiles);
+            } catch (CudaFail&) {
+                return cudaErrorMemoryAllocation;
             }
-        }
-        if (variant != 0) {
-            // the tile queue lives next to the ray counters; every launch starts it at zero (the first launch of a
-            // call finds it already zeroed together with the ray counters)
-            if (!queue_is_zero) {
-                cudaError_t e = cudaMemsetAsync(d_counters.p + CNT_TILE_QUEUE, 0, sizeof(unsigned long long), stream);
+            sc->last_use = ++schedule_clock;
+            if (sc->restart_costs) {
+                RT_CUDA_RET(cudaMemsetAsync(sc->cost.p, 0, tiles * sizeof(uint32_t), stream));
+                sc->restart_costs = false;
+            }
+            // re-sort after the 1st and 2nd recorded launch of a view, then every 32nd (the one-block sort costs
+            // ~45 us for a 1080p frame; per-tile costs of an unchanged view move little between frames)
+            if (sc->launches == 1 || sc->launches == 2 || (sc->launches > 2 && sc->launches % kResortEvery == 0)) {
+                const uint32_t warps = (uint32_t)((use_pool ? pool_blocks : blocks_per_sm[a][b]) * num_sms * 8);
+                const uint32_t level = (a != 0 && !use_pool && split_quarters > 0) ? sc->max_level : 0u;
+                // a launch that cannot fill the resident warps even once has issue slots to spare: split from 5 us of work on
+                const uint32_t min_cycles = tiles < warps ? 10000u : 40000u;
+                cudaError_t e = launch_tile_sort(sc->cost.p, sc->order.p, tiles, warps, (uint32_t)split_quarters, level, min_cycles,
+                                                 sc->order.p + (sc->order.n - 1), stream);
                 if (e != cudaSuccess) return e;
+                ++total_kernels;
+                ++last.kernels_launched;
+                sc->have_order = true;
             }
-            queue_is_zero = false;
+            if (use_pool) {
+                // the pool kernel ADDS every camera ray's steps to its tile's cost: record only the launches a sort
+                // will read (the one before each re-sort), starting from zero
+                const bool record = sc->launches <= 1 || sc->launches % kResortEvery == kResortEvery - 1;
+                if (record && sc->launches > 0) RT_CUDA_RET(cudaMemsetAsync(sc->cost.p, 0, tiles * sizeof(uint32_t), stream));
+                p.tile_cost = record ? sc->cost.p : nullptr;
+            } else {
+                p.tile_cost = sc->cost.p;
+            }
+            p.tile_order = sc->have_order ? sc->order.p : nullptr;
+            p.queue_items = sc->order.p + (sc->order.n - 1);
+            ++sc->launches;
         }
-        if (use_pool) return launch_trace(p, a, 2, pool_blocks * num_sms, stream);
-        if (wavefront_applies(p)) return launch_wavefront(p, a);
-        return launch_trace(p, a, variant == 0 ? 0 : 1, blocks_per_sm[a][b] * num_sms, stream);
+        cudaError_t e;
+        if (use_pool) e = launch_trace(p, a, 2, pool_blocks * num_sms, stream);
+        else if (wavefront_applies(p)) e = launch_wavefront(p, a);
+        else e = launch_trace(p, a, variant == 0 ? 0 : 1, blocks_per_sm[a][b] * num_sms, stream);
+        if (e != cudaSuccess) return e;
+        if (variant == 0) {
+            // the one-thread-per-pixel kernel has no last warp out (warp_checkout): the host zeroes the other per-call counter set
+            const int other = call_parity ? CNT_SET_A : CNT_SET_B;
+            e = cudaMemsetAsync(d_counters.p + other, 0, 4 * sizeof(unsigned long long), stream);
+        }
+        return e;
     }
 
     // ---- bounce wavefront (kernels.cu: trace_pixel BOUNCE = 2, wf_bounce_kernel, wf_combine_kernel) ----
@@ -717,8 +801,9 @@ struct rt_raytracer {
             launch_rows = (uint32_t)row_list_cache.size();
         }
         p.first_row = first_row;
-        RT_CUDA(cudaMemsetAsync(d_counters.p, 0, CNT_QUEUE_ITEMS * sizeof(unsigned long long), stream));  // keeps the item count
-        queue_is_zero = true;
+        // no memset: this call counts into the counter set the previous call's last warp out left zeroed (kernels.cu, warp_checkout)
+        call_parity ^= 1;
+        mark_rows_dirty(first_row, n_rows);
         last = rt_launch_stats{};
         last_timed = time_launches != 0;
         if (last_timed) RT_CUDA(cudaEventRecord(ev_start, stream));
@@ -745,6 +830,7 @@ struct rt_raytracer {
             p.n_rows = launch_rows;
             p.lane_samples_log2 = s_log2;
             for (uint32_t s = 0; s < spp; s += 1u << s_log2) {
+                arm_done = done_flag && s + (1u << s_log2) >= spp;
                 RT_CUDA(launch_one(p));
                 ++launches;
             }
@@ -770,9 +856,19 @@ struct rt_raytracer {
         } else {
             p.n_rows = launch_rows;
             for (uint32_t s = 0; s < spp; ++s) {
+                arm_done = done_flag && s + 1u == spp;
                 RT_CUDA(launch_one(p));
                 ++launches;
             }
+        }
+        arm_done = false;
+        if (done_flag) {  // one-shot: rt_set_done_signal arms it for one trace call
+            if (!done_published) {
+                RT_CUDA(launch_flag_signal(done_flag, done_value, stream));
+                ++launches;
+            }
+            done_flag = nullptr;
+            done_published = false;
         }
         if (last_timed) RT_CUDA(cudaEventRecord(ev_stop, stream));
         // the ray counters are fetched only if somebody asks for them before the next trace call (finish_stats)
@@ -790,8 +886,9 @@ struct rt_raytracer {
         float ms = 0.f;
         if (last_timed) RT_CUDA(cudaEventElapsedTime(&ms, ev_start, ev_stop));
         last.trace_kernel_ms = ms;
-        last.n_shadow = h_counters[CNT_SHADOW];
-        last.n_bounce = h_counters[CNT_BOUNCE];
+        const int set = call_parity ? CNT_SET_B : CNT_SET_A;
+        last.n_shadow = h_counters[set + CNT_SHADOW];
+        last.n_bounce = h_counters[set + CNT_BOUNCE];
         stats_pending = false;
     }
 };
@@ -852,7 +949,7 @@ int rt_scene_load_file(const char* collada_filename, rt_scene** out, char* err, 
     if (!collada_filename || !out) return RT_ERR_INVALID;
     auto s = std::make_unique<rt_scene>();
     std::string e;
-    if (!load_collada_file(collada_filename, &s->scene, &e)) {
+    if (!load_guarded([&] { return load_collada_file(collada_filename, &s->scene, &e); }, &e)) {
         copy_err(e, err, err_len);
         return RT_ERR_LOAD;
     }
@@ -864,7 +961,7 @@ int rt_scene_load_str(const char* collada_doc, const char* data_dir, rt_scene** 
     if (!collada_doc || !out) return RT_ERR_INVALID;
     auto s = std::make_unique<rt_scene>();
     std::string e;
-    if (!load_collada_str(collada_doc, data_dir, &s->scene, &e)) {
+    if (!load_guarded([&] { return load_collada_str(collada_doc, data_dir, &s->scene, &e); }, &e)) {
         copy_err(e, err, err_len);
         return RT_ERR_LOAD;
     }
@@ -925,7 +1022,7 @@ int rt_create_raytracer(const char* collada_doc, size_t triangles_per_leaf, size
     if (!collada_doc || !out) return RT_ERR_INVALID;
     HostScene sc;
     std::string e;
-    if (!load_collada_str(collada_doc, nullptr, &sc, &e)) {
+    if (!load_guarded([&] { return load_collada_str(collada_doc, nullptr, &sc, &e); }, &e)) {
         copy_err(e, err, err_len);
         return RT_ERR_LOAD;
     }
@@ -940,7 +1037,7 @@ int rt_create_raytracer_from_file(const char* collada_filename, size_t triangles
     if (!collada_filename || !out) return RT_ERR_INVALID;
     HostScene sc;
     std::string e;
-    if (!load_collada_file(collada_filename, &sc, &e)) {
+    if (!load_guarded([&] { return load_collada_file(collada_filename, &sc, &e); }, &e)) {
         copy_err(e, err, err_len);
         return RT_ERR_LOAD;
     }
@@ -970,6 +1067,7 @@ int rt_configure(rt_raytracer* rt, int32_t recursions, uint32_t sub_spread, int3
         rt->cfg.sub_spread = sub_spread;
         rt->cfg.jitter_mode = jitter_mode;
         rt->cfg.seed = seed;
+        if (rt->cfg.accel != accel) rt->reset_schedules();  // tile costs of one structure say little about another
         rt->cfg.accel = accel;
         if (!rt->host_only) {
             rt->bind_device();
@@ -1016,6 +1114,29 @@ int rt_get_tonemapped_pixels(rt_raytracer* rt, uint32_t* out) {
             RT_CUDA(cudaStreamSynchronize(rt->stream));
             if (out == rt->host_frame) rt->host_frame_stale = false;
         }
+    });
+}
+
+int rt_get_tonemapped_pixels_delta(rt_raytracer* rt, uint32_t* out) {
+    RT_GUARD(rt, {
+        if (!out) throw std::invalid_argument("null output");
+        const uint32_t W = rt->cfg.width, H = rt->cfg.height;
+        if (out != rt->delta_host) rt->mark_frame_dirty_all();  // another buffer: nothing is known about its contents
+        // one copy per run of consecutive changed rows (rows are contiguous in the frame)
+        uint32_t r = 0;
+        while (r < H) {
+            if (!rt->dirty_rows[r]) {
+                ++r;
+                continue;
+            }
+            uint32_t e = r;
+            while (e < H && rt->dirty_rows[e]) ++e;
+            RT_CUDA(cudaMemcpyAsync(out + (size_t)r * W, rt->d_ldr.p + (size_t)r * W, (size_t)(e - r) * W * 4, cudaMemcpyDeviceToHost, rt->stream));
+            r = e;
+        }
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+        std::fill(rt->dirty_rows.begin(), rt->dirty_rows.end(), (uint8_t)0);
+        rt->delta_host = out;
     });
 }
 
@@ -1090,6 +1211,42 @@ int rt_get_film(rt_raytracer* rt, float* out) {
     });
 }
 
+int rt_set_film(rt_raytracer* rt, const float* in) {
+    RT_GUARD(rt, {
+        if (!in) throw std::invalid_argument("null input");
+        const size_t n = rt->npix();
+        std::vector<float4> sum(n), sq(n);
+        for (size_t i = 0; i < n; ++i) {
+            const float* o = in + 7 * i;
+            if (!(o[6] >= 0.0f && o[6] < 4294967296.0f)) throw std::invalid_argument("num_samples out of range");
+            const uint32_t cnt = (uint32_t)o[6];
+            float w;
+            std::memcpy(&w, &cnt, 4);
+            sum[i] = make_float4(o[0], o[1], o[2], w);
+            sq[i] = make_float4(o[3], o[4], o[5], 0.f);
+        }
+        RT_CUDA(cudaMemcpyAsync(rt->d_film_sum.p, sum.data(), n * sizeof(float4), cudaMemcpyHostToDevice, rt->stream));
+        RT_CUDA(cudaMemcpyAsync(rt->d_film_sq.p, sq.data(), n * sizeof(float4), cudaMemcpyHostToDevice, rt->stream));
+        // the packed frame follows the film (get_tonemapped_pixels is a function of the film alone, mod.rs:120-128)
+        RT_CUDA(launch_tonemap(rt->d_film_sum.p, rt->d_ldr.p, (uint32_t)n, rt->stream));
+        ++rt->total_kernels;
+        rt->mark_frame_dirty_all();
+        RT_CUDA(cudaStreamSynchronize(rt->stream));  // `sum` / `sq` go out of scope
+    });
+}
+
+int rt_get_estimated_variances(rt_raytracer* rt, float* out) {
+    RT_GUARD(rt, {
+        if (!out) throw std::invalid_argument("null output");
+        const size_t n = rt->npix();
+        if (rt->d_variance.n < 3 * n) rt->d_variance.alloc(3 * n);
+        RT_CUDA(launch_film_variance(rt->d_film_sum.p, rt->d_film_sq.p, rt->d_variance.p, (uint32_t)n, rt->stream));
+        ++rt->total_kernels;
+        RT_CUDA(cudaMemcpyAsync(out, rt->d_variance.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, rt->stream));
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+    });
+}
+
 int rt_get_primary_ids(rt_raytracer* rt, uint32_t* out) {
     RT_GUARD(rt, {
         if (!out) throw std::invalid_argument("null output");
@@ -1149,7 +1306,26 @@ int rt_get_ldr_device_ptr(rt_raytracer* rt, void** dev_ptr) {
 }
 int rt_set_ldr_target(rt_raytracer* rt, void* dev_ptr) {
     if (!rt) return RT_ERR_INVALID;
+    if (rt->host_only) {
+        rt->last_error = "this handle was created with RT_DEVICE_NONE";
+        return RT_ERR_CUDA;
+    }
+    if (rt->host_frame) {  // the second store target is taken by the registered host frame (rt_set_host_frame): refuse rather than
+                           // silently stop updating a frame whose readback only synchronises
+        rt->last_error = "a host frame is registered (rt_set_host_frame); unregister it before setting an LDR target";
+        return RT_ERR_INVALID;
+    }
     rt->ldr_remote = (uint32_t*)dev_ptr;
+    return RT_OK;
+}
+int rt_set_done_signal(rt_raytracer* rt, void* dev_flag, uint32_t value) {
+    if (!rt) return RT_ERR_INVALID;
+    if (rt->host_only) {
+        rt->last_error = "this handle was created with RT_DEVICE_NONE";
+        return RT_ERR_CUDA;
+    }
+    rt->done_flag = (uint32_t*)dev_flag;
+    rt->done_value = value;
     return RT_OK;
 }
 int rt_get_owned_ldr_rows_device(rt_raytracer* rt, void* dev_out, uint32_t* n_rows) {
@@ -1240,7 +1416,7 @@ int rt_sync_timeouts(rt_raytracer* rt, uint32_t* count) {
 }
 int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr) {
     if (!rt || !dev_ptr || rt->host_only) return RT_ERR_INVALID;
-    *dev_ptr = rt->d_counters.p;
+    *dev_ptr = rt->d_counters.p + (rt->call_parity ? CNT_SET_B : CNT_SET_A);  // the set the last trace call counted into
     return RT_OK;
 }
 uint32_t rt_launch_param_bytes(void) { return (uint32_t)sizeof(TraceParams); }
@@ -1248,7 +1424,18 @@ uint32_t rt_launch_param_bytes(void) { return (uint32_t)sizeof(TraceParams); }
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     if (!rt) return RT_ERR_INVALID;
     if (key == RT_TUNE_KERNEL_VARIANT && value >= 0 && value <= 2) {
+        if (rt->variant != value) rt->reset_schedules();  // an order holds items in the units and granularity of one kernel
         rt->variant = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_MIN_SCHEDULE_TILES && value >= 1) {
+        rt->min_schedule_tiles = value;
+        rt->reset_schedules();
+        return RT_OK;
+    }
+    if (key == RT_TUNE_MAX_SPLIT_LEVEL && value >= 0 && value <= 3) {
+        rt->max_split_level = value;
+        rt->reset_schedules();
         return RT_OK;
     }
     if (key == RT_TUNE_POOL_REFILL && value >= 1 && value <= 32) {
@@ -1265,8 +1452,7 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     }
     if (key == RT_TUNE_SPLIT_QUARTERS && value >= 0 && value <= 64) {
         rt->split_quarters = value;
-        rt->sched_have_order = false;
-        rt->sched_launches = 0;
+        rt->reset_schedules();
         return RT_OK;
     }
     if (key == RT_TUNE_BOUNCE_WAVEFRONT && (value == 0 || value == 1)) {
@@ -1291,8 +1477,7 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     }
     if (key == RT_TUNE_TILE_SCHEDULE && (value == 0 || value == 1)) {
         rt->lpt_schedule = value;
-        rt->sched_have_order = false;
-        rt->sched_launches = 0;
+        rt->reset_schedules();
         return RT_OK;
     }
     rt->last_error = "unknown tuning key or value";

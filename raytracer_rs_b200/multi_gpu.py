@@ -53,7 +53,7 @@ class FrameGather:
     device_gather() -> (rank 0) read_frame_into(pinned_host_tensor), or the pipelined read_frame_async(pinned) ...
     wait_frame(), or device_gather(release=True) when the frame stays on the device."""
 
-    def __init__(self, tracer, rank: int, world: int, device, stream, mode: str = "peer", band_rows: int = 8):
+    def __init__(self, tracer, rank: int, world: int, device, stream, mode: str = "peer", band_rows: int = 8, fused_signal: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -66,8 +66,10 @@ class FrameGather:
         self.copy_stream, self.copy_events, self.copy_pending, self.copy_seq, self.flags_view = None, None, [], 0, None
         self.frame_no = 0
         nbytes = self.W * self.H * 4
-        cptr = tracer.counters_device_ptr()
-        self.counters = torch.as_tensor(_DevPtr(cptr, 32), device=device).view(torch.int64)  # zero copy view of the library's counters
+        # mode "peer": the trace kernel's last warp out publishes "my stores of frame k are done" itself (rt_set_done_signal)
+        # instead of a signal launch behind the kernel
+        self.fused_signal = fused_signal and mode == "peer"
+        self.buffer_copy_event = [None, None]  # rank 0: completion event of the last host copy that read each frame buffer
         if mode in ("peer", "peer_allreduce"):
             handles = [None, None, None]
             self.local_bufs = []
@@ -103,10 +105,16 @@ class FrameGather:
         torch.cuda.synchronize(device)
         dist.barrier()
 
+    def _counters(self):
+        """zero copy view of the library's ray counters of the LAST trace call (two sets alternate, so ask per call)"""
+        return self.torch.as_tensor(_DevPtr(self.tracer.counters_device_ptr(), 32), device=self.device).view(self.torch.int64)
+
     def begin_frame(self):
-        """Call before tracing a frame. Nothing is enqueued any more: in mode "peer" the wait for the buffer the frame
-        will be stored into ("frame k-2 has been read") sits in the fence launch at the end of frame k-1
-        (device_gather), which saves one launch per frame on every rank but 0. Kept for the call order of the API."""
+        """Call before tracing a frame. In mode "peer" the wait for the buffer the frame will be stored into ("frame k-2 has
+        been read") sits in the fence launch at the end of frame k-1 (device_gather); with fused_signal the trace call is
+        armed to publish this rank's "frame k is done" flag from its last warp out."""
+        if self.fused_signal:
+            self.tracer.set_done_signal(self.flags + 4 * self.rank, self.frame_no + 1)
 
     def device_gather(self, release: bool = False):
         """Enqueue (on the tracer's stream) whatever makes the frame just traced complete on rank 0. release=True
@@ -115,25 +123,37 @@ class FrameGather:
         with torch.cuda.stream(self.stream):
             if self.mode == "peer":
                 k = self.frame_no
+                fused = self.fused_signal  # flags[rank] = k + 1 was published by the trace kernel itself
                 if self.rank == 0:
-                    # one launch: my stores of frame k are done -> wait for everybody's -> (optionally) frame k is read
-                    self.tracer.wait_flags(self.flags, self.world, k + 1, 0, self.world if release else -1)
+                    # one launch: (my stores of frame k are done ->) wait for everybody's -> (optionally) frame k is read
+                    self.tracer.wait_flags(self.flags, self.world, k + 1, -1 if fused else 0, self.world if release else -1)
+                    self.kernels += 1
                     if release:
                         self.consumed_signalled = k + 1
                 elif k >= 1:
-                    # one launch: my stores of frame k are done -> frame k+1 (same buffer as frame k-1) may be stored once
+                    # one launch: (my stores of frame k are done ->) frame k+1 (same buffer as frame k-1) may be stored once
                     # rank 0 has read frame k-1, which it publishes as flags[world] = k
-                    self.tracer.signal_then_wait(self.flags + 4 * self.rank, k + 1, self.flags + 4 * self.world, k)
-                else:
+                    if fused:
+                        self.tracer.wait_flags(self.flags + 4 * self.world, 1, k)
+                    else:
+                        self.tracer.signal_then_wait(self.flags + 4 * self.rank, k + 1, self.flags + 4 * self.world, k)
+                    self.kernels += 1
+                elif not fused:
                     self.tracer.signal_flag(self.flags + 4 * self.rank, k + 1)  # my stores of frame 0 are done
+                    self.kernels += 1
                 self.ready = k & 1
                 self.frame_no += 1
-                self.tracer.set_ldr_target(self.targets[self.frame_no & 1])
-                self.kernels += 1
+                nxt = self.frame_no & 1
+                self.tracer.set_ldr_target(self.targets[nxt])
+                if self.rank == 0 and self.buffer_copy_event[nxt] is not None:
+                    # rank 0's own trace kernel is not held by the flag protocol: before it stores the next frame into this
+                    # buffer, the pipelined host copy that last read the buffer must have finished
+                    self.stream.wait_event(self.buffer_copy_event[nxt])
+                    self.buffer_copy_event[nxt] = None
             elif self.mode == "peer_allreduce":
                 # global ray counters + completion fence: once this all-reduce has finished on rank 0, every rank's
                 # trace kernel (earlier on its stream) has completed, so its peer stores are visible
-                dist.all_reduce(self.counters)
+                dist.all_reduce(self._counters())
                 self.ready = self.frame_no & 1
                 self.frame_no += 1
                 self.tracer.set_ldr_target(self.targets[self.frame_no & 1])
@@ -179,6 +199,7 @@ class FrameGather:
                 self.consumed_signalled = self.frame_no
             done.record(self.copy_stream)
         self.copy_pending.append(done)
+        self.buffer_copy_event[self.ready] = done
 
     def wait_frame(self, keep: int = 0):
         """Blocks until at most `keep` of the copies enqueued by read_frame_async are still in flight (oldest first)."""
@@ -197,7 +218,7 @@ class FrameGather:
     def global_counters(self):
         """[shadow rays, primary hits, bounce rays, blocked] of the last frame summed over ranks (collective call)."""
         with self.torch.cuda.stream(self.stream):
-            c = self.counters.clone()
+            c = self._counters().clone()
             if self.mode != "peer_allreduce":
                 self.dist.all_reduce(c)
         self.stream.synchronize()

@@ -47,6 +47,8 @@ int main(int argc, char** argv) {
     CHECK(rt_scene_get_desc(scene, &desc));
     printf("triangles %u\ngeometries %u\nlights %u\ntextures %u\nfov %.9g\n", desc.num_triangles, desc.num_geometries, desc.num_lights,
            desc.num_textures, (double)desc.camera_fov_deg);
+    /* reserved per-vertex attributes: the loader keeps none (the reference reads past them, colladaloader.rs:587-593) */
+    printf("reserved_arrays %s\n", (desc.normals == NULL && desc.uvs == NULL) ? "null" : "set");
 
     rt_config_default(&cfg, 96, 54);
     cfg.recursions = 0;
@@ -79,6 +81,28 @@ int main(int argc, char** argv) {
         CHECK(rt_get_tonemapped_pixels(rt, frame));
         for (i = 0; i < cfg.width * cfg.height; ++i) sum += frame[i];
         printf("trace_rc %d\nprimary_rays %u\nframe_checksum %llu\n", rc, n_rays, sum);
+        {
+            /* the band loop with one frame buffer the host keeps (rt_get_tonemapped_pixels_delta), then Film::get_estimated_variances */
+            uint32_t* keep = (uint32_t*)calloc((size_t)cfg.width * cfg.height, 4);
+            float* var = (float*)malloc((size_t)cfg.width * cfg.height * 3 * sizeof(float));
+            unsigned long long sum_keep = 0, sum_full = 0, finite = 0;
+            int call;
+            if (!keep || !var) return 5;
+            for (call = 0; call < 3; ++call) {
+                CHECK(rt_trace_frame_additive(rt, &n_rays));
+                CHECK(rt_get_tonemapped_pixels_delta(rt, keep));
+            }
+            CHECK(rt_get_tonemapped_pixels(rt, frame));
+            for (i = 0; i < cfg.width * cfg.height; ++i) {
+                sum_keep += keep[i];
+                sum_full += frame[i];
+            }
+            CHECK(rt_get_estimated_variances(rt, var));
+            for (i = 0; i < cfg.width * cfg.height * 3; ++i) finite += (var[i] == var[i]) ? 1u : 0u;
+            printf("delta_matches_full %d\nvariance_finite_values %llu\n", sum_keep == sum_full, finite);
+            free(keep);
+            free(var);
+        }
         free(frame);
     }
     rt_destroy(rt);

@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
         L.orc_get_tonemapped_pixels.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_get_primary_ids.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_get_film.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_get_estimated_variances.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_film.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_get_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_octree_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_octree_export.restype = C.c_uint64
@@ -206,6 +208,19 @@ class Oracle:
         out = np.zeros((self.width * self.height, 7), np.float32)
         self.L.orc_get_film(self.h, _p(out))
         return out
+
+    def get_estimated_variances(self):
+        """Film::get_estimated_variances (film.rs:50-67): [W*H, 3]"""
+        out = np.zeros((self.width * self.height, 3), np.float32)
+        self.L.orc_get_estimated_variances(self.h, _p(out))
+        return out
+
+    def set_film(self, film7, n=None):
+        """overwrite the film: film7 [W*H, 7] as get_film returns it; n (uint32 per pixel) overrides column 6 when given"""
+        a = np.ascontiguousarray(film7, np.float32)
+        assert a.shape == (self.width * self.height, 7)
+        nn = None if n is None else np.ascontiguousarray(n, np.uint32)
+        self.L.orc_set_film(self.h, _p(a), _p(nn) if nn is not None else None)
 
     def counters(self, reset=False):
         raw = np.zeros(20, np.uint64)

@@ -88,6 +88,7 @@ def test_plain_c_client_drives_the_host_side_of_the_abi(tmp_path):
     scene = rt.load_scene(os.path.join(ROOT, "data", "thai2.dae"))
     assert int(got["triangles"]) == scene.vertices.shape[0] == 20049 and int(got["lights"]) == len(scene.lights)
     assert np.float32(got["fov"]) == scene.camera_fov_deg
+    assert got["reserved_arrays"] == "null"  # rt_scene_desc.normals / uvs: a slot the loader leaves empty, as the reference does
     t = rt.RayTracer.from_scene(scene, rt.Config(96, 54, recursions=0, jitter_mode=rt.JITTER_FIXED_HALF, accel=rt.ACCEL_OCTREE,
                                                  device=api.DEVICE_NONE))
     st = t.octree_stats()

@@ -1,0 +1,223 @@
+"""GPU tests added in round 2: Film::get_estimated_variances (film.rs:50-67), the incremental readback of the reference's
+band loop (main.rs:200-201), per-call ray counters without a memset, the per-geometry tile schedules (bands, camera moves,
+finer heavy-tile splits) and the kernel-variant switch on a live handle. Everything goes through the C ABI."""
+import numpy as np
+import pytest
+
+import raytracer_rs_b200 as rt
+from conftest import CONFIGS
+from oracle_lib import JITTER_FIXED, JITTER_HASHED, Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def tracer_for(scene, w, h, accel=rt.ACCEL_BVH, jitter=rt.JITTER_FIXED_HALF, seed=0, **kw):
+    return rt.RayTracer.from_scene(scene, rt.Config(w, h, recursions=0, jitter_mode=jitter, seed=seed, accel=accel, **kw))
+
+
+def same_bits(a, b):
+    """bit-for-bit equality except that any NaN equals any NaN (0/0 is -qNaN on x86 and +qNaN on the GPU)"""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    nan = np.isnan(a) & np.isnan(b)
+    return bool(np.all(nan | (a.view(np.uint32) == b.view(np.uint32))))
+
+
+def test_estimated_variances_match_the_oracle(scenes):
+    """f-4: rows with 3 samples, rows with 1 sample (x/0 - y/0 = NaN) and never-sampled rows (n = 0: the wrapping u32 product
+    n * (n - 1) is 0, NaN again), hashed jitter so that the samples of a pixel differ. The oracle evaluates film.rs:50-67 on the
+    GPU's own film (its sums differ from the oracle's render by the documented <= 1 ulp of powf on a few pixels)."""
+    w, h = 160, 90
+    s = scenes("ico3_tex")
+    t = tracer_for(s, w, h, jitter=rt.JITTER_HASHED, seed=3)
+    t.trace_rows(0, 60, 1)
+    t.trace_rows(0, 30, 2)
+    film = t.film.pixel_datas()
+    assert set(np.unique(film[:, 6])) == {0.0, 1.0, 3.0}
+    var = t.film.get_estimated_variances()
+    o = Oracle(s, w, h)
+    o.set_film(film)
+    var_o = o.get_estimated_variances()
+    assert same_bits(var, var_o)
+    n = film[:, 6]
+    assert np.isnan(var[n <= 1]).all() and np.isfinite(var[n == 3]).all()
+    assert (var[n == 3] >= -1e-3).all() and var[n == 3].max() > 0  # an unbiased variance estimate, times 50
+    # the whole render agrees with the oracle's as well wherever the two films are bit-identical
+    o2 = Oracle(s, w, h)
+    o2.configure(recursions=0, jitter=JITTER_HASHED, seed=3)
+    o2.trace_rows(0, 60, 1, threads=0)
+    o2.trace_rows(0, 30, 2, threads=0)
+    film_o = o2.get_film()
+    eq = (film.view(np.uint32) == film_o.view(np.uint32)).all(axis=1)
+    assert eq.mean() > 0.99
+    assert same_bits(var[eq], o2.get_estimated_variances()[eq])
+    t.close()
+
+
+def test_estimated_variances_wrapping_sample_count(scenes):
+    """n * (n - 1) wraps in u32 before the conversion to f32 (the reference's release build): n = 65 537 gives 65 536, n = 2^31
+    gives 2^31 (wrapped) — injected through rt_set_film, compared with the oracle on the same film."""
+    w, h = 8, 4
+    s = scenes("4boxes")
+    t = tracer_for(s, w, h)
+    rng = np.random.default_rng(5)
+    film = np.zeros((w * h, 7), np.float32)
+    film[:, 0:3] = rng.uniform(0, 50, (w * h, 3)).astype(np.float32)
+    film[:, 3:6] = rng.uniform(0, 500, (w * h, 3)).astype(np.float32)
+    film[:, 6] = np.array([0, 1, 2, 3, 65536, 65537, 92682, 2 ** 31] * 4, np.float32)
+    t.film.set_pixel_datas(film)
+    assert np.array_equal(t.film.pixel_datas(), film)
+    o = Oracle(s, w, h)
+    o.set_film(film)
+    assert same_bits(t.film.get_estimated_variances(), o.get_estimated_variances())
+    assert np.array_equal(t.get_tonemapped_pixels(), o.get_tonemapped_pixels())  # the packed frame follows the film
+    t.close()
+
+
+def test_delta_readback_follows_the_band_loop(scenes):
+    """The reference's loop — trace_frame_additive (50 rows), get_tonemapped_pixels (whole frame), main.rs:200-201 — with the
+    incremental readback into one buffer the host keeps: after every call the buffer equals the full readback, across the wrap
+    at the bottom of the image, a camera move with film.clear() (main.rs:124-162) and a change of buffer."""
+    w, h = 320, 180
+    t = tracer_for(scenes("thai2"), w, h)
+    keep = np.zeros(w * h, np.uint32)
+    for call in range(9):  # 9 x 50 rows: two and a half laps
+        t.trace_frame_additive()
+        t.get_tonemapped_pixels_delta_into(keep.ctypes.data)
+        assert np.array_equal(keep, t.get_tonemapped_pixels()), call
+        if call == 4:
+            t.camera.move_rel(0.1, 0.0, 0.2)
+            t.film.clear()
+    other = np.full(w * h, 0x12345678, np.uint32)  # a buffer the library has never seen: whole frame
+    t.get_tonemapped_pixels_delta_into(other.ctypes.data)
+    assert np.array_equal(other, keep)
+    t.trace_rows(10, 3, 1)
+    t.get_tonemapped_pixels_delta_into(other.ctypes.data)
+    assert np.array_equal(other, t.get_tonemapped_pixels())
+    t.close()
+
+
+def test_per_call_ray_counters_without_host_resets(scenes):
+    """Consecutive trace calls with nothing in between (no stream synchronisation, no counter read): every call's shadow-ray
+    count is exact — the two per-call counter sets alternate and the last warp out of a launch zeroes the other one."""
+    w, h = 256, 144
+    s = scenes("ico2")
+    o = Oracle(s, w, h)
+    o.configure(recursions=0, jitter=JITTER_FIXED)
+    expect = []
+    for first, rows in ((0, 144), (0, 50), (50, 50), (100, 44), (0, 144)):
+        o.counters(reset=True)
+        o.trace_rows(first, rows, 1, threads=0)
+        expect.append(o.counters()["rays"]["shadow"])
+    for variant in (1, 2, 0):
+        t = tracer_for(s, w, h)
+        t.set_tuning(0, variant)
+        t.trace_rows(0, 144, 1, want_shadow=False)  # asynchronous calls first: their counters are never read
+        t.trace_rows(0, 50, 1, want_shadow=False)
+        got = [t.trace_rows(first, rows, 1)[1] for first, rows in ((50, 50), (100, 44), (0, 144))]
+        assert got == expect[2:], (variant, got, expect)
+        tot = t.ray_totals()
+        assert tot["shadow"] == sum(expect) and tot["primary"] == w * (144 + 50 + 50 + 44 + 144)
+        t.close()
+
+
+@pytest.mark.parametrize("name", ["thai2", "ico3_tex"])
+def test_band_schedules_and_fine_splits_leave_the_film_alone(scenes, name):
+    """Schedules only reorder and regroup work. A handle that walks over a 1080p frame in 50-row bands with per-band cost feedback,
+    a split threshold low enough that heavy tiles become 8 and 16 items, and a camera move in between leaves the same film, ids
+    and frame, bit for bit, as a handle that runs everything in image order."""
+    _, w, h = CONFIGS[name]
+    s = scenes(name)
+    a, b = tracer_for(s, w, h), tracer_for(s, w, h)
+    a.set_tuning(1, 0)  # image order, no cost feedback
+    b.set_tuning(11, 256)  # schedule even small launches
+    b.set_tuning(7, 1)  # split from a quarter of the balanced launch time on
+    calls = 3 * ((h + 49) // 50)
+    for c in range(calls):
+        na, nb = a.trace_frame_additive(), b.trace_frame_additive()
+        assert na == nb == 50 * w
+        if c == calls // 2:
+            for t in (a, b):
+                t.camera.add_y_angle(0.05)  # the film is deliberately not cleared: old and new view accumulate
+    assert np.array_equal(a.get_primary_ids(), b.get_primary_ids())
+    assert np.array_equal(a.get_tonemapped_pixels(), b.get_tonemapped_pixels())
+    assert np.array_equal(a.film.pixel_datas().view(np.uint32), b.film.pixel_datas().view(np.uint32))
+    # whole frames on the same handles (another launch geometry, with its own schedule); 4 frames so that the sorted, split
+    # queue is in use
+    for _ in range(4):
+        a.trace_rows(0, h, 1, want_shadow=False)
+        b.trace_rows(0, h, 1, want_shadow=False)
+    assert np.array_equal(a.film.pixel_datas().view(np.uint32), b.film.pixel_datas().view(np.uint32))
+    assert np.array_equal(a.get_tonemapped_pixels(), b.get_tonemapped_pixels())
+    a.close()
+    b.close()
+
+
+def test_sharded_sample_lanes_with_fine_splits(scenes):
+    """The shard one rank of 8 owns, 8 samples per launch in sample lanes, low split threshold: parts must hold whole pixels
+    (a part of an S = 8 item is 8 lanes), so the film equals one launch per sample."""
+    w, h = 1920, 1080
+    s = scenes("thai2")
+    films = []
+    for multi, split in ((0, 4), (1, 1)):
+        t = tracer_for(s, w, h, jitter=rt.JITTER_HASHED, seed=11, shard_index=3, shard_count=8, band_rows=8)
+        t.set_tuning(5, multi)
+        t.set_tuning(7, split)
+        for _ in range(4):
+            t.trace_rows(0, h, 8, want_shadow=False)
+        films.append(t.film.pixel_datas())
+        t.close()
+    assert np.array_equal(films[0].view(np.uint32), films[1].view(np.uint32))
+    assert films[0][:, 6].max() == 32
+
+
+def test_switching_the_kernel_variant_on_a_live_handle(scenes):
+    """rt_set_tuning never changes results: after several 1080p frames of the persistent kernel (sorted queue with split
+    tiles) the handle switches to the ray-pool kernel, which takes whole tiles — an order written for the other kernel must
+    not reach it (it would trace split tiles once per part). Film and sample counts equal a fresh handle's."""
+    _, w, h = CONFIGS["thai2"]
+    s = scenes("thai2")
+    t = tracer_for(s, w, h)
+    for _ in range(4):
+        t.trace_rows(0, h, 1, want_shadow=False)
+    t.set_tuning(0, 2)
+    for _ in range(4):
+        t.trace_rows(0, h, 1, want_shadow=False)
+    t.set_tuning(0, 1)
+    t.trace_rows(0, h, 1, want_shadow=False)
+    ref = tracer_for(s, w, h)
+    for _ in range(9):
+        ref.trace_rows(0, h, 1, want_shadow=False)
+    f, fr = t.film.pixel_datas(), ref.film.pixel_datas()
+    assert np.array_equal(f[:, 6], np.full(w * h, 9, np.float32))
+    assert np.array_equal(f.view(np.uint32), fr.view(np.uint32))
+    assert np.array_equal(t.get_tonemapped_pixels(), ref.get_tonemapped_pixels())
+    # the same with the structure: costs recorded for one tree must not schedule another
+    t.configure(recursions=0, jitter_mode=rt.JITTER_FIXED_HALF, accel=rt.ACCEL_BVH4)
+    ref.configure(recursions=0, jitter_mode=rt.JITTER_FIXED_HALF, accel=rt.ACCEL_BVH4)
+    for _ in range(3):
+        t.trace_rows(0, h, 1, want_shadow=False)
+        ref.trace_rows(0, h, 1, want_shadow=False)
+    assert np.array_equal(t.film.pixel_datas().view(np.uint32), ref.film.pixel_datas().view(np.uint32))
+    t.close()
+    ref.close()
+
+
+def test_reserved_normals_and_uvs_are_ignored(scenes):
+    """rt_scene_desc.normals / uvs (north star: "triangle, normal, UV and texture buffers") are accepted and, as in the reference
+    (colladaloader.rs:587-593 reads past them), have no influence on the image."""
+    import types
+
+    w, h = 160, 90
+    s = scenes("ico3_tex")
+    rng = np.random.default_rng(1)
+    n = s.vertices.shape[0]
+    with_attrs = types.SimpleNamespace(**{k: getattr(s, k) for k in ("vertices", "tri_geom", "materials", "lights", "textures",
+                                                                     "camera_orientation", "camera_fov_deg")},
+                                       normals=rng.normal(size=(n, 9)).astype(np.float32), uvs=rng.uniform(size=(n, 6)).astype(np.float32))
+    a, b = tracer_for(s, w, h), tracer_for(with_attrs, w, h)
+    a.trace_rows(0, h, 1)
+    b.trace_rows(0, h, 1)
+    assert np.array_equal(a.get_tonemapped_pixels(), b.get_tonemapped_pixels())
+    assert np.array_equal(a.film.pixel_datas().view(np.uint32), b.film.pixel_datas().view(np.uint32))
+    a.close()
+    b.close()

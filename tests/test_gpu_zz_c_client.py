@@ -25,4 +25,10 @@ def test_plain_c_client_renders_the_same_frame_as_the_python_binding(tmp_path):
     assert int(got["trace_rc"]) == 0 and int(got["primary_rays"]) == n == 50 * 96
     assert int(got["frame_checksum"]) == int(frame.astype(np.uint64).sum())
     assert (frame[: 50 * 96] != 0xFFFFFFFF).all() and (frame[50 * 96:] == 0xFFFFFFFF).all()  # rows 50..53 were never sampled
+    # three more 50-row calls read back incrementally into one buffer, then Film::get_estimated_variances
+    assert int(got["delta_matches_full"]) == 1
+    for _ in range(3):
+        t.trace_frame_additive()
+    var = t.film.get_estimated_variances()
+    assert int(got["variance_finite_values"]) == int(np.isfinite(var).sum()) > 0
     t.close()

@@ -131,6 +131,7 @@ def test_pipelined_readback_keeps_one_copy_in_flight():
     g.mode, g.device, g.stream, g.world = "peer", None, Stream(name="render"), 4
     g.copy_stream, g.copy_events, g.copy_pending, g.copy_seq, g.flags_view = None, None, [], 0, None
     g.local_bufs, g.frames, g.consumed_signalled = [0, 0, 0], ["buffer0", "buffer1"], 0
+    g.buffer_copy_event = [None, None]
     hosts = [Host(), Host()]
     for k in range(5):
         g.ready, g.frame_no = k & 1, k + 1  # what device_gather leaves behind for frame k
@@ -151,32 +152,38 @@ def test_pipelined_readback_keeps_one_copy_in_flight():
 
 
 def test_peer_fence_protocol_calls():
-    """FrameGather.device_gather in mode "peer" with a recording stand-in for the tracer: every rank issues exactly one
-    fence launch per frame. Rank r != 0 signals "frame k done" as flags[r] = k + 1 and, from frame 1 on, waits in the
-    same launch for flags[world] >= k ("frame k-1 has been read": frame k+1 reuses its buffer); rank 0 signals its own
-    slot, waits for all slots and, when the frame stays on the device, publishes "read" in that launch too. The store
-    target alternates between the two frame buffers."""
+    """FrameGather.device_gather in mode "peer" with a recording stand-in for the tracer, both forms of the fence.
+    Separate signal (fused_signal=False): every rank issues exactly one fence launch per frame — rank r != 0 signals "frame k
+    done" as flags[r] = k + 1 and, from frame 1 on, waits in the same launch for flags[world] >= k ("frame k-1 has been read":
+    frame k+1 reuses its buffer); rank 0 signals its own slot, waits for all slots and, when the frame stays on the device,
+    publishes "read" in that launch too. Fused signal (default): begin_frame arms the trace call to publish flags[r] = k + 1
+    from its last warp out (rt_set_done_signal), the fence launch only waits (rank r != 0: nothing at all for frame 0).
+    The store target alternates between the two frame buffers; rank 0's render stream waits for the host copy that last
+    read a buffer before its own kernel stores into it again."""
     import contextlib
     import types
 
     from raytracer_rs_b200.multi_gpu import FrameGather
 
-    def gather(rank, world):
+    def gather(rank, world, fused):
         calls = []
         tracer = types.SimpleNamespace(
             signal_flag=lambda p, v: calls.append(("signal", p, v)),
             signal_then_wait=lambda p, v, q, t: calls.append(("signal_then_wait", p, v, q, t)),
             wait_flags=lambda p, n, t, s=-1, r=-1: calls.append(("wait", p, n, t, s, r)),
+            set_done_signal=lambda p, v: calls.append(("arm", p, v)),
             set_ldr_target=lambda p: calls.append(("target", p)))
         g = FrameGather.__new__(FrameGather)
         g.torch = types.SimpleNamespace(cuda=types.SimpleNamespace(stream=lambda s: contextlib.nullcontext()))
-        g.dist, g.tracer, g.rank, g.world, g.mode, g.stream = None, tracer, rank, world, "peer", None
+        g.dist, g.tracer, g.rank, g.world, g.mode = None, tracer, rank, world, "peer"
+        g.stream = types.SimpleNamespace(wait_event=lambda ev: calls.append(("render_waits_for_copy", ev)))
         g.flags, g.targets, g.frame_no, g.kernels, g.consumed_signalled = 1000, [0xA000, 0xB000], 0, 0, 0
+        g.fused_signal, g.buffer_copy_event = fused, [None, None]
         return g, calls
 
-    g, calls = gather(rank=2, world=4)
+    g, calls = gather(rank=2, world=4, fused=False)
     for _ in range(4):
-        g.begin_frame()  # enqueues nothing any more
+        g.begin_frame()  # enqueues nothing in this form
         g.device_gather()
     assert calls == [("signal", 1008, 1), ("target", 0xB000),
                      ("signal_then_wait", 1008, 2, 1016, 1), ("target", 0xA000),
@@ -184,8 +191,27 @@ def test_peer_fence_protocol_calls():
                      ("signal_then_wait", 1008, 4, 1016, 3), ("target", 0xA000)]
     assert g.kernels == 4 and g.frame_no == 4
 
-    g, calls = gather(rank=0, world=4)
+    g, calls = gather(rank=0, world=4, fused=False)
     g.device_gather(release=True)
     g.device_gather()
     assert calls == [("wait", 1000, 4, 1, 0, 4), ("target", 0xB000), ("wait", 1000, 4, 2, 0, -1), ("target", 0xA000)]
     assert g.consumed_signalled == 1 and g.ready == 1 and g.kernels == 2
+
+    g, calls = gather(rank=2, world=4, fused=True)
+    for _ in range(3):
+        g.begin_frame()
+        g.device_gather()
+    assert calls == [("arm", 1008, 1), ("target", 0xB000),
+                     ("arm", 1008, 2), ("wait", 1016, 1, 1, -1, -1), ("target", 0xA000),
+                     ("arm", 1008, 3), ("wait", 1016, 1, 2, -1, -1), ("target", 0xB000)]
+    assert g.kernels == 2 and g.frame_no == 3  # the first frame needs no fence launch at all on this rank
+
+    g, calls = gather(rank=0, world=4, fused=True)
+    g.begin_frame()
+    g.device_gather(release=True)
+    g.buffer_copy_event[0] = "copy-of-buffer-0"  # what read_frame_async leaves behind
+    g.begin_frame()
+    g.device_gather()
+    assert calls == [("arm", 1000, 1), ("wait", 1000, 4, 1, -1, 4), ("target", 0xB000),
+                     ("arm", 1000, 2), ("wait", 1000, 4, 2, -1, -1), ("target", 0xA000), ("render_waits_for_copy", "copy-of-buffer-0")]
+    assert g.buffer_copy_event == [None, None] and g.kernels == 2
