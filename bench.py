@@ -6,20 +6,27 @@ rays (recursions = 0, fixed sub-pixel offset 0.5: the pinned parity mode), accum
   value    : Mrays/s (primary + shadow), scene/film resident in HBM, timed with CUDA events on the launching stream
   e2e      : same metric through the public API with HOST buffers: camera state in, 8.3 MB LDR frame out (pinned),
              every step, wall clock
-  roofline : algorithmic bytes of the reference algorithm (24 B per cube test + 36 B per triangle test + 4 B per
-             pixel) / measured duration of the trace kernel, against the measured HBM copy peak
+  roofline : frac = the resource that binds the trace kernel — warp-instruction issue slots (ncu count of one launch /
+             measured kernel time, against 4 schedulers x SMs x the SM clock sampled during the run); achieved / peak /
+             traffic_equivalent = algorithmic bytes of the reference algorithm (24 B per cube test + 36 B per triangle
+             test + 4 B per pixel) / measured kernel duration against the measured HBM copy peak
   cpu_baseline / --impl reference : the CPU oracle (C++ restatement of the reference, oracle/) on the host cores
+Extra blocks on the same line (N = 1): value_long (>= 0.5 s of GPU time), e2e_reference_call_pattern (the reference's own
+50-row band loop), first_frame_after_move_ms, configs (the other BASELINE configurations, each checked against an oracle band),
+recursions2 (the reference's default RECURSIONS = 2 mode).
 
 N > 1 (torchrun, one process per GPU): the frame is sharded by interleaved 8-row bands, the scene is replicated,
 rank 0 receives the packed frame over NVLink (see --gather), no other exchange.
   --scaling weak (default): a step renders N samples per pixel of the frame (hashed jitter), so every rank traces
       H/N rows x N samples = as many camera rays as the single GPU does in its step; value = all rays of all ranks / time
-  --scaling strong: a step is one sample per pixel whatever N is (each rank traces H/N rows); a 0.23 ms frame cut in
-      N pieces is bounded by launch + fence latency and by the slowest tile, see DESIGN.md section 7
+  --scaling strong: a step is one sample per pixel whatever N is (each rank traces H/N rows)
+  The weak line also carries a `strong` block (the fixed 1-spp frame over the N GPUs), `configs.thai2_4k_16spp` sharded over the
+  N GPUs, and e2e.frame_matches_device: the gathered host frame compared bit for bit with rank 0's own unsharded render.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -39,9 +46,9 @@ WORKLOADS = {
     "ico3_tex_1080p": ("ico3_tex.dae", 1920, 1080, 1),
     "thai2_4k_16spp": ("thai2.dae", 3840, 2160, 16),
 }
-# Exact work of the REFERENCE algorithm (octree, triangles_per_leaf = 70) for one pinned-mode frame, counted by
-# the oracle (tools/count_work.py; checked again against the live oracle in the cpu_baseline leg):
-# (primary rays, shadow rays, cube tests, triangle tests)
+# Exact work of the REFERENCE algorithm (octree, triangles_per_leaf = 70) for one pinned-mode frame, counted by the oracle's
+# per-ray counters (oracle/rt_oracle.cpp `Counters`; checked against the live oracle in the cpu_baseline leg of every run and
+# by tests/test_host_logic.py): (primary rays, shadow rays, cube tests, triangle tests)
 REFERENCE_WORK = {
     "thai2_1080p": (2073600, 525594, 64718736 + 21902544, 83666141 + 36577192),
     "ico2_1024x768": (786432, 313374, 17397368 + 6640944, 28736151 + 16316966),
@@ -64,6 +71,25 @@ def measured_hbm_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads() -> int:
+    """Host threads this process may use. torch.distributed.run exports OMP_NUM_THREADS=1 to every rank, so the OpenMP default
+    is not a usable answer under torchrun; the affinity mask is."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def kernel_source_hash() -> str:
+    """sha256 (16 hex digits) of the kernel sources the loaded library was built from is compiled into the library
+    (rt_kernels_hash); this is the same digest computed from the sources in the tree."""
+    h = hashlib.sha256()
+    for name in ("kernels.cu", "device_types.h"):
+        with open(os.path.join(ROOT, "raytracer_rs_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler(threading.Thread):
@@ -116,67 +142,90 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
 
 
+def load_scene_for_oracle(fname):
+    """The scene for the CPU arm comes from the independent numpy Collada reader (tests/collada_ref.py), so that neither
+    `--impl reference` nor the oracle checks of the configs block depend on the product's loader (librt_b200.so is not even
+    mapped into the reference arm)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from collada_ref import load_collada
+
+    return load_collada(os.path.join(ROOT, "data", fname))
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (the oracle port; the Rust original cannot be
-    built here) on all host threads. Rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path (the oracle port; the Rust original cannot be built
+    here) on all host threads, on the configuration the b200 arm runs with the same --gpus / --scaling. Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)  # before liboracle.so (and with it libgomp) is loaded
+    os.environ.setdefault("OMP_DYNAMIC", "FALSE")
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import raytracer_rs_b200 as rt  # product loader only flattens the scene file; the render below is the oracle's
-    from oracle_lib import JITTER_FIXED, Oracle, lib as orc_lib
+    from oracle_lib import JITTER_FIXED, JITTER_HASHED, Oracle
 
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     fname, w, h, spp = WORKLOADS[args.workload]
-    scene = rt.load_scene(os.path.join(ROOT, "data", fname))
-    orc = Oracle(scene, w, h, rt.DEFAULT_TRIANGLES_PER_LEAF)
-    orc.configure(recursions=0, jitter=JITTER_FIXED)
-    threads = orc_lib().orc_max_threads()
+    if world > 1 and args.scaling == "weak":
+        spp *= world  # the b200 arm's step at this N
+    scene = load_scene_for_oracle(fname)
+    orc = Oracle(scene, w, h, 70)  # DEFAULT_TRIANGLES_PER_LEAF (oct_tree_intersector.rs:12)
+    orc.configure(recursions=0, jitter=JITTER_FIXED if spp == 1 else JITTER_HASHED, seed=0)
     # Bounded sample: a step is the whole frame unless steps + warmup whole frames would take longer than --reference-budget
     # seconds on this host; then a step is one of `parts` equal row ranges, rotating over the frame from step to step, so
     # that any `parts` consecutive steps cover the frame once (rays are counted exactly either way).
     t1 = time.perf_counter()
-    orc.trace_rows(0, h, spp, threads=threads)
-    orc.get_tonemapped_pixels()
-    t_frame = time.perf_counter() - t1
+    probe_rows = max(8, h // 16)
+    orc.trace_rows(h // 4, probe_rows, spp, threads=threads)
+    t_frame = (time.perf_counter() - t1) * h / probe_rows
     parts = max(1, min(h // 8, int(-(-t_frame * (args.steps + args.warmup) // args.reference_budget))))
     rows = -(-h // parts)
+    orc.film_clear()
 
-    def step(i):
+    def step(i, n_threads):
         first = (i % parts) * rows
-        orc.trace_rows(first, min(rows, h - first), spp, threads=threads)
+        orc.trace_rows(first, min(rows, h - first), spp, threads=n_threads)
         orc.get_tonemapped_pixels()
 
     for i in range(args.warmup):
-        step(i)
+        step(i, threads)
     orc.counters(reset=True)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        step(i)
+        step(i, threads)
     dt = time.perf_counter() - t0
-    c = orc.counters()
+    c = orc.counters(reset=True)
     rays = c["rays"]["primary"] + c["rays"]["shadow"]
     value = rays / dt / 1e6
+    # the single thread the reference actually ships (one render thread, raytracer/src/main.rs:194), on one part of the frame
+    t0 = time.perf_counter()
+    orc.trace_rows(h // 4, max(8, min(rows, h // 8)), spp, threads=1)
+    dt1 = time.perf_counter() - t0
+    c1 = orc.counters(reset=True)
+    single = (c1["rays"]["primary"] + c1["rays"]["shadow"]) / dt1 / 1e6
     line = {
         "impl": "reference",
         "metric": METRIC,
         "value": value,
         "unit": UNIT,
-        "n_gpus": args.gpus,
+        "n_gpus": world,
         "steps": args.steps,
         "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": args.scaling if world > 1 else "weak",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "reference scene fixture data/%s (the upstream repository's own scene), pinned camera" % fname,
-        "config": {"workload": args.workload, "width": w, "height": h, "spp": spp, "recursions": 0, "jitter": "fixed 0.5",
-                   "accel": "reference octree, triangles_per_leaf 70",
+        "config": {"workload": args.workload, "width": w, "height": h, "spp": spp, "recursions": 0,
+                   "jitter": "fixed 0.5" if spp == 1 else "hashed seed 0",
+                   "accel": "reference octree, triangles_per_leaf 70", "scene_loader": "tests/collada_ref.py (independent of the product)",
                    "step": ("one full frame" if parts == 1 else "%d rows (1/%d of the frame, rotating)" % (rows, parts)) + " + get_tonemapped_pixels"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "single_thread_value": single,
+                         "omp_num_threads_env_at_start": os.environ.get("OMP_NUM_THREADS"),
                          "sample": ("%d full frames" % args.steps if parts == 1 else
                                     "%d steps of %d rows each (1/%d of the frame, rotating over it)" % (args.steps, rows, parts))
-                                   + " (%d rays) of the same workload, OpenMP over rows" % rays},
+                                   + " (%d rays) of the same workload, OpenMP over rows on %d threads" % (rays, threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -185,13 +234,13 @@ def run_reference(args):
 def cpu_baseline(workload, rt, scene):
     """Oracle timed on the GPU box's host cores: all threads (value) and one thread (what the reference ships)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_lib import JITTER_FIXED, Oracle, lib as orc_lib
+    from oracle_lib import JITTER_FIXED, Oracle
 
     _f, w, h, spp = WORKLOADS[workload]
     spp = min(spp, 1)  # bounded sample: one sample per pixel
     orc = Oracle(scene, w, h, rt.DEFAULT_TRIANGLES_PER_LEAF)
     orc.configure(recursions=0, jitter=JITTER_FIXED)
-    threads = orc_lib().orc_max_threads()
+    threads = host_threads()
     orc.trace_rows(0, h, 1, threads=threads)  # warm
     orc.counters(reset=True)
     frames = 0
@@ -230,11 +279,28 @@ def cpu_baseline(workload, rt, scene):
     }
 
 
-class _DevPtr:
-    """Wraps a raw device pointer for torch.as_tensor (zero copy)."""
+def oracle_band_check(rt, np, tracer_factory, fname, w, h, spp, band):
+    """Parity of one configuration inside the benchmark run: a fresh handle renders the whole frame once, the oracle (scene from
+    the independent loader) renders `band` = (first row, rows) with the same settings; returns primitive-id agreement and the
+    largest 8-bit channel difference over the band."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import JITTER_FIXED, JITTER_HASHED, Oracle
 
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    first, rows = band
+    orc = Oracle(load_scene_for_oracle(fname), w, h, rt.DEFAULT_TRIANGLES_PER_LEAF)
+    orc.configure(recursions=0, jitter=JITTER_FIXED if spp == 1 else JITTER_HASHED, seed=0)
+    orc.trace_rows(first, rows, spp, threads=host_threads())
+    t = tracer_factory()
+    t.trace_rows(0, h, spp)
+    sl = slice(first * w, (first + rows) * w)
+    ids, ids_o = t.get_primary_ids()[sl], orc.get_primary_ids()[sl]
+    ldr, ldr_o = t.get_tonemapped_pixels()[sl], orc.get_tonemapped_pixels()[sl]
+    lsb = np.max([np.abs(((ldr >> k) & 255).astype(np.int32) - ((ldr_o >> k) & 255).astype(np.int32)) for k in (0, 8, 16, 24)], axis=0)
+    t.close()
+    # with several jittered samples per pixel the id buffer holds the LAST sample's hit; a sample on a grazing ray may pick the
+    # neighbouring triangle in the BVH (true closest hit) vs the octree order: report the fraction of pixels within the bar
+    return {"band_rows": [first, first + rows], "ids_agree": float((ids == ids_o).mean()), "max_lsb_diff": int(lsb.max()),
+            "pixels_within_1_lsb": float((lsb <= 1).mean())}
 
 
 def main():
@@ -248,11 +314,17 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "peer_allreduce", "nccl"], help="N>1: how rank 0 receives the frame")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: samples per pixel per step = N (weak) or 1 (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip value_long, configs, recursions2, strong, first-frame-after-move blocks")
     ap.add_argument("--reference-budget", type=float, default=150.0,
                     help="--impl reference: seconds the whole run may take; longer runs trace a rotating part of the frame per step")
-    ap.add_argument("--no-launch-timing", action="store_true",
-                    help="developer: RT_TUNE_TIME_LAUNCHES = 0 in the device-timed and end-to-end legs (the library then skips the two CUDA "
-                         "events behind launch_stats().trace_kernel_ms); the roofline leg, which needs that figure, switches them back on")
+    ap.add_argument("--launch-timing", action="store_true",
+                    help="developer: keep RT_TUNE_TIME_LAUNCHES = 1 (two CUDA events per trace call behind launch_stats().trace_kernel_ms) in the "
+                         "device-timed and end-to-end legs; by default only the roofline leg, which needs that figure, records them")
+    ap.add_argument("--e2e-gather", default="host", choices=["host", "nvlink"],
+                    help="N>1, end-to-end leg: 'host' = every rank copies the rows it owns over its own PCIe link into one frame in shared, "
+                         "page-locked host memory (multi_gpu.HostFrameGather); 'nvlink' = the frame is gathered on rank 0 over NVLink (--gather) "
+                         "and copied to the host over rank 0's link alone")
+    ap.add_argument("--separate-signal", action="store_true", help="N>1, --gather peer: signal 'frame done' with a launch of its own instead of from the trace kernel's last warp")
     ap.add_argument("--tune", default="", help="developer: comma separated key=value pairs passed to rt_set_tuning")
     ap.add_argument("--sync-readback", action="store_true",
                     help="e2e leg (N=1): blocking rt_get_tonemapped_pixels after every trace call instead of the pipelined "
@@ -287,201 +359,388 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    fname, W, H, spp = WORKLOADS[args.workload]
-    base_spp = spp
-    if world > 1 and args.scaling == "weak":
-        spp = spp * world  # per-GPU work stays what one GPU does at N = 1
+    fname, W, H, base_spp = WORKLOADS[args.workload]
     scene = rt.load_scene(os.path.join(ROOT, "data", fname))
     accel = {"bvh": rt.ACCEL_BVH, "octree": rt.ACCEL_OCTREE, "cwbvh": rt.ACCEL_CWBVH, "bvh4": rt.ACCEL_BVH4, "lbvh": rt.ACCEL_LBVH}[args.accel]
-    cfg = rt.Config(W, H, recursions=0, jitter_mode=rt.JITTER_FIXED_HALF if spp == 1 else rt.JITTER_HASHED, accel=accel,
-                    device=local_rank, shard_index=rank, shard_count=world, band_rows=8)
+
+    def jitter_for(spp):
+        return rt.JITTER_FIXED_HALF if spp == 1 else rt.JITTER_HASHED
+
+    def make_tracer(scene_, w, h, spp, sharded=True, recursions=0):
+        t = rt.RayTracer.from_scene(scene_, rt.Config(w, h, recursions=recursions, jitter_mode=jitter_for(spp), seed=0, accel=accel, device=local_rank,
+                                                      shard_index=rank if sharded else 0, shard_count=world if sharded else 1, band_rows=8))
+        for kv in filter(None, args.tune.split(",")):
+            k, v = kv.split("=")
+            t.set_tuning(int(k), int(v))
+        return t
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    tracer = rt.RayTracer.from_scene(scene, cfg)
-    for kv in filter(None, args.tune.split(",")):
-        k, v = kv.split("=")
-        tracer.set_tuning(int(k), int(v))
-    if args.no_launch_timing:
-        tracer.set_tuning(10, 0)
     stream = torch.cuda.Stream(device=dev)
-    tracer.set_stream(stream.cuda_stream)
-
-    # ---- multi-GPU plumbing -------------------------------------------------------------------------
-    from raytracer_rs_b200 import multi_gpu
-
-    gather = multi_gpu.FrameGather(tracer, rank, world, dev, stream, mode=args.gather) if world > 1 else None
-
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    host_frame = torch.empty(W * H, dtype=torch.int32).pin_memory()
-    host_frames = [host_frame, torch.empty(W * H, dtype=torch.int32).pin_memory()]
-    pipelined = world == 1 and not args.sync_readback and not args.zero_copy
+    from raytracer_rs_b200 import multi_gpu
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def device_step():
-        if gather is not None:
-            gather.begin_frame()
-        tracer.trace_rows(0, H, spp, want_shadow=False)
-        if gather is not None:
-            gather.device_gather(release=True)  # device-timed leg: the frame stays on rank 0
-
-    def global_ray_totals():
-        t = tracer.ray_totals()  # exact device counters since the handle was created (synchronises this rank's stream)
-        v = torch.tensor([t["primary"], t["shadow"]], dtype=torch.int64, device=dev)
+    def max_over_ranks(x):
+        v = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(v)
-        return int(v[0]), int(v[1])
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v)
 
-    # ---- device-timed leg ------------------------------------------------------------------------------
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            flush.zero_()
-            device_step()
-    barrier()
-    rays0 = global_ray_totals()
-    launches0 = tracer.kernels_launched() + (gather.kernels if gather else 0)
-    sampler.ready.wait(timeout=10)
-    t_region0 = time.perf_counter()
-    events = []
-    kernel_ms = []
-    with torch.cuda.stream(stream):
-        for _ in range(args.steps):
-            flush.zero_()  # L2 flush between timed iterations (not inside the event pair)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            device_step()
-            e1.record(stream)
-            events.append((e0, e1))
-    barrier()
-    clocks = sampler.window(t_region0, time.perf_counter())
-    launches = tracer.kernels_launched() + (gather.kernels if gather else 0) - launches0
-    rays1 = global_ray_totals()
-    # rays of the timed steps, counted on the device (with hashed jitter every step draws new samples, so the shadow-ray
-    # count differs slightly from step to step)
-    n_primary_total, n_shadow_total = (rays1[0] - rays0[0]) / args.steps, (rays1[1] - rays0[1]) / args.steps
-    rays_per_step = n_primary_total + n_shadow_total
-    step_ms = [a.elapsed_time(b) for a, b in events]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms)
-    value = rays_per_step * args.steps / (total_ms * 1e-3) / 1e6
+    def run_legs(tracer, gather, w, h, spp, steps, warmup, e2e=True, kernel_timing=True):
+        """device-timed leg (+ kernel duration for the roofline) and end-to-end leg of one configuration on the current handles"""
+        host_frames = [torch.empty(w * h, dtype=torch.int32).pin_memory(), torch.empty(w * h, dtype=torch.int32).pin_memory()]
+        pipelined = world == 1 and not args.sync_readback and not args.zero_copy
+        tracer.set_tuning(10, 1 if args.launch_timing else 0)
 
-    # ---- trace-kernel duration for the roofline (library's own CUDA events around the kernel, same stream) ----
-    tracer.set_tuning(10, 1)
-    with torch.cuda.stream(stream):
-        for _ in range(20):
-            flush.zero_()
-            tracer.trace_rows(0, H, spp, want_shadow=False)
-            kernel_ms.append(tracer.launch_stats()["trace_kernel_ms"])
-    if args.no_launch_timing:
-        tracer.set_tuning(10, 0)
-    kms = float(np.mean(kernel_ms))
-    kms_t = torch.tensor([kms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(kms_t, op=dist.ReduceOp.MAX)
-    kms = float(kms_t)
+        def device_step():
+            if gather is not None:
+                gather.begin_frame()
+            tracer.trace_rows(0, h, spp, want_shadow=False)
+            if gather is not None:
+                gather.device_gather(release=True)  # device-timed leg: the frame stays on rank 0
 
-    # ---- end-to-end leg: public API, host buffers, every step ---------------------------------------------------
-    def e2e_step(i):
-        # per-step input: camera state from the host (travels to the device as the kernel's launch parameters)
-        tracer.camera.set_state(0.0, 0.0, (0.0, 0.0, 0.0))
-        if gather is not None:
-            gather.begin_frame()
-        tracer.trace_rows(0, H, spp, want_shadow=False)
-        if gather is not None:
-            gather.device_gather()
-        if pipelined:
-            # frame i-1 (copied on the copy stream while frame i traces) is now complete in host memory; then hand
-            # frame i to the copy stream
-            tracer.wait_pixels()
-            tracer.get_tonemapped_pixels_async(host_frames[i & 1].data_ptr())
-        elif gather is not None and not args.sync_readback:
-            if rank == 0:  # same pipelining on rank 0 of a multi-GPU run: hand frame i to the copy stream, then make sure
-                # frame i-1 (the other host buffer) has arrived
-                gather.read_frame_async(host_frames[i & 1])
-                gather.wait_frame(keep=1)
-        elif rank == 0:
-            tracer_or_gather_readback()
+        def global_ray_totals():
+            t = tracer.ray_totals()  # exact device counters since the handle was created (synchronises this rank's stream)
+            v = torch.tensor([t["primary"], t["shadow"]], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(v)
+            return int(v[0]), int(v[1])
 
-    def tracer_or_gather_readback():
-        if gather is not None:
-            gather.read_frame_into(host_frame)
+        def kernels_now():
+            return tracer.kernels_launched() + (gather.kernels if gather else 0)
+
+        def timed(n_steps):
+            rays0, launches0 = global_ray_totals(), kernels_now()
+            t_region0 = time.perf_counter()
+            events = []
+            with torch.cuda.stream(stream):
+                for _ in range(n_steps):
+                    flush.zero_()  # L2 flush between timed iterations (not inside the event pair)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    device_step()
+                    e1.record(stream)
+                    events.append((e0, e1))
+            barrier()
+            clocks = sampler.window(t_region0, time.perf_counter())
+            launches = kernels_now() - launches0
+            rays1 = global_ray_totals()
+            # rays of the timed steps, counted on the device (with hashed jitter every step draws new samples, so the shadow-ray
+            # count differs slightly from step to step)
+            n_primary, n_shadow = (rays1[0] - rays0[0]) / n_steps, (rays1[1] - rays0[1]) / n_steps
+            total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in events))
+            return {"value": (n_primary + n_shadow) * n_steps / (total_ms * 1e-3) / 1e6, "ms_per_step": total_ms / n_steps, "clocks": clocks,
+                    "launches": launches, "primary": n_primary, "shadow": n_shadow, "steps": n_steps}
+
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                flush.zero_()
+                device_step()
+        barrier()
+        sampler.ready.wait(timeout=10)
+        res = {"dev": timed(steps)}
+        rays_per_step = res["dev"]["primary"] + res["dev"]["shadow"]
+
+        # ---- trace-kernel duration for the roofline (library's own CUDA events around the kernel, same stream) ----
+        if kernel_timing:
+            tracer.set_tuning(10, 1)
+            kernel_ms = []
+            with torch.cuda.stream(stream):
+                for _ in range(20):
+                    flush.zero_()
+                    tracer.trace_rows(0, h, spp, want_shadow=False)
+                    kernel_ms.append(tracer.launch_stats()["trace_kernel_ms"])
+            tracer.set_tuning(10, 1 if args.launch_timing else 0)
+            res["kernel_ms"] = max_over_ranks(float(np.mean(kernel_ms)))
+        if not e2e:
+            return res
+
+        # ---- end-to-end leg: public API, host buffers, every step ---------------------------------------------------
+        hgather = None
+        if gather is not None and args.e2e_gather == "host":
+            shm_seq[0] += 1
+            hgather = multi_gpu.HostFrameGather(tracer, rank, world, dev, stream, "rtb200_%s_%d" % (os.environ.get("MASTER_PORT", "0"), shm_seq[0]))
+
+        def e2e_step(i):
+            # per-step input: camera state from the host (travels to the device as the kernel's launch parameters)
+            tracer.camera.set_state(0.0, 0.0, (0.0, 0.0, 0.0))
+            if hgather is not None:
+                # every rank delivers the rows it owns over its own PCIe link (pipelined: the copy of frame i overlaps the trace of i+1)
+                hgather.begin_frame()
+                tracer.trace_rows(0, h, spp, want_shadow=False)
+                hgather.publish()
+                if rank == 0:
+                    hgather.wait_frame(keep=1)
+                return
+            if gather is not None:
+                gather.begin_frame()
+            tracer.trace_rows(0, h, spp, want_shadow=False)
+            if gather is not None:
+                gather.device_gather()
+            if pipelined:
+                # frame i-1 (copied on the copy stream while frame i traces) is now complete in host memory; then hand
+                # frame i to the copy stream
+                tracer.wait_pixels()
+                tracer.get_tonemapped_pixels_async(host_frames[i & 1].data_ptr())
+            elif gather is not None and not args.sync_readback:
+                if rank == 0:  # same pipelining on rank 0 of a multi-GPU run: hand frame i to the copy stream, then make sure
+                    # frame i-1 (the other host buffer) has arrived
+                    gather.read_frame_async(host_frames[i & 1])
+                    gather.wait_frame(keep=1)
+            elif rank == 0:
+                if gather is not None:
+                    gather.read_frame_into(host_frames[0])
+                else:
+                    tracer.get_tonemapped_pixels_into(host_frames[0].data_ptr())
+
+        def e2e_drain():
+            if hgather is not None:
+                if rank == 0:
+                    hgather.wait_frame()
+            elif pipelined:
+                tracer.wait_pixels()  # the last frame is delivered inside the timed region too
+            elif gather is not None and rank == 0:
+                gather.wait_frame()
+
+        if gather is None and args.zero_copy:
+            tracer.set_host_frame(host_frames[0].data_ptr())  # the kernel stores packed pixels straight into the pinned frame
+        for i in range(warmup):
+            e2e_step(i)
+        e2e_drain()
+        barrier()
+        rays0 = global_ray_totals()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            e2e_step(i)
+        e2e_drain()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        rays1 = global_ray_totals()
+        e2e_rays = (rays1[0] - rays0[0]) + (rays1[1] - rays0[1])
+        e2e_s = max_over_ranks(e2e_s)
+        res["e2e"] = {"value": e2e_rays / e2e_s / 1e6, "ms_per_step": e2e_s / steps * 1e3}
+
+        # ---- the frame the end-to-end path delivers must be the frame the device holds ----
+        frame_ok = None
+        if gather is None:
+            check = np.empty(w * h, np.uint32)
+            tracer.set_host_frame(None)
+            tracer.get_tonemapped_pixels(check)
+            last = host_frames[(steps - 1) & 1] if pipelined else host_frames[0]
+            frame_ok = bool(np.array_equal(check, last.numpy().view(np.uint32)))
         else:
-            tracer.get_tonemapped_pixels_into(host_frame.data_ptr())
+            # N > 1: every rank clears its film, ONE more frame goes through the same gather + host copy, and rank 0 compares it bit
+            # for bit with its own UNSHARDED render of that frame (same samples: a sample's number is the pixel's film count)
+            tracer.film.clear()
+            e2e_step(0)
+            e2e_drain()
+            barrier()
+            if rank == 0:
+                solo = make_tracer(scene_of[(w, h)], w, h, spp, sharded=False)
+                solo.trace_rows(0, h, spp, want_shadow=False)
+                got = hgather.frame(hgather.frame_no - 1) if hgather is not None else host_frames[0].numpy().view(np.uint32)
+                frame_ok = bool(np.array_equal(solo.get_tonemapped_pixels(), got))
+                solo.close()
+        if hgather is not None:
+            res["e2e"]["kernels"] = hgather.kernels
+            hgather.close()
+            gather.rearm()
+        res["e2e"]["host_gather"] = hgather is not None
+        res["e2e"]["frame_matches_device"] = frame_ok
+        res["e2e"]["pipelined"] = pipelined
+        res["rays_per_step"] = rays_per_step
+        return res
 
-    if gather is None and args.zero_copy:
-        tracer.set_host_frame(host_frame.data_ptr())  # the kernel stores packed pixels straight into the pinned frame
-    for i in range(args.warmup):
-        e2e_step(i)
-    barrier()
-    rays0 = global_ray_totals()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(i)
-    if pipelined:
-        tracer.wait_pixels()  # the last frame is delivered inside the timed region too
-    elif gather is not None and rank == 0:
-        gather.wait_frame()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    rays1 = global_ray_totals()
-    e2e_rays = (rays1[0] - rays0[0]) + (rays1[1] - rays0[1])
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_t)
-    e2e_value = e2e_rays / e2e_s / 1e6
-    sampler.stop()
-    e2e_frame_ok = None
-    if rank == 0 and gather is None:
-        # the frame delivered by the last e2e step must equal the device frame
-        check = np.empty(W * H, np.uint32)
-        tracer.set_host_frame(None)
-        tracer.get_tonemapped_pixels(check)
-        last = host_frames[(args.steps - 1) & 1] if pipelined else host_frame
-        e2e_frame_ok = bool(np.array_equal(check, last.numpy().view(np.uint32)))
+    scene_of = {(W, H): scene}
+    shm_seq = [0]
+    spp = base_spp * (world if (world > 1 and args.scaling == "weak") else 1)
+    tracer = make_tracer(scene, W, H, spp)
+    tracer.set_stream(stream.cuda_stream)
+    gather = multi_gpu.FrameGather(tracer, rank, world, dev, stream, mode=args.gather, fused_signal=not args.separate_signal) if world > 1 else None
+    main_res = run_legs(tracer, gather, W, H, spp, args.steps, args.warmup)
+    extras = not args.no_extras
 
-    # ---- the reference's own call pattern: 50-row bands, full-frame readback after every band (main.rs:200-201) ----
-    band = None
-    if world == 1 and spp == 1:
+    # ---- a long run of the same step (>= 0.5 s of GPU time): the driver-sized figure above lasts a few milliseconds ----
+    long_res = None
+    if extras:
+        n_long = int(max(args.steps, min(20000, 0.5e3 / max(main_res["dev"]["ms_per_step"], 1e-3))))
+        tracer.film.clear()
+        long_res = run_legs(tracer, gather, W, H, spp, n_long, 3, e2e=False, kernel_timing=False)["dev"]
+
+    # ---- N > 1, weak line: the fixed frame (1 sample per pixel) over the same N GPUs ----
+    strong_res = None
+    if extras and world > 1 and args.scaling == "weak":
+        tracer.configure(recursions=0, jitter_mode=jitter_for(base_spp), seed=0, accel=accel)
+        tracer.film.clear()
+        strong_res = run_legs(tracer, gather, W, H, base_spp, args.steps, args.warmup, kernel_timing=True)
+        tracer.configure(recursions=0, jitter_mode=jitter_for(spp), seed=0, accel=accel)
+
+    timeouts = tracer.sync_timeouts() if world > 1 else 0
+    timeouts = int(max_over_ranks(float(timeouts)))
+
+    # ---- single-GPU extras on the headline handle ----
+    band = first_move = None
+    if world == 1 and spp == 1 and extras:
+        # the reference's own call pattern: 50-row bands, frame readback after every band (main.rs:200-201)
+        host_frame = torch.empty(W * H, dtype=torch.int32).pin_memory()
+        clone = np.empty(W * H, np.uint32)
         tracer.set_rows_per_call(50)
         calls = (H + 49) // 50
-        for _ in range(2 * calls):
-            tracer.trace_frame_additive()
-            tracer.get_tonemapped_pixels_into(host_frame.data_ptr())
-        torch.cuda.synchronize(dev)
-        reps = max(1, min(args.steps, 40))
-        t0 = time.perf_counter()
-        for _ in range(reps * calls):
-            tracer.trace_frame_additive()
-            tracer.get_tonemapped_pixels_into(host_frame.data_ptr())
-        dtb = time.perf_counter() - t0
-        band_rays = rays_per_step * (calls * 50 / H) * reps
-        band = {"value": band_rays / dtb / 1e6, "unit": UNIT, "calls_per_frame": calls,
-                "d2h_bytes_per_call": W * H * 4, "note": "trace_frame_additive (50 rows) + get_tonemapped_pixels per call"}
+        rays_frame = main_res["rays_per_step"] * (calls * 50 / H)
 
+        def band_loop(readback, reps):
+            for _ in range(reps * calls):
+                tracer.trace_frame_additive()
+                readback()
+
+        def band_rate(readback):
+            band_loop(readback, 3)  # every band's schedule is learned
+            torch.cuda.synchronize(dev)
+            reps = max(1, min(args.steps, 20))
+            t0 = time.perf_counter()
+            band_loop(readback, reps)
+            return rays_frame * reps / (time.perf_counter() - t0) / 1e6
+
+        def delta_and_clone():
+            tracer.get_tonemapped_pixels_delta_into(host_frame.data_ptr())
+            np.copyto(clone, host_frame.numpy().view(np.uint32))  # the fresh Vec<u32> the reference's signature returns (mod.rs:120)
+
+        v_delta = band_rate(lambda: tracer.get_tonemapped_pixels_delta_into(host_frame.data_ptr()))
+        check = np.empty(W * H, np.uint32)
+        tracer.get_tonemapped_pixels(check)
+        delta_ok = bool(np.array_equal(check, host_frame.numpy().view(np.uint32)))
+        band = {"value": v_delta, "unit": UNIT, "calls_per_frame": calls, "d2h_bytes_per_call": 50 * W * 4,
+                "readback": "rt_get_tonemapped_pixels_delta into one pinned frame the host keeps: only the 50 rows traced by the call are copied",
+                "frame_matches_device": delta_ok,
+                "value_with_host_vec_clone": band_rate(delta_and_clone),
+                "value_full_frame_readback": band_rate(lambda: tracer.get_tonemapped_pixels_into(host_frame.data_ptr())),
+                "d2h_bytes_per_call_full_frame": W * H * 4,
+                "note": "trace_frame_additive (50 rows) + frame readback per call, synchronous, as main.rs:200-201 does"}
+
+        # first frame after a camera key (main.rs:124-162 moves the camera and clears the film): the tile schedule of the old view
+        # is kept for it; compared with the steady state of the same handle
+        def frame_ms(prepare=None):
+            ms = []
+            for _ in range(8):
+                if prepare:
+                    prepare()
+                    torch.cuda.synchronize(dev)
+                with torch.cuda.stream(stream):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    tracer.trace_rows(0, H, 1, want_shadow=False)
+                    e1.record(stream)
+                torch.cuda.synchronize(dev)
+                ms.append(e0.elapsed_time(e1))
+            return float(np.median(ms))
+
+        for _ in range(4):
+            tracer.trace_rows(0, H, 1, want_shadow=False)
+        steady = frame_ms()
+
+        def key_press():
+            for _ in range(3):  # the frames in between re-learn the schedule, as during interactive use
+                tracer.trace_rows(0, H, 1, want_shadow=False)
+            tracer.camera.move_rel(0.0, 0.0, 0.1)  # the 'w' key of the native binary (main.rs:125-127)
+            tracer.film.clear()
+
+        first_move = {"first_frame_after_move_ms": frame_ms(key_press), "steady_state_ms": steady,
+                      "note": "median of 8: camera.move_rel(0, 0, 0.1) + film.clear(), then one frame, timed with CUDA events"}
+        first_move["ratio"] = first_move["first_frame_after_move_ms"] / steady
+        tracer.camera.set_state(0.0, 0.0, (0.0, 0.0, 0.0))
+        tracer.film.clear()
+
+    # ---- the other BASELINE configurations and the reference's default mode, in the same run ----
+    configs, rec2 = None, None
+    if extras and args.workload == "thai2_1080p":
+        configs = {}
+        names = ["ico2_1024x768", "4boxes_1080p", "ico3_tex_1080p", "thai2_4k_16spp"] if world == 1 else ["thai2_4k_16spp"]
+        if gather is not None:
+            gather.close()
+            gather = None
+        tracer.close()
+        tracer = None
+        for name in names:
+            f2, w2, h2, spp2 = WORKLOADS[name]
+            sc2 = scene if f2 == fname else rt.load_scene(os.path.join(ROOT, "data", f2))
+            scene_of[(w2, h2)] = sc2
+            t2 = make_tracer(sc2, w2, h2, spp2)
+            t2.set_stream(stream.cuda_stream)
+            g2 = multi_gpu.FrameGather(t2, rank, world, dev, stream, mode=args.gather, fused_signal=not args.separate_signal) if world > 1 else None
+            r2 = run_legs(t2, g2, w2, h2, spp2, max(5, min(args.steps, 20)), 3, kernel_timing=False)
+            entry = {"value": r2["dev"]["value"], "unit": UNIT, "ms_per_step": r2["dev"]["ms_per_step"], "e2e": r2["e2e"]["value"],
+                     "e2e_frame_matches_device": r2["e2e"]["frame_matches_device"], "spp": spp2, "n_gpus": world,
+                     "rays_per_step": r2["rays_per_step"]}
+            if g2 is not None:
+                g2.close()
+            t2.close()
+            if rank == 0:
+                # parity inside the run: an oracle band through the middle of the geometry (Q1 squeezes it into the upper ~56 % of the rows)
+                band_rows = (h2 // 4, 16 if spp2 > 1 else 48)
+                entry["oracle_check"] = oracle_band_check(rt, np, lambda: make_tracer(sc2, w2, h2, spp2, sharded=False), f2, w2, h2, spp2, band_rows)
+            barrier()
+            configs[name] = entry
+        if world == 1:
+            # RECURSIONS = 2, SUB_SPREAD = 1, jittered: what the reference binary always runs (mod.rs:81-82); bounce wavefront
+            t3 = rt.RayTracer.from_scene(scene, rt.Config(W, H, recursions=2, sub_spread=1, jitter_mode=rt.JITTER_HASHED, seed=0, accel=accel, device=local_rank))
+            t3.set_stream(stream.cuda_stream)
+            for _ in range(4):
+                t3.trace_rows(0, H, 1, want_shadow=False)
+            tot0 = t3.ray_totals()
+            ev = []
+            n3 = max(5, min(args.steps, 20))
+            with torch.cuda.stream(stream):
+                for _ in range(n3):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    t3.trace_rows(0, H, 1, want_shadow=False)
+                    e1.record(stream)
+                    ev.append((e0, e1))
+            torch.cuda.synchronize(dev)
+            tot1 = t3.ray_totals()
+            ms3 = sum(a.elapsed_time(b) for a, b in ev) / n3
+            rays3 = {k: (tot1[k] - tot0[k]) / n3 for k in tot0}
+            rec2 = {"frame_ms": ms3, "rays_per_frame": rays3, "grays_per_s_all_rays": sum(rays3.values()) / ms3 / 1e6,
+                    "value_primary_shadow": (rays3["primary"] + rays3["shadow"]) / ms3 / 1e3, "unit": UNIT,
+                    "note": "thai2 1080p, recursions 2, sub_spread 1, hashed jitter, 1 spp per step; primary + shadow + bounce rays"}
+            t3.close()
+
+    sampler.stop()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    if timeouts:
+        raise SystemExit("bench.py: %d frame-fence waits timed out (rt_sync_timeouts): a frame may be torn, no number is reported" % timeouts)
 
+    dev_res, e2e_res, kms = main_res["dev"], main_res["e2e"], main_res["kernel_ms"]
+    clocks = dev_res["clocks"]
+    rays_per_step = main_res["rays_per_step"]
     peak, peak_src = measured_hbm_peak()
     alg = algorithmic_bytes(args.workload)
-    traffic, warp_inst = None, None
+    prof, traffic, warp_inst, stale = {}, None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             prof = json.load(f)
         traffic = prof.get("%s/%s" % (args.workload, args.accel))
         warp_inst = prof.get("warp_instructions", {}).get("%s/%s" % (args.workload, args.accel))
+        # the ncu counts describe ONE build of the kernels: compare the digest recorded with them against the digest compiled into
+        # the loaded library and against the sources in the tree
+        lib_hash = rt.lib().rt_kernels_hash().decode()
+        stale = not (prof.get("kernels_hash") == lib_hash == kernel_source_hash())
     except Exception:
         pass
     roofline = None
     if alg is not None:
-        note = "traffic-equivalent of the reference algorithm's reads; the <= 2 MB scene is L1/L2 resident, so frac may exceed 1"
+        note = ("achieved/peak: traffic-equivalent of the reference algorithm's reads (the <= 2 MB scene is L1/L2 resident, so it exceeds the HBM "
+                "peak); frac: the binding physical resource")
         if world == 1 and spp == 1:
             per_launch = float(alg)  # exact oracle counters of the pinned frame
         else:
@@ -490,31 +749,45 @@ def main():
             per_launch = alg / (p0 + s0) * rays_per_step / world
             note += "; per-launch bytes estimated from the pinned frame's average bytes per ray"
         achieved = per_launch / (kms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic if world == 1 and spp == 1 else None,
-                    "peak_source": peak_src, "kernel": "trace_shade_persistent_kernel<%s>" % args.accel, "kernel_ms": kms,
-                    "algorithmic_bytes_per_launch": per_launch, "note": note}
+        single = world == 1 and spp == 1
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "traffic_equivalent": achieved / peak,
+                    "traffic": traffic if single else None, "peak_source": peak_src, "kernel": "trace_shade_persistent_kernel<%s>" % args.accel,
+                    "kernel_ms": kms, "algorithmic_bytes_per_launch": per_launch, "note": note, "stale": stale,
+                    "counters_from": "profiles/traffic.json (ncu --set full capture of one launch; kernels_hash %s)" % prof.get("kernels_hash")}
         if roofline["traffic"]:
             # what actually crosses the HBM interface (ncu dram__bytes of one launch, profiles/traffic.json): the film
             roofline["dram_achieved"] = roofline["traffic"] / (kms * 1e-3) / 1e9
             roofline["dram_frac"] = roofline["dram_achieved"] / peak
-            roofline["bound_in_practice"] = ("instruction issue at partly filled warps + latency of dependent node loads "
-                                             "(ncu: issue slots 65 % busy, 22 of 32 lanes active; profiles/README.md)")
-        if warp_inst and world == 1 and spp == 1 and clocks.get("sm_mhz"):
-            # the resource that actually binds: warp instructions issued (ncu smsp__inst_executed.sum of one launch,
-            # profiles/traffic.json) / measured kernel time, against 4 schedulers x SMs x the SM clock measured during the run
+        if warp_inst and single and clocks.get("sm_mhz"):
+            # the resource that actually binds: warp instructions issued (ncu smsp__inst_executed.sum of one launch) / measured
+            # kernel time, against 4 schedulers x SMs x the SM clock measured during the run
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             peak_issue = 4.0 * sms * clocks["sm_mhz"] * 1e6
             roofline["issue_slots"] = {"warp_instructions_per_launch": warp_inst, "achieved_ginst_s": warp_inst / (kms * 1e-3) / 1e9,
                                        "peak_ginst_s": peak_issue / 1e9, "frac": warp_inst / (kms * 1e-3) / peak_issue,
-                                       "note": "one warp instruction per scheduler and cycle; 22 of 32 lanes active on average"}
+                                       "lanes_active_per_instruction": prof.get("lanes_per_instruction", {}).get("%s/%s" % (args.workload, args.accel))}
+            roofline["frac"] = roofline["issue_slots"]["frac"]
+            roofline["frac_of"] = "SM issue slots over the whole launch (one warp instruction per scheduler and cycle)"
+        else:
+            roofline["frac"] = roofline["traffic_equivalent"]
+            roofline["frac_of"] = "traffic equivalent (no instruction count recorded for this configuration)"
+    gather_note = "" if world == 1 else (" (%d spp per GPU-count unit: %s scaling), rows sharded by interleaved 8-row bands, every rank traces its rows x all "
+                                          "samples in one launch, packed frame stored into rank 0's buffer over NVLink (%s, frame-done signal %s)"
+                                          % (base_spp, args.scaling, args.gather, "from a separate launch" if args.separate_signal else "fused into the trace kernel"))
+    readback = (("every rank copies the rows it owns over its own PCIe link into one frame in shared page-locked host memory (copy stream, overlaps "
+                 "the next frame; arrival flags in the same shared memory)") if e2e_res.get("host_gather") else
+                ("gather to rank 0 (%s) + %s copy to pinned host memory" % (args.gather, "blocking" if args.sync_readback else "pipelined (copy stream, overlaps the next frame)"))) if world > 1 else (
+        "zero-copy stores from the trace kernel into the pinned frame" if args.zero_copy else (
+            "pipelined: device snapshot + copy stream, the copy of frame k overlaps the trace of frame k+1, every frame delivered inside the timed region"
+            if e2e_res["pipelined"] else "blocking cudaMemcpyAsync after the kernel"))
     line = {
         "metric": METRIC,
-        "value": value,
+        "value": dev_res["value"],
         "unit": UNIT,
         "n_gpus": world,
         "steps": args.steps,
         "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps,
+        "ms_per_step": dev_res["ms_per_step"],
         "higher_is_better": True,
         "scaling": args.scaling if world > 1 else "weak",
         "vs_baseline": None,
@@ -522,19 +795,32 @@ def main():
         "data": "reference scene fixture data/%s (the upstream repository's own scene), pinned camera" % fname,
         "config": {"workload": args.workload, "width": W, "height": H, "spp": spp, "recursions": 0,
                    "jitter": "fixed 0.5" if spp == 1 else "hashed seed 0", "accel": args.accel, "l2_flush_between_steps": True,
-                   "step": "one full frame: trace %d rows x %d spp%s" % (H, spp, "" if world == 1 else " (%d spp per GPU-count unit: %s scaling), rows sharded by interleaved 8-row bands, every rank traces its rows x all samples in one launch, packed frame stored into rank 0's buffer over NVLink (%s)" % (base_spp, args.scaling, args.gather)),
-                   "primary_rays_per_step": n_primary_total, "shadow_rays_per_step": n_shadow_total},
-        "frames_per_s": args.steps / (total_ms * 1e-3),
+                   "step": "one full frame: trace %d rows x %d spp%s" % (H, spp, gather_note),
+                   "primary_rays_per_step": dev_res["primary"], "shadow_rays_per_step": dev_res["shadow"]},
+        "frames_per_s": 1e3 / dev_res["ms_per_step"],
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rt.lib().rt_launch_param_bytes()), "d2h_bytes_per_step": W * H * 4 + 32,
-                "ms_per_step": e2e_s / args.steps * 1e3, "readback": ("gather to rank 0 (%s) + %s copy to pinned host memory" % (args.gather, "blocking" if args.sync_readback else "pipelined (copy stream, overlaps the next frame)")) if world > 1 else ("zero-copy stores from the trace kernel into the pinned frame" if args.zero_copy else ("pipelined: device snapshot + copy stream, the copy of frame k overlaps the trace of frame k+1, every frame delivered inside the timed region" if pipelined else "blocking cudaMemcpyAsync after the kernel")),
-                "frame_matches_device": e2e_frame_ok,
+        "e2e": {"value": e2e_res["value"], "unit": UNIT, "h2d_bytes_per_step": int(rt.lib().rt_launch_param_bytes()), "d2h_bytes_per_step": W * H * 4 + 32,
+                "ms_per_step": e2e_res["ms_per_step"], "readback": readback, "frame_matches_device": e2e_res["frame_matches_device"],
+                "sync_timeouts": timeouts,
                 "note": "camera state in (launch parameters), packed LDR frame out to pinned host memory, wall clock"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(dev_res["launches"]),
         "roofline": roofline,
     }
+    if long_res:
+        line["value_long"] = {"value": long_res["value"], "unit": UNIT, "steps": long_res["steps"], "ms_per_step": long_res["ms_per_step"],
+                              "gpu_seconds": long_res["ms_per_step"] * long_res["steps"] * 1e-3, "clocks": long_res["clocks"]}
+    if strong_res:
+        line["strong"] = {"value": strong_res["dev"]["value"], "unit": UNIT, "ms_per_step": strong_res["dev"]["ms_per_step"], "spp": base_spp,
+                          "kernel_ms": strong_res["kernel_ms"], "e2e": strong_res["e2e"],
+                          "note": "the fixed frame (%d sample per pixel) sharded over the %d GPUs: strong scaling of BASELINE configs[3]" % (base_spp, world)}
     if band:
         line["e2e_reference_call_pattern"] = band
+    if first_move:
+        line["first_frame_after_move"] = first_move
+    if configs:
+        line["configs"] = configs
+    if rec2:
+        line["recursions2"] = rec2
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.workload, rt, scene)
     print(json.dumps(line), flush=True)

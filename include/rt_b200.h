@@ -238,6 +238,17 @@ int rt_sync_timeouts(rt_raytracer* rt, uint32_t* count);
    kernel does not finish the pixels itself (sample planes, bounce wavefront, the one-thread-per-pixel variant) append
    the signal as a launch of its own; either way the flag is published exactly once per armed call. */
 int rt_set_done_signal(rt_raytracer* rt, void* dev_flag, uint32_t value);
+/* Host-side frame delivery for one process per GPU: every rank copies the rows IT owns over its OWN PCIe link into one frame in
+   host memory that all processes share (POSIX shared memory, page-locked in every process with rt_host_register), instead of
+   funnelling the whole frame through rank 0's link. rt_copy_owned_rows copies the owned bands of `src_frame` (a device frame this
+   handle stored its pixels into, e.g. an rt_set_ldr_target buffer) to the same rows of `dst_frame` (one strided 2-D copy) on
+   `cuda_stream` (NULL = the handle's stream); rt_signal_flag_on_stream stores `value` into a flag (device address of mapped host
+   memory or device memory) behind it in stream order, which is how a rank tells the consumer that its rows of frame k have arrived.
+   rt_host_register returns the device address of the registered range through *dev_ptr (may be NULL). */
+int rt_host_register(rt_raytracer* rt, void* host_ptr, size_t bytes, void** dev_ptr);
+int rt_host_unregister(rt_raytracer* rt, void* host_ptr);
+int rt_copy_owned_rows(rt_raytracer* rt, const void* src_frame, void* dst_frame, void* cuda_stream);
+int rt_signal_flag_on_stream(rt_raytracer* rt, void* dev_flag, uint32_t value, void* cuda_stream);
 /* Device pointer to the 4 uint64 ray counters of the LAST trace call: shadow rays, primary hits, bounce rays, blocked
    shadow rays. Two sets alternate from call to call (the kernel of one call zeroes the set of the next, so a call needs no
    memset): ask again after every trace call. */
@@ -280,12 +291,31 @@ uint32_t rt_launch_param_bytes(void);
    rt_launch_stats.trace_kernel_ms is available; 0 skips them (trace_kernel_ms reads 0) — two stream operations less per
    call for hosts that time frames themselves. */
 #define RT_TUNE_TIME_LAUNCHES 10
-/* RT_TUNE_MIN_SCHEDULE_TILES: launches with fewer 32-lane tiles than this run in image order without cost feedback
-   (default 1024: a 50-row band of a 1024-wide frame has 1664). RT_TUNE_MAX_SPLIT_LEVEL: finest split of a heavy tile,
-   0 never, 1 / 2 / 3 = up to 4 / 8 / 16 items of 8 / 4 / 2 pixels (default 3; the finer levels only engage when a tile
-   alone costs more than 4x / 8x the balanced launch time, i.e. when the launch cannot fill the GPU). */
+/* RT_TUNE_MIN_SCHEDULE_TILES: launches with fewer 32-lane tiles than this (default 4096) get no cost-feedback schedule of their own
+   (the reference's 50-row bands walk over the image with a period of lcm(50, height) rows, 108 geometries at 1080p); they run in
+   image order with EVERY tile handed out in 4 or 8 parts, since such a launch cannot fill the GPU and lasts as long as its
+   heaviest item. RT_TUNE_MAX_SPLIT_LEVEL: finest split of a tile, 0 never, 1 / 2 / 3 = up to 4 / 8 / 16 items of 8 / 4 / 2
+   pixels (default 3; with cost feedback the finer levels only engage when a tile alone costs more than 4x / 8x the balanced
+   launch time, i.e. when the launch cannot fill the GPU). */
 #define RT_TUNE_MIN_SCHEDULE_TILES 11
 #define RT_TUNE_MAX_SPLIT_LEVEL 12
+/* RT_TUNE_BOUNCE_STREAM: 1 (default) every level of the bounce wavefront runs as a ray stream on the binary BVH — bounce rays
+   and the shadow rays of their hits share the lanes of a warp, and lanes whose ray ended are refilled RT_TUNE_STREAM_REFILL
+   (1..32, default 16) at a time; 0 the lockstep form (one kernel traces 32 bounce rays per warp, a second shades the
+   compacted hits). Same rays, same film. Other structures always use the lockstep form. */
+#define RT_TUNE_BOUNCE_STREAM 13
+#define RT_TUNE_STREAM_REFILL 14
+/* RT_TUNE_STREAM_MIN_INNER: the ray-stream kernel leaves its inner-node loop when fewer lanes than this are still descending while
+   other lanes wait at a leaf (0..32, default 8; 0 = classic while-while rounds). */
+#define RT_TUNE_STREAM_MIN_INNER 15
+/* RT_TUNE_STREAM_BLOCKS: resident 256-thread blocks per SM the ray-stream kernel is compiled and launched for (3, 4 or 5: a register
+   budget of 80, 64 or 48; default 4). RT_TUNE_WF_BLOCKS: cap on the resident blocks per SM of the lockstep wavefront kernels (0 = as many as fit). */
+#define RT_TUNE_STREAM_BLOCKS 16
+#define RT_TUNE_WF_BLOCKS 17
+/* RT_TUNE_STREAM_CHAIN: 1 (default) when every bounce level from the second on sends one ray per hit (the reference's RECURSIONS = 2,
+   SUB_SPREAD = 1), a lane of the ray-stream kernel that completes a hit continues in place with that hit's bounce ray, so one launch
+   walks the whole bounce tree; 0 one launch per level. */
+#define RT_TUNE_STREAM_CHAIN 18
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {
@@ -351,6 +381,9 @@ int rt_benchmark_report(const rt_benchmark* b, char* out, size_t out_len);
 
 /* Library identification: "rt_b200 <version> sm_100a". */
 const char* rt_version(void);
+/* First 16 hex digits of the sha256 of the kernel sources (csrc/kernels.cu + csrc/device_types.h) this library was built from.
+   Profiler counts quoted by the benchmark (profiles/traffic.json) carry the digest of the build they were measured on. */
+const char* rt_kernels_hash(void);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,7 @@ from .api import (  # noqa: F401
     lib_path,
     load_scene,
     version,
+    kernels_hash,
 )
 
 __all__ = [
@@ -57,4 +58,5 @@ __all__ = [
     "lib_path",
     "load_scene",
     "version",
+    "kernels_hash",
 ]

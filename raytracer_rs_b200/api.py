@@ -100,11 +100,12 @@ ABI_SYMBOLS = [
     "rt_get_ldr_device_ptr", "rt_set_ldr_target", "rt_get_owned_ldr_rows_device", "rt_get_launch_stats",
     "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_get_counters_device_ptr",
     "rt_stream_signal_flag", "rt_stream_signal_then_wait", "rt_stream_wait_flags", "rt_sync_timeouts", "rt_set_done_signal",
-    "rt_launch_param_bytes", "rt_set_tuning", "rt_set_host_frame",
+    "rt_launch_param_bytes", "rt_set_tuning", "rt_set_host_frame", "rt_host_register", "rt_host_unregister", "rt_copy_owned_rows",
+    "rt_signal_flag_on_stream",
     "rt_kernels_launched", "rt_get_ray_totals", "rt_octree_stats", "rt_octree_export", "rt_bvh_stats", "rt_bvh_export", "rt_bvh4_stats", "rt_bvh4_export", "rt_lbvh_build", "rt_lbvh_export", "rt_cwbvh_stats",
     "rt_cwbvh_export", "rt_stats_new",
     "rt_stats_free", "rt_stats_stats", "rt_stats_mean_stats", "rt_benchmark_new", "rt_benchmark_free",
-    "rt_benchmark_start", "rt_benchmark_stop", "rt_benchmark_report", "rt_version",
+    "rt_benchmark_start", "rt_benchmark_stop", "rt_benchmark_report", "rt_version", "rt_kernels_hash",
 ]  # fmt: skip
 
 _lib = None
@@ -177,6 +178,10 @@ def lib() -> C.CDLL:
         "rt_launch_param_bytes": (u32, []),
         "rt_set_tuning": (C.c_int, [vp, i32, i32]),
         "rt_set_host_frame": (C.c_int, [vp, vp]),
+        "rt_host_register": (C.c_int, [vp, vp, sz, P(vp)]),
+        "rt_host_unregister": (C.c_int, [vp, vp]),
+        "rt_copy_owned_rows": (C.c_int, [vp, vp, vp, vp]),
+        "rt_signal_flag_on_stream": (C.c_int, [vp, vp, u32, vp]),
         "rt_kernels_launched": (u64, [vp]),
         "rt_octree_stats": (C.c_int, [vp, vp]),
         "rt_octree_export": (C.c_int, [vp, vp, vp, vp, vp, P(u64)]),
@@ -199,6 +204,7 @@ def lib() -> C.CDLL:
         "rt_benchmark_stop": (C.c_int, [vp, cp]),
         "rt_benchmark_report": (C.c_int, [vp, cp, sz]),
         "rt_version": (cp, []),
+        "rt_kernels_hash": (cp, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the .so does not export what the header declares
@@ -210,6 +216,11 @@ def lib() -> C.CDLL:
 
 def version() -> str:
     return lib().rt_version().decode()
+
+
+def kernels_hash() -> str:
+    """digest of the kernel sources the loaded library was built from (rt_kernels_hash)"""
+    return lib().rt_kernels_hash().decode()
 
 
 def _ptr(a: np.ndarray):
@@ -496,6 +507,22 @@ class RayTracer:
     def set_host_frame(self, pinned_host_ptr: int | None) -> None:
         """Zero-copy readback into a page-locked host buffer (rt_set_host_frame)."""
         self._check(lib().rt_set_host_frame(self._h, C.c_void_p(pinned_host_ptr or 0)))
+
+    def host_register(self, host_ptr: int, nbytes: int) -> int:
+        """page-locks a host range (e.g. shared memory) for this process and returns its device address"""
+        p = C.c_void_p()
+        self._check(lib().rt_host_register(self._h, C.c_void_p(host_ptr), nbytes, C.byref(p)))
+        return p.value
+
+    def host_unregister(self, host_ptr: int) -> None:
+        self._check(lib().rt_host_unregister(self._h, C.c_void_p(host_ptr)))
+
+    def copy_owned_rows(self, src_frame: int, dst_frame: int, cuda_stream: int = 0) -> None:
+        """copies the rows this shard owns from one frame to the same rows of another (device or page-locked host)"""
+        self._check(lib().rt_copy_owned_rows(self._h, C.c_void_p(src_frame), C.c_void_p(dst_frame), C.c_void_p(cuda_stream or 0)))
+
+    def signal_flag_on_stream(self, dev_flag: int, value: int, cuda_stream: int = 0) -> None:
+        self._check(lib().rt_signal_flag_on_stream(self._h, C.c_void_p(dev_flag), value, C.c_void_p(cuda_stream or 0)))
 
     def set_tuning(self, key: int, value: int) -> None:
         self._check(lib().rt_set_tuning(self._h, key, value))

@@ -56,6 +56,7 @@ struct TraceParams {
     const float4* oct_nodes;
     const float4* oct_tris;
     const float4* bvh_nodes;
+    uint32_t bvh_top_count;  // nodes [0, bvh_top_count) of bvh_nodes are in breadth-first order (host SAH tree; 0 for the GPU-built tree)
     const float4* bvh_tris;
     const float4* bvh4_nodes;  // 4-wide BVH, 8 float4 per node (bvh4_build.cpp)
     const float4* bvh4_tris;
@@ -79,6 +80,7 @@ struct TraceParams {
     // every warp's peer stores ("my stores of this frame are done", the signal half of the frame fence)
     uint32_t* done_flag;
     uint32_t done_value;
+    uint32_t static_level;        // launches without a tile order: every tile is handed out in 2^(static_level + 1) parts (0 = whole tiles)
     const uint32_t* queue_items;  // number of entries of tile_order (written by tile_sort_kernel); unused when tile_order is null
     // cost-feedback tile schedule of the persistent kernel (either may be null): cycles spent per 8x4 tile in this
     // launch (written), queue slot -> tile id (read)
@@ -100,6 +102,7 @@ struct TraceParams {
     unsigned int* wf_counts;     // [0, L): nodes per level; [L, 2L): ray-queue head per level; [2L, 3L): shade-queue head (L = kWfLevels)
     uint32_t wf_level;           // level processed by wf_bounce_kernel / wf_combine_kernel
     WfLevel wf[kWfLevels];
+    uint32_t wf_chain;           // ray-stream kernel: a lane continues in place with the single bounce ray of a node it completed
     uint32_t queue_batch, queue_batch_from_pct;  // persistent kernel: slots claimed at a time in the cheap tail of the sorted queue
     uint32_t pool_refill;        // ray-pool kernel: idle lanes of a warp that trigger a refill
     uint32_t pool_min_inner;     // ray-pool kernel: the inner-node loop yields when fewer lanes than this still descend

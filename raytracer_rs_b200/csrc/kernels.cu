@@ -391,6 +391,36 @@ __device__ __forceinline__ bool octree_closest_hit_ww(const TraceParams& P, cons
     }
 }
 
+// Build-time experiments on the traversal stack and the top of the tree (A/B runs documented in profiles/r2_default_kernel_ab.md;
+// none is part of the default build):
+//   RT_STACK_SMEM=K    the first K stack entries of every thread live in shared memory ([K][256] int2), deeper ones in local memory
+//   RT_STACK_REGTOP=1  the top of the stack is cached in two registers: a push spills the previous top to local memory only when
+//                      there is one, a pop reads local memory only when the cached entry is gone
+//   RT_TOP_SMEM=N      every block stages the first N nodes of the (breadth-first ordered) node array in shared memory and reads
+//                      node references < N with LDS instead of LDG
+#ifndef RT_STACK_SMEM
+#define RT_STACK_SMEM 0
+#endif
+#ifndef RT_STACK_REGTOP
+#define RT_STACK_REGTOP 0
+#endif
+#ifndef RT_TOP_SMEM
+#define RT_TOP_SMEM 0
+#endif
+#if RT_TOP_SMEM > 0
+__device__ __forceinline__ float4* top_nodes_smem() {
+    __shared__ float4 top_nodes[4 * RT_TOP_SMEM];
+    return top_nodes;
+}
+// called by all threads of a block before its first traversal
+__device__ __forceinline__ void stage_top_nodes(const TraceParams& P) {
+    float4* top = top_nodes_smem();
+    const uint32_t n = min((uint32_t)RT_TOP_SMEM, P.bvh_top_count);
+    for (uint32_t i = threadIdx.x; i < 4u * n; i += blockDim.x) top[i] = __ldg(P.bvh_nodes + i);
+    __syncthreads();
+}
+#endif
+
 __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V3& o, const V3& d, float t_limit, float early_t, HitRec* out) {
     // The lanes that enter together stay in one loop and meet at its head after every round (one vote per round).
     // Without this the hardware is free to let sub-groups of the warp that left a leaf at different times run the
@@ -400,9 +430,57 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
     const uint32_t mask = __activemask();
     const float ix = rcp_approx(d.x), iy = rcp_approx(d.y), iz = rcp_approx(d.z);  // box tests only (padded boxes)
     const float ox = -o.x * ix, oy = -o.y * iy, oz = -o.z * iz;
-    int2 stack[kBvhStack];  // (node reference, entry distance as float bits): one 8-byte local store / load per entry
-    stack[0] = make_int2(kSentinel, __float_as_int(-FLT_MAX));
+    // stack entries: (node reference, entry distance as float bits): one 8-byte store / load per entry
+#if RT_STACK_SMEM > 0
+    __shared__ int2 s_stack[RT_STACK_SMEM][256];
+    int2 l_stack[kBvhStack > RT_STACK_SMEM ? kBvhStack - RT_STACK_SMEM : 1];
+#define RT_STK_ST(i, v)                                        \
+    {                                                          \
+        if ((i) < RT_STACK_SMEM) s_stack[(i)][threadIdx.x] = (v); \
+        else l_stack[(i) - RT_STACK_SMEM] = (v);               \
+    }
+#define RT_STK_LD(i) ((i) < RT_STACK_SMEM ? s_stack[(i)][threadIdx.x] : l_stack[(i) - RT_STACK_SMEM])
+#else
+    int2 stack[kBvhStack];
+#define RT_STK_ST(i, v) stack[(i)] = (v)
+#define RT_STK_LD(i) stack[(i)]
+#endif
+    RT_STK_ST(0, make_int2(kSentinel, __float_as_int(-FLT_MAX)));
     int sp = 1;
+#if RT_STACK_REGTOP
+    int2 top = make_int2(0, 0);
+    bool top_valid = false;
+#define RT_PUSH(v)                     \
+    {                                  \
+        if (top_valid) {               \
+            RT_STK_ST(sp, top);        \
+            ++sp;                      \
+        }                              \
+        top = (v);                     \
+        top_valid = true;              \
+    }
+#define RT_POP(e)                      \
+    {                                  \
+        if (top_valid) {               \
+            e = top;                   \
+            top_valid = false;         \
+        } else {                       \
+            --sp;                      \
+            e = RT_STK_LD(sp);         \
+        }                              \
+    }
+#else
+#define RT_PUSH(v)          \
+    {                       \
+        RT_STK_ST(sp, (v)); \
+        ++sp;               \
+    }
+#define RT_POP(e)           \
+    {                       \
+        --sp;               \
+        e = RT_STK_LD(sp);  \
+    }
+#endif
     HitRec best;
     best.t = t_limit;
     best.u = 0.f;
@@ -415,8 +493,17 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
 #ifdef RT_DEBUG_STEP_COUNTS
             ++g_dbg_nodes;
 #endif
-            const float4* n = P.bvh_nodes + 4 * (size_t)cur;
-            const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+            float4 q0, q1, q2, q3;
+#if RT_TOP_SMEM > 0
+            if ((uint32_t)cur < min((uint32_t)RT_TOP_SMEM, P.bvh_top_count)) {
+                const float4* n = top_nodes_smem() + 4 * cur;
+                q0 = n[0], q1 = n[1], q2 = n[2], q3 = n[3];
+            } else
+#endif
+            {
+                const float4* n = P.bvh_nodes + 4 * (size_t)cur;
+                q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+            }
             const float a0x = fmaf(q0.x, ix, ox), b0x = fmaf(q0.w, ix, ox);
             const float a0y = fmaf(q0.y, iy, oy), b0y = fmaf(q1.x, iy, oy);
             const float a0z = fmaf(q0.z, iz, oz), b0z = fmaf(q1.y, iz, oz);
@@ -431,15 +518,14 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
             const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
             const bool go1 = h1 && (!h0 || n1 < n0);  // child 1 first (child 0 wins ties, as before)
             if (h0 && h1) {  // the far child waits on the stack (predicated stores: no local-memory traffic otherwise)
-                stack[sp] = make_int2(go1 ? c0 : c1, __float_as_int(go1 ? n0 : n1));
-                ++sp;
+                RT_PUSH(make_int2(go1 ? c0 : c1, __float_as_int(go1 ? n0 : n1)));
             }
             if (h0 || h1) {
                 cur = go1 ? c1 : c0;
             } else {
                 int2 e;
                 do {
-                    e = stack[--sp];
+                    RT_POP(e);
                 } while (__int_as_float(e.y) > best.t);
                 cur = e.x;
             }
@@ -472,12 +558,16 @@ __device__ __forceinline__ bool bvh_closest_hit_ww(const TraceParams& P, const V
             } else {
                 int2 e;
                 do {
-                    e = stack[--sp];
+                    RT_POP(e);
                 } while (__int_as_float(e.y) > best.t);
                 cur = e.x;
             }
         }
     }
+#undef RT_PUSH
+#undef RT_POP
+#undef RT_STK_ST
+#undef RT_STK_LD
     if (best.tri == kNoHit) return false;
     if (!early) {
         const V3 hp = vadd(o, vscale(d, best.t));
@@ -796,7 +886,11 @@ __device__ __forceinline__ float pow32(float x) {
 }
 
 __device__ __forceinline__ uint32_t to_u8(float x) {  // color.rs:89-93: (x.min(1).max(0) * 255) as u8
-    return __float2uint_rz(fmul(fmaxf(fminf(x, 1.0f), 0.0f), 255.0f));
+    // Rust's f32::min drops a NaN operand, so NaN -> 1.0 -> 255 (never-sampled pixels are white). The NaN case is
+    // spelled out: ptxas may fold fmaxf(fminf(x, 1), 0) into a saturating move, and .sat turns NaN into +0 (seen on the
+    // full-frame tonemap kernel: inf / (1 + inf) came out black).
+    const float c = (x != x) ? 1.0f : x;
+    return __float2uint_rz(fmul(fmaxf(fminf(c, 1.0f), 0.0f), 255.0f));
 }
 __device__ __forceinline__ uint32_t tonemap_pack(float sr, float sg, float sb, uint32_t n) {
     const float inv = fdiv(1.0f, (float)n);  // film.rs:46: pixel_sum * (1.0 / num_samples as f32)
@@ -1219,6 +1313,9 @@ __global__ void __launch_bounds__(256) trace_shade_kernel(const __grid_constant_
 template <int ACCEL, int BOUNCE, bool SAMPLE_LANES = false>
 __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_persistent_kernel(const __grid_constant__ TraceParams P) {
     const uint32_t lane = threadIdx.x & 31u;
+#if RT_TOP_SMEM > 0
+    if (ACCEL == 1) stage_top_nodes(P);
+#endif
     // A warp item is 32 lanes = item_cols x item_rows pixels x S samples (sample innermost, then column, then row):
     // 8 x 4 x 1 for single-sample launches; with SAMPLE_LANES 8 x 2 x 2, 8 x 1 x 4 or 4 x 1 x 8: the lanes of an item
     // share pixels (finish_sample_lanes). Any 8 consecutive lanes hold whole pixels, which the heavy-item split relies on.
@@ -1227,19 +1324,25 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
     LaneCounters cnt;
     // queue length: n_tiles in image order, or the item count the last tile_sort_kernel produced (heavy tiles are
     // split into four 8-pixel items so that their serial divergent chain is spread over four warps)
-    const uint32_t n_items = P.tile_order ? *P.queue_items : n_tiles;
+    const uint32_t n_items = P.tile_order ? *P.queue_items : (P.static_level ? n_tiles << (P.static_level + 1u) : n_tiles);
     // The next queue slot is claimed when a tile's rays are done, before its film update: the atomic's round trip
     // (~1 us) overlaps the epilogue instead of sitting in front of the next tile, and the claim is early by so little
     // that the heaviest-first order is not disturbed (claiming a whole tile ahead was measured 10 % slower).
     // In the cheap tail of the queue (with the cost-sorted order: the all-miss tiles, about a microsecond of work
     // each) a warp claims kQueueBatch slots at a time, so the tail of the launch is not 3 552 warps queueing for one counter.
     const uint32_t kQueueBatch = P.queue_batch;
-    const uint32_t batch_from = (P.tile_order && kQueueBatch > 1u) ? (uint32_t)((unsigned long long)n_items * P.queue_batch_from_pct / 100ull) : 0xffffffffu;
-    uint32_t slot = 0, slot_end = 0;  // this warp owns queue slots [slot, slot_end)
-    if (lane == 0) {
-        slot = (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], 1ull);
-        slot_end = slot + 1u;
-    }
+    // (only when every warp can expect several items: on a launch with fewer items than a few per resident warp — a 50-row band,
+    // the shard of one rank of eight — a batch claim leaves warps without work while one warp walks through its four items)
+    const uint32_t batch_from = (P.tile_order && kQueueBatch > 1u && n_items >= 4u * gridDim.x * (blockDim.x >> 5u))
+                                    ? (uint32_t)((unsigned long long)n_items * P.queue_batch_from_pct / 100ull)
+                                    : 0xffffffffu;
+    // The first item of every warp is assigned statically, block-interleaved: the G heaviest items of a sorted queue go to G different
+    // blocks (blocks are spread over the SMs round robin), the next G likewise. Claimed dynamically, the heaviest items would go to
+    // whichever blocks start first, i.e. pile up on a few SMs — on a launch with about one item per warp (a 50-row band, one rank's
+    // shard of a frame split eight ways) those SMs then run 24 heavy warps while the others idle. The counter serves slots from
+    // total_warps on.
+    const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+    uint32_t slot = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, slot_end = slot + 1u;  // this warp owns queue slots [slot, slot_end)
     for (;;) {
         uint32_t item = 0;
         bool last_of_batch = true;
@@ -1251,9 +1354,17 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         }
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item == 0xffffffffu) break;
-        const uint32_t tile = item & kItemTileMask;
-        const uint32_t level = (item >> kItemLevelShift) & 3u;
-        const uint32_t part = (item >> kItemPartShift) & 15u;
+        uint32_t tile = item & kItemTileMask;
+        uint32_t level = (item >> kItemLevelShift) & 3u;
+        uint32_t part = (item >> kItemPartShift) & 15u;
+        if (P.static_level != 0u && !P.tile_order) {
+            // small launch without cost feedback (a 50-row band): EVERY tile is handed out in 2^(static_level + 1) parts, in image
+            // order — the launch cannot fill the GPU anyway, so the issue slots are there, and its duration is that of its
+            // longest item (queue slot = tile * parts + part)
+            level = P.static_level;
+            part = item & ((2u << level) - 1u);
+            tile = item >> (level + 1u);
+        }
         const uint32_t tile_y = udiv_magic(tile, tiles_x, P.magic_tiles_x);
         uint32_t col, crow, lane_sample = 0u;
         if (SAMPLE_LANES) {
@@ -1282,7 +1393,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         if (lane == 0) {
             if (last_of_batch) {
                 const uint32_t k = slot >= batch_from ? kQueueBatch : 1u;
-                slot = (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], (unsigned long long)k);
+                slot = total_warps + (uint32_t)atomicAdd(&P.counters[CNT_TILE_QUEUE], (unsigned long long)k);
                 slot_end = slot + k;
             } else {
                 ++slot;
@@ -1312,7 +1423,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
 #endif
     }
     flush_counters(P, cnt, lane);
-    warp_checkout(P, lane, gridDim.x * (blockDim.x >> 5));
+    warp_checkout(P, lane, total_warps);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -2011,6 +2122,9 @@ __global__ void flag_wait_kernel(volatile uint32_t* flags, uint32_t n, uint32_t 
 // ------------------------------------------------------------------------------------------------------
 template <int ACCEL>
 __global__ void __launch_bounds__(256) wf_bounce_kernel(const __grid_constant__ TraceParams P) {
+#if RT_TOP_SMEM > 0
+    if (ACCEL == 1) stage_top_nodes(P);
+#endif
     const uint32_t l = P.wf_level;
     const WfLevel& L = P.wf[l];
     const uint32_t n_nodes = min(P.wf_counts[l], L.cap), nch = L.n_children;
@@ -2062,6 +2176,9 @@ __global__ void __launch_bounds__(256) wf_bounce_kernel(const __grid_constant__ 
 // {ray, hit} into node records {hit point, normal, shaded radiance}
 template <int ACCEL>
 __global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ TraceParams P) {
+#if RT_TOP_SMEM > 0
+    if (ACCEL == 1) stage_top_nodes(P);
+#endif
     const uint32_t l = P.wf_level;
     const WfLevel& L = P.wf[l];
     const uint32_t total = min(P.wf_counts[l], L.cap);
@@ -2087,6 +2204,328 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ T
         shade_hit<ACCEL, 1>(P, o2, rd, h, &nrm, &cr, &cg, &cb, cnt);
         const uint32_t pk = __float_as_uint(r3.x);
         wf_store_node(P, l, i, vadd(o2, vscale(rd, h.t)), __float_as_uint(r0.w), nrm, __float_as_uint(r1.w), cr, cg, cb, pk & 0x0fffffffu, pk >> 28);
+    }
+    flush_counters(P, cnt, lane);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// wf_stream_kernel: one bounce level of the wavefront as a RAY STREAM (binary BVH). It replaces wf_bounce_kernel +
+// wf_shade_kernel, whose warps traced 32 rays in lockstep: bounce rays (random hemisphere directions from surface points)
+// and the shadow rays of their hits differ in length by orders of magnitude, so a warp spent most of its instructions
+// waiting for its longest ray — 7.8 of 32 lanes active on thai2 (profiles/r2_bounce_before_ncu.txt). Here lanes are
+// decoupled from rays:
+//   * every lane owns one ray in flight — a bounce ray of the level (job j = (node, k), same hash / table walk as
+//     radiance_with_bounces, so the same ray) or the shadow ray of the hit such a ray found;
+//   * traversal runs in rounds like bvh_closest_hit_ww (all lanes descend to a leaf, then all test triangles);
+//   * when `refill` lanes have no ray in flight (their ray ended, or they are idle) the warp SERVICES them together:
+//     a finished bounce ray with a hit starts shade() (mod.rs:207-261) and becomes that hit's first shadow ray IN PLACE, a
+//     finished shadow ray adds its light's contribution and moves to the next light or appends the finished node to
+//     level l+1 (warp-aggregated append), idle lanes claim new jobs from the level's queue with one atomic.
+// (Tried and dropped: handing the level's rays out in direction-sorted order — counting sort of 8192-job chunks by 96 direction
+// bins in shared memory. The sort pass cost ~80 us per level and the sorted stream was no faster than node order, which already
+// keeps neighbouring surface points together: 1.04 vs 0.88 ms per thai2 frame, profiles/r2_bounce_stream_ab.log.)
+//   * with P.wf_chain (every level from the second on sends ONE bounce ray per hit, the reference's RECURSIONS = 2, SUB_SPREAD = 1:
+//     2 rays from a camera-ray hit, 1 from their hits) a lane that completes a node continues IN PLACE with that node's bounce ray,
+//     so the whole bounce tree of a frame is one launch: no second level launch with its own ramp-up and tail, no job queue for the
+//     deeper levels.
+// The state that outlives a ray (hit point, bounce direction, barycentrics, partial radiance) lives in shared memory, 17
+// words per lane. Every float operation is the one shade_hit / wf_bounce_kernel perform, in the same order, so the film is
+// bit-identical to the lockstep wavefront and to the depth-first walk.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kWsWords = 17;  // per-lane context words (see the enum below)
+enum WsField { WS_HPX = 0, WS_HPY, WS_HPZ, WS_RDX, WS_RDY, WS_RDZ, WS_TRI, WS_U, WS_V, WS_LIGHT, WS_CR, WS_CG, WS_CB, WS_PIXEL, WS_PATH, WS_PARENT,
+               WS_LEVEL /* level of the node the lane's bounce ray left from; its hit becomes a node of the next level */ };
+enum WsState { WS_IDLE = 0, WS_BOUNCE = 1, WS_SHADOW = 2 };
+
+// The bounce ray of job j = (node, k) of level P.wf_level: same hash / table walk as radiance_with_bounces (mod.rs:186-189), so the same ray.
+// Bounce direction of the sub ray `sub_path` of a hit: the first entry of the unit-vector table, from a hashed start index on, that lies in
+// the hemisphere of the normal (normalized_vec_pseudo / normalized_vec_lookup, mod.rs:186-189) — as in radiance_with_bounces, so the same ray.
+__device__ __forceinline__ V3 wf_bounce_dir(const TraceParams& P, const V3& normal, uint32_t pixel, uint32_t sub_path) {
+    const uint32_t sample = __float_as_uint(P.film_sum[pixel].w);  // the film is not touched before the last combine
+    uint32_t idx = (uint32_t)(((unsigned long long)hash4(P.seed ^ 0xb0c0ffeeU, pixel, sample, sub_path) * 65535ull) >> 32);
+    V3 rd = {P.sample_table[3 * idx], P.sample_table[3 * idx + 1], P.sample_table[3 * idx + 2]};
+    while (vdot(rd, normal) <= 0.0f) {
+        idx = (idx + 1u) % 65535u;
+        rd = V3{P.sample_table[3 * idx], P.sample_table[3 * idx + 1], P.sample_table[3 * idx + 2]};
+    }
+    return rd;
+}
+
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS) wf_stream_kernel(const __grid_constant__ TraceParams P) {
+    __shared__ uint32_t ctx[kWsWords][256];
+    const uint32_t full = 0xffffffffu;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t l = P.wf_level;
+    const WfLevel& L = P.wf[l];
+    const uint32_t n_nodes = min(P.wf_counts[l], L.cap), nch = L.n_children;
+    const uint32_t total = n_nodes * nch;
+    const uint32_t refill = max(P.pool_refill, 1u), min_inner = P.pool_min_inner;
+    LaneCounters cnt;
+    bool queue_empty = false;
+
+    // the ray this lane traverses
+    int2 stack[kBvhStack];
+    stack[0] = make_int2(kSentinel, __float_as_int(-FLT_MAX));
+    int state = WS_IDLE, cur = kSentinel, sp = 1;
+    V3 o = {0.f, 0.f, 0.f}, d = {0.f, 0.f, 0.f};
+    float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f, early_t = -1.0f;
+    bool early = false;
+    HitRec best;
+    best.t = 0.f;
+    best.u = 0.f;
+    best.v = 0.f;
+    best.tri = kNoHit;
+
+    auto start_ray = [&](const V3& ro, const V3& rd, float t_limit, float t_early) {
+        o = ro;
+        d = rd;
+        ix = rcp_approx(rd.x);  // box tests only (padded boxes)
+        iy = rcp_approx(rd.y);
+        iz = rcp_approx(rd.z);
+        ox = -ro.x * ix;
+        oy = -ro.y * iy;
+        oz = -ro.z * iz;
+        best.t = t_limit;
+        best.u = 0.f;
+        best.v = 0.f;
+        best.tri = kNoHit;
+        early_t = t_early;
+        early = false;
+        cur = 0;
+        sp = 1;
+    };
+    // shade()'s loop over the lights from light ctx[WS_LIGHT] on: the first light the surface faces becomes a shadow ray
+    // (returns true); no such light left: the node is complete (returns false)
+    auto next_shadow_ray = [&]() -> bool {
+        const V3 hp = {__uint_as_float(ctx[WS_HPX][tid]), __uint_as_float(ctx[WS_HPY][tid]), __uint_as_float(ctx[WS_HPZ][tid])};
+        const float4 sh = __ldg(&P.tri_shade[ctx[WS_TRI][tid]]);
+        const V3 nrm = {sh.x, sh.y, sh.z};
+        for (uint32_t li = ctx[WS_LIGHT][tid]; li < P.num_lights; ++li) {
+            const float4 lp = __ldg(&P.lights[2 * li]);
+            const V3 Lv = vsub(V3{lp.x, lp.y, lp.z}, hp);
+            const float ndl = vdot(nrm, vunit(Lv));
+            if (ndl < 0.0f) continue;
+            cnt.shadow_rays += 1;
+            ctx[WS_LIGHT][tid] = li;
+            // hits with t >= 1 can never block, a hit with t <= 0.01 decides "lit" at once (mod.rs:226-230)
+            start_ray(vadd(hp, vscale(Lv, 0.01f)), Lv, 1.0f, 0.01f);
+            return true;
+        }
+        return false;
+    };
+
+    for (;;) {
+        // ---- service: lanes without a ray in flight that have something to do (a finished ray, or jobs left to claim) ----
+        const bool waiting = cur == kSentinel;
+        const uint32_t m_trav = __ballot_sync(full, !waiting);
+        const uint32_t m_srv = __ballot_sync(full, waiting && (state != WS_IDLE || !queue_empty));
+        if (m_trav == 0u && m_srv == 0u) break;  // nothing in flight, nothing finished, the queue is empty
+        if (m_trav == 0u || (uint32_t)__popc(m_srv) >= refill) {
+            if (waiting && state == WS_BOUNCE) {
+                // closest hit of a bounce ray, root-cube acceptance rule as in bvh_closest_hit_ww
+                bool hit = best.tri != kNoHit;
+                V3 hp = {0.f, 0.f, 0.f};
+                if (hit) {
+                    hp = vadd(o, vscale(d, best.t));
+                    if (hp.x < P.root_lo[0] || hp.x > P.root_hi[0] || hp.y < P.root_lo[1] || hp.y > P.root_hi[1] || hp.z < P.root_lo[2] ||
+                        hp.z > P.root_hi[2])
+                        hit = false;
+                }
+                state = WS_IDLE;
+                if (hit) {  // shade_hit for this hit: ray.pos + t * ray.dir is the hit point (mod.rs:212)
+                    ctx[WS_HPX][tid] = __float_as_uint(hp.x);
+                    ctx[WS_HPY][tid] = __float_as_uint(hp.y);
+                    ctx[WS_HPZ][tid] = __float_as_uint(hp.z);
+                    ctx[WS_RDX][tid] = __float_as_uint(d.x);
+                    ctx[WS_RDY][tid] = __float_as_uint(d.y);
+                    ctx[WS_RDZ][tid] = __float_as_uint(d.z);
+                    ctx[WS_TRI][tid] = best.tri;
+                    ctx[WS_U][tid] = __float_as_uint(best.u);
+                    ctx[WS_V][tid] = __float_as_uint(best.v);
+                    ctx[WS_LIGHT][tid] = 0u;
+                    ctx[WS_CR][tid] = 0u;  // +0.0f
+                    ctx[WS_CG][tid] = 0u;
+                    ctx[WS_CB][tid] = 0u;
+                    state = WS_SHADOW + 1;  // shading in progress, no shadow ray chosen yet
+                }
+            } else if (waiting && state == WS_SHADOW) {
+                // blocked <=> the closest hit has 0.01 < t < 1.0 (mod.rs:226-230); the root-cube rule applies to a hit that did
+                // not end the search early
+                bool hit = best.tri != kNoHit;
+                if (hit && !early) {
+                    const V3 sp_ = vadd(o, vscale(d, best.t));
+                    if (sp_.x < P.root_lo[0] || sp_.x > P.root_hi[0] || sp_.y < P.root_lo[1] || sp_.y > P.root_hi[1] || sp_.z < P.root_lo[2] ||
+                        sp_.z > P.root_hi[2])
+                        hit = false;
+                }
+                const bool blocked = hit && best.t > 0.01f && best.t < 1.0f;
+                const uint32_t li = ctx[WS_LIGHT][tid];
+                if (blocked) {
+                    cnt.blocked += 1;
+                } else {  // Phong + texture for light li, the operations of shade_hit in its order
+                    const V3 hp = {__uint_as_float(ctx[WS_HPX][tid]), __uint_as_float(ctx[WS_HPY][tid]), __uint_as_float(ctx[WS_HPZ][tid])};
+                    const V3 rd = {__uint_as_float(ctx[WS_RDX][tid]), __uint_as_float(ctx[WS_RDY][tid]), __uint_as_float(ctx[WS_RDZ][tid])};
+                    const float4 sh = __ldg(&P.tri_shade[ctx[WS_TRI][tid]]);
+                    const V3 nrm = {sh.x, sh.y, sh.z};
+                    const uint32_t geom = __float_as_uint(sh.w);
+                    const float4 lp = __ldg(&P.lights[2 * li]), lc = __ldg(&P.lights[2 * li + 1]);
+                    const V3 Ln = vunit(vsub(V3{lp.x, lp.y, lp.z}, hp));
+                    const float ndl = vdot(nrm, Ln);
+                    const float4 mat = __ldg(&P.materials[geom]);
+                    float dr = mat.x, dg = mat.y, db = mat.z;
+                    const int tex = __float_as_int(mat.w);
+                    if (tex >= 0) {  // Texture::get_texel(hit.u, hit.v), texture.rs:21-27 (index clamped instead of panicking)
+                        const DevTexture T = P.textures[tex];
+                        const float fx = fmul(__uint_as_float(ctx[WS_U][tid]), (float)T.width), fy = fmul(__uint_as_float(ctx[WS_V][tid]), (float)T.height);
+                        const size_t x = fx > 0.0f ? (size_t)__float2ull_rz(fx) : 0, y = fy > 0.0f ? (size_t)__float2ull_rz(fy) : 0;
+                        size_t ti = y * T.width + x;
+                        const size_t last = (size_t)T.width * T.height - 1;
+                        if (ti > last) ti = last;
+                        dr = T.rgb[3 * ti];
+                        dg = T.rgb[3 * ti + 1];
+                        db = T.rgb[3 * ti + 2];
+                    }
+                    const V3 view = vunit(rd);
+                    const V3 refl = vsub(vscale(nrm, fmul(2.0f, ndl)), Ln);
+                    const float spec = pow32(vdot(view, refl));
+                    ctx[WS_CR][tid] = __float_as_uint(fadd(__uint_as_float(ctx[WS_CR][tid]), fmul(fadd(fmul(dr, ndl), spec), lc.x)));
+                    ctx[WS_CG][tid] = __float_as_uint(fadd(__uint_as_float(ctx[WS_CG][tid]), fmul(fadd(fmul(dg, ndl), spec), lc.y)));
+                    ctx[WS_CB][tid] = __float_as_uint(fadd(__uint_as_float(ctx[WS_CB][tid]), fmul(fadd(fmul(db, ndl), spec), lc.z)));
+                }
+                ctx[WS_LIGHT][tid] = li + 1u;
+                state = WS_SHADOW + 1;
+            }
+            // lanes in the middle of shade(): the next light the surface faces, or the node is complete
+            if (state == WS_SHADOW + 1) {
+                if (next_shadow_ray()) {
+                    state = WS_SHADOW;
+                } else {
+                    // the node is complete: append it to its level (lanes of a warp may be at different levels when rays are chained:
+                    // one warp-aggregated append per level)
+                    const uint32_t m = ctx[WS_LEVEL][tid] + 1u;
+                    uint32_t slot = 0;
+                    for (uint32_t lv = l + 1u; lv < (uint32_t)kWfLevels; ++lv)
+                        if (m == lv) slot = wf_append(&P.wf_counts[lv]);
+                    const float4 sh = __ldg(&P.tri_shade[ctx[WS_TRI][tid]]);
+                    const V3 nrm = {sh.x, sh.y, sh.z};
+                    const V3 hp = {__uint_as_float(ctx[WS_HPX][tid]), __uint_as_float(ctx[WS_HPY][tid]), __uint_as_float(ctx[WS_HPZ][tid])};
+                    const uint32_t pk = ctx[WS_PARENT][tid], pixel = ctx[WS_PIXEL][tid], path = ctx[WS_PATH][tid];
+                    wf_store_node(P, m, slot, hp, pixel, nrm, path, __uint_as_float(ctx[WS_CR][tid]), __uint_as_float(ctx[WS_CG][tid]),
+                                  __uint_as_float(ctx[WS_CB][tid]), pk & 0x0fffffffu, pk >> 28);
+                    state = WS_IDLE;
+                    if (P.wf_chain && P.wf[m].n_children == 1u && slot < P.wf[m].cap) {
+                        // the node's only bounce ray (k = 0) continues in this lane
+                        const uint32_t sub_path = path * 31u + 1u;
+                        const V3 rd = wf_bounce_dir(P, nrm, pixel, sub_path);
+                        cnt.bounce_rays += 1;
+                        ctx[WS_PATH][tid] = sub_path;
+                        ctx[WS_PARENT][tid] = slot;  // | (0 << 28)
+                        ctx[WS_LEVEL][tid] = m;
+                        start_ray(vadd(hp, vscale(rd, 0.00001f)), rd, FLT_MAX, -1.0f);
+                        state = WS_BOUNCE;
+                    }
+                }
+            }
+            __syncwarp();
+            // idle lanes claim the next jobs of the level: one atomic per warp
+            const uint32_t m_idle = __ballot_sync(full, state == WS_IDLE);
+            if (m_idle != 0u && !queue_empty) {
+                const uint32_t n_idle = (uint32_t)__popc(m_idle);
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&P.wf_counts[kWfLevels + l], n_idle);
+                base = __shfl_sync(full, base, 0);
+                if (base + n_idle >= total) queue_empty = true;
+                const uint32_t jj = base + (uint32_t)__popc(m_idle & ((1u << lane) - 1u));
+                if (state == WS_IDLE && jj < total) {  // job jj = (node, k) of level l
+                    const uint32_t parent = jj / nch, k = jj - parent * nch;
+                    const float4 r0 = L.rec[kWfRecWords * (size_t)parent], r1 = L.rec[kWfRecWords * (size_t)parent + 1];
+                    const uint32_t pixel = __float_as_uint(r0.w), sub_path = __float_as_uint(r1.w) * 31u + k + 1u;
+                    const V3 rd = wf_bounce_dir(P, V3{r1.x, r1.y, r1.z}, pixel, sub_path);
+                    cnt.bounce_rays += 1;
+                    ctx[WS_PIXEL][tid] = pixel;
+                    ctx[WS_PATH][tid] = sub_path;
+                    ctx[WS_PARENT][tid] = parent | (k << 28);
+                    ctx[WS_LEVEL][tid] = l;
+                    // ray.pos + t * ray.dir + 0.00001 * random_dir (mod.rs:192-193)
+                    start_ray(vadd(V3{r0.x, r0.y, r0.z}, vscale(rd, 0.00001f)), rd, FLT_MAX, -1.0f);
+                    state = WS_BOUNCE;
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- one traversal round (the steps of bvh_closest_hit_ww) ----
+        // The rays of a warp are unrelated, so the number of inner nodes between two leaves differs widely from lane to lane:
+        // the inner-node loop is left as soon as fewer than `min_inner` lanes still descend while others wait at a leaf (those
+        // are served first; the descending lanes resume in the next round). One vote per iteration.
+        for (;;) {
+            const bool inner = (unsigned)cur < (unsigned)kSentinel;
+            const uint32_t m_in = __ballot_sync(full, inner);
+            if (m_in == 0u) break;
+            if ((uint32_t)__popc(m_in) < min_inner && __any_sync(full, cur < 0)) break;
+            if (inner) {
+                const float4* n = P.bvh_nodes + 4 * (size_t)cur;
+                const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+                const float a0x = fmaf(q0.x, ix, ox), b0x = fmaf(q0.w, ix, ox);
+                const float a0y = fmaf(q0.y, iy, oy), b0y = fmaf(q1.x, iy, oy);
+                const float a0z = fmaf(q0.z, iz, oz), b0z = fmaf(q1.y, iz, oz);
+                const float a1x = fmaf(q1.z, ix, ox), b1x = fmaf(q2.y, ix, ox);
+                const float a1y = fmaf(q1.w, iy, oy), b1y = fmaf(q2.z, iy, oy);
+                const float a1z = fmaf(q2.x, iz, oz), b1z = fmaf(q2.w, iz, oz);
+                const float n0 = fmaxf(fmaxf(fminf(a0x, b0x), fminf(a0y, b0y)), fmaxf(fminf(a0z, b0z), 0.0f));
+                const float f0 = fminf(fminf(fmaxf(a0x, b0x), fmaxf(a0y, b0y)), fminf(fmaxf(a0z, b0z), best.t));
+                const float n1 = fmaxf(fmaxf(fminf(a1x, b1x), fminf(a1y, b1y)), fmaxf(fminf(a1z, b1z), 0.0f));
+                const float f1 = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), best.t));
+                const bool h0 = n0 <= f0, h1 = n1 <= f1;
+                const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+                const bool go1 = h1 && (!h0 || n1 < n0);
+                if (h0 && h1) {
+                    stack[sp] = make_int2(go1 ? c0 : c1, __float_as_int(go1 ? n0 : n1));
+                    ++sp;
+                }
+                if (h0 || h1) {
+                    cur = go1 ? c1 : c0;
+                } else {
+                    int2 e;
+                    do {
+                        e = stack[--sp];
+                    } while (__int_as_float(e.y) > best.t);
+                    cur = e.x;
+                }
+            }
+        }
+        if (cur < 0) {  // leaf
+            const uint32_t ref = (uint32_t)~cur;
+            const uint32_t count = ref & 15u;
+            const float4* tri = P.bvh_tris + 3 * (size_t)(ref >> 4);
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4 t0 = __ldg(tri + 3 * i), t1 = __ldg(tri + 3 * i + 1), t2 = __ldg(tri + 3 * i + 2);
+                float t, u, v;
+                if (!moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) continue;
+                const uint32_t id = __float_as_uint(t2.y);
+                if (t < best.t || (t == best.t && id < best.tri)) {
+                    best.t = t;
+                    best.u = u;
+                    best.v = v;
+                    best.tri = id;
+                    if (t <= early_t) {
+                        early = true;
+                        break;
+                    }
+                }
+            }
+            if (early) {
+                cur = kSentinel;
+            } else {
+                int2 e;
+                do {
+                    e = stack[--sp];
+                } while (__int_as_float(e.y) > best.t);
+                cur = e.x;
+            }
+        }
+        __syncwarp();
     }
     flush_counters(P, cnt, lane);
 }
@@ -2150,7 +2589,8 @@ static void launch_trace_t(const TraceParams& p, int variant, uint32_t blocks, c
 // bounce_mode: 0 none, 1 depth first in the thread, 2 wavefront (the trace kernel only emits level-0 nodes)
 cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persistent_blocks, cudaStream_t stream) {
     if (p.n_rows == 0) return cudaSuccess;
-    const uint32_t tiles = p.items_x * p.items_y;  // = 8x4 pixel tiles unless the launch uses sample lanes
+    // queue items: 8x4 pixel tiles (sample-lane items when the lanes of an item share pixels), each in 2^(static_level + 1) parts
+    const uint32_t tiles = (p.items_x * p.items_y) << (p.static_level ? p.static_level + 1u : 0u);
     uint32_t blocks = (uint32_t)persistent_blocks;
     if (blocks * 8u > tiles) blocks = (tiles + 7u) / 8u;
     const int bounce = p.recursions > 0 ? (p.wf_counts ? 2 : 1) : 0;
@@ -2191,6 +2631,33 @@ cudaError_t launch_wf_shade(const TraceParams& p, int accel, int blocks, cudaStr
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
+}
+cudaError_t launch_wf_stream(const TraceParams& p, int blocks_per_sm, int num_sms, cudaStream_t stream) {
+    switch (blocks_per_sm) {
+        case 3: wf_stream_kernel<3><<<3 * num_sms, 256, 0, stream>>>(p); break;
+        case 4: wf_stream_kernel<4><<<4 * num_sms, 256, 0, stream>>>(p); break;
+        case 5: wf_stream_kernel<5><<<5 * num_sms, 256, 0, stream>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+// resident 256-thread blocks per SM of the lockstep wavefront kernels (kind 0 = wf_bounce_kernel, 1 = wf_shade_kernel)
+int wf_blocks_per_sm(int kind, int accel) {
+    int n = 0;
+#define RT_OCC(K) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, K, 256, 0)
+    switch (kind * 4 + accel) {
+        case 0: RT_OCC(wf_bounce_kernel<0>); break;
+        case 1: RT_OCC(wf_bounce_kernel<1>); break;
+        case 2: RT_OCC(wf_bounce_kernel<2>); break;
+        case 3: RT_OCC(wf_bounce_kernel<3>); break;
+        case 4: RT_OCC(wf_shade_kernel<0>); break;
+        case 5: RT_OCC(wf_shade_kernel<1>); break;
+        case 6: RT_OCC(wf_shade_kernel<2>); break;
+        case 7: RT_OCC(wf_shade_kernel<3>); break;
+        default: break;
+    }
+#undef RT_OCC
+    return n > 0 ? n : 1;
 }
 cudaError_t launch_wf_combine(const TraceParams& p, int blocks, cudaStream_t stream) {
     wf_combine_kernel<<<blocks, 256, 0, stream>>>(p);

@@ -14,6 +14,10 @@ int persistent_blocks_per_sm(int accel, int bounce);
 // bounce wavefront: level p.wf_level -> level + 1 (one thread per (node, bounce ray)); bottom-up radiance combine
 cudaError_t launch_wf_bounce(const TraceParams& p, int accel, int blocks, cudaStream_t stream);
 cudaError_t launch_wf_shade(const TraceParams& p, int accel, int blocks, cudaStream_t stream);
+// binary BVH: level p.wf_level -> level + 1 as a ray stream (bounce rays and the shadow rays of their hits share the lanes of a
+// warp, finished lanes are refilled p.pool_refill at a time); replaces launch_wf_bounce + launch_wf_shade for that level
+cudaError_t launch_wf_stream(const TraceParams& p, int blocks_per_sm /* 3, 4 or 5 */, int num_sms, cudaStream_t stream);
+int wf_blocks_per_sm(int kind /* 0 wf_bounce_kernel, 1 wf_shade_kernel */, int accel);
 cudaError_t launch_wf_combine(const TraceParams& p, int blocks, cudaStream_t stream);
 // variant 2 (ray pool: binary BVH, recursions 0, one light; other configurations run variant 1)
 int pool_blocks_per_sm();

@@ -119,6 +119,13 @@ struct rt_raytracer {
     DevBuf<float> d_variance;  // rt_get_estimated_variances staging (allocated on first use)
     int multi_sample_launch = 1;      // RT_TUNE_MULTI_SAMPLE_LAUNCH: 0 one launch per sample, 1 sample lanes where they apply, else planes, 2 planes
     bool bounce_wavefront = true;     // RT_TUNE_BOUNCE_WAVEFRONT
+    bool bounce_stream = true;        // RT_TUNE_BOUNCE_STREAM: wavefront levels as a ray stream (binary BVH) instead of lockstep warps
+    bool stream_chain = true;         // RT_TUNE_STREAM_CHAIN
+    int stream_blocks = 4;            // RT_TUNE_STREAM_BLOCKS: resident blocks per SM the ray-stream kernel is compiled for (3, 4, 5)
+    int wf_blocks_cap = 0;            // RT_TUNE_WF_BLOCKS: cap on the resident blocks per SM of the lockstep wavefront kernels (0 = as many as fit)
+    int wf_occupancy[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    int stream_refill = 16;           // RT_TUNE_STREAM_REFILL: lanes without a ray in flight that trigger a service round
+    int stream_min_inner = 8;         // RT_TUNE_STREAM_MIN_INNER: the inner-node loop yields to waiting leaves below this many descending lanes
     DevBuf<float4> d_wf_rec;
     DevBuf<float> d_wf_child;
     DevBuf<unsigned int> d_wf_counts;
@@ -166,7 +173,7 @@ struct rt_raytracer {
     };
     std::vector<std::unique_ptr<TileSchedule>> schedules;
     uint64_t schedule_clock = 0;
-    int min_schedule_tiles = 1024;   // RT_TUNE_MIN_SCHEDULE_TILES: launches with fewer tiles run in image order, unsplit
+    int min_schedule_tiles = 4096;   // RT_TUNE_MIN_SCHEDULE_TILES: launches with fewer tiles run in image order, every tile in parts
     int max_split_level = 3;         // RT_TUNE_MAX_SPLIT_LEVEL: 0 never split, 1 / 2 / 3 = up to 4 / 8 / 16 items per tile
     int call_parity = 0;             // which per-call counter set the current trace call counts into (device_types.h)
     uint32_t* done_flag = nullptr;   // multi-GPU: the trace kernel's last warp publishes done_value here (rt_set_done_signal)
@@ -419,13 +426,29 @@ struct rt_raytracer {
             if (d_bvh_nodes.p) return;
             ensure_bvh_host();
             if (bvh.depth + 2 > (uint32_t)kBvhStack) throw CudaFail{"BVH deeper than the traversal stack"};
+            // The device array holds the nodes in BREADTH-FIRST order (the builder numbers them depth first): the top levels, which
+            // every ray visits, are then one contiguous run of cache lines (and the prefix an RT_TOP_SMEM build stages in shared
+            // memory). Only the numbering changes; rt_bvh_export keeps the builder's.
+            std::vector<int32_t> bfs_of(bvh.nodes.size(), -1), order;
+            order.reserve(bvh.nodes.size());
+            order.push_back(0);
+            bfs_of[0] = 0;
+            for (size_t q = 0; q < order.size(); ++q)
+                for (int k = 0; k < 2; ++k) {
+                    const int32_t c = bvh.nodes[(size_t)order[q]].child[k];
+                    if (c >= 0) {
+                        bfs_of[(size_t)c] = (int32_t)order.size();
+                        order.push_back(c);
+                    }
+                }
+            if (order.size() != bvh.nodes.size()) throw CudaFail{"BVH has unreachable nodes"};
             std::vector<float4> nodes(4 * bvh.nodes.size());
             for (size_t i = 0; i < bvh.nodes.size(); ++i) {
-                const FlatBvh::Node& n = bvh.nodes[i];
+                const FlatBvh::Node& n = bvh.nodes[(size_t)order[i]];
                 int32_t ref[2];
                 for (int k = 0; k < 2; ++k) {
                     if (n.child[k] >= 0)
-                        ref[k] = n.child[k];
+                        ref[k] = bfs_of[(size_t)n.child[k]];
                     else
                         ref[k] = ~(int32_t)(((uint32_t)(~n.child[k]) << 4) | (uint32_t)n.count[k]);
                 }
@@ -544,6 +567,7 @@ struct rt_raytracer {
         p->oct_tris = d_oct_tris.p;
         p->bvh_nodes = cfg.accel == RT_ACCEL_LBVH ? d_lbvh_nodes.p : d_bvh_nodes.p;
         p->bvh_tris = cfg.accel == RT_ACCEL_LBVH ? d_lbvh_tris.p : d_bvh_tris.p;
+        p->bvh_top_count = cfg.accel == RT_ACCEL_LBVH ? 0u : (uint32_t)bvh.nodes.size();
         p->bvh4_nodes = d_bvh4_nodes.p;
         p->bvh4_tris = d_bvh4_tris.p;
         p->cw_nodes = reinterpret_cast<const uint4*>(d_cw_nodes.p);
@@ -696,6 +720,16 @@ struct rt_raytracer {
             p.queue_items = sc->order.p + (sc->order.n - 1);
             ++sc->launches;
         }
+        if (!p.tile_order && variant == 1 && !use_pool && a != 0 && split_quarters > 0 && lpt_schedule && b == 0) {
+            // no cost feedback for this launch (too few tiles to be worth a schedule of its own — the reference's 50-row bands walk over
+            // the image with a period of lcm(50, height) rows, 108 different geometries at 1080p): hand every tile out in parts so that
+            // the launch, which cannot fill the GPU, at least is not as long as its heaviest 32-ray tile. Finest level that keeps the
+            // queue below 8 items per resident warp; a part must hold whole pixels.
+            const uint32_t warps = (uint32_t)(blocks_per_sm[a][b] * num_sms * 8);
+            uint32_t lv = (uint32_t)std::max(0, std::min(max_split_level, 2));
+            while (lv > 0 && ((32u >> (lv + 1u)) < (1u << p.lane_samples_log2) || ((uint64_t)tiles << (lv + 1u)) > 8ull * warps)) --lv;
+            p.static_level = lv;
+        }
         cudaError_t e;
         if (use_pool) e = launch_trace(p, a, 2, pool_blocks * num_sms, stream);
         else if (wavefront_applies(p)) e = launch_wavefront(p, a);
@@ -759,18 +793,40 @@ struct rt_raytracer {
         if (blocks_per_sm[a][0] == 0) blocks_per_sm[a][0] = persistent_blocks_per_sm(a, 0);
         RT_CUDA_RET(launch_trace(p, a, 1, blocks_per_sm[a][0] * num_sms, stream));
         const int wf_blocks = num_sms * 3;  // 80 registers: three 256-thread blocks per SM
-        for (int l = 0; l < R; ++l) {  // level l -> l + 1: trace the bounce rays, then shade the compacted hits
+        const bool stream_levels = bounce_stream && a == 1;  // ray-stream kernel (binary BVH): bounce + shadow rays share the lanes
+        // every level from the second on sends at most one bounce ray per hit (the reference's RECURSIONS = 2, SUB_SPREAD = 1): the ray-stream
+        // kernel chains them in place and ONE launch walks the whole bounce tree
+        bool chain = stream_levels && stream_chain;
+        for (int l = 1; l <= R; ++l) chain = chain && nch[l] <= 1;
+        p.wf_chain = chain ? 1u : 0u;
+        int stream_launches = 0;
+        for (int l = 0; l < (chain ? 1 : R); ++l) {  // level l -> l + 1
             p.wf_level = (uint32_t)l;
-            RT_CUDA_RET(launch_wf_bounce(p, a, wf_blocks, stream));
-            p.wf_level = (uint32_t)(l + 1);
-            RT_CUDA_RET(launch_wf_shade(p, a, wf_blocks, stream));
+            ++stream_launches;
+            if (stream_levels) {
+                p.pool_refill = (uint32_t)stream_refill;
+                p.pool_min_inner = (uint32_t)stream_min_inner;
+                RT_CUDA_RET(launch_wf_stream(p, stream_blocks, num_sms, stream));
+            } else {  // lockstep form: trace the bounce rays, then shade the compacted hits
+                // these kernels need far fewer registers than the trace kernel: as many blocks as fit (the rays are latency bound)
+                if (wf_occupancy[a][0] == 0) {
+                    wf_occupancy[a][0] = wf_blocks_per_sm(0, a);
+                    wf_occupancy[a][1] = wf_blocks_per_sm(1, a);
+                }
+                const int b0 = wf_blocks_cap > 0 ? std::min(wf_blocks_cap, wf_occupancy[a][0]) : wf_occupancy[a][0];
+                const int b1 = wf_blocks_cap > 0 ? std::min(wf_blocks_cap, wf_occupancy[a][1]) : wf_occupancy[a][1];
+                RT_CUDA_RET(launch_wf_bounce(p, a, num_sms * b0, stream));
+                p.wf_level = (uint32_t)(l + 1);
+                RT_CUDA_RET(launch_wf_shade(p, a, num_sms * b1, stream));
+            }
         }
         for (int l = R; l >= 0; --l) {  // bottom up; level 0 adds the radiance to the film
             p.wf_level = (uint32_t)l;
             RT_CUDA_RET(launch_wf_combine(p, wf_blocks, stream));
         }
-        total_kernels += (uint64_t)(3 * R + 1);
-        last.kernels_launched += (uint32_t)(3 * R + 1);
+        const int wf_kernels = (stream_levels ? stream_launches : 2 * R) + R + 1;
+        total_kernels += (uint64_t)wf_kernels;
+        last.kernels_launched += (uint32_t)wf_kernels;
         return cudaSuccess;
     }
 
@@ -925,7 +981,11 @@ struct rt_raytracer {
 
 extern "C" {
 
-const char* rt_version(void) { return "rt_b200 0.1.0 sm_100a"; }
+const char* rt_version(void) { return "rt_b200 0.2.0 sm_100a"; }
+#ifndef RT_KERNELS_HASH
+#define RT_KERNELS_HASH "unknown"
+#endif
+const char* rt_kernels_hash(void) { return RT_KERNELS_HASH; }
 
 void rt_config_default(rt_config* cfg, uint32_t width, uint32_t height) {
     if (!cfg) return;
@@ -1414,6 +1474,49 @@ int rt_sync_timeouts(rt_raytracer* rt, uint32_t* count) {
         }
     });
 }
+int rt_host_register(rt_raytracer* rt, void* host_ptr, size_t bytes, void** dev_ptr) {
+    RT_GUARD(rt, {
+        if (!host_ptr || bytes == 0) throw std::invalid_argument("bad registration request");
+        RT_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+        if (dev_ptr) {
+            void* d = nullptr;
+            RT_CUDA(cudaHostGetDevicePointer(&d, host_ptr, 0));
+            *dev_ptr = d;
+        }
+    });
+}
+int rt_host_unregister(rt_raytracer* rt, void* host_ptr) {
+    RT_GUARD(rt, {
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+        RT_CUDA(cudaHostUnregister(host_ptr));
+    });
+}
+int rt_copy_owned_rows(rt_raytracer* rt, const void* src_frame, void* dst_frame, void* cuda_stream) {
+    RT_GUARD(rt, {
+        if (!src_frame || !dst_frame) throw std::invalid_argument("null frame");
+        const size_t row_bytes = (size_t)rt->cfg.width * 4;
+        const uint32_t H = rt->cfg.height, B = rt->cfg.band_rows, N = rt->cfg.shard_count, r = rt->cfg.shard_index;
+        cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : rt->stream;
+        // owned bands r, r + N, r + 2N, ...: one strided 2-D copy for the full bands (a band is B consecutive rows = one contiguous
+        // run of the frame), one more for a partial band at the bottom of the image
+        const uint32_t full_bands = H / B;  // bands 0 .. full_bands - 1 have B rows
+        const uint32_t mine_full = full_bands > r ? (full_bands - r + N - 1) / N : 0;
+        const size_t band_bytes = (size_t)B * row_bytes, pitch = (size_t)N * band_bytes, off = (size_t)r * band_bytes;
+        if (mine_full)
+            RT_CUDA(cudaMemcpy2DAsync((char*)dst_frame + off, pitch, (const char*)src_frame + off, pitch, band_bytes, mine_full, cudaMemcpyDefault, st));
+        if (H % B != 0 && full_bands % N == r) {
+            const size_t tail = (size_t)full_bands * band_bytes;
+            RT_CUDA(cudaMemcpyAsync((char*)dst_frame + tail, (const char*)src_frame + tail, (size_t)(H % B) * row_bytes, cudaMemcpyDefault, st));
+        }
+    });
+}
+int rt_signal_flag_on_stream(rt_raytracer* rt, void* dev_flag, uint32_t value, void* cuda_stream) {
+    RT_GUARD(rt, {
+        if (!dev_flag) throw std::invalid_argument("null flag");
+        RT_CUDA(launch_flag_signal((uint32_t*)dev_flag, value, cuda_stream ? (cudaStream_t)cuda_stream : rt->stream));
+        ++rt->total_kernels;
+    });
+}
 int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr) {
     if (!rt || !dev_ptr || rt->host_only) return RT_ERR_INVALID;
     *dev_ptr = rt->d_counters.p + (rt->call_parity ? CNT_SET_B : CNT_SET_A);  // the set the last trace call counted into
@@ -1457,6 +1560,30 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     }
     if (key == RT_TUNE_BOUNCE_WAVEFRONT && (value == 0 || value == 1)) {
         rt->bounce_wavefront = value != 0;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_BOUNCE_STREAM && (value == 0 || value == 1)) {
+        rt->bounce_stream = value != 0;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_STREAM_REFILL && value >= 1 && value <= 32) {
+        rt->stream_refill = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_STREAM_CHAIN && (value == 0 || value == 1)) {
+        rt->stream_chain = value != 0;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_STREAM_BLOCKS && value >= 3 && value <= 5) {
+        rt->stream_blocks = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_WF_BLOCKS && value >= 0 && value <= 8) {
+        rt->wf_blocks_cap = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_STREAM_MIN_INNER && value >= 0 && value <= 32) {
+        rt->stream_min_inner = value;
         return RT_OK;
     }
     if (key == RT_TUNE_MULTI_SAMPLE_LAUNCH && value >= 0 && value <= 2) {

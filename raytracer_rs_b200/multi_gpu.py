@@ -48,6 +48,104 @@ class _DevPtr:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
+class HostFrameGather:
+    """Delivers full frames to HOST memory with every rank using its own PCIe link: the frame lives in POSIX shared memory that
+    every process page-locks (rt_host_register); a rank stores its pixels into one of two device staging frames (rt_set_ldr_target,
+    alternating), copies the bands it owns from there into the shared frame on a copy stream (one strided 2-D copy,
+    rt_copy_owned_rows) while its next frame traces, and publishes "my rows of frame k have arrived" in a shared flag array in stream
+    order. Rank 0's host waits for all flags. No NVLink, no NCCL, no funnel through one link: at 8 GPUs each link carries 1 MB of an
+    8.3 MB frame. Call order per frame: begin_frame() -> tracer.trace_rows(...) -> publish(); rank 0: wait_frame(keep) -> frame(k).
+
+    Reuse protocol: frame k uses staging / host buffer k & 1. A rank waits (on the device) for its own copy of frame k-2 before
+    frame k stores into the same staging buffer, and (on the host) for `consumed >= k - 1` — rank 0 publishes how many frames it has
+    taken — before it overwrites the host buffer of frame k-2."""
+
+    def __init__(self, tracer, rank: int, world: int, device, stream, name: str):
+        import torch
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+
+        self.torch, self.tracer, self.rank, self.world, self.device, self.stream = torch, tracer, rank, world, device, stream
+        self.W, self.H = tracer.width, tracer.height
+        self.nbytes = self.W * self.H * 4
+        total = 2 * self.nbytes + 4096  # two frames + one page of flags (flags[0..world): arrived, flags[world]: consumed)
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=total)
+            np.frombuffer(self.shm.buf, dtype=np.uint32, count=1024, offset=2 * self.nbytes)[:] = 0
+        dist.barrier()
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name, create=False)
+            try:  # only the creator may unlink the segment: keep this process's resource tracker out of it (Python < 3.13 has no track=False)
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.frames = [np.frombuffer(self.shm.buf, dtype=np.uint32, count=self.W * self.H, offset=k * self.nbytes) for k in (0, 1)]
+        self.flags = np.frombuffer(self.shm.buf, dtype=np.uint32, count=1024, offset=2 * self.nbytes)
+        self.host_base = self.frames[0].ctypes.data
+        self.dev_base = tracer.host_register(self.host_base, total)  # device address of the same range
+        self.staging = [tracer.device_alloc(self.nbytes), tracer.device_alloc(self.nbytes)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.copy_done = [None, None]
+        self.frame_no, self.taken, self.kernels = 0, 0, 0
+        torch.cuda.synchronize(device)
+        dist.barrier()
+
+    def begin_frame(self):
+        k = self.frame_no
+        if self.copy_done[k & 1] is not None:  # the copy of frame k-2 has left this staging buffer
+            self.stream.wait_event(self.copy_done[k & 1])
+        self.tracer.set_ldr_target(self.staging[k & 1])
+
+    def publish(self):
+        """enqueue: copy of this rank's rows of the frame just traced into the shared host frame, then the arrival flag"""
+        torch, k = self.torch, self.frame_no
+        while k >= 2 and int(self.flags[self.world]) < k - 1:  # the consumer still holds the host buffer of frame k-2
+            pass
+        traced = torch.cuda.Event()
+        traced.record(self.stream)
+        self.copy_stream.wait_event(traced)
+        cs = self.copy_stream.cuda_stream
+        self.tracer.copy_owned_rows(self.staging[k & 1], self.host_base + (k & 1) * self.nbytes, cs)
+        self.tracer.signal_flag_on_stream(self.dev_base + 2 * self.nbytes + 4 * self.rank, k + 1, cs)
+        self.kernels += 1
+        done = torch.cuda.Event()
+        done.record(self.copy_stream)
+        self.copy_done[k & 1] = done
+        self.frame_no += 1
+
+    def wait_frame(self, keep: int = 0):
+        """rank 0: blocks until all but the last `keep` published frames have arrived from every rank; marks them consumed"""
+        target = self.frame_no - keep
+        if target <= self.taken:
+            return
+        while int(self.flags[: self.world].min()) < target:
+            pass
+        self.taken = target
+        self.flags[self.world] = target
+
+    def frame(self, k: int) -> np.ndarray:
+        """host view of frame k (valid between wait_frame covering k and the publication of frame k + 2)"""
+        return self.frames[k & 1]
+
+    def close(self):
+        torch = self.torch
+        self.tracer.set_ldr_target(None)
+        torch.cuda.synchronize(self.device)
+        self.copy_stream.synchronize()
+        self.tracer.host_unregister(self.host_base)
+        for p in self.staging:
+            self.tracer.device_free(p)
+        self.frames, self.flags = None, None
+        import torch.distributed as dist
+
+        dist.barrier()
+        self.shm.close()
+        if self.rank == 0:
+            self.shm.unlink()
+
+
 class FrameGather:
     """Delivers full frames to rank 0. Call order per frame: begin_frame() -> tracer.trace_rows(0, H, spp) ->
     device_gather() -> (rank 0) read_frame_into(pinned_host_tensor), or the pipelined read_frame_async(pinned) ...
@@ -165,6 +263,11 @@ class FrameGather:
                     for r in range(self.world):
                         n = len(self.partition[r])
                         self.frame.index_copy_(0, self.row_index[r], self.recv[r][: n * self.W].view(n, self.W))
+
+    def rearm(self):
+        """after something else (HostFrameGather) used the tracer's LDR target: point it at this gather's next frame buffer again"""
+        if self.mode in ("peer", "peer_allreduce"):
+            self.tracer.set_ldr_target(self.targets[self.frame_no & 1])
 
     def release_frame(self):
         """rank 0, mode "peer": the completed frame is no longer needed on the device (it was copied out, or nobody wants

@@ -221,3 +221,41 @@ def test_reserved_normals_and_uvs_are_ignored(scenes):
     assert np.array_equal(a.film.pixel_datas().view(np.uint32), b.film.pixel_datas().view(np.uint32))
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("accel", [rt.ACCEL_BVH, rt.ACCEL_LBVH])
+@pytest.mark.parametrize("name,rec,spread,lights", [("thai2", 2, 1, 1), ("ico3_tex", 2, 1, 1), ("ico2", 3, 1, 1), ("4boxes", 1, 3, 3)])
+def test_bounce_ray_stream_equals_lockstep_wavefront_and_depth_first(scenes, accel, name, rec, spread, lights):
+    """f-2, RECURSIONS > 0 (mod.rs:132-196): the ray-stream form of a wavefront level (bounce rays and the shadow rays of their hits
+    share the lanes of a warp, finished lanes are refilled) traces the same rays and leaves the same film, bit for bit, as the
+    lockstep wavefront and as the depth-first walk — for every refill / yield threshold, with the bounce levels chained in one launch (a lane continues with the bounce ray of the hit it
+    just completed) or launched level by level, at every occupancy the kernel is compiled for, with textures, with several lights (shade()'s
+    loop continues in place from one shadow ray to the next) and with deeper recursion."""
+    import types
+
+    s = scenes(name)
+    if lights > 1:  # two more lights, one of them behind most surfaces
+        s = types.SimpleNamespace(**{k: getattr(s, k) for k in ("vertices", "tri_geom", "materials", "textures", "camera_orientation", "camera_fov_deg")},
+                                  lights=list(s.lights) + [(np.float32([-6, 8, -3]), np.float32([3, 2, 1])), (np.float32([0, -9, 0]), np.float32([1, 1, 4]))])
+    w, h = 480, 270
+    runs = []
+    # (wavefront, ray stream, refill threshold, inner-loop yield threshold, resident blocks per SM, bounce levels chained in one launch)
+    for wavefront, stream, refill, min_inner, blocks, chain in ((1, 1, 16, 8, 4, 1), (1, 1, 1, 0, 3, 1), (1, 1, 32, 32, 5, 0), (1, 1, 20, 4, 3, 0),
+                                                                (1, 0, 8, 8, 3, 0), (0, 0, 8, 8, 3, 0)):
+        t = rt.RayTracer.from_scene(s, rt.Config(w, h, recursions=rec, sub_spread=spread, jitter_mode=rt.JITTER_HASHED, seed=6, accel=accel))
+        t.set_tuning(6, wavefront)
+        t.set_tuning(13, stream)
+        t.set_tuning(14, refill)
+        t.set_tuning(15, min_inner)
+        t.set_tuning(16, blocks)
+        t.set_tuning(18, chain)
+        n_shadow = [t.trace_rows(0, h, 1)[1], t.trace_rows(40, 100, 1)[1]]
+        st = t.launch_stats()
+        runs.append((n_shadow, st["n_bounce"], t.get_primary_ids(), t.get_tonemapped_pixels(), t.film.pixel_datas().view(np.uint32)))
+        t.close()
+    ref = runs[-1]
+    assert ref[1] > 0
+    for r in runs[:-1]:
+        assert r[0] == ref[0] and r[1] == ref[1]
+        for x, y in zip(r[2:], ref[2:]):
+            assert np.array_equal(x, y)

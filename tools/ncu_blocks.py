@@ -1,15 +1,17 @@
 """Basic-block view of an ncu report's SASS page: executed warp instructions, share, average active lanes, stall samples.
-Usage: python tools/ncu_blocks.py report.ncu-rep [min_share_percent]"""
+Usage: python tools/ncu_blocks.py report.ncu-rep [min_share_percent] [launch index in the report, default 0]"""
 import csv, subprocess, sys
 path = sys.argv[1]; min_share = float(sys.argv[2]) if len(sys.argv) > 2 else 0.4
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 out = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-for i, r in enumerate(rows):
-    if r and r[0] == 'Address':
-        hdr = r; start = i + 1; break
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
+start = starts[which]; end = starts[which + 1] - 1 if which + 1 < len(starts) else len(rows)
+hdr = rows[start]
+if start > 0 and rows[start - 1] and rows[start - 1][0] == 'Kernel Name': print('kernel', rows[start - 1][1])
 ie = hdr.index('Instructions Executed'); te = hdr.index('Thread Instructions Executed'); ss = hdr.index('# Samples')
 blocks = []; cur = None; tot = 0; tot_t = 0
-for r in rows[start:]:
+for r in rows[start + 1:end]:
     try: i_ = int(r[ie]); t_ = int(r[te]); s_ = int(r[ss])
     except Exception: continue
     tot += i_; tot_t += t_
