@@ -483,10 +483,10 @@ def main():
             if gather is not None:
                 gather.device_gather()
             if pipelined:
-                # frame i-1 (copied on the copy stream while frame i traces) is now complete in host memory; then hand
-                # frame i to the copy stream
-                tracer.wait_pixels()
+                # hand frame i to the copy stream, THEN make sure frame i-1 (the other host buffer, copied while frame i traced) has
+                # arrived: the copy engine always has the next frame queued
                 tracer.get_tonemapped_pixels_async(host_frames[i & 1].data_ptr())
+                tracer.wait_pixels(1)
             elif gather is not None and not args.sync_readback:
                 if rank == 0:  # same pipelining on rank 0 of a multi-GPU run: hand frame i to the copy stream, then make sure
                     # frame i-1 (the other host buffer) has arrived

@@ -164,9 +164,13 @@ int rt_get_tonemapped_pixels_delta(rt_raytracer* rt, uint32_t* out);
    threads do (raytracer/src/main.rs:200-209): takes a device-side snapshot of the packed frame on the render stream
    (a few microseconds) and copies it to `pinned_out` (page-locked host memory) on a separate copy stream, so the
    device -> host transfer overlaps the NEXT trace call. Returns at once; the pixels are valid after rt_wait_pixels.
-   One copy may be in flight per handle: a second call waits (on the device) for the first to leave the snapshot. */
+   Two copies may be in flight per handle (two snapshots): a third call waits, on the device, for the first to leave its snapshot. */
 int rt_get_tonemapped_pixels_async(rt_raytracer* rt, uint32_t* pinned_out);
 int rt_wait_pixels(rt_raytracer* rt);
+/* Waits until at most `keep` of the copies started by rt_get_tonemapped_pixels_async are still in flight (they complete in order).
+   With keep = 1 and two alternating host buffers the host hands frame k to the copy engine BEFORE it waits for frame k-1, so the
+   PCIe link never idles while the host gets around to its next call (the library holds two snapshots for this). */
+int rt_wait_pixels_keep(rt_raytracer* rt, uint32_t keep);
 /* Film::clear (film.rs:37-41) through the pub field `film` (raytracer/src/main.rs:126). */
 int rt_film_clear(rt_raytracer* rt);
 /* Film contents: width*height*7 floats per pixel: sum rgb, sum of squares rgb, num_samples (film.rs:3-7). */

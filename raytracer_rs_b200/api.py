@@ -94,7 +94,7 @@ ABI_SYMBOLS = [
     "rt_config_default", "rt_scene_load_file", "rt_scene_load_str", "rt_scene_get_desc", "rt_scene_free",
     "rt_create_raytracer", "rt_create_raytracer_from_file", "rt_create", "rt_destroy", "rt_last_error",
     "rt_configure", "rt_set_rows_per_call", "rt_trace_frame_additive", "rt_trace_rows",
-    "rt_get_tonemapped_pixels", "rt_get_tonemapped_pixels_delta", "rt_get_tonemapped_pixels_async", "rt_wait_pixels", "rt_film_clear", "rt_get_film",
+    "rt_get_tonemapped_pixels", "rt_get_tonemapped_pixels_delta", "rt_get_tonemapped_pixels_async", "rt_wait_pixels", "rt_wait_pixels_keep", "rt_film_clear", "rt_get_film",
     "rt_set_film", "rt_get_estimated_variances", "rt_get_primary_ids", "rt_camera_move_rel",
     "rt_camera_add_x_angle", "rt_camera_add_y_angle", "rt_camera_get", "rt_camera_set_state", "rt_set_stream",
     "rt_get_ldr_device_ptr", "rt_set_ldr_target", "rt_get_owned_ldr_rows_device", "rt_get_launch_stats",
@@ -149,6 +149,7 @@ def lib() -> C.CDLL:
         "rt_get_tonemapped_pixels_delta": (C.c_int, [vp, vp]),
         "rt_get_tonemapped_pixels_async": (C.c_int, [vp, vp]),
         "rt_wait_pixels": (C.c_int, [vp]),
+        "rt_wait_pixels_keep": (C.c_int, [vp, u32]),
         "rt_film_clear": (C.c_int, [vp]),
         "rt_get_film": (C.c_int, [vp, vp]),
         "rt_set_film": (C.c_int, [vp, vp]),
@@ -459,8 +460,9 @@ class RayTracer:
         The pixels are valid after wait_pixels()."""
         self._check(lib().rt_get_tonemapped_pixels_async(self._h, C.c_void_p(pinned_host_ptr)))
 
-    def wait_pixels(self) -> None:
-        self._check(lib().rt_wait_pixels(self._h))
+    def wait_pixels(self, keep: int = 0) -> None:
+        """blocks until at most `keep` pipelined readbacks are still in flight"""
+        self._check(lib().rt_wait_pixels_keep(self._h, keep))
 
     # -- extensions used by tests / bench --
     def configure(self, recursions=0, sub_spread=1, jitter_mode=JITTER_FIXED_HALF, seed=0, accel=ACCEL_BVH) -> None:

@@ -2397,34 +2397,44 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) wf_stream_kernel(const __grid
                 state = WS_SHADOW + 1;
             }
             // lanes in the middle of shade(): the next light the surface faces, or the node is complete
+            uint32_t emit = 0u;  // level the lane's finished node belongs to (0 = none: level 0 is written by the trace kernel)
             if (state == WS_SHADOW + 1) {
-                if (next_shadow_ray()) {
-                    state = WS_SHADOW;
-                } else {
-                    // the node is complete: append it to its level (lanes of a warp may be at different levels when rays are chained:
-                    // one warp-aggregated append per level)
-                    const uint32_t m = ctx[WS_LEVEL][tid] + 1u;
-                    uint32_t slot = 0;
-                    for (uint32_t lv = l + 1u; lv < (uint32_t)kWfLevels; ++lv)
-                        if (m == lv) slot = wf_append(&P.wf_counts[lv]);
-                    const float4 sh = __ldg(&P.tri_shade[ctx[WS_TRI][tid]]);
-                    const V3 nrm = {sh.x, sh.y, sh.z};
-                    const V3 hp = {__uint_as_float(ctx[WS_HPX][tid]), __uint_as_float(ctx[WS_HPY][tid]), __uint_as_float(ctx[WS_HPZ][tid])};
-                    const uint32_t pk = ctx[WS_PARENT][tid], pixel = ctx[WS_PIXEL][tid], path = ctx[WS_PATH][tid];
-                    wf_store_node(P, m, slot, hp, pixel, nrm, path, __uint_as_float(ctx[WS_CR][tid]), __uint_as_float(ctx[WS_CG][tid]),
-                                  __uint_as_float(ctx[WS_CB][tid]), pk & 0x0fffffffu, pk >> 28);
-                    state = WS_IDLE;
-                    if (P.wf_chain && P.wf[m].n_children == 1u && slot < P.wf[m].cap) {
-                        // the node's only bounce ray (k = 0) continues in this lane
-                        const uint32_t sub_path = path * 31u + 1u;
-                        const V3 rd = wf_bounce_dir(P, nrm, pixel, sub_path);
-                        cnt.bounce_rays += 1;
-                        ctx[WS_PATH][tid] = sub_path;
-                        ctx[WS_PARENT][tid] = slot;  // | (0 << 28)
-                        ctx[WS_LEVEL][tid] = m;
-                        start_ray(vadd(hp, vscale(rd, 0.00001f)), rd, FLT_MAX, -1.0f);
-                        state = WS_BOUNCE;
-                    }
+                if (next_shadow_ray()) state = WS_SHADOW;
+                else emit = ctx[WS_LEVEL][tid] + 1u;
+            }
+            __syncwarp();
+            // warp-aggregated append, one per level (the lanes of a warp may be at different levels when rays are chained). Done in
+            // warp-uniform control flow with explicit ballots: inside divergent code the set of lanes an __activemask() reports is up to
+            // the compiler (an if-converted branch counts lanes that do not append, which leaves holes in the level's node list).
+            uint32_t slot = 0u;
+            for (uint32_t lv = l + 1u; lv <= (uint32_t)P.recursions; ++lv) {
+                const uint32_t m_emit = __ballot_sync(full, emit == lv);
+                if (m_emit != 0u) {
+                    const uint32_t leader = (uint32_t)__ffs((int)m_emit) - 1u;
+                    uint32_t base = 0u;
+                    if (lane == leader) base = atomicAdd(&P.wf_counts[lv], (unsigned int)__popc(m_emit));
+                    base = __shfl_sync(full, base, (int)leader);
+                    if (emit == lv) slot = base + (uint32_t)__popc(m_emit & ((1u << lane) - 1u));
+                }
+            }
+            if (emit != 0u) {
+                const float4 sh = __ldg(&P.tri_shade[ctx[WS_TRI][tid]]);
+                const V3 nrm = {sh.x, sh.y, sh.z};
+                const V3 hp = {__uint_as_float(ctx[WS_HPX][tid]), __uint_as_float(ctx[WS_HPY][tid]), __uint_as_float(ctx[WS_HPZ][tid])};
+                const uint32_t pk = ctx[WS_PARENT][tid], pixel = ctx[WS_PIXEL][tid], path = ctx[WS_PATH][tid];
+                wf_store_node(P, emit, slot, hp, pixel, nrm, path, __uint_as_float(ctx[WS_CR][tid]), __uint_as_float(ctx[WS_CG][tid]),
+                              __uint_as_float(ctx[WS_CB][tid]), pk & 0x0fffffffu, pk >> 28);
+                state = WS_IDLE;
+                if (P.wf_chain && P.wf[emit].n_children == 1u && slot < P.wf[emit].cap) {
+                    // the node's only bounce ray (k = 0) continues in this lane
+                    const uint32_t sub_path = path * 31u + 1u;
+                    const V3 rd = wf_bounce_dir(P, nrm, pixel, sub_path);
+                    cnt.bounce_rays += 1;
+                    ctx[WS_PATH][tid] = sub_path;
+                    ctx[WS_PARENT][tid] = slot;  // | (0 << 28)
+                    ctx[WS_LEVEL][tid] = emit;
+                    start_ray(vadd(hp, vscale(rd, 0.00001f)), rd, FLT_MAX, -1.0f);
+                    state = WS_BOUNCE;
                 }
             }
             __syncwarp();

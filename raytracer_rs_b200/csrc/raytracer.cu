@@ -139,10 +139,12 @@ struct rt_raytracer {
     bool host_frame_stale = true;         // rows traced before registration / film clear are not in it yet
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     // pipelined readback (rt_get_tonemapped_pixels_async): snapshot on the render stream, device -> host on a copy stream
+    // (two snapshots: the copy of frame k may still be running while frame k+1 is snapshotted and queued behind it, so the copy engine
+    // never waits for the host)
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_snapshot = nullptr, ev_copied = nullptr;
-    DevBuf<uint32_t> d_ldr_snapshot;
-    bool copy_in_flight = false;
+    cudaEvent_t ev_snapshot = nullptr, ev_copied[2] = {nullptr, nullptr};
+    DevBuf<uint32_t> d_ldr_snapshot[2];
+    uint64_t copies_issued = 0, copies_waited = 0;  // copy c uses snapshot / event c & 1
 
     // host state
     uint32_t current_row = 0;
@@ -190,7 +192,8 @@ struct rt_raytracer {
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_stop) cudaEventDestroy(ev_stop);
         if (ev_snapshot) cudaEventDestroy(ev_snapshot);
-        if (ev_copied) cudaEventDestroy(ev_copied);
+        for (cudaEvent_t e : ev_copied)
+            if (e) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 
@@ -1206,28 +1209,35 @@ int rt_get_tonemapped_pixels_async(rt_raytracer* rt, uint32_t* pinned_out) {
         if (!rt->copy_stream) {
             RT_CUDA(cudaStreamCreateWithFlags(&rt->copy_stream, cudaStreamNonBlocking));
             RT_CUDA(cudaEventCreateWithFlags(&rt->ev_snapshot, cudaEventDisableTiming));
-            RT_CUDA(cudaEventCreateWithFlags(&rt->ev_copied, cudaEventDisableTiming));
-            rt->d_ldr_snapshot.alloc(rt->npix());
+            for (int k = 0; k < 2; ++k) {
+                RT_CUDA(cudaEventCreateWithFlags(&rt->ev_copied[k], cudaEventDisableTiming));
+                rt->d_ldr_snapshot[k].alloc(rt->npix());
+            }
         }
         const size_t bytes = (size_t)rt->npix() * 4;
-        // the snapshot buffer is free again once the previous copy has left it
-        if (rt->copy_in_flight) RT_CUDA(cudaStreamWaitEvent(rt->stream, rt->ev_copied, 0));
-        RT_CUDA(cudaMemcpyAsync(rt->d_ldr_snapshot.p, rt->d_ldr.p, bytes, cudaMemcpyDeviceToDevice, rt->stream));
+        const int slot = (int)(rt->copies_issued & 1u);
+        // the snapshot buffer is free again once the copy that used it two calls ago has left it
+        if (rt->copies_issued >= 2) RT_CUDA(cudaStreamWaitEvent(rt->stream, rt->ev_copied[slot], 0));
+        RT_CUDA(cudaMemcpyAsync(rt->d_ldr_snapshot[slot].p, rt->d_ldr.p, bytes, cudaMemcpyDeviceToDevice, rt->stream));
         RT_CUDA(cudaEventRecord(rt->ev_snapshot, rt->stream));
         RT_CUDA(cudaStreamWaitEvent(rt->copy_stream, rt->ev_snapshot, 0));
-        RT_CUDA(cudaMemcpyAsync(pinned_out, rt->d_ldr_snapshot.p, bytes, cudaMemcpyDeviceToHost, rt->copy_stream));
-        RT_CUDA(cudaEventRecord(rt->ev_copied, rt->copy_stream));
-        rt->copy_in_flight = true;
+        RT_CUDA(cudaMemcpyAsync(pinned_out, rt->d_ldr_snapshot[slot].p, bytes, cudaMemcpyDeviceToHost, rt->copy_stream));
+        RT_CUDA(cudaEventRecord(rt->ev_copied[slot], rt->copy_stream));
+        // an event is about to be reused: the host must not still be counting on its previous recording
+        if (rt->copies_issued >= 2 && rt->copies_waited + 2 <= rt->copies_issued) rt->copies_waited = rt->copies_issued - 1;
+        ++rt->copies_issued;
     });
 }
-int rt_wait_pixels(rt_raytracer* rt) {
+int rt_wait_pixels_keep(rt_raytracer* rt, uint32_t keep) {
     RT_GUARD(rt, {
-        if (rt->copy_in_flight) {
-            RT_CUDA(cudaEventSynchronize(rt->ev_copied));
-            rt->copy_in_flight = false;
+        // copies complete in order on the copy stream: waiting for copy c implies every earlier one
+        while (rt->copies_issued - rt->copies_waited > (uint64_t)keep) {
+            RT_CUDA(cudaEventSynchronize(rt->ev_copied[rt->copies_waited & 1u]));
+            ++rt->copies_waited;
         }
     });
 }
+int rt_wait_pixels(rt_raytracer* rt) { return rt_wait_pixels_keep(rt, 0); }
 int rt_set_host_frame(rt_raytracer* rt, uint32_t* pinned_host_frame) {
     RT_GUARD(rt, {
         if (rt->ldr_remote && rt->ldr_remote != rt->host_frame_dev) throw std::invalid_argument("an LDR target is already set (rt_set_ldr_target)");

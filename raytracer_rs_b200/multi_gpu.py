@@ -57,8 +57,8 @@ class HostFrameGather:
     8.3 MB frame. Call order per frame: begin_frame() -> tracer.trace_rows(...) -> publish(); rank 0: wait_frame(keep) -> frame(k).
 
     Reuse protocol: frame k uses staging / host buffer k & 1. A rank waits (on the device) for its own copy of frame k-2 before
-    frame k stores into the same staging buffer, and (on the host) for `consumed >= k - 1` — rank 0 publishes how many frames it has
-    taken — before it overwrites the host buffer of frame k-2."""
+    frame k stores into the same staging buffer, and (on the host) for `consumed >= k - 1` — rank 0 publishes how many frames its
+    caller is done with — before it overwrites the host buffer of frame k-2."""
 
     def __init__(self, tracer, rank: int, world: int, device, stream, name: str):
         import torch
@@ -101,6 +101,7 @@ class HostFrameGather:
     def publish(self):
         """enqueue: copy of this rank's rows of the frame just traced into the shared host frame, then the arrival flag"""
         torch, k = self.torch, self.frame_no
+        self._mark_consumed()
         while k >= 2 and int(self.flags[self.world]) < k - 1:  # the consumer still holds the host buffer of frame k-2
             pass
         traced = torch.cuda.Event()
@@ -115,15 +116,21 @@ class HostFrameGather:
         self.copy_done[k & 1] = done
         self.frame_no += 1
 
+    def _mark_consumed(self):
+        # rank 0: the frames handed out by the previous wait_frame are done with (the caller came back for more)
+        if self.rank == 0:
+            self.flags[self.world] = self.taken
+
     def wait_frame(self, keep: int = 0):
-        """rank 0: blocks until all but the last `keep` published frames have arrived from every rank; marks them consumed"""
+        """rank 0: blocks until all but the last `keep` published frames have arrived from every rank. The frames this call hands out
+        (frame(k) for k < frame_no - keep) stay valid until rank 0's next publish() or wait_frame()."""
+        self._mark_consumed()
         target = self.frame_no - keep
         if target <= self.taken:
             return
         while int(self.flags[: self.world].min()) < target:
             pass
         self.taken = target
-        self.flags[self.world] = target
 
     def frame(self, k: int) -> np.ndarray:
         """host view of frame k (valid between wait_frame covering k and the publication of frame k + 2)"""

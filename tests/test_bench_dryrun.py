@@ -144,8 +144,8 @@ class FakeTracer:
     def sync_timeouts(self):
         return 0
 
-    def wait_pixels(self):
-        self.calls.append("wait")
+    def wait_pixels(self, keep=0):
+        self.calls.append("wait%d" % keep)
 
     def get_tonemapped_pixels_async(self, ptr):
         self.calls.append("async")
@@ -299,6 +299,8 @@ def test_bench_line_carries_the_whole_contract(monkeypatch):
     assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] > 0 and cpu["reference_work_matches_constants"] is True
     # the end-to-end leg hands every frame to the copy stream and waits for the previous one; camera state goes in every step
     assert tracer.calls.count("async") == 6 + 3 and tracer.calls.count("camera") == 6 + 3
+    pipe = [c for c in tracer.calls if c in ("async", "wait1", "wait0")]  # frame i is queued before the host waits for frame i-1
+    assert pipe == ["async", "wait1"] * 3 + ["wait0"] + ["async", "wait1"] * 6 + ["wait0"]
     assert tracer.tuning.get(10) == 0  # launch timing is off outside the roofline leg
     for key in ("value_long", "configs", "recursions2", "e2e_reference_call_pattern", "first_frame_after_move", "strong"):
         assert key not in line

@@ -259,3 +259,27 @@ def test_bounce_ray_stream_equals_lockstep_wavefront_and_depth_first(scenes, acc
         assert r[0] == ref[0] and r[1] == ref[1]
         for x, y in zip(r[2:], ref[2:]):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("world,height", [(2, 364), (3, 90), (8, 1080), (5, 37)])
+def test_copy_owned_rows_moves_exactly_the_owned_bands(scenes, world, height):
+    """rt_copy_owned_rows (one strided 2-D copy for the full bands a shard owns, one more for a partial band at the bottom): every shard
+    copies its rows of a device frame into one host frame; together they reproduce the frame, and no shard touches a row it does not own."""
+    import torch
+
+    w = 96
+    s = scenes("ico2")
+    src = torch.arange(w * height, dtype=torch.int32, device="cuda") * 7 + 1
+    assembled = torch.zeros(w * height, dtype=torch.int32).pin_memory()
+    for r in range(world):
+        t = tracer_for(s, w, height, shard_index=r, shard_count=world, band_rows=8)
+        mine = torch.full((w * height,), -1, dtype=torch.int32).pin_memory()
+        t.copy_owned_rows(src.data_ptr(), mine.data_ptr())
+        t.copy_owned_rows(src.data_ptr(), assembled.data_ptr())
+        torch.cuda.synchronize()
+        rows = np.arange(height)
+        owned = (rows // 8) % world == r
+        got = mine.numpy().reshape(height, w)
+        assert (got[owned] == src.cpu().numpy().reshape(height, w)[owned]).all() and (got[~owned] == -1).all()
+        t.close()
+    assert torch.equal(assembled, src.cpu())

@@ -294,6 +294,34 @@ def test_pipelined_readback_delivers_every_frame(scenes):
     ref.close()
 
 
+def test_pipelined_readback_two_frames_in_flight(scenes):
+    """rt_wait_pixels_keep(1): frame k is handed to the copy stream BEFORE the host waits for frame k-1 (two snapshots, two host
+    buffers), and every frame still arrives intact; a third call in a row (no wait in between) must not overwrite a snapshot that
+    is still being copied."""
+    import torch
+
+    s = scenes("ico3_tex")
+    w, h = 640, 360
+    t = gpu_tracer(s, w, h, rt.ACCEL_BVH, jitter=rt.JITTER_HASHED, seed=5)
+    ref = gpu_tracer(s, w, h, rt.ACCEL_BVH, jitter=rt.JITTER_HASHED, seed=5)
+    bufs = [torch.empty(w * h, dtype=torch.int32).pin_memory() for _ in range(3)]
+    expect = []
+    for k in range(7):
+        t.trace_rows(0, h, 1, want_shadow=False)
+        t.get_tonemapped_pixels_async(bufs[k % 3].data_ptr())
+        if k != 3:  # frame 3: three copies queued back to back before the host looks at any of them
+            t.wait_pixels(1)
+            if k > 0:
+                assert np.array_equal(bufs[(k - 1) % 3].numpy().view(np.uint32), expect[k - 1]), k
+        ref.trace_rows(0, h, 1, want_shadow=False)
+        expect.append(ref.get_tonemapped_pixels())
+    t.wait_pixels()
+    for k in (4, 5, 6):
+        assert np.array_equal(bufs[k % 3].numpy().view(np.uint32), expect[k]), k
+    t.close()
+    ref.close()
+
+
 def _subscene(scene, tri_index, lights=None):
     """A scene made of some triangles of `scene` (same camera, materials and textures; optionally other lights)."""
     from types import SimpleNamespace

@@ -215,3 +215,103 @@ def test_peer_fence_protocol_calls():
     assert calls == [("arm", 1000, 1), ("wait", 1000, 4, 1, -1, 4), ("target", 0xB000),
                      ("arm", 1000, 2), ("wait", 1000, 4, 2, -1, -1), ("target", 0xA000), ("render_waits_for_copy", "copy-of-buffer-0")]
     assert g.buffer_copy_event == [None, None] and g.kernels == 2
+
+
+def _host_gather_worker(rank, world, port, w, h, result_path):
+    """HostFrameGather between real processes over real POSIX shared memory; the device side (staging frames, strided copy, flag store) is
+    a numpy stand-in that applies the same band arithmetic as rt_copy_owned_rows, and CUDA streams / events are inert objects."""
+    sys.path.insert(0, ROOT)
+    import ctypes
+    import types
+
+    import torch
+    import torch.distributed as dist
+
+    from raytracer_rs_b200.multi_gpu import HostFrameGather
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    mine = band_partition(h, world, 8)[rank]
+    keep = []
+
+    def view(ptr, n):
+        return np.ctypeslib.as_array((ctypes.c_uint32 * n).from_address(ptr))
+
+    class Tracer:
+        width, height = w, h
+        target = None
+
+        def host_register(self, ptr, nbytes):
+            return ptr
+
+        def host_unregister(self, ptr):
+            pass
+
+        def device_alloc(self, nbytes):
+            keep.append(np.zeros(nbytes // 4, np.uint32))
+            return keep[-1].ctypes.data
+
+        def device_free(self, p):
+            pass
+
+        def set_ldr_target(self, p):
+            self.target = p
+
+        def copy_owned_rows(self, src, dst, stream=0):
+            s, d = view(src, w * h).reshape(h, w), view(dst, w * h).reshape(h, w)
+            d[mine] = s[mine]
+
+        def signal_flag_on_stream(self, flag, value, stream=0):
+            view(flag, 1)[0] = value
+
+    class Stream:
+        cuda_stream = 0
+
+        def __init__(self, device=None):
+            pass
+
+        def wait_event(self, ev):
+            pass
+
+        def synchronize(self):
+            pass
+
+    class Event:
+        def record(self, stream=None):
+            pass
+
+    torch.cuda.Stream, torch.cuda.Event, torch.cuda.synchronize = Stream, Event, lambda d=None: None
+    t = Tracer()
+    g = HostFrameGather(t, rank, world, None, Stream(), "rtb200_gloo_%d" % port)
+    ok = True
+    rows = np.arange(h, dtype=np.uint32)[:, None]
+    for k in range(7):
+        g.begin_frame()
+        stage = view(t.target, w * h).reshape(h, w)
+        stage[:] = 0xDEAD  # rows this rank does not own must never reach the shared frame
+        stage[mine] = (1000 * k + rows + np.arange(w, dtype=np.uint32)[None, :])[mine]
+        g.publish()
+        if rank == 0:
+            g.wait_frame(keep=1)
+            if k >= 1:  # frame k-1 is complete and stays valid until rank 0 publishes again
+                ok = ok and bool(np.array_equal(g.frame(k - 1).reshape(h, w), 1000 * (k - 1) + rows + np.arange(w, dtype=np.uint32)[None, :]))
+    if rank == 0:
+        g.wait_frame()
+        ok = ok and bool(np.array_equal(g.frame(6).reshape(h, w), 6000 + rows + np.arange(w, dtype=np.uint32)[None, :]))
+        ok = ok and g.taken == 7
+        with open(result_path, "w") as f:
+            f.write(str(ok))
+    dist.barrier()
+    g.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_host_frame_gather_over_shared_memory(tmp_path, world):
+    """The N > 1 end-to-end path of bench.py (every rank delivers the rows it owns into one shared host frame, rank 0's host waits for the
+    arrival flags, two alternating buffers with a consumed counter) between real processes; 37 rows: a partial band at the bottom."""
+    import torch.multiprocessing as mp
+
+    port = 31000 + (os.getpid() % 2000) + world
+    result = tmp_path / "result.txt"
+    mp.spawn(_host_gather_worker, args=(world, port, 24, 37, str(result)), nprocs=world, join=True)
+    assert result.read_text() == "True"
