@@ -543,7 +543,7 @@ def main():
             if rank == 0:
                 solo = make_tracer(scene_of[(w, h)], w, h, spp, sharded=False)
                 solo.trace_rows(0, h, spp, want_shadow=False)
-                got = hgather.frame(hgather.frame_no - 1) if hgather is not None else host_frames[0].numpy().view(np.uint32)
+                got = np.array(hgather.frame(hgather.frame_no - 1)) if hgather is not None else host_frames[0].numpy().view(np.uint32)
                 frame_ok = bool(np.array_equal(solo.get_tonemapped_pixels(), got))
                 solo.close()
         if hgather is not None:

@@ -295,12 +295,13 @@ uint32_t rt_launch_param_bytes(void);
    rt_launch_stats.trace_kernel_ms is available; 0 skips them (trace_kernel_ms reads 0) — two stream operations less per
    call for hosts that time frames themselves. */
 #define RT_TUNE_TIME_LAUNCHES 10
-/* RT_TUNE_MIN_SCHEDULE_TILES: launches with fewer 32-lane tiles than this (default 4096) get no cost-feedback schedule of their own
-   (the reference's 50-row bands walk over the image with a period of lcm(50, height) rows, 108 geometries at 1080p); they run in
-   image order with EVERY tile handed out in 4 or 8 parts, since such a launch cannot fill the GPU and lasts as long as its
-   heaviest item. RT_TUNE_MAX_SPLIT_LEVEL: finest split of a tile, 0 never, 1 / 2 / 3 = up to 4 / 8 / 16 items of 8 / 4 / 2
-   pixels (default 3; with cost feedback the finer levels only engage when a tile alone costs more than 4x / 8x the balanced
-   launch time, i.e. when the launch cannot fill the GPU). */
+/* RT_TUNE_MIN_SCHEDULE_TILES: launches with fewer 32-lane tiles than this (default 4096) get no cost-feedback schedule of their own and
+   run in image order (measured on the reference's 50-row bands, which walk over the image with a period of lcm(50, height) rows —
+   108 launch geometries at 1080p: per-band schedules 2.0 ms per 22 bands, image order 1.5 ms, every tile handed out in parts
+   1.6 ms; such a launch is bound by its chain of cold-cache node fetches, not by its heaviest tile — hence RT_TUNE_BAND_LOOKAHEAD).
+   RT_TUNE_MAX_SPLIT_LEVEL: finest split of a heavy tile in a scheduled launch, 0 never, 1 / 2 / 3 = up to 4 / 8 / 16 items of
+   8 / 4 / 2 pixels (default 3; the finer levels only engage when a tile alone costs more than 4x / 8x the balanced launch time,
+   i.e. when the launch cannot fill the GPU). */
 #define RT_TUNE_MIN_SCHEDULE_TILES 11
 #define RT_TUNE_MAX_SPLIT_LEVEL 12
 /* RT_TUNE_BOUNCE_STREAM: 1 (default) every level of the bounce wavefront runs as a ray stream on the binary BVH — bounce rays
@@ -320,6 +321,12 @@ uint32_t rt_launch_param_bytes(void);
    SUB_SPREAD = 1), a lane of the ray-stream kernel that completes a hit continues in place with that hit's bounce ray, so one launch
    walks the whole bounce tree; 0 one launch per level. */
 #define RT_TUNE_STREAM_CHAIN 18
+/* RT_TUNE_BAND_LOOKAHEAD: 1 (default) rt_trace_frame_additive traces a lap ahead — the first band call of a lap traces the next
+   sample of every row down to the bottom of the image in one launch (a 50-row launch cannot fill the GPU and lasts as long as its
+   slowest chain of cold-cache node fetches), every band call commits its rows from that plane; film, ids, frame and per-call ray
+   counts after every call equal band-by-band tracing, and anything that would make the plane stale (camera, film, configuration,
+   rt_trace_rows) drops it. 0: every call traces its own rows. */
+#define RT_TUNE_BAND_LOOKAHEAD 19
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {

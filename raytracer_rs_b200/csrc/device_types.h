@@ -80,7 +80,6 @@ struct TraceParams {
     // every warp's peer stores ("my stores of this frame are done", the signal half of the frame fence)
     uint32_t* done_flag;
     uint32_t done_value;
-    uint32_t static_level;        // launches without a tile order: every tile is handed out in 2^(static_level + 1) parts (0 = whole tiles)
     const uint32_t* queue_items;  // number of entries of tile_order (written by tile_sort_kernel); unused when tile_order is null
     // cost-feedback tile schedule of the persistent kernel (either may be null): cycles spent per 8x4 tile in this
     // launch (written), queue slot -> tile id (read)
@@ -94,6 +93,9 @@ struct TraceParams {
     // instead of the film, and film_accumulate_kernel adds them in sample order afterwards
     float4* planes;
     uint32_t n_planes, plane_rows, plane_rows_padded, magic_plane_rows;  // padded = plane_rows rounded up to 4
+    // lap traced ahead of the band loop (raytracer.cu): per pixel, shadow rays (low byte) and bounce rays (high byte) of the sample
+    // a lap build traced; the build launch writes it instead of the ray counters, the commit launch books it
+    uint16_t* lap_rays;
     uint32_t jitter_mode, seed;
     int32_t recursions;          // RECURSIONS (mod.rs:81); 0 = primary + shadow only
     uint32_t sub_spread;         // SUB_SPREAD (mod.rs:82)

@@ -1133,7 +1133,7 @@ struct PixelOut {
 };
 
 // first half of a pixel sample: camera ray -> closest hit -> shading (shadow / bounce rays)
-template <int ACCEL, int WW, int BOUNCE>
+template <int ACCEL, int WW, int BOUNCE, bool LAP = false>
 __device__ __forceinline__ void trace_pixel_radiance(const TraceParams& P, uint32_t col, uint32_t crow, uint32_t lane_sample, LaneCounters& cnt,
                                                      PixelOut& out) {
     const uint32_t W = P.cam.width, H = P.cam.height;
@@ -1157,6 +1157,10 @@ __device__ __forceinline__ void trace_pixel_radiance(const TraceParams& P, uint3
     float cr = 0.f, cg = 0.f, cb = 0.f;
     HitRec hit;
     uint32_t id = kNoHit;
+    if (LAP) {  // lap build: the pixel's rays are booked when its sample is committed (no lane totals, see flush_counters)
+        cnt.shadow_rays = 0u;
+        cnt.bounce_rays = 0u;
+    }
     if (closest_hit<ACCEL, WW>(P, o, d, &hit)) {
         cnt.prim_hit += 1;
         id = hit.tri;
@@ -1174,6 +1178,7 @@ __device__ __forceinline__ void trace_pixel_radiance(const TraceParams& P, uint3
             shade_hit<ACCEL, WW>(P, o, d, hit, &nrm, &cr, &cg, &cb, cnt);
         }
     }
+    if (LAP) P.lap_rays[idx] = (uint16_t)(min(cnt.shadow_rays, 255u) | (min(cnt.bounce_rays, 255u) << 8));
     out.cr = cr;
     out.cg = cg;
     out.cb = cb;
@@ -1310,7 +1315,10 @@ __global__ void __launch_bounds__(256) trace_shade_kernel(const __grid_constant_
 #ifndef RT_PERSISTENT_MIN_BLOCKS
 #define RT_PERSISTENT_MIN_BLOCKS 3
 #endif
-template <int ACCEL, int BOUNCE, bool SAMPLE_LANES = false>
+// LAP: the launch traces a lap ahead of the band loop into a frame-aligned sample plane (raytracer.cu, lap_build): per-pixel ray counts go
+// to P.lap_rays instead of the ray counters, which the commit books (film_accumulate_kernel). A template flag so that the default
+// instantiation, which sits at its register limit, does not carry the extra state.
+template <int ACCEL, int BOUNCE, bool SAMPLE_LANES = false, bool LAP = false>
 __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_persistent_kernel(const __grid_constant__ TraceParams P) {
     const uint32_t lane = threadIdx.x & 31u;
 #if RT_TOP_SMEM > 0
@@ -1324,7 +1332,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
     LaneCounters cnt;
     // queue length: n_tiles in image order, or the item count the last tile_sort_kernel produced (heavy tiles are
     // split into four 8-pixel items so that their serial divergent chain is spread over four warps)
-    const uint32_t n_items = P.tile_order ? *P.queue_items : (P.static_level ? n_tiles << (P.static_level + 1u) : n_tiles);
+    const uint32_t n_items = P.tile_order ? *P.queue_items : n_tiles;
     // The next queue slot is claimed when a tile's rays are done, before its film update: the atomic's round trip
     // (~1 us) overlaps the epilogue instead of sitting in front of the next tile, and the claim is early by so little
     // that the heaviest-first order is not disturbed (claiming a whole tile ahead was measured 10 % slower).
@@ -1354,17 +1362,9 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         }
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item == 0xffffffffu) break;
-        uint32_t tile = item & kItemTileMask;
-        uint32_t level = (item >> kItemLevelShift) & 3u;
-        uint32_t part = (item >> kItemPartShift) & 15u;
-        if (P.static_level != 0u && !P.tile_order) {
-            // small launch without cost feedback (a 50-row band): EVERY tile is handed out in 2^(static_level + 1) parts, in image
-            // order — the launch cannot fill the GPU anyway, so the issue slots are there, and its duration is that of its
-            // longest item (queue slot = tile * parts + part)
-            level = P.static_level;
-            part = item & ((2u << level) - 1u);
-            tile = item >> (level + 1u);
-        }
+        const uint32_t tile = item & kItemTileMask;
+        const uint32_t level = (item >> kItemLevelShift) & 3u;
+        const uint32_t part = (item >> kItemPartShift) & 15u;
         const uint32_t tile_y = udiv_magic(tile, tiles_x, P.magic_tiles_x);
         uint32_t col, crow, lane_sample = 0u;
         if (SAMPLE_LANES) {
@@ -1388,7 +1388,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
 #endif
         PixelOut pout;
         pout.mode = 0u;
-        if (mine) trace_pixel_radiance<ACCEL, 1, BOUNCE>(P, col, crow, lane_sample, cnt, pout);
+        if (mine) trace_pixel_radiance<ACCEL, 1, BOUNCE, LAP>(P, col, crow, lane_sample, cnt, pout);
         __syncwarp();
         if (lane == 0) {
             if (last_of_batch) {
@@ -1422,7 +1422,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         }
 #endif
     }
-    flush_counters(P, cnt, lane);
+    if (!LAP) flush_counters(P, cnt, lane);
     warp_checkout(P, lane, total_warps);
 }
 
@@ -2046,8 +2046,26 @@ __device__ __forceinline__ void accumulate_pixel(const TraceParams& P, uint32_t 
 __global__ void __launch_bounds__(256) film_accumulate_kernel(const __grid_constant__ TraceParams P) {
     const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t prow = blockIdx.y;
-    if (col >= P.cam.width || prow >= P.plane_rows) return;
-    accumulate_pixel(P, col, prow);
+    const bool mine = col < P.cam.width && prow < P.plane_rows;
+    if (mine) accumulate_pixel(P, col, prow);
+    if (P.lap_rays) {
+        // commit of a band of the lap traced ahead (raytracer.cu, lap_commit): the rays of these samples are booked now, so that
+        // the per-call counters and the running totals only ever hold rays whose samples are in the film
+        uint32_t rays = 0u;
+        if (mine) rays = P.lap_rays[((P.first_row + prow) % P.cam.height) * P.cam.width + col];
+        const uint32_t sh = __reduce_add_sync(0xffffffffu, rays & 255u), bo = __reduce_add_sync(0xffffffffu, rays >> 8);
+        if ((threadIdx.x & 31u) == 0u) {
+            unsigned long long* set = P.counters + P.counter_set;
+            if (sh) {
+                atomicAdd(&set[CNT_SHADOW], (unsigned long long)sh);
+                atomicAdd(&P.counters[CNT_SHADOW_TOTAL], (unsigned long long)sh);
+            }
+            if (bo) {
+                atomicAdd(&set[CNT_BOUNCE], (unsigned long long)bo);
+                atomicAdd(&P.counters[CNT_BOUNCE_TOTAL], (unsigned long long)bo);
+            }
+        }
+    }
 }
 
 __global__ void gather_rows_kernel(const uint32_t* __restrict__ ldr, const uint32_t* __restrict__ row_list, uint32_t n_rows, uint32_t width,
@@ -2592,6 +2610,7 @@ static void launch_trace_t(const TraceParams& p, int variant, uint32_t blocks, c
         trace_shade_persistent_kernel<ACCEL, BOUNCE><<<blocks, 256, 2048, stream>>>(p);
 #else
         if (BOUNCE == 0 && p.lane_samples_log2 != 0u) trace_shade_persistent_kernel<ACCEL, 0, true><<<blocks, 256, 0, stream>>>(p);
+        else if (p.lap_rays) trace_shade_persistent_kernel<ACCEL, BOUNCE, false, true><<<blocks, 256, 0, stream>>>(p);
         else trace_shade_persistent_kernel<ACCEL, BOUNCE><<<blocks, 256, 0, stream>>>(p);
 #endif
     }
@@ -2599,8 +2618,7 @@ static void launch_trace_t(const TraceParams& p, int variant, uint32_t blocks, c
 // bounce_mode: 0 none, 1 depth first in the thread, 2 wavefront (the trace kernel only emits level-0 nodes)
 cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persistent_blocks, cudaStream_t stream) {
     if (p.n_rows == 0) return cudaSuccess;
-    // queue items: 8x4 pixel tiles (sample-lane items when the lanes of an item share pixels), each in 2^(static_level + 1) parts
-    const uint32_t tiles = (p.items_x * p.items_y) << (p.static_level ? p.static_level + 1u : 0u);
+    const uint32_t tiles = p.items_x * p.items_y;  // = 8x4 pixel tiles unless the launch uses sample lanes
     uint32_t blocks = (uint32_t)persistent_blocks;
     if (blocks * 8u > tiles) blocks = (tiles + 7u) / 8u;
     const int bounce = p.recursions > 0 ? (p.wf_counts ? 2 : 1) : 0;

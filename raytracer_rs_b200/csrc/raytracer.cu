@@ -175,9 +175,18 @@ struct rt_raytracer {
     };
     std::vector<std::unique_ptr<TileSchedule>> schedules;
     uint64_t schedule_clock = 0;
-    int min_schedule_tiles = 4096;   // RT_TUNE_MIN_SCHEDULE_TILES: launches with fewer tiles run in image order, every tile in parts
+    int min_schedule_tiles = 4096;   // RT_TUNE_MIN_SCHEDULE_TILES: launches with fewer tiles run in image order, whole tiles
     int max_split_level = 3;         // RT_TUNE_MAX_SPLIT_LEVEL: 0 never split, 1 / 2 / 3 = up to 4 / 8 / 16 items per tile
     int call_parity = 0;             // which per-call counter set the current trace call counts into (device_types.h)
+    bool set_dirty[2] = {false, false};  // the set holds counts of an earlier call (a launch with warp_checkout cleans the OTHER set)
+    // start of a trace call: switch to the other per-call counter set; it is zero already unless the previous call launched no kernel
+    // that checks out (a pure commit of the band look-ahead), then it is zeroed here
+    void begin_call_counters() {
+        call_parity ^= 1;
+        if (set_dirty[call_parity])
+            RT_CUDA(cudaMemsetAsync(d_counters.p + (call_parity ? CNT_SET_B : CNT_SET_A), 0, 4 * sizeof(unsigned long long), stream));
+        set_dirty[call_parity] = true;
+    }
     uint32_t* done_flag = nullptr;   // multi-GPU: the trace kernel's last warp publishes done_value here (rt_set_done_signal)
     uint32_t done_value = 0;
     bool arm_done = false;           // the launch being issued is the last one of its trace call
@@ -551,6 +560,7 @@ struct rt_raytracer {
     void film_clear() {
         host_frame_stale = true;
         mark_frame_dirty_all();
+        drop_lap();
         RT_CUDA(launch_film_clear(d_film_sum.p, d_film_sq.p, d_ldr.p, d_ids.p, npix(), stream));
         ++total_kernels;
     }
@@ -607,6 +617,7 @@ struct rt_raytracer {
     // does (a key press moves the camera by a fraction of the scene, main.rs:124-162), so every schedule keeps its order for the
     // next launch, restarts its cost record from zero and re-sorts after that launch and the one after it.
     void invalidate_schedule() {
+        drop_lap();  // (the camera moved)
         for (auto& sc : schedules) {
             sc->launches = 0;
             sc->restart_costs = true;
@@ -723,16 +734,6 @@ struct rt_raytracer {
             p.queue_items = sc->order.p + (sc->order.n - 1);
             ++sc->launches;
         }
-        if (!p.tile_order && variant == 1 && !use_pool && a != 0 && split_quarters > 0 && lpt_schedule && b == 0) {
-            // no cost feedback for this launch (too few tiles to be worth a schedule of its own — the reference's 50-row bands walk over
-            // the image with a period of lcm(50, height) rows, 108 different geometries at 1080p): hand every tile out in parts so that
-            // the launch, which cannot fill the GPU, at least is not as long as its heaviest 32-ray tile. Finest level that keeps the
-            // queue below 8 items per resident warp; a part must hold whole pixels.
-            const uint32_t warps = (uint32_t)(blocks_per_sm[a][b] * num_sms * 8);
-            uint32_t lv = (uint32_t)std::max(0, std::min(max_split_level, 2));
-            while (lv > 0 && ((32u >> (lv + 1u)) < (1u << p.lane_samples_log2) || ((uint64_t)tiles << (lv + 1u)) > 8ull * warps)) --lv;
-            p.static_level = lv;
-        }
         cudaError_t e;
         if (use_pool) e = launch_trace(p, a, 2, pool_blocks * num_sms, stream);
         else if (wavefront_applies(p)) e = launch_wavefront(p, a);
@@ -743,6 +744,7 @@ struct rt_raytracer {
             const int other = call_parity ? CNT_SET_A : CNT_SET_B;
             e = cudaMemsetAsync(d_counters.p + other, 0, 4 * sizeof(unsigned long long), stream);
         }
+        set_dirty[call_parity ^ 1] = false;
         return e;
     }
 
@@ -833,8 +835,98 @@ struct rt_raytracer {
         return cudaSuccess;
     }
 
+    // ---- the band loop, traced a lap ahead ------------------------------------------------------------------------------------
+    // The reference's render loop asks for 50 rows at a time (trace_frame_additive, mod.rs:87; main.rs:200). A launch over 50 rows
+    // cannot fill a B200: at 1080p it holds 3 120 tiles for 3 552 resident warps, every warp starts with a cold L1, and the launch
+    // lasts as long as its slowest chain of dependent node fetches from L2 — 20 to 130 us per band, 1.5 ms for the 22 bands of a frame
+    // that one full-frame launch traces in 0.15 ms. So the first band call of a lap traces the NEXT SAMPLE OF EVERY ROW from its first
+    // row to the bottom of the image in ONE launch, into a frame-aligned sample plane (radiance + primitive id per pixel, ray counts per
+    // pixel), and every band call — this one included — COMMITS its rows from the plane: PixelData::add_sample, mean, tonemap, pack, the
+    // call's ray counts. A sample's number is the film count of its pixel, which only a commit changes, so the committed samples are
+    // exactly the ones band-by-band tracing would have produced: same film, ids, frame and per-call counters after every call.
+    // Anything that makes the plane stale drops it (camera, film, configuration, an explicit rt_trace_rows); the rows not yet
+    // committed are then simply traced again when their band comes up.
+    DevBuf<float4> d_lap;
+    DevBuf<uint16_t> d_lap_rays;
+    bool lap_valid = false;
+    uint32_t lap_next = 0;   // rows [lap_next, height) of the plane are traced and not yet committed
+    int band_lookahead = 1;  // RT_TUNE_BAND_LOOKAHEAD
+    uint64_t lap_builds = 0, lap_drops = 0;
+    void drop_lap() {
+        if (lap_valid) ++lap_drops;
+        lap_valid = false;
+    }
+    bool lookahead_applies(uint32_t rows) const {
+        return band_lookahead && !sharded() && variant == 1 && rows < cfg.height && cfg.recursions <= 4 && scene.lights.size() < 255;
+    }
+    void lap_build(uint32_t from) {
+        const uint32_t rows = cfg.height - from, padded = (rows + 3u) & ~3u;
+        if (!d_lap.p) {
+            d_lap.alloc(npix());
+            d_lap_rays.alloc(npix());
+        }
+        TraceParams q;
+        fill_params(&q);
+        q.first_row = from;
+        q.planes = d_lap.p + (size_t)from * cfg.width;  // compact row c of the launch = image row from + c: the plane is frame aligned
+        q.n_planes = 1;
+        q.plane_rows = rows;
+        q.plane_rows_padded = padded;
+        q.magic_plane_rows = udiv_magic_of(padded);
+        q.n_rows = padded;
+        q.lap_rays = d_lap_rays.p;
+        RT_CUDA(launch_one(q));
+        ++total_kernels;
+        ++last.kernels_launched;
+        ++lap_builds;
+        lap_valid = true;
+        lap_next = from;
+    }
+    void lap_commit(uint32_t r0, uint32_t r1) {
+        TraceParams q;
+        fill_params(&q);
+        q.first_row = r0;
+        q.planes = d_lap.p + (size_t)r0 * cfg.width;
+        q.n_planes = 1;
+        q.plane_rows = r1 - r0;
+        q.plane_rows_padded = r1 - r0;
+        q.lap_rays = d_lap_rays.p;
+        q.counter_set = call_parity ? CNT_SET_B : CNT_SET_A;
+        RT_CUDA(launch_film_accumulate(q, stream));
+        ++total_kernels;
+        ++last.kernels_launched;
+        lap_next = r1;
+        if (lap_next >= cfg.height) lap_valid = false;  // used up (not a drop)
+    }
+    // trace_frame_additive through the lap plane: rows [first, first + rows) modulo height, one sample
+    void trace_band_lookahead(uint32_t first, uint32_t rows) {
+        if (cfg.recursions > 0) ensure_sample_table();
+        ensure_accel(cfg.accel);
+        begin_call_counters();  // (most band calls are pure commits: their counter set is zeroed by a 32-byte memset)
+        mark_rows_dirty(first, rows);
+        last = rt_launch_stats{};
+        last_timed = time_launches != 0;
+        if (last_timed) RT_CUDA(cudaEventRecord(ev_start, stream));
+        uint32_t r = first % cfg.height, remaining = rows;
+        while (remaining) {
+            if (!lap_valid || lap_next != r) {
+                drop_lap();
+                lap_build(r);
+            }
+            const uint32_t take = std::min(remaining, cfg.height - r);
+            lap_commit(r, r + take);
+            r = (r + take) % cfg.height;
+            remaining -= take;
+        }
+        if (last_timed) RT_CUDA(cudaEventRecord(ev_stop, stream));
+        last.n_primary = (uint64_t)rows * cfg.width;
+        total_primary += last.n_primary;
+        stats_pending = true;
+    }
+
     // rows [first_row, first_row + n_rows) modulo height, `spp` passes
     void trace_rows(uint32_t first_row, uint32_t n_rows, uint32_t spp) {
+        drop_lap();  // the film counts of these rows move: samples traced ahead for them would no longer be the next ones
         if (cfg.recursions > 4) throw CudaFail{"recursions > 4 is not supported (the reference uses 2)"};
         if (cfg.recursions > 0) ensure_sample_table();
         ensure_accel(cfg.accel);
@@ -861,7 +953,7 @@ struct rt_raytracer {
         }
         p.first_row = first_row;
         // no memset: this call counts into the counter set the previous call's last warp out left zeroed (kernels.cu, warp_checkout)
-        call_parity ^= 1;
+        begin_call_counters();
         mark_rows_dirty(first_row, n_rows);
         last = rt_launch_stats{};
         last_timed = time_launches != 0;
@@ -1126,6 +1218,7 @@ int rt_configure(rt_raytracer* rt, int32_t recursions, uint32_t sub_spread, int3
         if (accel != RT_ACCEL_OCTREE && accel != RT_ACCEL_BVH && accel != RT_ACCEL_CWBVH && accel != RT_ACCEL_BVH4 && accel != RT_ACCEL_LBVH) throw std::invalid_argument("unknown accel");
         if (jitter_mode != RT_JITTER_FIXED_HALF && jitter_mode != RT_JITTER_HASHED) throw std::invalid_argument("unknown jitter mode");
         if (recursions < 0) throw std::invalid_argument("negative recursions");
+        rt->drop_lap();
         rt->cfg.recursions = recursions;
         rt->cfg.sub_spread = sub_spread;
         rt->cfg.jitter_mode = jitter_mode;
@@ -1149,7 +1242,8 @@ int rt_set_rows_per_call(rt_raytracer* rt, uint32_t rows) {
 int rt_trace_frame_additive(rt_raytracer* rt, uint32_t* num_primary_rays) {
     RT_GUARD(rt, {
         const uint32_t rows = rt->cfg.rows_per_call;
-        rt->trace_rows(rt->current_row, rows, 1);
+        if (rt->lookahead_applies(rows)) rt->trace_band_lookahead(rt->current_row, rows);
+        else rt->trace_rows(rt->current_row, rows, 1);
         rt->current_row = (rt->current_row + rows) % rt->cfg.height;
         // mod.rs:113-116 returns rows * width; a sharded handle traces (and reports) only the rows it owns
         if (num_primary_rays) *num_primary_rays = (uint32_t)rt->last.n_primary;
@@ -1295,6 +1389,7 @@ int rt_set_film(rt_raytracer* rt, const float* in) {
             sum[i] = make_float4(o[0], o[1], o[2], w);
             sq[i] = make_float4(o[3], o[4], o[5], 0.f);
         }
+        rt->drop_lap();
         RT_CUDA(cudaMemcpyAsync(rt->d_film_sum.p, sum.data(), n * sizeof(float4), cudaMemcpyHostToDevice, rt->stream));
         RT_CUDA(cudaMemcpyAsync(rt->d_film_sq.p, sq.data(), n * sizeof(float4), cudaMemcpyHostToDevice, rt->stream));
         // the packed frame follows the film (get_tonemapped_pixels is a function of the film alone, mod.rs:120-128)
@@ -1539,6 +1634,7 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     if (key == RT_TUNE_KERNEL_VARIANT && value >= 0 && value <= 2) {
         if (rt->variant != value) rt->reset_schedules();  // an order holds items in the units and granularity of one kernel
         rt->variant = value;
+        rt->drop_lap();
         return RT_OK;
     }
     if (key == RT_TUNE_MIN_SCHEDULE_TILES && value >= 1) {
@@ -1578,6 +1674,11 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     }
     if (key == RT_TUNE_STREAM_REFILL && value >= 1 && value <= 32) {
         rt->stream_refill = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_BAND_LOOKAHEAD && (value == 0 || value == 1)) {
+        rt->band_lookahead = value;
+        rt->drop_lap();
         return RT_OK;
     }
     if (key == RT_TUNE_STREAM_CHAIN && (value == 0 || value == 1)) {

@@ -70,8 +70,7 @@ class HostFrameGather:
         self.nbytes = self.W * self.H * 4
         total = 2 * self.nbytes + 4096  # two frames + one page of flags (flags[0..world): arrived, flags[world]: consumed)
         if rank == 0:
-            self.shm = shared_memory.SharedMemory(name=name, create=True, size=total)
-            np.frombuffer(self.shm.buf, dtype=np.uint32, count=1024, offset=2 * self.nbytes)[:] = 0
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=total)  # a fresh segment is zero-filled: all flags start at 0
         dist.barrier()
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name, create=False)
@@ -81,9 +80,14 @@ class HostFrameGather:
                 resource_tracker.unregister(self.shm._name, "shared_memory")
             except Exception:
                 pass
-        self.frames = [np.frombuffer(self.shm.buf, dtype=np.uint32, count=self.W * self.H, offset=k * self.nbytes) for k in (0, 1)]
-        self.flags = np.frombuffer(self.shm.buf, dtype=np.uint32, count=1024, offset=2 * self.nbytes)
-        self.host_base = self.frames[0].ctypes.data
+        # views by ADDRESS, not through the buffer protocol: a view a caller still holds must not keep the segment from being closed
+        import ctypes
+
+        anchor = ctypes.c_char.from_buffer(self.shm.buf)
+        self.host_base = ctypes.addressof(anchor)
+        del anchor
+        self.frames = [np.ctypeslib.as_array((ctypes.c_uint32 * (self.W * self.H)).from_address(self.host_base + k * self.nbytes)) for k in (0, 1)]
+        self.flags = np.ctypeslib.as_array((ctypes.c_uint32 * 1024).from_address(self.host_base + 2 * self.nbytes))
         self.dev_base = tracer.host_register(self.host_base, total)  # device address of the same range
         self.staging = [tracer.device_alloc(self.nbytes), tracer.device_alloc(self.nbytes)]
         self.copy_stream = torch.cuda.Stream(device=device)
@@ -133,7 +137,8 @@ class HostFrameGather:
         self.taken = target
 
     def frame(self, k: int) -> np.ndarray:
-        """host view of frame k (valid between wait_frame covering k and the publication of frame k + 2)"""
+        """host view of frame k (valid between the wait_frame that covers k and rank 0's next publish() / wait_frame(); dangling after
+        close(): copy what must outlive the gather)"""
         return self.frames[k & 1]
 
     def close(self):

@@ -283,3 +283,43 @@ def test_copy_owned_rows_moves_exactly_the_owned_bands(scenes, world, height):
         assert (got[owned] == src.cpu().numpy().reshape(height, w)[owned]).all() and (got[~owned] == -1).all()
         t.close()
     assert torch.equal(assembled, src.cpu())
+
+
+@pytest.mark.parametrize("name,w,h,rec", [("thai2", 640, 360, 0), ("ico3_tex", 320, 170, 0), ("ico2", 256, 190, 2)])
+def test_band_lookahead_equals_band_by_band_tracing(scenes, name, w, h, rec):
+    """rt_trace_frame_additive with the lap traced ahead (one launch traces the next sample of every remaining row, band calls commit
+    their rows) against the same handle settings tracing every band on its own: after EVERY call the frame, and at the end film, ids and
+    per-call ray counts, are bit-identical — with hashed jitter (a sample's number is its pixel's film count), across the wrap at the
+    bottom of the image (heights that are no multiple of 50), a camera move + film.clear() in the middle of a lap, an explicit
+    rt_trace_rows in the middle of a lap, a change of rows_per_call, and with bounce rays (RECURSIONS = 2)."""
+    s = scenes(name)
+    cfg = dict(recursions=rec, sub_spread=1, jitter_mode=rt.JITTER_HASHED, seed=8, accel=rt.ACCEL_BVH)
+    a = rt.RayTracer.from_scene(s, rt.Config(w, h, **cfg))
+    b = rt.RayTracer.from_scene(s, rt.Config(w, h, **cfg))
+    a.set_tuning(19, 0)  # every call traces its own rows
+    keep_a, keep_b = np.zeros(w * h, np.uint32), np.zeros(w * h, np.uint32)
+    calls = 4 * ((h + 49) // 50) + 3
+    for c in range(calls):
+        na, nb = a.trace_frame_additive(), b.trace_frame_additive()
+        sa, sb = a.launch_stats(), b.launch_stats()
+        assert na == nb and (sa["n_primary"], sa["n_shadow"], sa["n_bounce"]) == (sb["n_primary"], sb["n_shadow"], sb["n_bounce"]), c
+        a.get_tonemapped_pixels_delta_into(keep_a.ctypes.data)
+        b.get_tonemapped_pixels_delta_into(keep_b.ctypes.data)
+        assert np.array_equal(keep_a, keep_b), c
+        if c == 5:  # a key press in the middle of a lap (main.rs:124-162)
+            for t in (a, b):
+                t.camera.add_y_angle(0.07)
+                t.film.clear()
+        if c == 9:  # an explicit row range in the middle of a lap: its film counts move
+            for t in (a, b):
+                t.trace_rows(3, 21, 2)
+        if c == 12:
+            for t in (a, b):
+                t.set_rows_per_call(70)
+    assert np.array_equal(a.get_primary_ids(), b.get_primary_ids())
+    assert np.array_equal(a.film.pixel_datas().view(np.uint32), b.film.pixel_datas().view(np.uint32))
+    assert np.array_equal(a.get_tonemapped_pixels(), b.get_tonemapped_pixels())
+    ta, tb = a.ray_totals(), b.ray_totals()
+    assert ta["primary"] == tb["primary"] and ta["shadow"] == tb["shadow"] and ta["bounce"] == tb["bounce"]
+    a.close()
+    b.close()

@@ -11,8 +11,8 @@ scene = rt.load_scene(os.path.join(ROOT, "data", "thai2.dae"))
 host = torch.empty(w * h, dtype=torch.int32).pin_memory()
 calls = (h + 49) // 50
 rays_frame = 2599194 * (calls * 50 / h)
-for label, tune in (("image order, whole tiles", {1: 0}), ("default: static parts", {}), ("static parts <= 4", {12: 1}), ("static parts <= 8", {12: 2}),
-                    ("per-band schedules", {11: 1024})):
+for label, tune in (("default: lap traced ahead", {}), ("band by band, static parts", {19: 0}), ("band by band, whole tiles", {19: 0, 1: 0}),
+                    ("band by band, schedules", {19: 0, 11: 1024})):
     t = rt.RayTracer.from_scene(scene, rt.Config(w, h, recursions=0, jitter_mode=rt.JITTER_FIXED_HALF, accel=rt.ACCEL_BVH))
     for k, v in tune.items():
         t.set_tuning(k, v)
