@@ -335,6 +335,10 @@ typedef struct rt_launch_stats {
     uint64_t n_primary, n_shadow, n_bounce;
 } rt_launch_stats;
 int rt_get_launch_stats(const rt_raytracer* rt, rt_launch_stats* out);
+/* Schedule introspection: SM cycles the last scheduled launch spent per 32-lane tile (a split tile reports parts x its slowest part),
+   for the most recently used launch geometry; *n_items = entries of its sorted queue (0 before the first sort). Any pointer may be NULL.
+   What the critical-path figures of DESIGN.md section 7 are computed from. */
+int rt_get_tile_costs(rt_raytracer* rt, uint32_t* out, uint32_t capacity, uint32_t* n_tiles, uint32_t* n_items);
 /* Rays issued by this handle since creation: out3 = primary, shadow, bounce (synchronises the stream). Exact totals
    over any number of asynchronous trace calls. */
 int rt_get_ray_totals(rt_raytracer* rt, uint64_t* out3);

@@ -102,7 +102,7 @@ ABI_SYMBOLS = [
     "rt_stream_signal_flag", "rt_stream_signal_then_wait", "rt_stream_wait_flags", "rt_sync_timeouts", "rt_set_done_signal",
     "rt_launch_param_bytes", "rt_set_tuning", "rt_set_host_frame", "rt_host_register", "rt_host_unregister", "rt_copy_owned_rows",
     "rt_signal_flag_on_stream",
-    "rt_kernels_launched", "rt_get_ray_totals", "rt_octree_stats", "rt_octree_export", "rt_bvh_stats", "rt_bvh_export", "rt_bvh4_stats", "rt_bvh4_export", "rt_lbvh_build", "rt_lbvh_export", "rt_cwbvh_stats",
+    "rt_kernels_launched", "rt_get_ray_totals", "rt_get_tile_costs", "rt_octree_stats", "rt_octree_export", "rt_bvh_stats", "rt_bvh_export", "rt_bvh4_stats", "rt_bvh4_export", "rt_lbvh_build", "rt_lbvh_export", "rt_cwbvh_stats",
     "rt_cwbvh_export", "rt_stats_new",
     "rt_stats_free", "rt_stats_stats", "rt_stats_mean_stats", "rt_benchmark_new", "rt_benchmark_free",
     "rt_benchmark_start", "rt_benchmark_stop", "rt_benchmark_report", "rt_version", "rt_kernels_hash",
@@ -189,6 +189,7 @@ def lib() -> C.CDLL:
         "rt_bvh_stats": (C.c_int, [vp, vp]),
         "rt_bvh_export": (C.c_int, [vp, vp, vp, vp, vp]),
         "rt_get_ray_totals": (C.c_int, [vp, vp]),
+        "rt_get_tile_costs": (C.c_int, [vp, vp, u32, P(u32), P(u32)]),
         "rt_lbvh_build": (C.c_int, [vp, vp, P(f32)]),
         "rt_lbvh_export": (C.c_int, [vp, vp, vp, vp, vp]),
         "rt_bvh4_stats": (C.c_int, [vp, vp]),
@@ -610,6 +611,14 @@ class RayTracer:
         raw = np.zeros(3, np.uint64)
         self._check(lib().rt_get_ray_totals(self._h, _ptr(raw)))
         return dict(zip(["primary", "shadow", "bounce"], (int(x) for x in raw)))
+
+    def tile_costs(self):
+        """(cycles per 32-lane tile of the last scheduled launch geometry, items in its sorted queue)"""
+        n, items = C.c_uint32(), C.c_uint32()
+        self._check(lib().rt_get_tile_costs(self._h, None, 0, C.byref(n), C.byref(items)))
+        out = np.zeros(max(1, n.value), np.uint32)
+        self._check(lib().rt_get_tile_costs(self._h, _ptr(out), n.value, C.byref(n), C.byref(items)))
+        return out[: n.value], int(items.value)
 
     def lbvh_build(self) -> dict:
         """(re)builds the BVH on the GPU; returns nodes, depth, triangles and the device time of the build (ms)"""

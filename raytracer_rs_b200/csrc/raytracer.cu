@@ -1722,6 +1722,20 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     return RT_ERR_INVALID;
 }
 
+int rt_get_tile_costs(rt_raytracer* rt, uint32_t* out, uint32_t capacity, uint32_t* n_tiles, uint32_t* n_items) {
+    RT_GUARD(rt, {
+        const rt_raytracer::TileSchedule* sc = nullptr;
+        for (auto& s : rt->schedules)
+            if (!sc || s->last_use > sc->last_use) sc = s.get();
+        if (n_tiles) *n_tiles = sc ? sc->tiles : 0;
+        if (n_items) *n_items = 0;
+        if (!sc) return RT_OK;
+        if (out && capacity) RT_CUDA(cudaMemcpyAsync(out, sc->cost.p, sizeof(uint32_t) * std::min(capacity, sc->tiles), cudaMemcpyDeviceToHost, rt->stream));
+        if (n_items && sc->have_order) RT_CUDA(cudaMemcpyAsync(n_items, sc->order.p + (sc->order.n - 1), 4, cudaMemcpyDeviceToHost, rt->stream));
+        RT_CUDA(cudaStreamSynchronize(rt->stream));
+    });
+}
+
 int rt_get_launch_stats(const rt_raytracer* rt_c, rt_launch_stats* out) {
     rt_raytracer* rt = const_cast<rt_raytracer*>(rt_c);
     RT_GUARD(rt, {

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, mode, result_path, fused=True):
+def _worker(rank, world, port, mode, result_path, fused=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -59,7 +59,7 @@ def _worker(rank, world, port, mode, result_path, fused=True):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,fused", [("peer", True), ("peer", False), ("peer_allreduce", True), ("nccl", True)])
+@pytest.mark.parametrize("mode,fused", [("peer", False), ("peer", True), ("peer_allreduce", False), ("nccl", False)])
 def test_two_rank_gather(tmp_path, mode, fused):
     """mode "peer" twice: the frame-done signal published by the trace kernel's last warp out (rt_set_done_signal), and as a launch of its own"""
     import torch

@@ -156,7 +156,7 @@ def test_peer_fence_protocol_calls():
     Separate signal (fused_signal=False): every rank issues exactly one fence launch per frame — rank r != 0 signals "frame k
     done" as flags[r] = k + 1 and, from frame 1 on, waits in the same launch for flags[world] >= k ("frame k-1 has been read":
     frame k+1 reuses its buffer); rank 0 signals its own slot, waits for all slots and, when the frame stays on the device,
-    publishes "read" in that launch too. Fused signal (default): begin_frame arms the trace call to publish flags[r] = k + 1
+    publishes "read" in that launch too. Fused signal (optional): begin_frame arms the trace call to publish flags[r] = k + 1
     from its last warp out (rt_set_done_signal), the fence launch only waits (rank r != 0: nothing at all for frame 0).
     The store target alternates between the two frame buffers; rank 0's render stream waits for the host copy that last
     read a buffer before its own kernel stores into it again."""
