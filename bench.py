@@ -324,6 +324,9 @@ def main():
                     help="N>1, end-to-end leg: 'host' = every rank copies the rows it owns over its own PCIe link into one frame in shared, "
                          "page-locked host memory (multi_gpu.HostFrameGather); 'nvlink' = the frame is gathered on rank 0 over NVLink (--gather) "
                          "and copied to the host over rank 0's link alone")
+    ap.add_argument("--fence", default="kernel", choices=["kernel", "memops"],
+                    help="N>1, --gather peer: per-frame fence made of flag kernels (bounded waits) or of stream memory operations "
+                         "(cuStreamWriteValue32 / cuStreamWaitValue32: no launch, no timeout)")
     ap.add_argument("--fused-signal", action="store_true",
                     help="N>1, --gather peer: publish 'frame done' from the trace kernel's last warp out (rt_set_done_signal) instead of a signal launch "
                          "of its own; measured slower (every warp fences its peer stores at system scope), kept as an option")
@@ -563,7 +566,7 @@ def main():
     spp = base_spp * (world if (world > 1 and args.scaling == "weak") else 1)
     tracer = make_tracer(scene, W, H, spp)
     tracer.set_stream(stream.cuda_stream)
-    gather = multi_gpu.FrameGather(tracer, rank, world, dev, stream, mode=args.gather, fused_signal=args.fused_signal) if world > 1 else None
+    gather = multi_gpu.FrameGather(tracer, rank, world, dev, stream, mode=args.gather, fused_signal=args.fused_signal, fence=args.fence) if world > 1 else None
     main_res = run_legs(tracer, gather, W, H, spp, args.steps, args.warmup)
     extras = not args.no_extras
 
@@ -674,7 +677,7 @@ def main():
             scene_of[(w2, h2)] = sc2
             t2 = make_tracer(sc2, w2, h2, spp2)
             t2.set_stream(stream.cuda_stream)
-            g2 = multi_gpu.FrameGather(t2, rank, world, dev, stream, mode=args.gather, fused_signal=args.fused_signal) if world > 1 else None
+            g2 = multi_gpu.FrameGather(t2, rank, world, dev, stream, mode=args.gather, fused_signal=args.fused_signal, fence=args.fence) if world > 1 else None
             r2 = run_legs(t2, g2, w2, h2, spp2, max(5, min(args.steps, 20)), 3, kernel_timing=False)
             entry = {"value": r2["dev"]["value"], "unit": UNIT, "ms_per_step": r2["dev"]["ms_per_step"], "e2e": r2["e2e"]["value"],
                      "e2e_frame_matches_device": r2["e2e"]["frame_matches_device"], "spp": spp2, "n_gpus": world,
@@ -774,8 +777,8 @@ def main():
             roofline["frac"] = roofline["traffic_equivalent"]
             roofline["frac_of"] = "traffic equivalent (no instruction count recorded for this configuration)"
     gather_note = "" if world == 1 else (" (%d spp per GPU-count unit: %s scaling), rows sharded by interleaved 8-row bands, every rank traces its rows x all "
-                                          "samples in one launch, packed frame stored into rank 0's buffer over NVLink (%s, frame-done signal %s)"
-                                          % (base_spp, args.scaling, args.gather, "fused into the trace kernel" if args.fused_signal else "from a separate launch"))
+                                          "samples in one launch, packed frame stored into rank 0's buffer over NVLink (%s, frame-done signal %s, fence: %s)"
+                                          % (base_spp, args.scaling, args.gather, "fused into the trace kernel" if args.fused_signal else "from a separate launch", args.fence))
     readback = (("every rank copies the rows it owns over its own PCIe link into one frame in shared page-locked host memory (copy stream, overlaps "
                  "the next frame; arrival flags in the same shared memory)") if e2e_res.get("host_gather") else
                 ("gather to rank 0 (%s) + %s copy to pinned host memory" % (args.gather, "blocking" if args.sync_readback else "pipelined (copy stream, overlaps the next frame)"))) if world > 1 else (

@@ -236,6 +236,13 @@ int rt_stream_signal_then_wait(rt_raytracer* rt, void* dev_signal_flag, uint32_t
 int rt_stream_wait_flags(rt_raytracer* rt, void* dev_flags, uint32_t n_flags, uint32_t target, int32_t signal_slot,
                          int32_t release_slot);
 int rt_sync_timeouts(rt_raytracer* rt, uint32_t* count);
+/* The same fence without kernel launches: stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32, fetched from the
+   driver at run time). rt_stream_write_value stores `value` into *dev_flag once everything enqueued before it has finished, behind a
+   system-wide memory barrier; rt_stream_wait_value holds the stream until (int32)(*dev_flag - value) >= 0. The stream's front end
+   executes them, no SM is occupied. Unlike the flag kernels a wait has NO timeout: a peer that dies leaves the stream waiting until
+   the process is torn down. RT_ERR_UNSUPPORTED when the driver does not offer them for this address. */
+int rt_stream_write_value(rt_raytracer* rt, void* dev_flag, uint32_t value);
+int rt_stream_wait_value(rt_raytracer* rt, void* dev_flag, uint32_t value);
 /* Fuses the "my stores of this frame are done" half of that fence into the NEXT trace call (one-shot): the last warp out of
    the call's last kernel stores `value` into *dev_flag at system scope, after every warp has fenced its own stores into
    the peer-mapped frame — no separate signal launch, and the flag is on its way while the launch drains. Calls whose last

@@ -99,7 +99,7 @@ ABI_SYMBOLS = [
     "rt_camera_add_x_angle", "rt_camera_add_y_angle", "rt_camera_get", "rt_camera_set_state", "rt_set_stream",
     "rt_get_ldr_device_ptr", "rt_set_ldr_target", "rt_get_owned_ldr_rows_device", "rt_get_launch_stats",
     "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_get_counters_device_ptr",
-    "rt_stream_signal_flag", "rt_stream_signal_then_wait", "rt_stream_wait_flags", "rt_sync_timeouts", "rt_set_done_signal",
+    "rt_stream_signal_flag", "rt_stream_signal_then_wait", "rt_stream_wait_flags", "rt_sync_timeouts", "rt_set_done_signal", "rt_stream_write_value", "rt_stream_wait_value",
     "rt_launch_param_bytes", "rt_set_tuning", "rt_set_host_frame", "rt_host_register", "rt_host_unregister", "rt_copy_owned_rows",
     "rt_signal_flag_on_stream",
     "rt_kernels_launched", "rt_get_ray_totals", "rt_get_tile_costs", "rt_octree_stats", "rt_octree_export", "rt_bvh_stats", "rt_bvh_export", "rt_bvh4_stats", "rt_bvh4_export", "rt_lbvh_build", "rt_lbvh_export", "rt_cwbvh_stats",
@@ -176,6 +176,8 @@ def lib() -> C.CDLL:
         "rt_stream_wait_flags": (C.c_int, [vp, vp, u32, u32, i32, i32]),
         "rt_sync_timeouts": (C.c_int, [vp, P(u32)]),
         "rt_set_done_signal": (C.c_int, [vp, vp, u32]),
+        "rt_stream_write_value": (C.c_int, [vp, vp, u32]),
+        "rt_stream_wait_value": (C.c_int, [vp, vp, u32]),
         "rt_launch_param_bytes": (u32, []),
         "rt_set_tuning": (C.c_int, [vp, i32, i32]),
         "rt_set_host_frame": (C.c_int, [vp, vp]),
@@ -564,6 +566,14 @@ class RayTracer:
     def set_done_signal(self, dev_flag: int | None, value: int) -> None:
         """the next trace call publishes `value` at *dev_flag when its last pixel is stored (rt_set_done_signal)"""
         self._check(lib().rt_set_done_signal(self._h, C.c_void_p(dev_flag or 0), value))
+
+    def stream_write_value(self, dev_flag: int, value: int) -> None:
+        """stream memory operation: *dev_flag = value after everything enqueued before (no kernel launch)"""
+        self._check(lib().rt_stream_write_value(self._h, C.c_void_p(dev_flag), value))
+
+    def stream_wait_value(self, dev_flag: int, value: int) -> None:
+        """stream memory operation: hold the stream until *dev_flag >= value (cyclic); no timeout"""
+        self._check(lib().rt_stream_wait_value(self._h, C.c_void_p(dev_flag), value))
 
     def sync_timeouts(self) -> int:
         n = C.c_uint32()

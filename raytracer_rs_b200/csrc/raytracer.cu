@@ -3,6 +3,7 @@
 // Host-side mirror of raytracer_lib's public surface (lib.rs:15-44, raytracer/mod.rs:32-128): construction wires
 // loader -> acceleration structure -> renderer, the render calls launch the fused kernel of kernels.cu on the
 // handle's stream. There is deliberately no CPU rendering path in this library.
+#include <cuda.h>  // types of the two driver entry points fetched at run time (no link dependency on libcuda)
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -1567,6 +1568,47 @@ int rt_stream_signal_then_wait(rt_raytracer* rt, void* dev_signal_flag, uint32_t
         }
         RT_CUDA(launch_flag_signal_wait((uint32_t*)dev_signal_flag, value, (uint32_t*)dev_wait_flag, target, rt->d_sync_timeouts.p, rt->stream));
         ++rt->total_kernels;
+    });
+}
+// Stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32), fetched from the driver at run time: a frame fence without
+// a kernel launch — the stream's front end stores / polls the flag itself.
+namespace {
+typedef CUresult (*StreamValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamValueFn driver_fn(const char* name) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return (StreamValueFn)fn;
+}
+}  // namespace
+int rt_stream_write_value(rt_raytracer* rt, void* dev_flag, uint32_t value) {
+    RT_GUARD(rt, {
+        static StreamValueFn fn = driver_fn("cuStreamWriteValue32");
+        if (!fn || !dev_flag) {
+            rt->last_error = "cuStreamWriteValue32 is not available";
+            return RT_ERR_UNSUPPORTED;
+        }
+        // default flags: a system-wide memory barrier precedes the write, so everything the stream did before is visible first
+        const CUresult r = fn((CUstream)rt->stream, (CUdeviceptr)(uintptr_t)dev_flag, value, CU_STREAM_WRITE_VALUE_DEFAULT);
+        if (r != CUDA_SUCCESS) {
+            rt->last_error = "cuStreamWriteValue32 failed (" + std::to_string((int)r) + ")";
+            return RT_ERR_UNSUPPORTED;
+        }
+    });
+}
+int rt_stream_wait_value(rt_raytracer* rt, void* dev_flag, uint32_t value) {
+    RT_GUARD(rt, {
+        static StreamValueFn fn = driver_fn("cuStreamWaitValue32");
+        if (!fn || !dev_flag) {
+            rt->last_error = "cuStreamWaitValue32 is not available";
+            return RT_ERR_UNSUPPORTED;
+        }
+        // GEQ is cyclic: (int32)(*flag - value) >= 0, the comparison the flag kernels use
+        const CUresult r = fn((CUstream)rt->stream, (CUdeviceptr)(uintptr_t)dev_flag, value, CU_STREAM_WAIT_VALUE_GEQ);
+        if (r != CUDA_SUCCESS) {
+            rt->last_error = "cuStreamWaitValue32 failed (" + std::to_string((int)r) + ")";
+            return RT_ERR_UNSUPPORTED;
+        }
     });
 }
 int rt_sync_timeouts(rt_raytracer* rt, uint32_t* count) {

@@ -163,7 +163,7 @@ class FrameGather:
     device_gather() -> (rank 0) read_frame_into(pinned_host_tensor), or the pipelined read_frame_async(pinned) ...
     wait_frame(), or device_gather(release=True) when the frame stays on the device."""
 
-    def __init__(self, tracer, rank: int, world: int, device, stream, mode: str = "peer", band_rows: int = 8, fused_signal: bool = False):
+    def __init__(self, tracer, rank: int, world: int, device, stream, mode: str = "peer", band_rows: int = 8, fused_signal: bool = False, fence: str = "kernel"):
         import torch
         import torch.distributed as dist
 
@@ -181,6 +181,10 @@ class FrameGather:
         # the separate launch — every warp has to fence its peer stores at system scope before it checks out, which costs more than
         # the launch it saves — so the separate launch is the default.
         self.fused_signal = fused_signal and mode == "peer"
+        # mode "peer", fence "memops": the per-frame fence is made of stream memory operations (rt_stream_write_value /
+        # rt_stream_wait_value: the stream's front end stores / polls the flag, no kernel launch) instead of the flag kernels; no timeout
+        self.fence = fence if mode == "peer" else "kernel"
+        assert self.fence in ("kernel", "memops")
         self.buffer_copy_event = [None, None]  # rank 0: completion event of the last host copy that read each frame buffer
         if mode in ("peer", "peer_allreduce"):
             handles = [None, None, None]
@@ -236,7 +240,20 @@ class FrameGather:
             if self.mode == "peer":
                 k = self.frame_no
                 fused = self.fused_signal  # flags[rank] = k + 1 was published by the trace kernel itself
-                if self.rank == 0:
+                if self.fence == "memops":
+                    t = self.tracer
+                    if self.rank == 0:
+                        for r in range(1, self.world):  # (rank 0's own stores are ordered by its stream)
+                            t.stream_wait_value(self.flags + 4 * r, k + 1)
+                        if release:
+                            t.stream_write_value(self.flags + 4 * self.world, k + 1)
+                            self.consumed_signalled = k + 1
+                    else:
+                        if not fused:
+                            t.stream_write_value(self.flags + 4 * self.rank, k + 1)
+                        if k >= 1:
+                            t.stream_wait_value(self.flags + 4 * self.world, k)
+                elif self.rank == 0:
                     # one launch: (my stores of frame k are done ->) wait for everybody's -> (optionally) frame k is read
                     self.tracer.wait_flags(self.flags, self.world, k + 1, -1 if fused else 0, self.world if release else -1)
                     self.kernels += 1

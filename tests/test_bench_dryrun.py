@@ -178,7 +178,7 @@ class FakeGather:
     last = None
     all = []
 
-    def __init__(self, tracer, rank, world, dev, stream, mode="peer", fused_signal=False):
+    def __init__(self, tracer, rank, world, dev, stream, mode="peer", fused_signal=False, fence="kernel"):
         self.kernels, self.calls, self.mode, self.fused = 0, [], mode, fused_signal
         FakeGather.last = self
         FakeGather.all.append(self)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, mode, result_path, fused=False):
+def _worker(rank, world, port, mode, result_path, fused=False, fence="kernel"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -27,7 +27,7 @@ def _worker(rank, world, port, mode, result_path, fused=False):
     t = rt.RayTracer.from_scene(scene, rt.Config(w, h, device=rank, shard_index=rank, shard_count=world, band_rows=8, **cfg))
     stream = torch.cuda.Stream(device=dev)
     t.set_stream(stream.cuda_stream)
-    g = FrameGather(t, rank, world, dev, stream, mode=mode, fused_signal=fused)
+    g = FrameGather(t, rank, world, dev, stream, mode=mode, fused_signal=fused, fence=fence)
     host = torch.empty(w * h, dtype=torch.int32).pin_memory()
     ok = True
     for frame in range(5):  # alternates between the two peer buffers
@@ -59,9 +59,11 @@ def _worker(rank, world, port, mode, result_path, fused=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,fused", [("peer", False), ("peer", True), ("peer_allreduce", False), ("nccl", False)])
-def test_two_rank_gather(tmp_path, mode, fused):
-    """mode "peer" twice: the frame-done signal published by the trace kernel's last warp out (rt_set_done_signal), and as a launch of its own"""
+@pytest.mark.parametrize("mode,fused,fence", [("peer", False, "kernel"), ("peer", True, "kernel"), ("peer", False, "memops"), ("peer_allreduce", False, "kernel"),
+                                              ("nccl", False, "kernel")])
+def test_two_rank_gather(tmp_path, mode, fused, fence):
+    """mode "peer" three times: the frame-done signal as a launch of its own, published by the trace kernel's last warp out
+    (rt_set_done_signal), and the whole fence made of stream memory operations (no kernel launch)"""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -69,7 +71,7 @@ def test_two_rank_gather(tmp_path, mode, fused):
     import torch.multiprocessing as mp
 
     result = tmp_path / "r.txt"
-    mp.spawn(_worker, args=(2, 29600 + os.getpid() % 1000, mode, str(result), fused), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29600 + os.getpid() % 1000, mode, str(result), fused, fence), nprocs=2, join=True)
     assert result.read_text() == "True"
 
 
