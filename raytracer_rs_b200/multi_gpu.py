@@ -70,7 +70,13 @@ class HostFrameGather:
         self.nbytes = self.W * self.H * 4
         total = 2 * self.nbytes + 4096  # two frames + one page of flags (flags[0..world): arrived, flags[world]: consumed)
         if rank == 0:
-            self.shm = shared_memory.SharedMemory(name=name, create=True, size=total)  # a fresh segment is zero-filled: all flags start at 0
+            try:
+                self.shm = shared_memory.SharedMemory(name=name, create=True, size=total)  # a fresh segment is zero-filled: all flags start at 0
+            except FileExistsError:  # left behind by a run that died: take it over
+                stale = shared_memory.SharedMemory(name=name, create=False)
+                stale.close()
+                stale.unlink()
+                self.shm = shared_memory.SharedMemory(name=name, create=True, size=total)
         dist.barrier()
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name, create=False)
@@ -183,6 +189,9 @@ class FrameGather:
         self.fused_signal = fused_signal and mode == "peer"
         # mode "peer", fence "memops": the per-frame fence is made of stream memory operations (rt_stream_write_value /
         # rt_stream_wait_value: the stream's front end stores / polls the flag, no kernel launch) instead of the flag kernels; no timeout
+        # (measured at 2 GPUs, 100 steps: 0.1601 ms per step against 0.1629 with the flag kernels; with only the signals as stream
+        # writes and the waits still kernels: 0.1627 — what the memory operations save is rank 0's wait launch. The flag kernels stay
+        # the default because their waits are bounded.)
         self.fence = fence if mode == "peer" else "kernel"
         assert self.fence in ("kernel", "memops")
         self.buffer_copy_event = [None, None]  # rank 0: completion event of the last host copy that read each frame buffer
