@@ -158,6 +158,7 @@ def test_peer_fence_protocol_calls():
     frame k+1 reuses its buffer); rank 0 signals its own slot, waits for all slots and, when the frame stays on the device,
     publishes "read" in that launch too. Fused signal (optional): begin_frame arms the trace call to publish flags[r] = k + 1
     from its last warp out (rt_set_done_signal), the fence launch only waits (rank r != 0: nothing at all for frame 0).
+    Fence "memops": the same protocol as stream memory operations (write_value / wait_value), no kernel launch.
     The store target alternates between the two frame buffers; rank 0's render stream waits for the host copy that last
     read a buffer before its own kernel stores into it again."""
     import contextlib
@@ -165,9 +166,11 @@ def test_peer_fence_protocol_calls():
 
     from raytracer_rs_b200.multi_gpu import FrameGather
 
-    def gather(rank, world, fused):
+    def gather(rank, world, fused, fence="kernel"):
         calls = []
         tracer = types.SimpleNamespace(
+            stream_write_value=lambda p, v: calls.append(("write_value", p, v)),
+            stream_wait_value=lambda p, v: calls.append(("wait_value", p, v)),
             signal_flag=lambda p, v: calls.append(("signal", p, v)),
             signal_then_wait=lambda p, v, q, t: calls.append(("signal_then_wait", p, v, q, t)),
             wait_flags=lambda p, n, t, s=-1, r=-1: calls.append(("wait", p, n, t, s, r)),
@@ -178,7 +181,7 @@ def test_peer_fence_protocol_calls():
         g.dist, g.tracer, g.rank, g.world, g.mode = None, tracer, rank, world, "peer"
         g.stream = types.SimpleNamespace(wait_event=lambda ev: calls.append(("render_waits_for_copy", ev)))
         g.flags, g.targets, g.frame_no, g.kernels, g.consumed_signalled = 1000, [0xA000, 0xB000], 0, 0, 0
-        g.fused_signal, g.buffer_copy_event = fused, [None, None]
+        g.fused_signal, g.buffer_copy_event, g.fence = fused, [None, None], fence
         return g, calls
 
     g, calls = gather(rank=2, world=4, fused=False)
@@ -215,6 +218,22 @@ def test_peer_fence_protocol_calls():
     assert calls == [("arm", 1000, 1), ("wait", 1000, 4, 1, -1, 4), ("target", 0xB000),
                      ("arm", 1000, 2), ("wait", 1000, 4, 2, -1, -1), ("target", 0xA000), ("render_waits_for_copy", "copy-of-buffer-0")]
     assert g.buffer_copy_event == [None, None] and g.kernels == 2
+
+    # the same fence made of stream memory operations: no kernel at all
+    g, calls = gather(rank=2, world=4, fused=False, fence="memops")
+    for _ in range(3):
+        g.begin_frame()
+        g.device_gather()
+    assert calls == [("write_value", 1008, 1), ("target", 0xB000),
+                     ("write_value", 1008, 2), ("wait_value", 1016, 1), ("target", 0xA000),
+                     ("write_value", 1008, 3), ("wait_value", 1016, 2), ("target", 0xB000)]
+    assert g.kernels == 0
+    g, calls = gather(rank=0, world=3, fused=False, fence="memops")
+    g.device_gather(release=True)
+    g.device_gather()
+    assert calls == [("wait_value", 1004, 1), ("wait_value", 1008, 1), ("write_value", 1012, 1), ("target", 0xB000),
+                     ("wait_value", 1004, 2), ("wait_value", 1008, 2), ("target", 0xA000)]
+    assert g.consumed_signalled == 1 and g.kernels == 0
 
 
 def _host_gather_worker(rank, world, port, w, h, result_path):
