@@ -311,11 +311,10 @@ uint32_t rt_launch_param_bytes(void);
    i.e. when the launch cannot fill the GPU). */
 #define RT_TUNE_MIN_SCHEDULE_TILES 11
 #define RT_TUNE_MAX_SPLIT_LEVEL 12
-/* RT_TUNE_BOUNCE_STREAM: every level of the bounce wavefront as a ray stream on the binary BVH — bounce rays and the shadow rays of
-   their hits share the lanes of a warp, and lanes whose ray ended are refilled RT_TUNE_STREAM_REFILL (1..32, default 16) at a time —
-   or in the lockstep form (one kernel traces 32 bounce rays per warp, a second shades the compacted hits). 1 always the stream,
-   0 never, 2 (default) the stream for trees of 4096 nodes and more (where rays are long and the tree outgrows L1), lockstep below.
-   Same rays, same film. Other structures always use the lockstep form. */
+/* RT_TUNE_BOUNCE_STREAM: 1 (default) every level of the bounce wavefront runs as a ray stream on the binary BVH — bounce rays and the
+   shadow rays of their hits share the lanes of a warp, and lanes whose ray ended are refilled RT_TUNE_STREAM_REFILL (1..32, default
+   16) at a time; 0 the lockstep form (one kernel traces 32 bounce rays per warp, a second shades the compacted hits). Same rays, same
+   film. Other structures always use the lockstep form. */
 #define RT_TUNE_BOUNCE_STREAM 13
 #define RT_TUNE_STREAM_REFILL 14
 /* RT_TUNE_STREAM_MIN_INNER: the ray-stream kernel leaves its inner-node loop when fewer lanes than this are still descending while

@@ -1115,13 +1115,16 @@ __device__ __forceinline__ uint32_t wf_append(unsigned int* counter) {
     return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
 }
 __device__ __forceinline__ void wf_store_node(const TraceParams& P, uint32_t level, uint32_t slot, const V3& hp, uint32_t pixel, const V3& nrm,
-                                              uint32_t path, float sr, float sg, float sb, uint32_t parent, uint32_t k) {
+                                              uint32_t path, float sr, float sg, float sb, uint32_t parent, uint32_t k, uint32_t sample) {
     const WfLevel& L = P.wf[level];
     if (slot >= L.cap) return;  // cannot happen: capacities are worst case
     float4* rec = L.rec + kWfRecWords * (size_t)slot;
     rec[0] = make_float4(hp.x, hp.y, hp.z, __uint_as_float(pixel));
     rec[1] = make_float4(nrm.x, nrm.y, nrm.z, __uint_as_float(path));
     rec[2] = make_float4(sr, sg, sb, __uint_as_float(parent | (k << 28)));
+    // the sample number of the pixel (its film count when the frame began): the bounce rays of this node hash it, and reading it
+    // here saves them a dependent fetch of the film record
+    rec[3] = make_float4(__uint_as_float(sample), 0.f, 0.f, 0.f);
     for (uint32_t c = 0; c < 3u * L.n_children; ++c) L.child_r[(size_t)slot * 3u * L.n_children + c] = 0.0f;  // RGB::black
 }
 
@@ -1168,7 +1171,7 @@ __device__ __forceinline__ void trace_pixel_radiance(const TraceParams& P, uint3
             V3 nrm;
             shade_hit<ACCEL, WW>(P, o, d, hit, &nrm, &cr, &cg, &cb, cnt);
             const uint32_t slot = wf_append(&P.wf_counts[0]);
-            wf_store_node(P, 0u, slot, vadd(o, vscale(d, hit.t)), idx, nrm, 0u, cr, cg, cb, 0u, 0u);
+            wf_store_node(P, 0u, slot, vadd(o, vscale(d, hit.t)), idx, nrm, 0u, cr, cg, cb, 0u, 0u, nsamp);
             P.primary_ids[idx] = id;
             return;
         } else if (BOUNCE == 1) {
@@ -2221,7 +2224,8 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ T
         float cr, cg, cb;
         shade_hit<ACCEL, 1>(P, o2, rd, h, &nrm, &cr, &cg, &cb, cnt);
         const uint32_t pk = __float_as_uint(r3.x);
-        wf_store_node(P, l, i, vadd(o2, vscale(rd, h.t)), __float_as_uint(r0.w), nrm, __float_as_uint(r1.w), cr, cg, cb, pk & 0x0fffffffu, pk >> 28);
+        wf_store_node(P, l, i, vadd(o2, vscale(rd, h.t)), __float_as_uint(r0.w), nrm, __float_as_uint(r1.w), cr, cg, cb, pk & 0x0fffffffu, pk >> 28,
+                      __float_as_uint(P.film_sum[__float_as_uint(r0.w)].w));
     }
     flush_counters(P, cnt, lane);
 }
@@ -2246,27 +2250,34 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ T
 //     2 rays from a camera-ray hit, 1 from their hits) a lane that completes a node continues IN PLACE with that node's bounce ray,
 //     so the whole bounce tree of a frame is one launch: no second level launch with its own ramp-up and tail, no job queue for the
 //     deeper levels.
-// The state that outlives a ray (hit point, bounce direction, barycentrics, partial radiance) lives in shared memory, 17
+// The state that outlives a ray (hit point, bounce direction, barycentrics, partial radiance) lives in shared memory, 18
 // words per lane. Every float operation is the one shade_hit / wf_bounce_kernel perform, in the same order, so the film is
 // bit-identical to the lockstep wavefront and to the depth-first walk.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kWsWords = 17;  // per-lane context words (see the enum below)
+constexpr int kWsWords = 18;  // per-lane context words (see the enum below)
 enum WsField { WS_HPX = 0, WS_HPY, WS_HPZ, WS_RDX, WS_RDY, WS_RDZ, WS_TRI, WS_U, WS_V, WS_LIGHT, WS_CR, WS_CG, WS_CB, WS_PIXEL, WS_PATH, WS_PARENT,
-               WS_LEVEL /* level of the node the lane's bounce ray left from; its hit becomes a node of the next level */ };
+               WS_LEVEL /* level of the node the lane's bounce ray left from; its hit becomes a node of the next level */,
+               WS_SAMPLE /* sample number of the pixel */ };
 enum WsState { WS_IDLE = 0, WS_BOUNCE = 1, WS_SHADOW = 2 };
 
 // The bounce ray of job j = (node, k) of level P.wf_level: same hash / table walk as radiance_with_bounces (mod.rs:186-189), so the same ray.
 // Bounce direction of the sub ray `sub_path` of a hit: the first entry of the unit-vector table, from a hashed start index on, that lies in
 // the hemisphere of the normal (normalized_vec_pseudo / normalized_vec_lookup, mod.rs:186-189) — as in radiance_with_bounces, so the same ray.
-__device__ __forceinline__ V3 wf_bounce_dir(const TraceParams& P, const V3& normal, uint32_t pixel, uint32_t sub_path) {
-    const uint32_t sample = __float_as_uint(P.film_sum[pixel].w);  // the film is not touched before the last combine
+__device__ __forceinline__ V3 wf_bounce_dir(const TraceParams& P, const V3& normal, uint32_t pixel, uint32_t sample, uint32_t sub_path) {
     uint32_t idx = (uint32_t)(((unsigned long long)hash4(P.seed ^ 0xb0c0ffeeU, pixel, sample, sub_path) * 65535ull) >> 32);
-    V3 rd = {P.sample_table[3 * idx], P.sample_table[3 * idx + 1], P.sample_table[3 * idx + 2]};
-    while (vdot(rd, normal) <= 0.0f) {
-        idx = (idx + 1u) % 65535u;
-        rd = V3{P.sample_table[3 * idx], P.sample_table[3 * idx + 1], P.sample_table[3 * idx + 2]};
+    // The walk takes the first table entry from idx on that lies in the hemisphere; half of the entries do, so it usually ends at the
+    // first or second. Three consecutive candidates are fetched per round trip (they share one or two lines): the service phase of
+    // the ray stream runs with a few lanes, and a chain of dependent fetches there stalls the lanes that are traversing.
+    for (;;) {
+        const uint32_t i1 = (idx + 1u) % 65535u, i2 = (i1 + 1u) % 65535u;
+        const V3 a = {P.sample_table[3 * idx], P.sample_table[3 * idx + 1], P.sample_table[3 * idx + 2]};
+        const V3 b = {P.sample_table[3 * i1], P.sample_table[3 * i1 + 1], P.sample_table[3 * i1 + 2]};
+        const V3 c = {P.sample_table[3 * i2], P.sample_table[3 * i2 + 1], P.sample_table[3 * i2 + 2]};
+        if (vdot(a, normal) > 0.0f) return a;
+        if (vdot(b, normal) > 0.0f) return b;
+        if (vdot(c, normal) > 0.0f) return c;
+        idx = (i2 + 1u) % 65535u;
     }
-    return rd;
 }
 
 template <int MIN_BLOCKS>
@@ -2282,9 +2293,29 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) wf_stream_kernel(const __grid
     LaneCounters cnt;
     bool queue_empty = false;
 
-    // the ray this lane traverses
+    // the ray this lane traverses. Its stack: the first RT_STREAM_STACK_SMEM entries in shared memory, deeper ones in local memory.
+    // With unrelated rays in the lanes the L1 is full of node lines that are used once, and the stack lines of 32 warps (a warp's
+    // entry i is 256 bytes) do not survive between a push and its pop: in the first version of this kernel the two pop loops,
+    // running at 2-4 lanes, collected 16 % of all stall samples waiting for local-memory loads that had gone to L2 — as much
+    // as the node fetches themselves (profiles/r2_bounce_stream_blocks.txt).
+#ifndef RT_STREAM_STACK_SMEM
+#define RT_STREAM_STACK_SMEM 8
+#endif
+#if RT_STREAM_STACK_SMEM > 0
+    __shared__ int2 s_stack[RT_STREAM_STACK_SMEM][256];
+    int2 l_stack[kBvhStack > RT_STREAM_STACK_SMEM ? kBvhStack - RT_STREAM_STACK_SMEM : 1];
+#define WS_STK_ST(i, v)                                           \
+    {                                                             \
+        if ((i) < RT_STREAM_STACK_SMEM) s_stack[(i)][tid] = (v);  \
+        else l_stack[(i) - RT_STREAM_STACK_SMEM] = (v);           \
+    }
+#define WS_STK_LD(i) ((i) < RT_STREAM_STACK_SMEM ? s_stack[(i)][tid] : l_stack[(i) - RT_STREAM_STACK_SMEM])
+#else
     int2 stack[kBvhStack];
-    stack[0] = make_int2(kSentinel, __float_as_int(-FLT_MAX));
+#define WS_STK_ST(i, v) stack[(i)] = (v)
+#define WS_STK_LD(i) stack[(i)]
+#endif
+    WS_STK_ST(0, make_int2(kSentinel, __float_as_int(-FLT_MAX)));
     int state = WS_IDLE, cur = kSentinel, sp = 1;
     V3 o = {0.f, 0.f, 0.f}, d = {0.f, 0.f, 0.f};
     float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f, early_t = -1.0f;
@@ -2441,12 +2472,12 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) wf_stream_kernel(const __grid
                 const V3 hp = {__uint_as_float(ctx[WS_HPX][tid]), __uint_as_float(ctx[WS_HPY][tid]), __uint_as_float(ctx[WS_HPZ][tid])};
                 const uint32_t pk = ctx[WS_PARENT][tid], pixel = ctx[WS_PIXEL][tid], path = ctx[WS_PATH][tid];
                 wf_store_node(P, emit, slot, hp, pixel, nrm, path, __uint_as_float(ctx[WS_CR][tid]), __uint_as_float(ctx[WS_CG][tid]),
-                              __uint_as_float(ctx[WS_CB][tid]), pk & 0x0fffffffu, pk >> 28);
+                              __uint_as_float(ctx[WS_CB][tid]), pk & 0x0fffffffu, pk >> 28, ctx[WS_SAMPLE][tid]);
                 state = WS_IDLE;
                 if (P.wf_chain && P.wf[emit].n_children == 1u && slot < P.wf[emit].cap) {
                     // the node's only bounce ray (k = 0) continues in this lane
                     const uint32_t sub_path = path * 31u + 1u;
-                    const V3 rd = wf_bounce_dir(P, nrm, pixel, sub_path);
+                    const V3 rd = wf_bounce_dir(P, nrm, pixel, ctx[WS_SAMPLE][tid], sub_path);
                     cnt.bounce_rays += 1;
                     ctx[WS_PATH][tid] = sub_path;
                     ctx[WS_PARENT][tid] = slot;  // | (0 << 28)
@@ -2468,10 +2499,12 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) wf_stream_kernel(const __grid
                 if (state == WS_IDLE && jj < total) {  // job jj = (node, k) of level l
                     const uint32_t parent = jj / nch, k = jj - parent * nch;
                     const float4 r0 = L.rec[kWfRecWords * (size_t)parent], r1 = L.rec[kWfRecWords * (size_t)parent + 1];
+                    const uint32_t sample = __float_as_uint(L.rec[kWfRecWords * (size_t)parent + 3].x);
                     const uint32_t pixel = __float_as_uint(r0.w), sub_path = __float_as_uint(r1.w) * 31u + k + 1u;
-                    const V3 rd = wf_bounce_dir(P, V3{r1.x, r1.y, r1.z}, pixel, sub_path);
+                    const V3 rd = wf_bounce_dir(P, V3{r1.x, r1.y, r1.z}, pixel, sample, sub_path);
                     cnt.bounce_rays += 1;
                     ctx[WS_PIXEL][tid] = pixel;
+                    ctx[WS_SAMPLE][tid] = sample;
                     ctx[WS_PATH][tid] = sub_path;
                     ctx[WS_PARENT][tid] = parent | (k << 28);
                     ctx[WS_LEVEL][tid] = l;
@@ -2509,7 +2542,7 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) wf_stream_kernel(const __grid
                 const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
                 const bool go1 = h1 && (!h0 || n1 < n0);
                 if (h0 && h1) {
-                    stack[sp] = make_int2(go1 ? c0 : c1, __float_as_int(go1 ? n0 : n1));
+                    WS_STK_ST(sp, make_int2(go1 ? c0 : c1, __float_as_int(go1 ? n0 : n1)));
                     ++sp;
                 }
                 if (h0 || h1) {
@@ -2517,7 +2550,8 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) wf_stream_kernel(const __grid
                 } else {
                     int2 e;
                     do {
-                        e = stack[--sp];
+                        --sp;
+                        e = WS_STK_LD(sp);
                     } while (__int_as_float(e.y) > best.t);
                     cur = e.x;
                 }
@@ -2548,13 +2582,16 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) wf_stream_kernel(const __grid
             } else {
                 int2 e;
                 do {
-                    e = stack[--sp];
+                    --sp;
+                    e = WS_STK_LD(sp);
                 } while (__int_as_float(e.y) > best.t);
                 cur = e.x;
             }
         }
         __syncwarp();
     }
+#undef WS_STK_ST
+#undef WS_STK_LD
     flush_counters(P, cnt, lane);
 }
 

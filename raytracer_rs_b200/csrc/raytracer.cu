@@ -120,7 +120,7 @@ struct rt_raytracer {
     DevBuf<float> d_variance;  // rt_get_estimated_variances staging (allocated on first use)
     int multi_sample_launch = 1;      // RT_TUNE_MULTI_SAMPLE_LAUNCH: 0 one launch per sample, 1 sample lanes where they apply, else planes, 2 planes
     bool bounce_wavefront = true;     // RT_TUNE_BOUNCE_WAVEFRONT
-    int bounce_stream = 2;            // RT_TUNE_BOUNCE_STREAM: wavefront levels as a ray stream (binary BVH): 0 never, 1 always, 2 for trees of >= 4096 nodes
+    bool bounce_stream = true;        // RT_TUNE_BOUNCE_STREAM: wavefront levels as a ray stream (binary BVH) instead of lockstep warps
     bool stream_chain = true;         // RT_TUNE_STREAM_CHAIN
     int stream_blocks = 4;            // RT_TUNE_STREAM_BLOCKS: resident blocks per SM the ray-stream kernel is compiled for (3, 4, 5)
     int wf_blocks_cap = 0;            // RT_TUNE_WF_BLOCKS: cap on the resident blocks per SM of the lockstep wavefront kernels (0 = as many as fit)
@@ -799,11 +799,7 @@ struct rt_raytracer {
         if (blocks_per_sm[a][0] == 0) blocks_per_sm[a][0] = persistent_blocks_per_sm(a, 0);
         RT_CUDA_RET(launch_trace(p, a, 1, blocks_per_sm[a][0] * num_sms, stream));
         const int wf_blocks = num_sms * 3;  // 80 registers: three 256-thread blocks per SM
-        // ray-stream kernel (binary BVH): bounce + shadow rays share the lanes. It pays when the tree outgrows L1 and rays are long
-        // (thai2: 12 549 nodes, 0.867 vs 0.920 ms per frame); on the 609-triangle scenes, whose trees are L1 resident, the lockstep
-        // kernels at full occupancy are 4-5 % faster — RT_TUNE_BOUNCE_STREAM 2 (default) decides by the size of the tree
-        const size_t tree_nodes = cfg.accel == RT_ACCEL_LBVH ? (size_t)lbvh_nodes : bvh.nodes.size();
-        const bool stream_levels = a == 1 && (bounce_stream == 1 || (bounce_stream == 2 && tree_nodes >= 4096));
+        const bool stream_levels = bounce_stream && a == 1;  // ray-stream kernel (binary BVH): bounce + shadow rays share the lanes
         // every level from the second on sends at most one bounce ray per hit (the reference's RECURSIONS = 2, SUB_SPREAD = 1): the ray-stream
         // kernel chains them in place and ONE launch walks the whole bounce tree
         bool chain = stream_levels && stream_chain;
@@ -1714,8 +1710,8 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
         rt->bounce_wavefront = value != 0;
         return RT_OK;
     }
-    if (key == RT_TUNE_BOUNCE_STREAM && value >= 0 && value <= 2) {
-        rt->bounce_stream = value;
+    if (key == RT_TUNE_BOUNCE_STREAM && (value == 0 || value == 1)) {
+        rt->bounce_stream = value != 0;
         return RT_OK;
     }
     if (key == RT_TUNE_STREAM_REFILL && value >= 1 && value <= 32) {

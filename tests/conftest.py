@@ -59,6 +59,22 @@ def scenes():
     return get
 
 
+@pytest.fixture(scope="session")
+def ref_scenes():
+    """The same scenes through the INDEPENDENT numpy Collada reader (tests/collada_ref.py, written from the Rust loader's sources): what
+    the oracle is fed in the full-resolution parity tests, so that those tests do not share a loader with the product they check."""
+    from collada_ref import load_collada
+
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = load_collada(os.path.join(DATA, CONFIGS[name][0]))
+        return cache[name]
+
+    return get
+
+
 def channel_diff(a, b):
     """max per-channel |difference| between two packed 0xAARRGGBB frames"""
     import numpy as np

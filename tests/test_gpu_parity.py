@@ -40,14 +40,15 @@ def check_frame(tracer, oracle, exact_ids):
 
 
 @pytest.fixture(scope="module")
-def oracle_frames(scenes):
-    """Full-resolution pinned-mode oracle frames of the four BASELINE configurations (computed once, all host threads)."""
+def oracle_frames(ref_scenes):
+    """Full-resolution pinned-mode oracle frames of the four BASELINE configurations (computed once, all host threads). The oracle's
+    scene comes from the independent loader (tests/collada_ref.py), the GPU's from the product's: no common-mode loader."""
     cache = {}
 
     def get(name):
         if name not in cache:
             _, w, h = CONFIGS[name]
-            o = Oracle(scenes(name), w, h)
+            o = Oracle(ref_scenes(name), w, h)
             o.configure(recursions=0, jitter=JITTER_FIXED)
             o.trace_rows(0, h, 1, threads=0)
             cache[name] = o

@@ -14,3 +14,7 @@ build top128 "-DRT_TOP_SMEM=128"
 build top512 "-DRT_TOP_SMEM=512"
 build blocks4 "-DRT_PERSISTENT_MIN_BLOCKS=4"
 build stk8blocks4 "-DRT_STACK_SMEM=8 -DRT_PERSISTENT_MIN_BLOCKS=4"
+# ray-stream kernel: how much of the traversal stack lives in shared memory (default build: 8 entries)
+build streamstk0 "-DRT_STREAM_STACK_SMEM=0"
+build streamstk12 "-DRT_STREAM_STACK_SMEM=12"
+build streamstk16 "-DRT_STREAM_STACK_SMEM=16"
