@@ -112,8 +112,8 @@ class HostFrameGather:
         """enqueue: copy of this rank's rows of the frame just traced into the shared host frame, then the arrival flag"""
         torch, k = self.torch, self.frame_no
         self._mark_consumed()
-        while k >= 2 and int(self.flags[self.world]) < k - 1:  # the consumer still holds the host buffer of frame k-2
-            pass
+        if k >= 2:  # the consumer may still hold the host buffer of frame k-2
+            self._spin(lambda: int(self.flags[self.world]) >= k - 1, "rank 0 to release the host buffer of frame %d" % (k - 2))
         traced = torch.cuda.Event()
         traced.record(self.stream)
         self.copy_stream.wait_event(traced)
@@ -125,6 +125,18 @@ class HostFrameGather:
         done.record(self.copy_stream)
         self.copy_done[k & 1] = done
         self.frame_no += 1
+
+    def _spin(self, done, what: str, timeout_s: float = 30.0):
+        """busy-waits on a condition over the shared flags; a peer that died turns into an error instead of a hang"""
+        import time
+
+        n, t0 = 0, None
+        while not done():
+            n += 1
+            if n & 0x3FF == 0:
+                t0 = t0 or time.perf_counter()
+                if time.perf_counter() - t0 > timeout_s:
+                    raise RuntimeError("HostFrameGather (rank %d): timed out after %.0f s waiting for %s" % (self.rank, timeout_s, what))
 
     def _mark_consumed(self):
         # rank 0: the frames handed out by the previous wait_frame are done with (the caller came back for more)
@@ -138,8 +150,7 @@ class HostFrameGather:
         target = self.frame_no - keep
         if target <= self.taken:
             return
-        while int(self.flags[: self.world].min()) < target:
-            pass
+        self._spin(lambda: int(self.flags[: self.world].min()) >= target, "the rows of frame %d from every rank" % (target - 1))
         self.taken = target
 
     def frame(self, k: int) -> np.ndarray:
