@@ -326,7 +326,7 @@ def main():
                          "and copied to the host over rank 0's link alone")
     ap.add_argument("--fence", default="kernel", choices=["kernel", "memops"],
                     help="N>1, --gather peer: per-frame fence made of flag kernels (bounded waits, default) or of stream memory operations "
-                         "(cuStreamWriteValue32 / cuStreamWaitValue32: no launch, no timeout; 0.1601 vs 0.1629 ms per step at 2 GPUs)")
+                         "(cuStreamWriteValue32 / cuStreamWaitValue32: no launch, no timeout; faster at 2 GPUs, slower at 8)")
     ap.add_argument("--fused-signal", action="store_true",
                     help="N>1, --gather peer: publish 'frame done' from the trace kernel's last warp out (rt_set_done_signal) instead of a signal launch "
                          "of its own; measured slower (every warp fences its peer stores at system scope), kept as an option")

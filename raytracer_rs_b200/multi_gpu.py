@@ -200,9 +200,9 @@ class FrameGather:
         self.fused_signal = fused_signal and mode == "peer"
         # mode "peer", fence "memops": the per-frame fence is made of stream memory operations (rt_stream_write_value /
         # rt_stream_wait_value: the stream's front end stores / polls the flag, no kernel launch) instead of the flag kernels; no timeout
-        # (measured at 2 GPUs, 100 steps: 0.1601 ms per step against 0.1629 with the flag kernels; with only the signals as stream
-        # writes and the waits still kernels: 0.1627 — what the memory operations save is rank 0's wait launch. The flag kernels stay
-        # the default because their waits are bounded.)
+        # (measured, 100 steps: 2 GPUs 0.1601 ms per step against 0.1629 with the flag kernels — what the memory operations save is
+        # rank 0's wait launch —, 4 GPUs 0.1575 vs 0.1570, 8 GPUs 0.1603 vs 0.1544: seven wait operations in a row cost more than one
+        # kernel polling eight flags. The flag kernels stay the default; their waits are also bounded.)
         self.fence = fence if mode == "peer" else "kernel"
         assert self.fence in ("kernel", "memops")
         self.buffer_copy_event = [None, None]  # rank 0: completion event of the last host copy that read each frame buffer
