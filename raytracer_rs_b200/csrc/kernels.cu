@@ -10,13 +10,21 @@
 // BVH box tests are allowed to use FMAs because the boxes are padded and only decide which triangles get tested.
 //
 // Kernels in this file:
-//   trace_shade_persistent_kernel<ACCEL, BOUNCE>  the default: persistent warps, cost-sorted 8x4 tile queue (variant 1);
-//                                                 <ACCEL, 0, true>: multi-sample launches, the lanes of an item hold the samples of a pixel
+//   trace_shade_persistent_kernel<ACCEL, BOUNCE, SAMPLE_LANES, LAP>
+//                                                 the default: persistent warps, cost-sorted 8x4 tile queue (variant 1), one launch per trace
+//                                                 call and nothing else (the last warp out resets queue and counters, warp_checkout);
+//                                                 SAMPLE_LANES: multi-sample launches, the lanes of an item hold the samples of a pixel;
+//                                                 LAP: traces a lap ahead of the band loop into a frame-aligned sample plane
 //   trace_shade_kernel<ACCEL, BOUNCE>             one thread per pixel (variant 0, kept for A/B runs)
 //   trace_shade_pool_kernel                       ray pool with shared-memory ray rings (variant 2)
-//   wf_bounce_kernel<ACCEL>, wf_shade_kernel<ACCEL>, wf_combine_kernel    bounce wavefront (RECURSIONS > 0)
-//   film_accumulate_kernel                        ordered accumulation of the sample planes of a multi-sample launch (odd spp)
-//   tile_sort_kernel                              heaviest-first order of the tile queue from last launch's tile costs
+//   wf_stream_kernel<MIN_BLOCKS>                  bounce wavefront (RECURSIONS > 0) on the binary BVH as a ray stream: lanes decoupled from
+//                                                 rays, hits shaded in place, bounce levels chained in one launch
+//   wf_bounce_kernel<ACCEL>, wf_shade_kernel<ACCEL>   the lockstep form of a bounce level (other structures)
+//   wf_combine_kernel                             bottom-up radiance combine of the bounce tree; level 0 adds to the film
+//   film_accumulate_kernel                        ordered accumulation of sample planes (odd spp) / commit of a band of the lap plane
+//   film_variance_kernel                          Film::get_estimated_variances (film.rs:50-67)
+//   tile_sort_kernel                              heaviest-first order of the tile queue from last launch's tile costs; heavy tiles
+//                                                 become 4, 8 or 16 items
 //   flag_signal_kernel, flag_signal_wait_kernel, flag_wait_kernel    cross-GPU frame fence of the fused peer-store gather
 //   film_clear_kernel, tonemap_pack_kernel, gather_rows_kernel
 // ACCEL: 0 exact octree, 1 binary BVH (host SAH or GPU LBVH), 2 compressed 8-wide BVH, 3 4-wide BVH.
@@ -2234,7 +2242,7 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const __grid_constant__ T
 // wf_stream_kernel: one bounce level of the wavefront as a RAY STREAM (binary BVH). It replaces wf_bounce_kernel +
 // wf_shade_kernel, whose warps traced 32 rays in lockstep: bounce rays (random hemisphere directions from surface points)
 // and the shadow rays of their hits differ in length by orders of magnitude, so a warp spent most of its instructions
-// waiting for its longest ray — 7.8 of 32 lanes active on thai2 (profiles/r2_bounce_before_ncu.txt). Here lanes are
+// waiting for its longest ray — 7.8 of 32 lanes active on thai2 (profiles/r2_ncu_summary.txt). Here lanes are
 // decoupled from rays:
 //   * every lane owns one ray in flight — a bounce ray of the level (job j = (node, k), same hash / table walk as
 //     radiance_with_bounces, so the same ray) or the shadow ray of the hit such a ray found;
