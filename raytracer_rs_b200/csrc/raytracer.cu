@@ -582,11 +582,14 @@ struct rt_raytracer {
         p->bvh_nodes = cfg.accel == RT_ACCEL_LBVH ? d_lbvh_nodes.p : d_bvh_nodes.p;
         p->bvh_tris = cfg.accel == RT_ACCEL_LBVH ? d_lbvh_tris.p : d_bvh_tris.p;
         p->bvh_top_count = cfg.accel == RT_ACCEL_LBVH ? 0u : (uint32_t)bvh.nodes.size();
+        p->bvh_node_lines = (uint32_t)(((cfg.accel == RT_ACCEL_LBVH ? d_lbvh_nodes.n : d_bvh_nodes.n) * sizeof(float4)) / 128u);
+        p->bvh_tri_lines = (uint32_t)(((cfg.accel == RT_ACCEL_LBVH ? d_lbvh_tris.n : d_bvh_tris.n) * sizeof(float4)) / 128u);
         p->bvh4_nodes = d_bvh4_nodes.p;
         p->bvh4_tris = d_bvh4_tris.p;
         p->cw_nodes = reinterpret_cast<const uint4*>(d_cw_nodes.p);
         p->cw_tris = d_cw_tris.p;
         p->tri_shade = d_tri_shade.p;
+        p->tri_shade_lines = (uint32_t)(d_tri_shade.n * sizeof(float4) / 128u);
         p->materials = d_materials.p;
         p->lights = d_lights.p;
         p->textures = d_textures.p;
@@ -689,6 +692,7 @@ struct rt_raytracer {
         p.pool_refill = (uint32_t)pool_refill;
         p.pool_min_inner = (uint32_t)pool_min_inner;
         p.counter_set = call_parity ? CNT_SET_B : CNT_SET_A;
+        p.film_prefetch = (uint32_t)film_prefetch;
         // the frame-done signal of a multi-GPU run rides on the last launch of the call when that launch is the one that finishes
         // the pixels (persistent / ray-pool kernel writing the film itself); otherwise trace_rows appends a signal launch
         const bool finishes_pixels = variant != 0 && !p.planes && !wavefront_applies(p);
@@ -852,6 +856,7 @@ struct rt_raytracer {
     bool lap_valid = false;
     uint32_t lap_next = 0;   // rows [lap_next, height) of the plane are traced and not yet committed
     int band_lookahead = 1;  // RT_TUNE_BAND_LOOKAHEAD
+    int film_prefetch = 3;   // RT_TUNE_FILM_PREFETCH
     uint64_t lap_builds = 0, lap_drops = 0;
     void drop_lap() {
         if (lap_valid) ++lap_drops;
@@ -1716,6 +1721,10 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     }
     if (key == RT_TUNE_STREAM_REFILL && value >= 1 && value <= 32) {
         rt->stream_refill = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_FILM_PREFETCH && value >= 0 && value <= 3) {
+        rt->film_prefetch = value;
         return RT_OK;
     }
     if (key == RT_TUNE_BAND_LOOKAHEAD && (value == 0 || value == 1)) {
