@@ -337,8 +337,9 @@ uint32_t rt_launch_param_bytes(void);
 /* RT_TUNE_FILM_PREFETCH: L2 prefetches of the trace kernel, for frames that start with a cold cache. 0 off; 1 a pixel's film sums
    are requested before its rays are traced (they are read when the sample is added, after the traversal; with a cold film the add
    otherwise waits for DRAM); 2 also the sums of squares of a pixel whose camera ray hit; 3 (default) the launch also requests the
-   whole binary BVH (nodes, triangles, shading records) up front instead of discovering it level by level, one DRAM round trip per
-   level of the first rays. Measured with the L2 flushed between frames: 0.1535 / 0.1500 / 0.1491 / 0.1473 ms per frame. */
+   whole binary BVH (nodes, triangles, shading records) and the tile queue up front instead of discovering them level by level, one
+   DRAM round trip per level of the first rays. Measured with the L2 flushed between frames: 0.1535 / 0.1500 / 0.1491 / 0.1464 ms
+   per frame (requesting the whole film up front as well: 0.1522 ms, not kept). */
 #define RT_TUNE_FILM_PREFETCH 20
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */

@@ -1347,11 +1347,13 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
     if (ACCEL == 1 && P.film_prefetch > 2u) {
         // a cold L2 (first frame, or a frame after other work went through the cache): ask for the whole tree at once instead of
         // discovering it level by level, one DRAM round trip per level of the first rays
-        const uint32_t nt = P.bvh_node_lines + P.bvh_tri_lines;
-        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt + P.tri_shade_lines; t += gridDim.x * blockDim.x) {
+        const uint32_t nt = P.bvh_node_lines + P.bvh_tri_lines, ns = nt + P.tri_shade_lines;
+        const uint32_t nq = P.tile_order ? n_tiles / 32u : 0u;  // the queue holds at least one entry per tile
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ns + nq; t += gridDim.x * blockDim.x) {
             const char* line = t < P.bvh_node_lines ? (const char*)P.bvh_nodes + 128ull * t
                                : t < nt             ? (const char*)P.bvh_tris + 128ull * (t - P.bvh_node_lines)
-                                                    : (const char*)P.tri_shade + 128ull * (t - nt);
+                               : t < ns             ? (const char*)P.tri_shade + 128ull * (t - nt)
+                                                    : (const char*)P.tile_order + 128ull * (t - ns);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
         }
     }

@@ -323,3 +323,23 @@ def test_band_lookahead_equals_band_by_band_tracing(scenes, name, w, h, rec):
     assert ta["primary"] == tb["primary"] and ta["shadow"] == tb["shadow"] and ta["bounce"] == tb["bounce"]
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("accel", [rt.ACCEL_BVH, rt.ACCEL_LBVH, rt.ACCEL_OCTREE])
+def test_l2_prefetch_levels_leave_the_film_alone(scenes, accel):
+    """RT_TUNE_FILM_PREFETCH 0..3 (film record, sums of squares of a hit, the whole tree + tile queue at the start of a launch) are
+    hints to the cache: film, ids, frame and ray counts are the same for every level, on a full frame (cost-sorted queue from the
+    second launch on) and on a wrapping band."""
+    w, h = 320, 184
+    s = scenes("thai2")
+    want = None
+    for level in (0, 1, 2, 3):
+        t = tracer_for(s, w, h, accel=accel, jitter=rt.JITTER_HASHED, seed=5)
+        t.set_tuning(20, level)
+        shadow = [t.trace_rows(0, h, 1)[1] for _ in range(3)]
+        shadow.append(t.trace_rows(h - 20, 50, 1)[1])
+        got = (t.film.pixel_datas().tobytes(), t.get_primary_ids().tobytes(), t.get_tonemapped_pixels().tobytes(), tuple(shadow))
+        t.close()
+        if want is None:
+            want = got
+        assert got == want, level
