@@ -1059,6 +1059,12 @@ __device__ __forceinline__ uint32_t udiv_magic(uint32_t n, uint32_t d, uint32_t 
     if (n - q * d >= d) ++q;
     return q;
 }
+// compact row c of a launch over consecutive image rows -> image row (first_row + c) mod height; the host keeps first_row < height and
+// c < n_rows <= height (a launch that wraps more than once goes through row_list), so one conditional subtraction is the modulo
+__device__ __forceinline__ uint32_t wrap_row(const TraceParams& P, uint32_t c) {
+    const uint32_t r = P.first_row + c;
+    return r >= P.cam.height ? r - P.cam.height : r;
+}
 __device__ __forceinline__ V3 camera_ray_dir(const TraceParams& P, uint32_t idx, uint32_t col, uint32_t nsamp) {
     const uint32_t W = P.cam.width, H = P.cam.height;
     float xi1 = 0.5f, xi2 = 0.5f;
@@ -1157,7 +1163,7 @@ __device__ __forceinline__ void trace_pixel_radiance(const TraceParams& P, uint3
         prow = crow - plane * P.plane_rows_padded;
         if (prow >= P.plane_rows) return;
     }
-    const uint32_t row = P.row_list ? P.row_list[prow] : (P.first_row + prow) % H;
+    const uint32_t row = P.row_list ? P.row_list[prow] : wrap_row(P, prow);
     const uint32_t idx = row * W + col;
     // the sample's number in the film only matters for the hashed sub-pixel offset and the bounce directions; the film
     // record itself is read when the sample is added (finish_pixel), not kept in registers through the traversal
@@ -1432,7 +1438,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         __syncwarp();
 #ifdef RT_DEBUG_STEP_COUNTS  // developer build only: (inner nodes visited | triangles tested << 16) instead of the primitive id
         if (mine) {
-            const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % P.cam.height;
+            const uint32_t row = P.row_list ? P.row_list[crow] : wrap_row(P, crow);
             P.primary_ids[row * P.cam.width + col] = min(g_dbg_nodes, 65535u) | (min(g_dbg_tris, 65535u) << 16);
         }
 #endif
@@ -1445,7 +1451,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
         }
 #ifdef RT_DEBUG_TILE_CLOCKS  // developer build only (tools/): per-item cycle count instead of the primitive id
         if (mine) {
-            const uint32_t row = P.row_list ? P.row_list[crow] : (P.first_row + crow) % P.cam.height;
+            const uint32_t row = P.row_list ? P.row_list[crow] : wrap_row(P, crow);
             P.primary_ids[row * P.cam.width + col] = (uint32_t)dt;
         }
 #endif
@@ -2038,7 +2044,7 @@ __global__ void film_variance_kernel(const float4* __restrict__ sum, const float
 // them — was measured slower: the per-item __threadfence + atomic costs more than this 15 us pass.)
 __device__ __forceinline__ void accumulate_pixel(const TraceParams& P, uint32_t col, uint32_t prow) {
     const uint32_t W = P.cam.width, H = P.cam.height;
-    const uint32_t row = P.row_list ? P.row_list[prow] : (P.first_row + prow) % H;
+    const uint32_t row = P.row_list ? P.row_list[prow] : wrap_row(P, prow);
     const uint32_t idx = row * W + col;
     float4 fs_ = P.film_sum[idx];
     uint32_t n = __float_as_uint(fs_.w), id = kNoHit;
@@ -2080,7 +2086,7 @@ __global__ void __launch_bounds__(256) film_accumulate_kernel(const __grid_const
         // commit of a band of the lap traced ahead (raytracer.cu, lap_commit): the rays of these samples are booked now, so that
         // the per-call counters and the running totals only ever hold rays whose samples are in the film
         uint32_t rays = 0u;
-        if (mine) rays = P.lap_rays[((P.first_row + prow) % P.cam.height) * P.cam.width + col];
+        if (mine) rays = P.lap_rays[wrap_row(P, prow) * P.cam.width + col];
         const uint32_t sh = __reduce_add_sync(0xffffffffu, rays & 255u), bo = __reduce_add_sync(0xffffffffu, rays >> 8);
         if ((threadIdx.x & 31u) == 0u) {
             unsigned long long* set = P.counters + P.counter_set;
