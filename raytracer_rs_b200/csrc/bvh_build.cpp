@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <numeric>
 
@@ -170,11 +171,233 @@ struct Builder {
     }
 };
 
+// ------------------------------------------------------------------------------------------------------
+// Insertion-based optimisation of the finished tree (after Bittner, Hapala, Havran: "Fast insertion-based optimization of
+// bounding volume hierarchies", CGF 2013): a subtree is cut out together with its parent (the sibling moves up), the position
+// where putting it back adds the least surface area is found by branch and bound over the whole tree, and the freed parent
+// node is re-used there. The position it came from is one of the candidates, so the summed area of the inner nodes — the
+// part of the SAH cost a fixed set of leaves leaves open — never grows. Leaves (and with them tri_order and the tie-break
+// order inside a leaf) are untouched; only which boxes a ray has to walk through changes, never the outcome of a triangle test.
+// ------------------------------------------------------------------------------------------------------
+struct Reinserter {
+    // ids [0, n_inner) are inner nodes, [n_inner, n_inner + n_leaf) leaves
+    std::vector<Aabb> box;
+    std::vector<int32_t> parent, kid[2];
+    std::vector<int32_t> leaf_ref, leaf_count;  // per leaf id - n_inner
+    int32_t n_inner = 0, root = 0;
+
+    static Aabb unite(const Aabb& a, const Aabb& b) {
+        Aabb r = a;
+        r.grow(b);
+        return r;
+    }
+    bool is_leaf(int32_t id) const { return id >= n_inner; }
+
+    void load(const FlatBvh& t) {
+        n_inner = (int32_t)t.nodes.size();
+        size_t leaves = 0;
+        for (const auto& n : t.nodes) leaves += (n.child[0] < 0) + (n.child[1] < 0);
+        const size_t total = (size_t)n_inner + leaves;
+        box.assign(total, Aabb());
+        parent.assign(total, -1);
+        kid[0].assign(total, -1);
+        kid[1].assign(total, -1);
+        int32_t next_leaf = n_inner;
+        for (int32_t i = 0; i < n_inner; ++i) {
+            const FlatBvh::Node& n = t.nodes[(size_t)i];
+            for (int k = 0; k < 2; ++k) {
+                int32_t id = n.child[k];
+                if (id < 0) {
+                    id = next_leaf++;
+                    leaf_ref.push_back(n.child[k]);
+                    leaf_count.push_back(n.count[k]);
+                }
+                kid[k][(size_t)i] = id;
+                parent[(size_t)id] = i;
+                for (int a = 0; a < 3; ++a) {  // the stored (padded) child box
+                    box[(size_t)id].lo[a] = n.lo[k][a];
+                    box[(size_t)id].hi[a] = n.hi[k][a];
+                }
+            }
+        }
+        box[0] = unite(box[(size_t)kid[0][0]], box[(size_t)kid[1][0]]);
+        root = 0;
+    }
+
+    double inner_area() const {
+        double s = 0.0;
+        for (int32_t i = 0; i < n_inner; ++i) s += box[(size_t)i].half_area();
+        return s;
+    }
+
+    void refit_up(int32_t id) {
+        while (id >= 0) {
+            box[(size_t)id] = unite(box[(size_t)kid[0][(size_t)id]], box[(size_t)kid[1][(size_t)id]]);
+            id = parent[(size_t)id];
+        }
+    }
+
+    // best node to pair `n` with (n is detached): minimises area(new parent) + the growth of every ancestor
+    int32_t find_target(int32_t n) {
+        const Aabb& nb = box[(size_t)n];
+        const float n_area = nb.half_area();
+        float best = FLT_MAX;
+        int32_t best_id = root;
+        std::vector<std::pair<float, int32_t>> heap;  // (induced cost, node), smallest induced cost first
+        auto cmp = [](const std::pair<float, int32_t>& a, const std::pair<float, int32_t>& b) { return a.first > b.first; };
+        heap.emplace_back(0.f, root);
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            const auto [induced, x] = heap.back();
+            heap.pop_back();
+            if (induced + n_area >= best) break;  // nothing cheaper is left
+            const float direct = unite(box[(size_t)x], nb).half_area();
+            const float total = induced + direct;
+            if (total < best) {
+                best = total;
+                best_id = x;
+            }
+            if (!is_leaf(x)) {
+                const float child_induced = total - box[(size_t)x].half_area();
+                if (child_induced + n_area < best)
+                    for (int k = 0; k < 2; ++k) {
+                        heap.emplace_back(child_induced, kid[k][(size_t)x]);
+                        std::push_heap(heap.begin(), heap.end(), cmp);
+                    }
+            }
+        }
+        return best_id;
+    }
+
+    // cut n (and its parent p) out, put it back at the best place; returns false when n cannot move (child of the root)
+    bool reinsert(int32_t n) {
+        const int32_t p = parent[(size_t)n];
+        if (p < 0 || p == root) return false;
+        const int32_t g = parent[(size_t)p];
+        const int side = kid[0][(size_t)p] == n ? 0 : 1;
+        const int32_t s = kid[1 - side][(size_t)p];
+        kid[kid[0][(size_t)g] == p ? 0 : 1][(size_t)g] = s;
+        parent[(size_t)s] = g;
+        refit_up(g);
+        const int32_t x = find_target(n);
+        const int32_t xp = parent[(size_t)x];
+        kid[0][(size_t)p] = x;
+        kid[1][(size_t)p] = n;
+        parent[(size_t)x] = p;
+        parent[(size_t)n] = p;
+        parent[(size_t)p] = xp;
+        if (xp < 0) root = p;
+        else kid[kid[0][(size_t)xp] == x ? 0 : 1][(size_t)xp] = p;
+        refit_up(p);
+        return true;
+    }
+
+    uint32_t depth_of(int32_t id) const {  // levels of inner nodes below and including id (iterative: the tree may be deep)
+        uint32_t deepest = 0;
+        std::vector<std::pair<int32_t, uint32_t>> st{{id, 0u}};
+        while (!st.empty()) {
+            const auto [x, d] = st.back();
+            st.pop_back();
+            if (is_leaf(x)) continue;
+            deepest = std::max(deepest, d);
+            st.emplace_back(kid[0][(size_t)x], d + 1);
+            st.emplace_back(kid[1][(size_t)x], d + 1);
+        }
+        return deepest;
+    }
+
+    void store(FlatBvh& t) const {
+        std::vector<int32_t> new_index((size_t)n_inner, -1), order;
+        order.reserve((size_t)n_inner);
+        order.push_back(root);
+        new_index[(size_t)root] = 0;
+        for (size_t q = 0; q < order.size(); ++q)
+            for (int k = 0; k < 2; ++k) {
+                const int32_t c = kid[k][(size_t)order[q]];
+                if (!is_leaf(c)) {
+                    new_index[(size_t)c] = (int32_t)order.size();
+                    order.push_back(c);
+                }
+            }
+        // triangle slots are handed out again in depth-first order, so that every subtree owns one contiguous run of tri_order (the 4- and
+        // 8-wide builders merge subtrees into leaves by run)
+        std::vector<int32_t> new_ref(leaf_ref.size(), 0);
+        std::vector<uint32_t> tri_order;
+        tri_order.reserve(t.tri_order.size());
+        {
+            std::vector<int32_t> st{root};
+            while (!st.empty()) {
+                const int32_t x = st.back();
+                st.pop_back();
+                if (is_leaf(x)) {
+                    const size_t l = (size_t)(x - n_inner);
+                    const uint32_t first = (uint32_t)~leaf_ref[l];
+                    new_ref[l] = ~(int32_t)tri_order.size();
+                    for (int32_t i = 0; i < leaf_count[l]; ++i) tri_order.push_back(t.tri_order[first + (uint32_t)i]);
+                } else {
+                    st.push_back(kid[1][(size_t)x]);
+                    st.push_back(kid[0][(size_t)x]);
+                }
+            }
+        }
+        std::vector<FlatBvh::Node> nodes(order.size());
+        for (size_t i = 0; i < order.size(); ++i) {
+            const int32_t id = order[i];
+            for (int k = 0; k < 2; ++k) {
+                const int32_t c = kid[k][(size_t)id];
+                for (int a = 0; a < 3; ++a) {
+                    nodes[i].lo[k][a] = box[(size_t)c].lo[a];
+                    nodes[i].hi[k][a] = box[(size_t)c].hi[a];
+                }
+                nodes[i].child[k] = is_leaf(c) ? new_ref[(size_t)(c - n_inner)] : new_index[(size_t)c];
+                nodes[i].count[k] = is_leaf(c) ? leaf_count[(size_t)(c - n_inner)] : 0;
+            }
+        }
+        t.nodes.swap(nodes);
+        t.tri_order.swap(tri_order);
+        t.depth = depth_of(root) + 1;  // the builder counts the level of the deepest leaf
+    }
+};
+
+// returns the summed inner-node area after / before (1 = nothing gained)
+float optimize_by_reinsertion(FlatBvh& t, int max_passes, uint32_t max_depth) {
+    if (t.nodes.size() < 3) return 1.f;
+    Reinserter r;
+    r.load(t);
+    const double before = r.inner_area();
+    double prev = before;
+    const int32_t total = (int32_t)r.box.size();
+    std::vector<int32_t> cand;
+    for (int pass = 0; pass < max_passes; ++pass) {
+        cand.clear();
+        for (int32_t id = 0; id < total; ++id)
+            if (id != r.root) cand.push_back(id);
+        // large nodes first: moving them changes the most area, and later (smaller) moves then see the improved upper tree
+        std::stable_sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) { return r.box[(size_t)a].half_area() > r.box[(size_t)b].half_area(); });
+        for (int32_t id : cand) r.reinsert(id);
+        const double now = r.inner_area();
+        if (now > prev * 0.998) {
+            prev = now;
+            break;
+        }
+        prev = now;
+    }
+    if (r.depth_of(r.root) + 1 > max_depth) return 1.f;  // deeper than the traversal stacks allow: keep the builder's tree
+    r.store(t);
+    return (float)(prev / before);
+}
+
 }  // namespace
 
 FlatBvh build_bvh(const HostScene& scene, uint32_t max_leaf_size) {
     Builder b(scene, std::max(1u, max_leaf_size));
     b.run();
+    int passes = 8;
+    if (const char* e = std::getenv("RT_BVH_REINSERT_PASSES")) passes = std::atoi(e);  // developer override, 0 = the builder's tree as is
+    if (passes > 0) {
+        const float ratio = optimize_by_reinsertion(b.out, passes, 40u);
+        if (std::getenv("RT_BVH_VERBOSE")) std::fprintf(stderr, "bvh: reinsertion left %.4f of the inner-node area, depth %u\n", ratio, b.out.depth);
+    }
     return std::move(b.out);
 }
 

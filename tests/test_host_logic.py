@@ -159,6 +159,55 @@ def test_bvh_invariants(scenes, name):
     assert seen.all()
 
 
+@pytest.mark.parametrize("name", ["ico2", "thai2"])
+def test_bvh_reinsertion_keeps_the_leaves_and_shrinks_the_inner_nodes(scenes, name, monkeypatch):
+    """The insertion-based optimisation pass of the host BVH (csrc/bvh_build.cpp, Reinserter) moves subtrees, nothing else: the same leaves
+    (as sets of triangle ids) as the builder's tree, every subtree still one contiguous run of tri_order (the wide builders rely on it), a
+    smaller summed area of the inner nodes, a depth the traversal stacks hold."""
+    s = scenes(name)
+
+    def export(passes):
+        monkeypatch.setenv("RT_BVH_REINSERT_PASSES", str(passes))
+        r = host_tracer(s)
+        out = r.bvh_export() + (r.bvh_stats(),)
+        r.close()
+        return out
+
+    def leaves_and_area(boxes, children, counts, order):
+        leaves, area = set(), 0.0
+        runs = {}
+
+        def walk(node):  # returns (first slot, count) of the subtree
+            first, total = None, 0
+            for k in range(2):
+                c, cnt = int(children[node, k]), int(counts[node, k])
+                if c >= 0:
+                    d = boxes[node, k, 1].astype(np.float64) - boxes[node, k, 0]
+                    nonlocal area
+                    area += d[0] * d[1] + d[1] * d[2] + d[2] * d[0]
+                    f, n = walk(c)
+                else:
+                    f, n = ~c, cnt
+                    leaves.add(tuple(order[f:f + n].tolist()))
+                assert first is None or f == first + total  # child 1's run follows child 0's
+                first = f if first is None else first
+                total += n
+            return first, total
+
+        import sys
+        sys.setrecursionlimit(10000)
+        assert walk(0) == (0, len(order))
+        return leaves, area
+
+    b0, c0, n0, o0, st0 = export(0)
+    b1, c1, n1, o1, st1 = export(8)
+    leaves0, area0 = leaves_and_area(b0, c0, n0, o0)
+    leaves1, area1 = leaves_and_area(b1, c1, n1, o1)
+    assert leaves0 == leaves1 and st0["nodes"] == st1["nodes"] and st0["leaves"] == st1["leaves"]
+    assert area1 < 0.99 * area0
+    assert st1["depth"] + 2 <= 48  # kBvhStack
+
+
 @pytest.mark.parametrize("name", ["4boxes", "ico2", "thai2"])
 def test_bvh4_invariants(scenes, name):
     """4-wide BVH (csrc/bvh4_build.cpp): every triangle in exactly one leaf, stored child boxes strictly contain their
