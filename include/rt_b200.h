@@ -341,6 +341,10 @@ uint32_t rt_launch_param_bytes(void);
    DRAM round trip per level of the first rays. Measured with the L2 flushed between frames: 0.1535 / 0.1500 / 0.1491 / 0.1464 ms
    per frame (requesting the whole film up front as well: 0.1522 ms, not kept). */
 #define RT_TUNE_FILM_PREFETCH 20
+/* RT_TUNE_FILM_PREFETCH_ROWS_MB (with RT_TUNE_FILM_PREFETCH = 3): launches that need a pixel's sample number before they can form its rays
+   (hashed sub-pixel offsets, bounce rays) read the film record first thing; such a launch requests the records of all its rows up front
+   when they are at most this many MB (default 48: a 1080p frame is 33 MB; 0 = never). */
+#define RT_TUNE_FILM_PREFETCH_ROWS_MB 21
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {

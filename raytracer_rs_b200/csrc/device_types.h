@@ -97,6 +97,7 @@ struct TraceParams {
     // a lap build traced; the build launch writes it instead of the ray counters, the commit launch books it
     uint16_t* lap_rays;
     uint32_t film_prefetch;      // RT_TUNE_FILM_PREFETCH: 1 = ask L2 for a pixel's film record before its rays are traced, 2 = also for the sums of squares of a hit, 3 = also the whole tree at the start of the launch
+    uint32_t film_prefetch_rows;  // 1 = the launch also requests the film records of all its rows up front (set by the host when they fit a share of L2)
     uint32_t bvh_node_lines, bvh_tri_lines, tri_shade_lines;  // 128-byte lines of bvh_nodes / bvh_tris / tri_shade (film_prefetch 3: the launch asks L2 for the whole tree first)
     uint32_t jitter_mode, seed;
     int32_t recursions;          // RECURSIONS (mod.rs:81); 0 = primary + shadow only

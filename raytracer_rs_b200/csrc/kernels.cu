@@ -1362,6 +1362,16 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
                                                     : (const char*)P.tile_order + 128ull * (t - ns);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
         }
+        // launches that need a pixel's sample number before they can form its rays (hashed sub-pixel offsets, bounce directions) read the
+        // film record first thing, with nothing to hide a cold read behind: ask for the records of all rows of the launch now
+        if ((P.jitter_mode == 1 || BOUNCE != 0) && !P.planes && P.film_prefetch_rows) {
+            const uint32_t per_row = (P.cam.width + 7u) / 8u;  // 128-byte lines of film_sum per image row
+            for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < per_row * P.n_rows; t += gridDim.x * blockDim.x) {
+                const uint32_t c = t / per_row;
+                const uint32_t row = P.row_list ? P.row_list[c] : wrap_row(P, c);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(P.film_sum + (size_t)row * P.cam.width) + 128ull * (t - c * per_row)));
+            }
+        }
     }
     LaneCounters cnt;
     // queue length: n_tiles in image order, or the item count the last tile_sort_kernel produced (heavy tiles are

@@ -693,6 +693,7 @@ struct rt_raytracer {
         p.pool_min_inner = (uint32_t)pool_min_inner;
         p.counter_set = call_parity ? CNT_SET_B : CNT_SET_A;
         p.film_prefetch = (uint32_t)film_prefetch;
+        p.film_prefetch_rows = film_prefetch >= 3 && (size_t)p.n_rows * cfg.width * 16u <= ((size_t)film_prefetch_rows_mb << 20) ? 1u : 0u;
         // the frame-done signal of a multi-GPU run rides on the last launch of the call when that launch is the one that finishes
         // the pixels (persistent / ray-pool kernel writing the film itself); otherwise trace_rows appends a signal launch
         const bool finishes_pixels = variant != 0 && !p.planes && !wavefront_applies(p);
@@ -857,6 +858,7 @@ struct rt_raytracer {
     uint32_t lap_next = 0;   // rows [lap_next, height) of the plane are traced and not yet committed
     int band_lookahead = 1;  // RT_TUNE_BAND_LOOKAHEAD
     int film_prefetch = 3;   // RT_TUNE_FILM_PREFETCH
+    int film_prefetch_rows_mb = 48;  // RT_TUNE_FILM_PREFETCH_ROWS_MB
     uint64_t lap_builds = 0, lap_drops = 0;
     void drop_lap() {
         if (lap_valid) ++lap_drops;
@@ -1721,6 +1723,10 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     }
     if (key == RT_TUNE_STREAM_REFILL && value >= 1 && value <= 32) {
         rt->stream_refill = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_FILM_PREFETCH_ROWS_MB && value >= 0 && value <= 1024) {
+        rt->film_prefetch_rows_mb = value;
         return RT_OK;
     }
     if (key == RT_TUNE_FILM_PREFETCH && value >= 0 && value <= 3) {
