@@ -345,6 +345,12 @@ uint32_t rt_launch_param_bytes(void);
    (hashed sub-pixel offsets, bounce rays) read the film record first thing; such a launch requests the records of all its rows up front
    when they are at most this many MB (default 48: a 1080p frame is 33 MB; 0 = never). */
 #define RT_TUNE_FILM_PREFETCH_ROWS_MB 21
+/* RT_TUNE_CAMERA_GRID (binary BVH structures, persistent kernel): camera rays all leave one point, so the sample plane of Camera::get_ray
+   is itself an index. 2..5 (default 3): the plane is cut into cells of 4..32 pixels, every cell lists the triangles whose projection (plus
+   a margin of one pixel) can reach it — rebuilt on the device whenever the camera, the resolution or the tree changes (three small
+   kernels and one 4-byte readback) — and a camera ray tests its cell's list instead of walking the tree (same Moller-Trumbore test, same
+   tie rule, same root-cube acceptance: the same hit). Shadow and bounce rays walk the tree. 0 = camera rays walk the tree as well. */
+#define RT_TUNE_CAMERA_GRID 22
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {

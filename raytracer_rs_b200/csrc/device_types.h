@@ -58,6 +58,11 @@ struct TraceParams {
     const float4* bvh_nodes;
     uint32_t bvh_top_count;  // nodes [0, bvh_top_count) of bvh_nodes are in breadth-first order (host SAH tree; 0 for the GPU-built tree)
     const float4* bvh_tris;
+    // perspective grid of the camera rays (pgrid_build.cu; instantiation ACCEL = 4 of the trace kernels): the (u, v) sample plane of
+    // Camera::get_ray cut into square cells of 2^pg_shift pixels, per cell the slots of bvh_tris whose projection can reach it
+    const uint32_t* pg_start;  // cell -> first entry of pg_tris; n_cells + 1 offsets
+    const uint32_t* pg_tris;
+    uint32_t pg_nx, pg_shift;
     const float4* bvh4_nodes;  // 4-wide BVH, 8 float4 per node (bvh4_build.cpp)
     const float4* bvh4_tris;
     const uint4* cw_nodes;   // compressed 8-wide BVH, 5 words per node

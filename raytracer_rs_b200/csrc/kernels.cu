@@ -852,7 +852,52 @@ __device__ __forceinline__ bool cwbvh_closest_hit(const TraceParams& P, const V3
     return true;
 }
 
-// ACCEL: 0 octree / 1 binary BVH / 2 compressed 8-wide BVH / 3 4-wide BVH; WW: 0 single-loop, 1 while-while
+// ------------------------------------------------------------------------------------------------------
+// Camera rays through the perspective grid (ACCEL = 4; pgrid_build.cu, after Hunt & Mark, "Ray-specialized acceleration structures
+// for ray tracing", 2008): all camera rays leave one point, so the sample plane of Camera::get_ray is itself an index — the pixel's
+// (u, v) names a cell, the cell lists every triangle whose projection (plus a margin of a pixel) can reach it, and the closest hit is
+// the minimum over that list of the same Moller-Trumbore test with the same tie rule and the same root-cube acceptance as
+// bvh_closest_hit. No tree is walked: a background pixel costs one empty list. Shadow and bounce rays of an ACCEL = 4 kernel go
+// through the binary BVH (they do not start at the eye).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pgrid_closest_hit(const TraceParams& P, const V3& o, const V3& d, uint32_t pu, uint32_t pv, HitRec* out) {
+    const uint32_t mask = __activemask();  // the lanes of a tile share one or two cells: walk the lists in step
+    const uint32_t cell = (pv >> P.pg_shift) * P.pg_nx + (pu >> P.pg_shift);
+    uint32_t i = __ldg(P.pg_start + cell);
+    const uint32_t end = __ldg(P.pg_start + cell + 1u);
+    HitRec best;
+    best.t = FLT_MAX;
+    best.u = 0.f;
+    best.v = 0.f;
+    best.tri = kNoHit;
+    while (__any_sync(mask, i < end)) {
+        if (i < end) {
+            const float4* tri = P.bvh_tris + 3 * (size_t)__ldg(P.pg_tris + i);
+            const float4 t0 = __ldg(tri), t1 = __ldg(tri + 1), t2 = __ldg(tri + 2);
+            float t, u, v;
+            if (moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) {
+                const uint32_t id = __float_as_uint(t2.y);
+                if (t < best.t || (t == best.t && id < best.tri)) {
+                    best.t = t;
+                    best.u = u;
+                    best.v = v;
+                    best.tri = id;
+                }
+            }
+            ++i;
+        }
+    }
+    if (best.tri == kNoHit) return false;
+    const V3 hp = vadd(o, vscale(d, best.t));
+    const bool outside = hp.x < P.root_lo[0] || hp.x > P.root_hi[0] || hp.y < P.root_lo[1] || hp.y > P.root_hi[1] || hp.z < P.root_lo[2] ||
+                         hp.z > P.root_hi[2];
+    if (outside) return false;
+    *out = best;
+    return true;
+}
+
+// ACCEL: 0 octree / 1 binary BVH / 2 compressed 8-wide BVH / 3 4-wide BVH / 4 binary BVH with the camera rays through the perspective grid
+// (closest_hit and shadow_blocked treat 4 as 1; trace_pixel_radiance sends the camera ray to pgrid_closest_hit); WW: 0 single-loop, 1 while-while
 template <int ACCEL, int WW>
 __device__ __forceinline__ bool closest_hit(const TraceParams& P, const V3& o, const V3& d, HitRec* out) {
     if (ACCEL == 0) return WW ? octree_closest_hit_ww(P, o, d, out) : octree_closest_hit(P, o, d, out);
@@ -1181,7 +1226,7 @@ __device__ __forceinline__ void trace_pixel_radiance(const TraceParams& P, uint3
         cnt.shadow_rays = 0u;
         cnt.bounce_rays = 0u;
     }
-    if (closest_hit<ACCEL, WW>(P, o, d, &hit)) {
+    if (ACCEL == 4 ? pgrid_closest_hit(P, o, d, col, udiv_magic(idx, P.cam.height, P.magic_h), &hit) : closest_hit<ACCEL, WW>(P, o, d, &hit)) {
         cnt.prim_hit += 1;
         id = hit.tri;
         if (P.film_prefetch > 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.film_sq + idx));  // a hit: the sums of squares will be touched too
@@ -1350,7 +1395,7 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
     // share pixels (finish_sample_lanes). Any 8 consecutive lanes hold whole pixels, which the heavy-item split relies on.
     const uint32_t tiles_x = SAMPLE_LANES ? P.items_x : (P.cam.width + 7u) / 8u;
     const uint32_t n_tiles = SAMPLE_LANES ? P.items_x * P.items_y : tiles_x * ((P.n_rows + 3u) / 4u);
-    if (ACCEL == 1 && P.film_prefetch > 2u) {
+    if ((ACCEL == 1 || ACCEL == 4) && P.film_prefetch > 2u) {
         // a cold L2 (first frame, or a frame after other work went through the cache): ask for the whole tree at once instead of
         // discovering it level by level, one DRAM round trip per level of the first rays
         const uint32_t nt = P.bvh_node_lines + P.bvh_tri_lines, ns = nt + P.tri_shade_lines;
@@ -2714,6 +2759,9 @@ cudaError_t launch_trace(const TraceParams& p, int accel, int variant, int persi
         case 9: launch_trace_t<3, 0>(p, variant, blocks, stream); break;
         case 10: launch_trace_t<3, 1>(p, variant, blocks, stream); break;
         case 11: trace_shade_persistent_kernel<3, 2><<<blocks, 256, 0, stream>>>(p); break;
+        case 12: launch_trace_t<4, 0>(p, 1, blocks, stream); break;  // persistent kernel only (raytracer.cu selects 4 for variant 1)
+        case 13: launch_trace_t<4, 1>(p, 1, blocks, stream); break;
+        case 14: trace_shade_persistent_kernel<4, 2><<<blocks, 256, 0, stream>>>(p); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -2787,6 +2835,8 @@ int persistent_blocks_per_sm(int accel, int bounce) {
         case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<2, 1>, 256, 0); break;
         case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<3, 0>, 256, 0); break;
         case 7: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<3, 1>, 256, 0); break;
+        case 8: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<4, 0>, 256, 0); break;
+        case 9: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_shade_persistent_kernel<4, 1>, 256, 0); break;
         default: break;
     }
     return n > 0 ? n : 1;

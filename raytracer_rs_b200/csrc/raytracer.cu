@@ -20,6 +20,7 @@
 #include "device_types.h"
 #include "host_scene.h"
 #include "kernels.h"
+#include "pgrid_build.h"
 
 using namespace rtb;
 
@@ -192,7 +193,18 @@ struct rt_raytracer {
     uint32_t done_value = 0;
     bool arm_done = false;           // the launch being issued is the last one of its trace call
     bool done_published = false;     // ... and carried the signal
-    int blocks_per_sm[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [accel][bounce]
+    int blocks_per_sm[5][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [kernel accel][bounce]; 4 = binary BVH + camera grid
+    // perspective grid of the camera rays (pgrid_build.cu): rebuilt when the camera, the resolution or the triangle array changes
+    int camera_grid_log2 = 3;  // RT_TUNE_CAMERA_GRID: 0 = camera rays walk the BVH, 2..5 = grid cells of 4..32 pixels
+    DevBuf<uint32_t> d_pg_count, d_pg_start, d_pg_cursor, d_pg_entries, d_pg_total;
+    struct PGridKey {
+        float cam[21];  // rotation[16], ray origin[3], max_x, max_y
+        uint32_t w, h, shift, n_slots;
+        const float4* tris;
+    } pg_key{};
+    bool pg_valid = false;
+    uint32_t pg_nx = 0, pg_entries = 0;
+    uint64_t pg_builds = 0;
     int num_sms = 0;
     rt_launch_stats last{};
     bool stats_pending = false;
@@ -678,6 +690,84 @@ struct rt_raytracer {
         return schedules.back().get();
     }
 
+    // (Re)builds the camera grid for the current view over `tris` and fills p's grid fields; false = no grid for this launch (switched off,
+    // or the camera matrix cannot be inverted): the camera rays walk the BVH.
+    bool ensure_pgrid(TraceParams* p) {
+        if (camera_grid_log2 <= 0 || !p->bvh_tris) return false;
+        PGridKey key{};
+        std::memcpy(key.cam, camera.rotation.data(), 64);
+        const f3 o = camera.ray_origin();
+        key.cam[16] = o.x, key.cam[17] = o.y, key.cam[18] = o.z, key.cam[19] = camera.max_x, key.cam[20] = camera.max_y;
+        key.w = cfg.width, key.h = cfg.height, key.shift = (uint32_t)camera_grid_log2;
+        key.tris = p->bvh_tris;
+        key.n_slots = (uint32_t)((cfg.accel == RT_ACCEL_LBVH ? d_lbvh_tris.n : d_bvh_tris.n) / 3);
+        if (!pg_valid || std::memcmp(&key, &pg_key, sizeof(key)) != 0) {
+            pg_valid = false;
+            // dir = a e0 + b e1 + e2 with a = dir_x, b = -dir_y (camera.rs:85-89): invert [e0 e1 e2] in binary64
+            const float* R = camera.rotation.data();
+            const double e[3][3] = {{R[0], R[1], R[2]}, {R[4], R[5], R[6]}, {(double)R[8] + R[12], (double)R[9] + R[13], (double)R[10] + R[14]}};
+            // columns of B are e0, e1, e2; rows of its inverse are cross products / det
+            const double c0[3] = {e[1][1] * e[2][2] - e[1][2] * e[2][1], e[1][2] * e[2][0] - e[1][0] * e[2][2], e[1][0] * e[2][1] - e[1][1] * e[2][0]};
+            const double c1[3] = {e[2][1] * e[0][2] - e[2][2] * e[0][1], e[2][2] * e[0][0] - e[2][0] * e[0][2], e[2][0] * e[0][1] - e[2][1] * e[0][0]};
+            const double c2[3] = {e[0][1] * e[1][2] - e[0][2] * e[1][1], e[0][2] * e[1][0] - e[0][0] * e[1][2], e[0][0] * e[1][1] - e[0][1] * e[1][0]};
+            const double det = e[0][0] * c0[0] + e[0][1] * c0[1] + e[0][2] * c0[2];
+            const double scale = std::fabs(e[0][0]) + std::fabs(e[0][1]) + std::fabs(e[0][2]) + std::fabs(e[1][0]) + std::fabs(e[1][1]) + std::fabs(e[1][2]) +
+                                 std::fabs(e[2][0]) + std::fabs(e[2][1]) + std::fabs(e[2][2]);
+            if (!(std::fabs(det) > 1e-9 * scale * scale * scale) || !(camera.max_x > 0.f) || !(camera.max_y > 0.f)) return false;
+            PGridParams g{};
+            const double W = cfg.width, H = cfg.height, sx = W / (2.0 * camera.max_x), sy = H / (2.0 * camera.max_y);
+            for (int k = 0; k < 3; ++k) {
+                const double i0 = c0[k] / det, i1 = c1[k] / det, i2 = c2[k] / det;  // (a c, b c, c) = (i0, i1, i2) . w
+                g.A[k] = sx * i0 + 0.5 * W * i2;       // U = W/2 + a W / (2 max_x)
+                g.A[3 + k] = -sy * i1 + 0.5 * H * i2;  // V = H/2 - b H / (2 max_y)   (dir_y = -b)
+                g.A[6 + k] = i2;
+            }
+            g.origin[0] = o.x, g.origin[1] = o.y, g.origin[2] = o.z;
+            double extent = 0.0;
+            for (int a = 0; a < 3; ++a) extent = std::max(extent, (double)root_hi[a] - (double)root_lo[a]);
+            g.z_eps = std::max(1e-9 * extent * std::sqrt(g.A[6] * g.A[6] + g.A[7] * g.A[7] + g.A[8] * g.A[8]), 1e-30);  // Z is in units of |row 2 of the inverse|
+            const uint32_t sh = key.shift;
+            const uint32_t pv_max = (uint32_t)(((uint64_t)cfg.width * cfg.height - 1u) / cfg.height);  // v = idx / height (mod.rs:96)
+            g.nx = ((cfg.width - 1u) >> sh) + 1u;
+            g.ny = (pv_max >> sh) + 1u;
+            g.cell = (double)(1u << sh);
+            const uint32_t n_cells = g.nx * g.ny;
+            if (d_pg_count.n < n_cells) {
+                RT_CUDA(cudaStreamSynchronize(stream));  // a launch in flight may still read the old arrays
+                d_pg_count.alloc(n_cells);
+                d_pg_start.alloc((size_t)n_cells + 1);
+                d_pg_cursor.alloc(n_cells);
+            }
+            if (!d_pg_total.p) d_pg_total.alloc(1);
+            g.tris = key.tris;
+            g.n_slots = key.n_slots;
+            g.count = d_pg_count.p;
+            g.start = d_pg_start.p;
+            g.cursor = d_pg_cursor.p;
+            g.total = d_pg_total.p;
+            g.entries = d_pg_entries.p;
+            RT_CUDA(pgrid_count(g, n_cells, num_sms, stream));
+            uint32_t total = 0;
+            RT_CUDA(cudaMemcpyAsync(&total, d_pg_total.p, 4, cudaMemcpyDeviceToHost, stream));
+            RT_CUDA(cudaStreamSynchronize(stream));  // (also: no launch still reads the old lists)
+            if (d_pg_entries.n < total) d_pg_entries.alloc((size_t)total + total / 2 + 1024);
+            g.entries = d_pg_entries.p;
+            RT_CUDA(pgrid_fill(g, num_sms, stream));
+            total_kernels += 3;
+            last.kernels_launched += 3;
+            pg_key = key;
+            pg_nx = g.nx;
+            pg_entries = total;
+            pg_valid = true;
+            ++pg_builds;
+        }
+        p->pg_start = d_pg_start.p;
+        p->pg_tris = d_pg_entries.p;
+        p->pg_nx = pg_nx;
+        p->pg_shift = pg_key.shift;
+        return true;
+    }
+
     cudaError_t launch_one(const TraceParams& p_in) {
         TraceParams p = p_in;
         set_item_geometry(&p, p.lane_samples_log2);
@@ -686,7 +776,16 @@ struct rt_raytracer {
         // the ray-pool kernel covers the headline configuration; everything else runs the persistent tile kernel
         const bool use_pool = variant == 2 && a == 1 && b == 0 && scene.lights.size() == 1 && !p.planes && p.lane_samples_log2 == 0;
         if (use_pool && pool_blocks == 0) pool_blocks = pool_blocks_per_sm();
-        if (!use_pool && variant != 0 && blocks_per_sm[a][b] == 0) blocks_per_sm[a][b] = persistent_blocks_per_sm(a, b);
+        // kernel instantiation: the binary-BVH kernels exist a second time with the camera rays sent through the perspective grid
+        int ka = a;
+        if (a == 1 && variant == 1 && !use_pool) {
+            try {
+                if (ensure_pgrid(&p)) ka = 4;
+            } catch (CudaFail&) {
+                return cudaErrorMemoryAllocation;
+            }
+        }
+        if (!use_pool && variant != 0 && blocks_per_sm[ka][b] == 0) blocks_per_sm[ka][b] = persistent_blocks_per_sm(ka, b);
         p.queue_batch = (uint32_t)queue_batch;
         p.queue_batch_from_pct = (uint32_t)queue_batch_from_pct;
         p.pool_refill = (uint32_t)pool_refill;
@@ -716,7 +815,7 @@ struct rt_raytracer {
             // re-sort after the 1st and 2nd recorded launch of a view, then every 32nd (the one-block sort costs
             // ~45 us for a 1080p frame; per-tile costs of an unchanged view move little between frames)
             if (sc->launches == 1 || sc->launches == 2 || (sc->launches > 2 && sc->launches % kResortEvery == 0)) {
-                const uint32_t warps = (uint32_t)((use_pool ? pool_blocks : blocks_per_sm[a][b]) * num_sms * 8);
+                const uint32_t warps = (uint32_t)((use_pool ? pool_blocks : blocks_per_sm[ka][b]) * num_sms * 8);
                 const uint32_t level = (a != 0 && !use_pool && split_quarters > 0) ? sc->max_level : 0u;
                 // a launch that cannot fill the resident warps even once has issue slots to spare: split from 5 us of work on
                 const uint32_t min_cycles = tiles < warps ? 10000u : 40000u;
@@ -742,8 +841,8 @@ struct rt_raytracer {
         }
         cudaError_t e;
         if (use_pool) e = launch_trace(p, a, 2, pool_blocks * num_sms, stream);
-        else if (wavefront_applies(p)) e = launch_wavefront(p, a);
-        else e = launch_trace(p, a, variant == 0 ? 0 : 1, blocks_per_sm[a][b] * num_sms, stream);
+        else if (wavefront_applies(p)) e = launch_wavefront(p, a, ka);
+        else e = launch_trace(p, ka, variant == 0 ? 0 : 1, blocks_per_sm[ka][b] * num_sms, stream);
         if (e != cudaSuccess) return e;
         if (variant == 0) {
             // the one-thread-per-pixel kernel has no last warp out (warp_checkout): the host zeroes the other per-call counter set
@@ -781,7 +880,7 @@ struct rt_raytracer {
         uint32_t nch[kWfLevels];
         return wf_layout(p, cap, nch, &rt_, &ct_);
     }
-    cudaError_t launch_wavefront(const TraceParams& p_in, int a) {
+    cudaError_t launch_wavefront(const TraceParams& p_in, int a, int ka /* instantiation of the trace kernel: a, or 4 = camera grid */) {
         TraceParams p = p_in;
         size_t cap[kWfLevels], rec_total = 0, child_total = 0;
         uint32_t nch[kWfLevels];
@@ -801,8 +900,8 @@ struct rt_raytracer {
         }
         p.wf_counts = d_wf_counts.p;
         RT_CUDA_RET(cudaMemsetAsync(d_wf_counts.p, 0, 3 * kWfLevels * sizeof(unsigned int), stream));
-        if (blocks_per_sm[a][0] == 0) blocks_per_sm[a][0] = persistent_blocks_per_sm(a, 0);
-        RT_CUDA_RET(launch_trace(p, a, 1, blocks_per_sm[a][0] * num_sms, stream));
+        if (blocks_per_sm[ka][0] == 0) blocks_per_sm[ka][0] = persistent_blocks_per_sm(ka, 0);
+        RT_CUDA_RET(launch_trace(p, ka, 1, blocks_per_sm[ka][0] * num_sms, stream));
         const int wf_blocks = num_sms * 3;  // 80 registers: three 256-thread blocks per SM
         const bool stream_levels = bounce_stream && a == 1;  // ray-stream kernel (binary BVH): bounce + shadow rays share the lanes
         // every level from the second on sends at most one bounce ray per hit (the reference's RECURSIONS = 2, SUB_SPREAD = 1): the ray-stream
@@ -1723,6 +1822,11 @@ int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     }
     if (key == RT_TUNE_STREAM_REFILL && value >= 1 && value <= 32) {
         rt->stream_refill = value;
+        return RT_OK;
+    }
+    if (key == RT_TUNE_CAMERA_GRID && (value == 0 || (value >= 2 && value <= 5))) {
+        rt->camera_grid_log2 = value;
+        rt->pg_valid = false;
         return RT_OK;
     }
     if (key == RT_TUNE_FILM_PREFETCH_ROWS_MB && value >= 0 && value <= 1024) {
