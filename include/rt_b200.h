@@ -351,6 +351,15 @@ uint32_t rt_launch_param_bytes(void);
    kernels and one 4-byte readback) — and a camera ray tests its cell's list instead of walking the tree (same Moller-Trumbore test, same
    tie rule, same root-cube acceptance: the same hit). Shadow and bounce rays walk the tree. 0 = camera rays walk the tree as well. */
 #define RT_TUNE_CAMERA_GRID 22
+/* RT_TUNE_CAMERA_GRID_AFTER: launches a view must have seen without changing before its grid is built (default 1: the second frame of a
+   view builds it; 0 = at once). A build costs about as much as a frame, so a camera that moves every frame keeps walking the tree. */
+#define RT_TUNE_CAMERA_GRID_AFTER 23
+/* RT_TUNE_LIGHT_GRID (launches that use the camera grid): shadow rays all end at their light, so the direction in which the light sees
+   the shaded point is an index as well. 6..9 (default 8): a cube of grids of 64..512 cells per face edge around every point light (up to
+   four; built once per tree) lists per cell the triangles that direction can meet, and a shadow ray tests that list (same test, same
+   decision as the tree walk: blocked iff the closest hit has 0.01 < t < 1). A ray long enough to reach a surface lying BEYOND the light
+   within its last hundredth walks the tree. 0 = all shadow rays walk the tree. */
+#define RT_TUNE_LIGHT_GRID 24
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value);
 /* Launch statistics of the last rt_trace_rows / rt_trace_frame_additive call. */
 typedef struct rt_launch_stats {

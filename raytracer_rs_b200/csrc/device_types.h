@@ -28,6 +28,7 @@ constexpr uint32_t kOctLeafFlag = 0x80000000u;
 constexpr uint32_t kNoHit = 0xFFFFFFFFu;
 constexpr int kOctStack = 64;  // >= 7 * depth + 1 with depth <= 9 (oct_tree_intersector.rs:108)
 constexpr int kBvhStack = 48;
+constexpr int kGridLights = 4;  // point lights that can have a shadow-ray grid (more: their shadow rays walk the BVH)
 constexpr int kBvh4Stack = 64;  // up to three pushes per level
 constexpr int kCwStack = 32;  // node groups only: at most one per level plus slack
 
@@ -61,8 +62,15 @@ struct TraceParams {
     // perspective grid of the camera rays (pgrid_build.cu; instantiation ACCEL = 4 of the trace kernels): the (u, v) sample plane of
     // Camera::get_ray cut into square cells of 2^pg_shift pixels, per cell the slots of bvh_tris whose projection can reach it
     const uint32_t* pg_start;  // cell -> first entry of pg_tris; n_cells + 1 offsets
-    const uint32_t* pg_tris;
+    const uint2* pg_tris;      // (slot of bvh_tris, smallest Z of the triangle as float bits), every list in ascending Z
     uint32_t pg_nx, pg_shift;
+    // cube of perspective grids around every point light, for shadow rays (null = shadow rays walk the BVH): light li, face f (2 * axis +
+    // (negative side)), cell (cy, cx) -> lg_start[((li * 6 + f) * lg_n + cy) * lg_n + cx]
+    const uint32_t* lg_start;
+    const uint2* lg_tris;      // (slot, lower bound of the triangle's distance from the light), every list in ascending distance
+    uint32_t lg_n, lg_shift;   // cells per face edge; cell edge = 2^lg_shift grid units
+    float lg_half;             // half a face edge in grid units
+    float lg_far2[kGridLights];  // |L|^2 from which a shadow ray of light li may reach surfaces lying beyond the light (it then walks the BVH)
     const float4* bvh4_nodes;  // 4-wide BVH, 8 float4 per node (bvh4_build.cpp)
     const float4* bvh4_tris;
     const uint4* cw_nodes;   // compressed 8-wide BVH, 5 words per node

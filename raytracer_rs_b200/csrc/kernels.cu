@@ -872,19 +872,26 @@ __device__ __forceinline__ bool pgrid_closest_hit(const TraceParams& P, const V3
     best.tri = kNoHit;
     while (__any_sync(mask, i < end)) {
         if (i < end) {
-            const float4* tri = P.bvh_tris + 3 * (size_t)__ldg(P.pg_tris + i);
-            const float4 t0 = __ldg(tri), t1 = __ldg(tri + 1), t2 = __ldg(tri + 2);
-            float t, u, v;
-            if (moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) {
-                const uint32_t id = __float_as_uint(t2.y);
-                if (t < best.t || (t == best.t && id < best.tri)) {
-                    best.t = t;
-                    best.u = u;
-                    best.v = v;
-                    best.tri = id;
+            const uint2 e = __ldg(P.pg_tris + i);
+            // the list is in ascending order of the triangles' smallest Z, and Z of a point on a camera ray is its t (pgrid_build.cu): nothing
+            // from here on can come closer than the hit already held (1e-4: rounding of the f32 t against the binary64 Z)
+            if (__uint_as_float(e.y) > best.t * 1.0001f) {
+                i = end;
+            } else {
+                const float4* tri = P.bvh_tris + 3 * (size_t)e.x;
+                const float4 t0 = __ldg(tri), t1 = __ldg(tri + 1), t2 = __ldg(tri + 2);
+                float t, u, v;
+                if (moller_trumbore(o, d, t0, t1, t2, &t, &u, &v)) {
+                    const uint32_t id = __float_as_uint(t2.y);
+                    if (t < best.t || (t == best.t && id < best.tri)) {
+                        best.t = t;
+                        best.u = u;
+                        best.v = v;
+                        best.tri = id;
+                    }
                 }
+                ++i;
             }
-            ++i;
         }
     }
     if (best.tri == kNoHit) return false;
@@ -905,6 +912,68 @@ __device__ __forceinline__ bool closest_hit(const TraceParams& P, const V3& o, c
     if (ACCEL == 3) return bvh4_closest_hit_ww(P, o, d, FLT_MAX, -1.0f, out);
     return WW ? bvh_closest_hit_ww(P, o, d, FLT_MAX, -1.0f, out) : bvh_closest_hit(P, o, d, FLT_MAX, -1.0f, out);
 }
+// Shadow rays through the cube of grids around their light (ACCEL = 4): every point of the segment from the shaded point to the light is
+// seen from the light in the same direction, so that direction names a cell whose list holds every triangle the segment can meet. The
+// decision is the one of shadow_blocked: c = the closest hit with t <= 1 — a hit with t <= 0.01 ends the search, the point is lit —,
+// blocked iff 0.01 < c < 1 and the hit point passes the root-cube rule. The ray runs 0.01 |L| past the light (t up to 1 from an origin
+// 0.01 L along, mod.rs:224-225); surfaces there are seen from the light in the opposite direction, so a ray long enough to reach the
+// nearest surface beyond the light (|L|^2 >= lg_far2) walks the BVH instead.
+template <int WW>
+__device__ __forceinline__ bool lgrid_shadow_blocked(const TraceParams& P, const V3& o, const V3& d, uint32_t li, const float4 lp) {
+    const uint32_t mask = __activemask();
+    const bool far = !(vdot(d, d) < P.lg_far2[li]);
+    uint32_t i = 0u, end = 0u;
+    if (!far) {
+        const float wx = o.x - lp.x, wy = o.y - lp.y, wz = o.z - lp.z;
+        const float ax = fabsf(wx), ay = fabsf(wy), az = fabsf(wz);
+        uint32_t face;
+        float xf, yf, zf;
+        if (ax >= ay && ax >= az) {
+            face = wx < 0.f ? 1u : 0u, zf = ax, xf = wy, yf = wz;
+        } else if (ay >= az) {
+            face = wy < 0.f ? 3u : 2u, zf = ay, xf = wz, yf = wx;
+        } else {
+            face = wz < 0.f ? 5u : 4u, zf = az, xf = wx, yf = wy;
+        }
+        const float top = 2.0f * P.lg_half - 1.0f;
+        const float u = fminf(fmaxf(P.lg_half * (1.0f + xf / zf), 0.0f), top), v = fminf(fmaxf(P.lg_half * (1.0f + yf / zf), 0.0f), top);
+        const uint32_t cell = ((li * 6u + face) * P.lg_n + ((uint32_t)v >> P.lg_shift)) * P.lg_n + ((uint32_t)u >> P.lg_shift);
+        i = __ldg(P.lg_start + cell);
+        end = __ldg(P.lg_start + cell + 1u);
+    }
+    float best = FLT_MAX;
+    // the list is in ascending order of the triangles' distance from the light (a lower bound of it): what lies farther from the light than
+    // the ray's origin (0.99 |L|) is behind the shaded surface and cannot be met with t >= 0
+    const float reach = 0.99f * sqrtf(vdot(d, d)) * 1.0001f;
+    while (__any_sync(mask, i < end)) {
+        if (i < end) {
+            const uint2 e = __ldg(P.lg_tris + i);
+            if (__uint_as_float(e.y) > reach) {
+                i = end;
+            } else {
+                const float4* tri = P.bvh_tris + 3 * (size_t)e.x;
+                const float4 t0 = __ldg(tri), t1 = __ldg(tri + 1), t2 = __ldg(tri + 2);
+                float t, u, v;
+                ++i;
+                if (moller_trumbore(o, d, t0, t1, t2, &t, &u, &v) && t <= 1.0f && t < best) {
+                    best = t;
+                    if (t <= 0.01f) i = end;  // decides "lit" whatever else lies on the segment
+                }
+            }
+        }
+    }
+    if (far) {
+        HitRec h;
+        if (!(WW ? bvh_closest_hit_ww(P, o, d, 1.0f, 0.01f, &h) : bvh_closest_hit(P, o, d, 1.0f, 0.01f, &h))) return false;
+        return h.t > 0.01f && h.t < 1.0f;
+    }
+    if (!(best > 0.01f && best < 1.0f)) return false;
+    const V3 hp = vadd(o, vscale(d, best));
+    const bool outside = hp.x < P.root_lo[0] || hp.x > P.root_hi[0] || hp.y < P.root_lo[1] || hp.y > P.root_hi[1] || hp.z < P.root_lo[2] ||
+                         hp.z > P.root_hi[2];
+    return !outside;
+}
+
 // blocked <=> the closest hit has 0.01 < t < 1.0 (mod.rs:226-230)
 template <int ACCEL, int WW>
 __device__ __forceinline__ bool shadow_blocked(const TraceParams& P, const V3& o, const V3& d) {
@@ -977,7 +1046,7 @@ __device__ __forceinline__ void shade_hit(const TraceParams& P, const V3& o, con
         if (ndl < 0.0f) continue;
         cnt.shadow_rays += 1;
         const V3 so = vadd(hp, vscale(L, 0.01f));
-        if (shadow_blocked<ACCEL, WW>(P, so, L)) {
+        if ((ACCEL == 4 && P.lg_start && li < (uint32_t)kGridLights) ? lgrid_shadow_blocked<WW>(P, so, L, li, lp) : shadow_blocked<ACCEL, WW>(P, so, L)) {
             cnt.blocked += 1;
             continue;
         }
@@ -1198,7 +1267,7 @@ struct PixelOut {
 template <int ACCEL, int WW, int BOUNCE, bool LAP = false>
 __device__ __forceinline__ void trace_pixel_radiance(const TraceParams& P, uint32_t col, uint32_t crow, uint32_t lane_sample, LaneCounters& cnt,
                                                      PixelOut& out) {
-    const uint32_t W = P.cam.width, H = P.cam.height;
+    const uint32_t W = P.cam.width;
     out.mode = 0u;
     // sample planes (several samples per pixel in one launch): compact row `crow` = plane * plane_rows + row of the pass;
     // sample lanes (persistent kernel): the lanes of a warp item hold `lane_sample` = 0 .. S-1 of the same pixel
@@ -2098,7 +2167,7 @@ __global__ void film_variance_kernel(const float4* __restrict__ sum, const float
 // single-sample launches leave. (Fusing this into the trace kernel — the warp that delivers a tile's last sample adds
 // them — was measured slower: the per-item __threadfence + atomic costs more than this 15 us pass.)
 __device__ __forceinline__ void accumulate_pixel(const TraceParams& P, uint32_t col, uint32_t prow) {
-    const uint32_t W = P.cam.width, H = P.cam.height;
+    const uint32_t W = P.cam.width;
     const uint32_t row = P.row_list ? P.row_list[prow] : wrap_row(P, prow);
     const uint32_t idx = row * W + col;
     float4 fs_ = P.film_sum[idx];

@@ -1,4 +1,6 @@
-// pgrid_build.cu — device build of the perspective grid of the camera rays (trace kernels, ACCEL = 4; kernels.cu, pgrid_closest_hit).
+// pgrid_build.cu — device build of the perspective grids (trace kernels, ACCEL = 4): the grid of the camera rays (kernels.cu,
+// pgrid_closest_hit) and the cube of grids around a point light for the shadow rays (lgrid_shadow_blocked; the same binning with six
+// frusta, A = the face's axes).
 //
 // Camera::get_ray (camera.rs:80-90) turns the pixel (u, v) and the sub-pixel offset (xi1, xi2) into the direction
 //     dir = a * r0 - dir_y * r1 + r2 + r3,   a = -max_x + 2 max_x (u + xi1) / W,   dir_y = -max_y + 2 max_y (v + xi2) / H
@@ -6,9 +8,9 @@
 // plane at (U, V) = (X / Z, Y / Z) with (X, Y, Z) = A (p - origin); the host folds the 3x3 inverse, max_x, max_y, W and H into A
 // (raytracer.cu, ensure_pgrid). Pixel (u, v) owns [u, u + 1) x [v, v + 1) of that plane whatever its offsets are.
 //
-// Per triangle (one warp each): the three vertices go through A in binary64, the part in front of the eye (Z >= z_eps) is
-// projected, and every cell the bounding box of the projection touches — widened by a margin of one pixel plus 1e-5 of the
-// coordinate, orders of magnitude more than the rounding of the f32 Moller-Trumbore test can move a hit — lists the triangle.
+// Per triangle (one warp each): the three vertices go through A in binary64, the triangle is clipped against the frustum, the rest is
+// projected, and every cell the bounding box of the projection touches — widened by a margin of one grid unit, orders of magnitude
+// more than the rounding of the f32 Moller-Trumbore test can move a hit — lists the triangle.
 // count -> exclusive scan -> fill; the lists are unordered (the closest-hit rule does not depend on the order of the tests).
 #include <cuda_runtime.h>
 
@@ -23,40 +25,54 @@ struct CellBox {
     int x0, x1, y0, y1;  // inclusive cell range; x0 > x1 = nothing
 };
 
-__device__ __forceinline__ CellBox triangle_cells(const PGridParams& g, const float4* tri) {
+struct HPoint {
+    double x, y, z;  // plane coordinates (U, V) = (x / z, y / z)
+};
+// Sutherland-Hodgman step: keeps the part of the polygon with a x + b y + c z + d >= 0
+__device__ __forceinline__ int clip_polygon(const HPoint* in, int n, HPoint* out, double a, double b, double c, double d) {
+    int m = 0;
+    for (int k = 0; k < n; ++k) {
+        const HPoint p = in[k], q = in[k + 1 == n ? 0 : k + 1];
+        const double fp = a * p.x + b * p.y + c * p.z + d, fq = a * q.x + b * q.y + c * q.z + d;
+        if (fp >= 0.0) out[m++] = p;
+        if ((fp >= 0.0) != (fq >= 0.0)) {
+            const double s = fp / (fp - fq);
+            out[m++] = HPoint{p.x + s * (q.x - p.x), p.y + s * (q.y - p.y), p.z + s * (q.z - p.z)};
+        }
+    }
+    return m;
+}
+
+// Cells the triangle can reach inside one frustum: the triangle is clipped against the frustum (the plane Z = z_eps and the four sides,
+// moved out by two grid units), what is left is projected, and the bounding box of the projection grows by the margin of one unit.
+__device__ __forceinline__ CellBox triangle_cells(const PGridParams& g, const double* A, const float4* tri, double* z_min) {
     const float4 t0 = tri[0], t1 = tri[1], t2 = tri[2];  // v0, e1 = v1 - v0, e2 = v2 - v0 (pack_triangle)
     const double vx[3] = {(double)t0.x, (double)t0.x + (double)t0.w, (double)t0.x + (double)t1.z};
     const double vy[3] = {(double)t0.y, (double)t0.y + (double)t1.x, (double)t0.y + (double)t1.w};
     const double vz[3] = {(double)t0.z, (double)t0.z + (double)t1.y, (double)t0.z + (double)t2.x};
-    double X[3], Y[3], Z[3];
+    HPoint pa[10], pb[10];
     for (int k = 0; k < 3; ++k) {
         const double wx = vx[k] - g.origin[0], wy = vy[k] - g.origin[1], wz = vz[k] - g.origin[2];
-        X[k] = g.A[0] * wx + g.A[1] * wy + g.A[2] * wz;
-        Y[k] = g.A[3] * wx + g.A[4] * wy + g.A[5] * wz;
-        Z[k] = g.A[6] * wx + g.A[7] * wy + g.A[8] * wz;
+        pa[k].x = A[0] * wx + A[1] * wy + A[2] * wz;
+        pa[k].y = A[3] * wx + A[4] * wy + A[5] * wz;
+        pa[k].z = A[6] * wx + A[7] * wy + A[8] * wz;
     }
-    double lo_u = 1e300, hi_u = -1e300, lo_v = 1e300, hi_v = -1e300;
-    bool any = false;
-    for (int k = 0; k < 3; ++k) {
-        const int n = k == 2 ? 0 : k + 1;
-        if (Z[k] >= g.z_eps) {
-            const double u = X[k] / Z[k], v = Y[k] / Z[k];
-            lo_u = fmin(lo_u, u), hi_u = fmax(hi_u, u), lo_v = fmin(lo_v, v), hi_v = fmax(hi_v, v);
-            any = true;
-        }
-        if ((Z[k] >= g.z_eps) != (Z[n] >= g.z_eps)) {  // the edge crosses the plane Z = z_eps: its crossing point bounds the visible part
-            const double s = (g.z_eps - Z[k]) / (Z[n] - Z[k]);
-            const double u = (X[k] + s * (X[n] - X[k])) / g.z_eps, v = (Y[k] + s * (Y[n] - Y[k])) / g.z_eps;
-            lo_u = fmin(lo_u, u), hi_u = fmax(hi_u, u), lo_v = fmin(lo_v, v), hi_v = fmax(hi_v, v);
-            any = true;
-        }
-    }
+    *z_min = fmin(pa[0].z, fmin(pa[1].z, pa[2].z));
+    const double u_end = (double)g.nx * g.cell, v_end = (double)g.ny * g.cell, m = 2.0;
     CellBox c = {1, 0, 1, 0};
-    if (!any) return c;  // entirely behind the eye: no camera ray (t >= 0) reaches it
-    const double mu = 1.0 + 1e-5 * fmax(fabs(lo_u), fabs(hi_u)), mv = 1.0 + 1e-5 * fmax(fabs(lo_v), fabs(hi_v));
-    lo_u -= mu, hi_u += mu, lo_v -= mv, hi_v += mv;
-    const double u_end = (double)g.nx * g.cell, v_end = (double)g.ny * g.cell;
-    if (!(hi_u >= 0.0 && lo_u < u_end && hi_v >= 0.0 && lo_v < v_end)) return c;  // off the sample plane
+    int n = clip_polygon(pa, 3, pb, 0.0, 0.0, 1.0, -g.z_eps);  // Z >= z_eps (behind the eye no ray with t >= 0 arrives)
+    if (n) n = clip_polygon(pb, n, pa, 1.0, 0.0, m, 0.0);           // U >= -m
+    if (n) n = clip_polygon(pa, n, pb, -1.0, 0.0, u_end + m, 0.0);  // U <= u_end + m
+    if (n) n = clip_polygon(pb, n, pa, 0.0, 1.0, m, 0.0);           // V >= -m
+    if (n) n = clip_polygon(pa, n, pb, 0.0, -1.0, v_end + m, 0.0);  // V <= v_end + m
+    if (n == 0) return c;
+    double lo_u = 1e300, hi_u = -1e300, lo_v = 1e300, hi_v = -1e300;
+    for (int k = 0; k < n; ++k) {
+        const double u = pb[k].x / pb[k].z, v = pb[k].y / pb[k].z;
+        lo_u = fmin(lo_u, u), hi_u = fmax(hi_u, u), lo_v = fmin(lo_v, v), hi_v = fmax(hi_v, v);
+    }
+    lo_u -= 1.0, hi_u += 1.0, lo_v -= 1.0, hi_v += 1.0;
+    if (!(hi_u >= 0.0 && lo_u < u_end && hi_v >= 0.0 && lo_v < v_end)) return c;  // off the plane
     c.x0 = (int)(fmax(lo_u, 0.0) / g.cell);
     c.x1 = (int)(fmin(hi_u, u_end - 0.5) / g.cell);
     c.y0 = (int)(fmax(lo_v, 0.0) / g.cell);
@@ -70,59 +86,133 @@ __global__ void __launch_bounds__(256) pgrid_bin_kernel(const PGridParams g) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < g.n_slots; slot += warps) {
-        const CellBox c = triangle_cells(g, g.tris + 3 * (size_t)slot);
-        if (c.x0 > c.x1 || c.y0 > c.y1) continue;
-        const uint32_t w = (uint32_t)(c.x1 - c.x0 + 1), n = w * (uint32_t)(c.y1 - c.y0 + 1);
-        for (uint32_t k = lane; k < n; k += 32u) {
-            const uint32_t cy = (uint32_t)c.y0 + k / w, cx = (uint32_t)c.x0 + k % w;
-            const uint32_t cell = cy * g.nx + cx;
-            if (FILL) g.entries[atomicAdd(&g.cursor[cell], 1u)] = slot;
-            else atomicAdd(&g.count[cell], 1u);
+        const float4* tri = g.tris + 3 * (size_t)slot;
+        float box_dist = 0.f;
+        if (g.dmin2 || g.key_mode == 1u) {  // distance from the origin to the triangle's bounding box, rounded down: a lower bound
+            const float4 t0 = tri[0], t1 = tri[1], t2 = tri[2];
+            const double v0[3] = {t0.x, t0.y, t0.z}, e1[3] = {t0.w, t1.x, t1.y}, e2[3] = {t1.z, t1.w, t2.x};
+            double d2 = 0.0;
+            for (int a = 0; a < 3; ++a) {
+                const double lo = v0[a] + fmin(0.0, fmin(e1[a], e2[a])), hi = v0[a] + fmax(0.0, fmax(e1[a], e2[a]));
+                const double d = fmax(0.0, fmax(lo - g.origin[a], g.origin[a] - hi));
+                d2 += d * d;
+            }
+            box_dist = __double2float_rd(sqrt(d2) * (1.0 - 1e-12));
+            // (non-negative floats order like their bit patterns)
+            if (!FILL && g.dmin2 && lane == 0u) atomicMin(reinterpret_cast<unsigned int*>(g.dmin2), __float_as_uint(__double2float_rd(d2 * (1.0 - 1e-12))));
+        }
+        for (uint32_t f = 0; f < g.n_frusta; ++f) {
+            double z_min;
+            const CellBox c = triangle_cells(g, g.A[f], tri, &z_min);
+            if (c.x0 > c.x1 || c.y0 > c.y1) continue;
+            const float key = g.key_mode == 1u ? box_dist : __double2float_rd(z_min);
+            const uint32_t base = g.cell_base + f * g.nx * g.ny;
+            const uint32_t w = (uint32_t)(c.x1 - c.x0 + 1), n = w * (uint32_t)(c.y1 - c.y0 + 1);
+            for (uint32_t k = lane; k < n; k += 32u) {
+                const uint32_t cy = (uint32_t)c.y0 + k / w, cx = (uint32_t)c.x0 + k % w;
+                const uint32_t cell = base + cy * g.nx + cx;
+                if (FILL) g.entries[atomicAdd(&g.cursor[cell], 1u)] = make_uint2(slot, __float_as_uint(key));
+                else atomicAdd(&g.count[cell], 1u);
+            }
         }
     }
 }
 
-// exclusive scan of count[0..n) into start[0..n], start[n] = total; one block (n is a few hundred thousand at most)
-__global__ void __launch_bounds__(1024) pgrid_scan_kernel(const uint32_t* __restrict__ count, uint32_t* __restrict__ start,
-                                                          uint32_t* __restrict__ cursor, uint32_t n, uint32_t* __restrict__ total) {
-    __shared__ uint32_t part[1024];
-    const uint32_t t = threadIdx.x, per = (n + 1023u) / 1024u;
-    const uint32_t b = min(t * per, n), e = min(b + per, n);
-    uint32_t s = 0;
-    for (uint32_t i = b; i < e; ++i) s += count[i];
-    part[t] = s;
+// one thread per cell: insertion sort of the cell's list by key (lists are a dozen entries long; a few reach a hundred)
+__global__ void __launch_bounds__(128) pgrid_sort_kernel(const uint32_t* __restrict__ start, uint2* __restrict__ entries, uint32_t n_cells) {
+    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    const uint32_t b = start[cell], e = start[cell + 1u];
+    for (uint32_t i = b + 1u; i < e; ++i) {
+        const uint2 x = entries[i];
+        const float kx = __uint_as_float(x.y);
+        uint32_t j = i;
+        while (j > b) {
+            const uint2 y = entries[j - 1u];
+            const float ky = __uint_as_float(y.y);
+            if (ky < kx || (ky == kx && y.x <= x.x)) break;  // (slot as the second key: the order does not depend on the atomics' timing)
+            entries[j] = y;
+            --j;
+        }
+        entries[j] = x;
+    }
+}
+
+// exclusive scan of count[0..n) into start[0..n] (start[n] = total) and cursor[0..n), three launches: sums of 1024-cell blocks, a scan of
+// those sums in one block (n <= 2^20 cells), the scan inside every block plus its offset
+__device__ __forceinline__ uint32_t block_scan_1024(uint32_t v, uint32_t* warp_sums /* [32] shared */, uint32_t* block_total) {
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    uint32_t x = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= (uint32_t)d) x += y;
+    }
+    if (lane == 31u) warp_sums[w] = x;
     __syncthreads();
-    for (uint32_t d = 1; d < 1024u; d <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partial sums
-        const uint32_t v = t >= d ? part[t - d] : 0u;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
+    if (w == 0u) {
+        uint32_t s = warp_sums[lane];
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= (uint32_t)d) s += y;
+        }
+        warp_sums[lane] = s;  // inclusive over warps
     }
-    uint32_t run = part[t] - s;
-    for (uint32_t i = b; i < e; ++i) {
-        start[i] = run;
-        cursor[i] = run;
-        run += count[i];
+    __syncthreads();
+    *block_total = warp_sums[31];
+    return x - v + (w ? warp_sums[w - 1u] : 0u);  // exclusive prefix of this thread
+}
+__global__ void __launch_bounds__(1024) pgrid_block_sums_kernel(const uint32_t* __restrict__ count, uint32_t* __restrict__ sums, uint32_t n) {
+    __shared__ uint32_t ws[32];
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    uint32_t total;
+    block_scan_1024(i < n ? count[i] : 0u, ws, &total);
+    if (threadIdx.x == 0u) sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) pgrid_scan_sums_kernel(uint32_t* __restrict__ sums, uint32_t nb, uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t ws[32];
+    uint32_t total;
+    const uint32_t v = threadIdx.x < nb ? sums[threadIdx.x] : 0u;
+    const uint32_t ex = block_scan_1024(v, ws, &total);
+    if (threadIdx.x < nb) sums[threadIdx.x] = ex;
+    if (threadIdx.x == 0u) *total_out = total;
+}
+__global__ void __launch_bounds__(1024) pgrid_scan_apply_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ sums,
+                                                                const uint32_t* __restrict__ total, uint32_t* __restrict__ start,
+                                                                uint32_t* __restrict__ cursor, uint32_t n) {
+    __shared__ uint32_t ws[32];
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    uint32_t block_total;
+    const uint32_t ex = block_scan_1024(i < n ? count[i] : 0u, ws, &block_total) + sums[blockIdx.x];
+    if (i < n) {
+        start[i] = ex;
+        cursor[i] = ex;
     }
-    if (t == 1023u) {
-        start[n] = part[1023];
-        *total = part[1023];
-    }
+    if (i == n) start[n] = *total;
 }
 
 }  // namespace
 
-cudaError_t pgrid_count(const PGridParams& g, uint32_t n_cells, int num_sms, cudaStream_t stream) {
-    cudaError_t e = cudaMemsetAsync(g.count, 0, (size_t)n_cells * sizeof(uint32_t), stream);
-    if (e != cudaSuccess) return e;
+cudaError_t pgrid_bin_count(const PGridParams& g, int num_sms, cudaStream_t stream) {
     const uint32_t blocks = (uint32_t)max(1, min(num_sms * 8, (int)((g.n_slots + 7u) / 8u)));
     pgrid_bin_kernel<false><<<blocks, 256, 0, stream>>>(g);
-    pgrid_scan_kernel<<<1, 1024, 0, stream>>>(g.count, g.start, g.cursor, n_cells, g.total);
     return cudaGetLastError();
 }
-cudaError_t pgrid_fill(const PGridParams& g, int num_sms, cudaStream_t stream) {
+cudaError_t pgrid_scan(const uint32_t* count, uint32_t* start, uint32_t* cursor, uint32_t n, uint32_t* total, uint32_t* block_sums, cudaStream_t stream) {
+    const uint32_t nb = n / 1024u + 1u;  // one more than needed when 1024 divides n: some block has to hold i == n
+    if (nb > 1024u) return cudaErrorInvalidValue;
+    pgrid_block_sums_kernel<<<nb, 1024, 0, stream>>>(count, block_sums, n);
+    pgrid_scan_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, nb, total);
+    pgrid_scan_apply_kernel<<<nb, 1024, 0, stream>>>(count, block_sums, total, start, cursor, n);
+    return cudaGetLastError();
+}
+cudaError_t pgrid_bin_fill(const PGridParams& g, int num_sms, cudaStream_t stream) {
     const uint32_t blocks = (uint32_t)max(1, min(num_sms * 8, (int)((g.n_slots + 7u) / 8u)));
     pgrid_bin_kernel<true><<<blocks, 256, 0, stream>>>(g);
+    return cudaGetLastError();
+}
+
+cudaError_t pgrid_sort_lists(const uint32_t* start, uint2* entries, uint32_t n_cells, cudaStream_t stream) {
+    pgrid_sort_kernel<<<(n_cells + 127u) / 128u, 128, 0, stream>>>(start, entries, n_cells);
     return cudaGetLastError();
 }
 
