@@ -70,6 +70,7 @@ struct TraceParams {
     const uint2* lg_tris;      // (slot, lower bound of the triangle's distance from the light), every list in ascending distance
     uint32_t lg_n, lg_shift;   // cells per face edge; cell edge = 2^lg_shift grid units
     float lg_half;             // half a face edge in grid units
+    uint32_t grid_lines[4];    // 128-byte lines of pg_start, pg_tris, lg_start, lg_tris (start-of-launch L2 prefetch)
     float lg_far2[kGridLights];  // |L|^2 from which a shadow ray of light li may reach surfaces lying beyond the light (it then walks the BVH)
     const float4* bvh4_nodes;  // 4-wide BVH, 8 float4 per node (bvh4_build.cpp)
     const float4* bvh4_tris;

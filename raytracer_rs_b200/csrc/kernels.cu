@@ -1476,6 +1476,16 @@ __global__ void __launch_bounds__(256, RT_PERSISTENT_MIN_BLOCKS) trace_shade_per
                                                     : (const char*)P.tile_order + 128ull * (t - ns);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
         }
+        if (ACCEL == 4) {  // and the grids: cell offsets and lists of the camera grid, then of the light grids
+            const uint32_t a = P.grid_lines[0], b = a + P.grid_lines[1], c = b + P.grid_lines[2], e = c + P.grid_lines[3];
+            for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < e; t += gridDim.x * blockDim.x) {
+                const char* line = t < a   ? (const char*)P.pg_start + 128ull * t
+                                   : t < b ? (const char*)P.pg_tris + 128ull * (t - a)
+                                   : t < c ? (const char*)P.lg_start + 128ull * (t - b)
+                                           : (const char*)P.lg_tris + 128ull * (t - c);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+            }
+        }
         // launches that need a pixel's sample number before they can form its rays (hashed sub-pixel offsets, bounce directions) read the
         // film record first thing, with nothing to hide a cold read behind: ask for the records of all rows of the launch now
         if ((P.jitter_mode == 1 || BOUNCE != 0) && !P.planes && P.film_prefetch_rows) {

@@ -60,16 +60,40 @@ __device__ __forceinline__ CellBox triangle_cells(const PGridParams& g, const do
     *z_min = fmin(pa[0].z, fmin(pa[1].z, pa[2].z));
     const double u_end = (double)g.nx * g.cell, v_end = (double)g.ny * g.cell, m = 2.0;
     CellBox c = {1, 0, 1, 0};
-    int n = clip_polygon(pa, 3, pb, 0.0, 0.0, 1.0, -g.z_eps);  // Z >= z_eps (behind the eye no ray with t >= 0 arrives)
-    if (n) n = clip_polygon(pb, n, pa, 1.0, 0.0, m, 0.0);           // U >= -m
-    if (n) n = clip_polygon(pa, n, pb, -1.0, 0.0, u_end + m, 0.0);  // U <= u_end + m
-    if (n) n = clip_polygon(pb, n, pa, 0.0, 1.0, m, 0.0);           // V >= -m
-    if (n) n = clip_polygon(pa, n, pb, 0.0, -1.0, v_end + m, 0.0);  // V <= v_end + m
-    if (n == 0) return c;
+    // the five planes of the frustum (Z >= z_eps: behind the eye no ray with t >= 0 arrives; the four sides moved out by m units). Almost every
+    // triangle lies entirely on one side of every plane: all vertices outside one plane -> nothing to list; all inside all planes -> nothing to clip
+    int outside_all = 0, outside_any = 0;
+    for (int pl = 0; pl < 5; ++pl) {
+        int out = 0;
+        for (int k = 0; k < 3; ++k) {
+            const double f = pl == 0   ? pa[k].z - g.z_eps
+                             : pl == 1 ? pa[k].x + m * pa[k].z
+                             : pl == 2 ? (u_end + m) * pa[k].z - pa[k].x
+                             : pl == 3 ? pa[k].y + m * pa[k].z
+                                       : (v_end + m) * pa[k].z - pa[k].y;
+            out += f < 0.0;
+        }
+        outside_all |= out == 3;
+        outside_any |= out != 0;
+    }
+    if (outside_all) return c;
     double lo_u = 1e300, hi_u = -1e300, lo_v = 1e300, hi_v = -1e300;
-    for (int k = 0; k < n; ++k) {
-        const double u = pb[k].x / pb[k].z, v = pb[k].y / pb[k].z;
-        lo_u = fmin(lo_u, u), hi_u = fmax(hi_u, u), lo_v = fmin(lo_v, v), hi_v = fmax(hi_v, v);
+    if (!outside_any) {
+        for (int k = 0; k < 3; ++k) {
+            const double u = pa[k].x / pa[k].z, v = pa[k].y / pa[k].z;
+            lo_u = fmin(lo_u, u), hi_u = fmax(hi_u, u), lo_v = fmin(lo_v, v), hi_v = fmax(hi_v, v);
+        }
+    } else {
+        int n = clip_polygon(pa, 3, pb, 0.0, 0.0, 1.0, -g.z_eps);
+        if (n) n = clip_polygon(pb, n, pa, 1.0, 0.0, m, 0.0);           // U >= -m
+        if (n) n = clip_polygon(pa, n, pb, -1.0, 0.0, u_end + m, 0.0);  // U <= u_end + m
+        if (n) n = clip_polygon(pb, n, pa, 0.0, 1.0, m, 0.0);           // V >= -m
+        if (n) n = clip_polygon(pa, n, pb, 0.0, -1.0, v_end + m, 0.0);  // V <= v_end + m
+        if (n == 0) return c;
+        for (int k = 0; k < n; ++k) {
+            const double u = pb[k].x / pb[k].z, v = pb[k].y / pb[k].z;
+            lo_u = fmin(lo_u, u), hi_u = fmax(hi_u, u), lo_v = fmin(lo_v, v), hi_v = fmax(hi_v, v);
+        }
     }
     lo_u -= 1.0, hi_u += 1.0, lo_v -= 1.0, hi_v += 1.0;
     if (!(hi_u >= 0.0 && lo_u < u_end && hi_v >= 0.0 && lo_v < v_end)) return c;  // off the plane
@@ -80,15 +104,23 @@ __device__ __forceinline__ CellBox triangle_cells(const PGridParams& g, const do
     return c;
 }
 
-// one warp per triangle; FILL = false counts, FILL = true writes the entries (cursor[] starts as a copy of start[])
+// One warp per triangle. Lane f works out the cells of frustum f (binary64 clipping and projection: once per frustum, not once per
+// lane), the warp then walks each frustum's cells together. FILL = false counts, FILL = true writes the entries (cursor[] starts as a
+// copy of start[]).
 template <bool FILL>
 __global__ void __launch_bounds__(256) pgrid_bin_kernel(const PGridParams g) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < g.n_slots; slot += warps) {
         const float4* tri = g.tris + 3 * (size_t)slot;
-        float box_dist = 0.f;
-        if (g.dmin2 || g.key_mode == 1u) {  // distance from the origin to the triangle's bounding box, rounded down: a lower bound
+        CellBox c = {1, 0, 1, 0};
+        float key = 0.f;
+        if (lane < g.n_frusta) {
+            double z_min;
+            c = triangle_cells(g, g.A[lane], tri, &z_min);
+            key = __double2float_rd(z_min);
+        }
+        if (lane == 0u && (g.dmin2 || g.key_mode == 1u)) {  // distance from the origin to the triangle's bounding box, rounded down: a lower bound
             const float4 t0 = tri[0], t1 = tri[1], t2 = tri[2];
             const double v0[3] = {t0.x, t0.y, t0.z}, e1[3] = {t0.w, t1.x, t1.y}, e2[3] = {t1.z, t1.w, t2.x};
             double d2 = 0.0;
@@ -97,44 +129,76 @@ __global__ void __launch_bounds__(256) pgrid_bin_kernel(const PGridParams g) {
                 const double d = fmax(0.0, fmax(lo - g.origin[a], g.origin[a] - hi));
                 d2 += d * d;
             }
-            box_dist = __double2float_rd(sqrt(d2) * (1.0 - 1e-12));
+            if (g.key_mode == 1u) key = __double2float_rd(sqrt(d2) * (1.0 - 1e-12));
             // (non-negative floats order like their bit patterns)
-            if (!FILL && g.dmin2 && lane == 0u) atomicMin(reinterpret_cast<unsigned int*>(g.dmin2), __float_as_uint(__double2float_rd(d2 * (1.0 - 1e-12))));
+            if (!FILL && g.dmin2) atomicMin(reinterpret_cast<unsigned int*>(g.dmin2), __float_as_uint(__double2float_rd(d2 * (1.0 - 1e-12))));
         }
+        if (g.key_mode == 1u) key = __shfl_sync(0xffffffffu, key, 0);  // one distance for all six faces
         for (uint32_t f = 0; f < g.n_frusta; ++f) {
-            double z_min;
-            const CellBox c = triangle_cells(g, g.A[f], tri, &z_min);
-            if (c.x0 > c.x1 || c.y0 > c.y1) continue;
-            const float key = g.key_mode == 1u ? box_dist : __double2float_rd(z_min);
+            const int x0 = __shfl_sync(0xffffffffu, c.x0, f), x1 = __shfl_sync(0xffffffffu, c.x1, f);
+            const int y0 = __shfl_sync(0xffffffffu, c.y0, f), y1 = __shfl_sync(0xffffffffu, c.y1, f);
+            const float kf = __shfl_sync(0xffffffffu, key, f);
+            if (x0 > x1 || y0 > y1) continue;
             const uint32_t base = g.cell_base + f * g.nx * g.ny;
-            const uint32_t w = (uint32_t)(c.x1 - c.x0 + 1), n = w * (uint32_t)(c.y1 - c.y0 + 1);
+            const uint32_t w = (uint32_t)(x1 - x0 + 1), n = w * (uint32_t)(y1 - y0 + 1);
             for (uint32_t k = lane; k < n; k += 32u) {
-                const uint32_t cy = (uint32_t)c.y0 + k / w, cx = (uint32_t)c.x0 + k % w;
+                const uint32_t cy = (uint32_t)y0 + k / w, cx = (uint32_t)x0 + k % w;
                 const uint32_t cell = base + cy * g.nx + cx;
-                if (FILL) g.entries[atomicAdd(&g.cursor[cell], 1u)] = make_uint2(slot, __float_as_uint(key));
+                if (FILL) g.entries[atomicAdd(&g.cursor[cell], 1u)] = make_uint2(slot, __float_as_uint(kf));
                 else atomicAdd(&g.count[cell], 1u);
             }
         }
     }
 }
 
-// one thread per cell: insertion sort of the cell's list by key (lists are a dozen entries long; a few reach a hundred)
-__global__ void __launch_bounds__(128) pgrid_sort_kernel(const uint32_t* __restrict__ start, uint2* __restrict__ entries, uint32_t n_cells) {
-    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= n_cells) return;
-    const uint32_t b = start[cell], e = start[cell + 1u];
-    for (uint32_t i = b + 1u; i < e; ++i) {
-        const uint2 x = entries[i];
-        const float kx = __uint_as_float(x.y);
-        uint32_t j = i;
-        while (j > b) {
-            const uint2 y = entries[j - 1u];
-            const float ky = __uint_as_float(y.y);
-            if (ky < kx || (ky == kx && y.x <= x.x)) break;  // (slot as the second key: the order does not depend on the atomics' timing)
-            entries[j] = y;
-            --j;
+// One warp per cell: the list goes through shared memory (up to 128 entries, bitonic network on (key, slot) — the slot as second key
+// makes the order independent of the timing of the fill's atomics). A longer list stays as it is and gets keys that never stop a walk.
+constexpr uint32_t kSortMax = 128;
+__global__ void __launch_bounds__(256) pgrid_sort_kernel(const uint32_t* __restrict__ start, uint2* __restrict__ entries, uint32_t n_cells) {
+    __shared__ unsigned long long buf[8][kSortMax];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cell < n_cells; cell += warps) {
+        const uint32_t b = start[cell], n = start[cell + 1u] - b;
+        if (n < 2u) continue;
+        if (n > kSortMax) {
+            for (uint32_t i = lane; i < n; i += 32u) entries[b + i].y = 0xff7fffffu;  // -FLT_MAX
+            continue;
         }
-        entries[j] = x;
+        uint32_t m = 2u;
+        while (m < n) m <<= 1;
+        for (uint32_t i = lane; i < m; i += 32u) {
+            unsigned long long v = ~0ull;  // padding sorts to the end
+            if (i < n) {
+                const uint2 e = entries[b + i];
+                // order-preserving map of the float key to an unsigned integer (keys can be negative: a triangle partly behind the eye)
+                const uint32_t k = (e.y & 0x80000000u) ? ~e.y : (e.y | 0x80000000u);
+                v = ((unsigned long long)k << 32) | e.x;
+            }
+            buf[w][i] = v;
+        }
+        __syncwarp();
+        for (uint32_t k = 2u; k <= m; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0u; j >>= 1) {
+                for (uint32_t i = lane; i < m; i += 32u) {
+                    const uint32_t p = i ^ j;
+                    if (p > i) {
+                        const unsigned long long x = buf[w][i], y = buf[w][p];
+                        const bool up = (i & k) == 0u;
+                        if ((x > y) == up) {
+                            buf[w][i] = y;
+                            buf[w][p] = x;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        for (uint32_t i = lane; i < n; i += 32u) {
+            const unsigned long long v = buf[w][i];
+            const uint32_t k = (uint32_t)(v >> 32);
+            entries[b + i] = make_uint2((uint32_t)v, (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+        }
+        __syncwarp();
     }
 }
 
@@ -212,7 +276,7 @@ cudaError_t pgrid_bin_fill(const PGridParams& g, int num_sms, cudaStream_t strea
 }
 
 cudaError_t pgrid_sort_lists(const uint32_t* start, uint2* entries, uint32_t n_cells, cudaStream_t stream) {
-    pgrid_sort_kernel<<<(n_cells + 127u) / 128u, 128, 0, stream>>>(start, entries, n_cells);
+    pgrid_sort_kernel<<<min((n_cells + 7u) / 8u, 148u * 8u), 256, 0, stream>>>(start, entries, n_cells);
     return cudaGetLastError();
 }
 

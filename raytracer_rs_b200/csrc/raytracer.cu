@@ -168,7 +168,9 @@ struct rt_raytracer {
     // bands (trace_frame_additive, mod.rs:87) retraces the same 22 geometries frame after frame and finds each band's schedule again
     struct TileSchedule {
         uint32_t first = ~0u, rows = ~0u, tiles = 0, samples_log2 = 0;
+        int kernel = -1;            // instantiation the costs were recorded with (a tile costs the grid kernels and the tree walkers differently)
         uint32_t launches = 0;      // launches recorded since the schedule was created / the view last changed
+        uint32_t recorded = 0;      // launches recorded since the schedule was created
         bool have_order = false;    // `order` holds a queue
         bool restart_costs = true;  // the next launch starts from zeroed costs (new schedule, or the view changed)
         uint32_t max_level = 0;     // finest split the order buffer has room for (kernels.cu, tile_sort_kernel)
@@ -211,7 +213,7 @@ struct rt_raytracer {
     DevBuf<uint2> d_lg_entries;
     DevBuf<float> d_lg_dmin2;
     const float4* lg_tris_key = nullptr;
-    uint32_t lg_slots_key = 0, lg_n = 0, lg_entries = 0;
+    uint32_t lg_slots_key = 0, lg_n = 0, lg_entries = 0, lg_cells = 0;
     int lg_log2_key = -1;
     bool lg_valid = false, lg_off = false;
     float lg_far2[kGridLights] = {0.f, 0.f, 0.f, 0.f};
@@ -219,7 +221,7 @@ struct rt_raytracer {
     uint32_t pg_seen_launches = 0;
     int camera_grid_after = 1;        // RT_TUNE_CAMERA_GRID_AFTER
     bool pg_valid = false;
-    uint32_t pg_nx = 0, pg_shift = 0, pg_entries = 0;
+    uint32_t pg_nx = 0, pg_shift = 0, pg_entries = 0, pg_cells = 0;
     uint64_t pg_builds = 0;
     int num_sms = 0;
     rt_launch_stats last{};
@@ -679,9 +681,10 @@ struct rt_raytracer {
         p->magic_tiles_x = udiv_magic_of(p->items_x);
     }
 
-    TileSchedule* find_schedule(const TraceParams& p, uint32_t tiles) {
+    TileSchedule* find_schedule(const TraceParams& p, uint32_t tiles, int kernel) {
         for (auto& sc : schedules)
-            if (sc->first == p.first_row && sc->rows == p.n_rows && sc->tiles == tiles && sc->samples_log2 == p.lane_samples_log2) return sc.get();
+            if (sc->first == p.first_row && sc->rows == p.n_rows && sc->tiles == tiles && sc->samples_log2 == p.lane_samples_log2 && sc->kernel == kernel)
+                return sc.get();
         if (schedules.size() >= 64) {  // drop the least recently used geometry
             size_t lru = 0;
             for (size_t i = 1; i < schedules.size(); ++i)
@@ -694,6 +697,7 @@ struct rt_raytracer {
         sc->rows = p.n_rows;
         sc->tiles = tiles;
         sc->samples_log2 = p.lane_samples_log2;
+        sc->kernel = kernel;
         // a part must hold whole pixels (32 >> (level + 1) lanes >= the samples of a pixel); big launches fill the GPU with
         // whole tiles and four-way splits, so their order buffer is not sized for the finer levels
         uint32_t lv = (uint32_t)std::max(0, std::min(max_split_level, 3));
@@ -787,6 +791,7 @@ struct rt_raytracer {
             last.kernels_launched += 6;
             pg_key = key;
             pg_nx = g.nx;
+            pg_cells = n_cells;
             pg_shift = sh;
             pg_entries = total;
             pg_valid = true;
@@ -794,6 +799,8 @@ struct rt_raytracer {
         }
         p->pg_start = d_pg_start.p;
         p->pg_tris = d_pg_entries.p;
+        p->grid_lines[0] = (uint32_t)(((size_t)pg_cells + 1) * 4 / 128);
+        p->grid_lines[1] = (uint32_t)((size_t)pg_entries * 8 / 128);
         p->pg_nx = pg_nx;
         p->pg_shift = pg_shift;
         return true;
@@ -870,11 +877,14 @@ struct rt_raytracer {
             lg_slots_key = n_slots;
             lg_log2_key = light_grid_log2;
             lg_n = n;
+            lg_cells = n_cells;
             lg_entries = total;
             lg_valid = true;
         }
         p->lg_start = d_lg_start.p;
         p->lg_tris = d_lg_entries.p;
+        p->grid_lines[2] = (uint32_t)(((size_t)lg_cells + 1) * 4 / 128);
+        p->grid_lines[3] = (uint32_t)((size_t)lg_entries * 8 / 128);
         p->lg_n = lg_n;
         p->lg_shift = 3u;
         p->lg_half = 0.5f * (float)(lg_n << 3u);
@@ -919,18 +929,22 @@ struct rt_raytracer {
         if (variant != 0 && lpt_schedule && tiles >= (uint32_t)min_schedule_tiles) {  // tiny launches are latency bound: image order
             TileSchedule* sc = nullptr;
             try {
-                sc = find_schedule(p, tiles);
+                sc = find_schedule(p, tiles, ka);
             } catch (CudaFail&) {
                 return cudaErrorMemoryAllocation;
             }
             sc->last_use = ++schedule_clock;
-            if (sc->restart_costs) {
+            // A schedule that is only ever used for the first frame of a view (the tree-walking kernel, while views that stay get the grid
+            // kernel) is invalidated before it reaches its first sort: the costs of its last launch describe an earlier view, which still
+            // predicts this one far better than image order does — sort them before they are zeroed.
+            const bool late_first_sort = sc->restart_costs && !sc->have_order && sc->recorded > 0;
+            if (sc->restart_costs && !late_first_sort) {
                 RT_CUDA_RET(cudaMemsetAsync(sc->cost.p, 0, tiles * sizeof(uint32_t), stream));
                 sc->restart_costs = false;
             }
             // re-sort after the 1st and 2nd recorded launch of a view, then every 32nd (the one-block sort costs
             // ~45 us for a 1080p frame; per-tile costs of an unchanged view move little between frames)
-            if (sc->launches == 1 || sc->launches == 2 || (sc->launches > 2 && sc->launches % kResortEvery == 0)) {
+            if (late_first_sort || sc->launches == 1 || sc->launches == 2 || (sc->launches > 2 && sc->launches % kResortEvery == 0)) {
                 const uint32_t warps = (uint32_t)((use_pool ? pool_blocks : blocks_per_sm[ka][b]) * num_sms * 8);
                 const uint32_t level = (a != 0 && !use_pool && split_quarters > 0) ? sc->max_level : 0u;
                 // a launch that cannot fill the resident warps even once has issue slots to spare: split from 5 us of work on
@@ -941,6 +955,10 @@ struct rt_raytracer {
                 ++total_kernels;
                 ++last.kernels_launched;
                 sc->have_order = true;
+                if (late_first_sort) {
+                    RT_CUDA_RET(cudaMemsetAsync(sc->cost.p, 0, tiles * sizeof(uint32_t), stream));
+                    sc->restart_costs = false;
+                }
             }
             if (use_pool) {
                 // the pool kernel ADDS every camera ray's steps to its tile's cost: record only the launches a sort
@@ -954,6 +972,7 @@ struct rt_raytracer {
             p.tile_order = sc->have_order ? sc->order.p : nullptr;
             p.queue_items = sc->order.p + (sc->order.n - 1);
             ++sc->launches;
+            ++sc->recorded;
         }
         cudaError_t e;
         if (use_pool) e = launch_trace(p, a, 2, pool_blocks * num_sms, stream);

@@ -344,3 +344,89 @@ def test_l2_prefetch_levels_leave_the_film_alone(scenes, accel):
         if want is None:
             want = got
         assert got == want, (level, rows_mb)
+
+
+def _render_digest(t, h, calls):
+    """film + ids + frame + per-call shadow-ray counts of a sequence of trace calls"""
+    shadow = [t.trace_rows(first, rows, spp)[1] for first, rows, spp in calls]
+    return (t.film.pixel_datas().tobytes(), t.get_primary_ids().tobytes(), t.get_tonemapped_pixels().tobytes(), tuple(shadow))
+
+
+@pytest.mark.parametrize("name,w,h", [("thai2", 480, 272), ("ico3_tex", 320, 180), ("4boxes", 256, 144)])
+@pytest.mark.parametrize("accel", [rt.ACCEL_BVH, rt.ACCEL_LBVH])
+def test_perspective_grids_equal_the_tree_walk(scenes, name, w, h, accel):
+    """Camera rays through the perspective grid of the view and shadow rays through the cube of grids around the light (trace kernels
+    ACCEL = 4, csrc/pgrid_build.cu) give the film, ids, frame and ray counts of the tree walk, bit for bit: every cell size, grids built at
+    once or from the second launch of a view, full frames, a wrapping band, two samples per call (sample lanes), bounce rays."""
+    s = scenes(name)
+    calls = [(0, h, 1), (0, h, 1), (h - 20, 50, 1), (0, h, 2), (0, h, 1)]
+    for rec in (0, 2):
+        want = None
+        for grid, after, light in ((0, 1, 0), (3, 0, 0), (3, 1, 8), (2, 0, 6), (4, 0, 9), (5, 1, 7)):
+            t = rt.RayTracer.from_scene(s, rt.Config(w, h, recursions=rec, sub_spread=1, jitter_mode=rt.JITTER_HASHED, seed=11, accel=accel))
+            t.set_tuning(22, grid)
+            t.set_tuning(23, after)
+            if light:
+                t.set_tuning(24, light)
+            else:
+                t.set_tuning(24, 0)
+            got = _render_digest(t, h, calls)
+            t.close()
+            if want is None:
+                want = got
+            assert got == want, (rec, grid, after, light)
+
+
+def test_perspective_grid_follows_the_camera(scenes):
+    """The grid belongs to one view: moves, turns and a view from inside the scene (triangles behind the eye, triangles cut by the eye
+    plane) rebuild it; every frame equals the tree walk's frame of the same view."""
+    w, h = 384, 216
+    s = scenes("thai2")
+    moves = [("move", (0.0, 0.0, 0.3)), ("y", 0.4), ("x", -0.2), ("move", (0.3, -0.2, 1.5)), ("y", 1.3), ("move", (0.0, 0.0, 2.0)), ("x", 0.9)]
+    frames = {}
+    for grid in (0, 3):
+        t = tracer_for(s, w, h, jitter=rt.JITTER_HASHED, seed=2)
+        t.set_tuning(22, grid)
+        t.set_tuning(23, 0)
+        out = []
+        for kind, arg in moves:
+            if kind == "move":
+                t.camera.move_rel(*arg)
+            elif kind == "y":
+                t.camera.add_y_angle(arg)
+            else:
+                t.camera.add_x_angle(arg)
+            t.film.clear()
+            shadow = [t.trace_rows(0, h, 1)[1] for _ in range(2)]
+            out.append((t.film.pixel_datas().tobytes(), t.get_primary_ids().tobytes(), tuple(shadow)))
+        frames[grid] = out
+        t.close()
+    hit_counts = [int((np.frombuffer(f[1], np.uint32) != 0xFFFFFFFF).sum()) for f in frames[0]]
+    assert max(hit_counts) > 1000  # the walk does look at the scene
+    for k, (a, b) in enumerate(zip(frames[0], frames[3])):
+        assert a == b, (k, moves[k])
+
+
+def test_light_grid_with_several_lights_and_a_light_close_to_a_surface(scenes):
+    """Three lights, one of them a hair away from a surface (its shadow rays can reach geometry lying beyond the light within their last
+    hundredth: those rays walk the tree) and one far outside the scene: same film as with shadow rays walking the tree."""
+    w, h = 320, 180
+    base = scenes("ico2")
+    import types
+
+    v = base.vertices.reshape(-1, 3, 3)
+    near = v[0].mean(0) + 1e-3 * np.cross(v[0][1] - v[0][0], v[0][2] - v[0][0])  # a hair above the first triangle
+    lights = [(np.float32([10, 10, 10]), np.float32([10, 10, 10])), (near.astype(np.float32), np.float32([3, 2, 1])),
+              (np.float32([-40, 25, 60]), np.float32([5, 5, 9]))]
+    s = types.SimpleNamespace(**{k: getattr(base, k) for k in ("vertices", "tri_geom", "materials", "textures", "camera_orientation", "camera_fov_deg")},
+                              lights=lights)
+    want = None
+    for light in (0, 8, 6):
+        t = tracer_for(s, w, h, jitter=rt.JITTER_HASHED, seed=4)
+        t.set_tuning(23, 0)
+        t.set_tuning(24, light)
+        got = _render_digest(t, h, [(0, h, 1), (0, h, 1)])
+        t.close()
+        if want is None:
+            want = got
+        assert got == want, light

@@ -459,7 +459,7 @@ def test_tuning_knobs_accept_their_documented_ranges(scenes):
     """rt_set_tuning (include/rt_b200.h): every knob takes its documented values and rejects the first value outside."""
     r = host_tracer(scenes("4boxes"))
     ranges = {0: (0, 2), 1: (0, 1), 2: (1, 32), 3: (0, 8), 4: (0, 32), 5: (0, 2), 6: (0, 1), 7: (0, 64), 8: (1, 64), 9: (0, 100), 10: (0, 1),
-              12: (0, 3), 13: (0, 1), 14: (1, 32), 15: (0, 32), 16: (3, 5), 17: (0, 8), 18: (0, 1), 19: (0, 1), 20: (0, 3), 21: (0, 1024)}
+              12: (0, 3), 13: (0, 1), 14: (1, 32), 15: (0, 32), 16: (3, 5), 17: (0, 8), 18: (0, 1), 19: (0, 1), 20: (0, 3), 21: (0, 1024), 22: (2, 5), 23: (0, 1000), 24: (6, 9)}
     for key, (lo, hi) in ranges.items():
         r.set_tuning(key, lo)
         r.set_tuning(key, hi)
