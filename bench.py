@@ -368,6 +368,8 @@ def main():
     scene = rt.load_scene(os.path.join(ROOT, "data", fname))
     accel = {"bvh": rt.ACCEL_BVH, "octree": rt.ACCEL_OCTREE, "cwbvh": rt.ACCEL_CWBVH, "bvh4": rt.ACCEL_BVH4, "lbvh": rt.ACCEL_LBVH}[args.accel]
 
+    grids_off = any(kv.strip() == "22=0" for kv in args.tune.split(","))  # RT_TUNE_CAMERA_GRID = 0: every ray walks the tree
+
     def jitter_for(spp):
         return rt.JITTER_FIXED_HALF if spp == 1 else rt.JITTER_HASHED
 
@@ -756,7 +758,7 @@ def main():
         achieved = per_launch / (kms * 1e-3) / 1e9
         single = world == 1 and spp == 1
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "traffic_equivalent": achieved / peak,
-                    "traffic": traffic if single else None, "peak_source": peak_src, "kernel": "trace_shade_persistent_kernel<%s>" % args.accel,
+                    "traffic": traffic if single else None, "peak_source": peak_src, "kernel": "trace_shade_persistent_kernel<%s>" % ("bvh + perspective grids" if args.accel in ("bvh", "lbvh") and not grids_off else args.accel),
                     "kernel_ms": kms, "algorithmic_bytes_per_launch": per_launch, "note": note, "stale": stale,
                     "counters_from": "profiles/traffic.json (ncu --set full capture of one launch; kernels_hash %s)" % prof.get("kernels_hash")}
         if roofline["traffic"]:
@@ -799,7 +801,11 @@ def main():
         "dtype": "f32",
         "data": "reference scene fixture data/%s (the upstream repository's own scene), pinned camera" % fname,
         "config": {"workload": args.workload, "width": W, "height": H, "spp": spp, "recursions": 0,
-                   "jitter": "fixed 0.5" if spp == 1 else "hashed seed 0", "accel": args.accel, "l2_flush_between_steps": True,
+                   "jitter": "fixed 0.5" if spp == 1 else "hashed seed 0", "accel": args.accel,
+                   "ray_index": ("none: every ray walks the tree" if grids_off or args.accel not in ("bvh", "lbvh") else
+                                 "camera rays through the perspective grid of the view, shadow rays through the cube of grids around the light "
+                                 "(built on the device; same hits as the tree walk, bit for bit), bounce rays and everything else through the tree"),
+                   "l2_flush_between_steps": True,
                    "step": "one full frame: trace %d rows x %d spp%s" % (H, spp, gather_note),
                    "primary_rays_per_step": dev_res["primary"], "shadow_rays_per_step": dev_res["shadow"]},
         "frames_per_s": 1e3 / dev_res["ms_per_step"],

@@ -45,7 +45,8 @@ __device__ __forceinline__ int clip_polygon(const HPoint* in, int n, HPoint* out
 
 // Cells the triangle can reach inside one frustum: the triangle is clipped against the frustum (the plane Z = z_eps and the four sides,
 // moved out by two grid units), what is left is projected, and the bounding box of the projection grows by the margin of one unit.
-__device__ __forceinline__ CellBox triangle_cells(const PGridParams& g, const double* A, const float4* tri, double* z_min) {
+__device__ __forceinline__ CellBox triangle_cells(const PGridParams& g, const double* A, const float4* tri, double* z_min, float* uv /* [6], valid when the return's tight flag is set */,
+                                              int* tight) {
     const float4 t0 = tri[0], t1 = tri[1], t2 = tri[2];  // v0, e1 = v1 - v0, e2 = v2 - v0 (pack_triangle)
     const double vx[3] = {(double)t0.x, (double)t0.x + (double)t0.w, (double)t0.x + (double)t1.z};
     const double vy[3] = {(double)t0.y, (double)t0.y + (double)t1.x, (double)t0.y + (double)t1.w};
@@ -78,11 +79,14 @@ __device__ __forceinline__ CellBox triangle_cells(const PGridParams& g, const do
     }
     if (outside_all) return c;
     double lo_u = 1e300, hi_u = -1e300, lo_v = 1e300, hi_v = -1e300;
+    *tight = 0;
     if (!outside_any) {
         for (int k = 0; k < 3; ++k) {
             const double u = pa[k].x / pa[k].z, v = pa[k].y / pa[k].z;
             lo_u = fmin(lo_u, u), hi_u = fmax(hi_u, u), lo_v = fmin(lo_v, v), hi_v = fmax(hi_v, v);
+            uv[2 * k] = (float)u, uv[2 * k + 1] = (float)v;
         }
+        *tight = 1;  // the whole triangle projects: its three edges can reject cells of the bounding box
     } else {
         int n = clip_polygon(pa, 3, pb, 0.0, 0.0, 1.0, -g.z_eps);
         if (n) n = clip_polygon(pb, n, pa, 1.0, 0.0, m, 0.0);           // U >= -m
@@ -114,10 +118,11 @@ __global__ void __launch_bounds__(256) pgrid_bin_kernel(const PGridParams g) {
     for (uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < g.n_slots; slot += warps) {
         const float4* tri = g.tris + 3 * (size_t)slot;
         CellBox c = {1, 0, 1, 0};
-        float key = 0.f;
+        float key = 0.f, uv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int tight = 0;
         if (lane < g.n_frusta) {
             double z_min;
-            c = triangle_cells(g, g.A[lane], tri, &z_min);
+            c = triangle_cells(g, g.A[lane], tri, &z_min, uv, &tight);
             key = __double2float_rd(z_min);
         }
         if (lane == 0u && (g.dmin2 || g.key_mode == 1u)) {  // distance from the origin to the triangle's bounding box, rounded down: a lower bound
@@ -138,11 +143,32 @@ __global__ void __launch_bounds__(256) pgrid_bin_kernel(const PGridParams g) {
             const int x0 = __shfl_sync(0xffffffffu, c.x0, f), x1 = __shfl_sync(0xffffffffu, c.x1, f);
             const int y0 = __shfl_sync(0xffffffffu, c.y0, f), y1 = __shfl_sync(0xffffffffu, c.y1, f);
             const float kf = __shfl_sync(0xffffffffu, key, f);
+            const int tf = __shfl_sync(0xffffffffu, tight, f);
+            float pu[3], pv[3];
+            for (int k = 0; k < 3; ++k) pu[k] = __shfl_sync(0xffffffffu, uv[2 * k], f), pv[k] = __shfl_sync(0xffffffffu, uv[2 * k + 1], f);
             if (x0 > x1 || y0 > y1) continue;
             const uint32_t base = g.cell_base + f * g.nx * g.ny;
             const uint32_t w = (uint32_t)(x1 - x0 + 1), n = w * (uint32_t)(y1 - y0 + 1);
+            // conservative rasterisation: a cell (grown by the margin of one unit and by the rounding of the f32 coordinates) that lies
+            // entirely beyond one edge of the projected triangle cannot be reached by it
+            const float area2 = (pu[1] - pu[0]) * (pv[2] - pv[0]) - (pu[2] - pu[0]) * (pv[1] - pv[0]);
+            const bool edges = tf && n > 1u && fabsf(area2) > 1e-3f;
+            const float sgn = area2 < 0.f ? -1.f : 1.f, cs = (float)g.cell;
             for (uint32_t k = lane; k < n; k += 32u) {
                 const uint32_t cy = (uint32_t)y0 + k / w, cx = (uint32_t)x0 + k % w;
+                if (edges) {
+                    const float grow = 1.0f + 2e-3f * cs + 1e-6f * ((float)(cx + cy + 2u) * cs);
+                    const float xl = (float)cx * cs - grow, xh = (float)(cx + 1u) * cs + grow, yl = (float)cy * cs - grow, yh = (float)(cy + 1u) * cs + grow;
+                    bool reach = true;
+                    for (int i = 0; i < 3; ++i) {
+                        const int j = i == 2 ? 0 : i + 1;
+                        const float a = sgn * (pu[j] - pu[i]), b = sgn * (pv[j] - pv[i]);  // inside: a (y - v_i) - b (x - u_i) >= 0
+                        const float best = a * ((a > 0.f ? yh : yl) - pv[i]) - b * ((b > 0.f ? xl : xh) - pu[i]);
+                        // (the products round: keep a cell unless it is beyond the edge by more than that)
+                        reach = reach && best >= -1e-4f * (fabsf(a) + fabsf(b)) * (fabsf(xh) + fabsf(yh) + fabsf(pu[i]) + fabsf(pv[i]));
+                    }
+                    if (!reach) continue;
+                }
                 const uint32_t cell = base + cy * g.nx + cx;
                 if (FILL) g.entries[atomicAdd(&g.cursor[cell], 1u)] = make_uint2(slot, __float_as_uint(kf));
                 else atomicAdd(&g.count[cell], 1u);
