@@ -108,72 +108,111 @@ __device__ __forceinline__ CellBox triangle_cells(const PGridParams& g, const do
     return c;
 }
 
-// One warp per triangle. Lane f works out the cells of frustum f (binary64 clipping and projection: once per frustum, not once per
-// lane), the warp then walks each frustum's cells together. FILL = false counts, FILL = true writes the entries (cursor[] starts as a
-// copy of start[]).
+// What one (triangle, frustum) pair contributes: its cell box, the projected vertices when nothing was clipped, its key.
+struct Footprint {
+    int x0, x1, y0, y1;
+    int tight;
+    float key;
+    float pu[3], pv[3];
+};
+// cells [first, first + step, ...) of the footprint's box (index k = row-major inside the box), for the lanes / threads of the caller
+template <bool FILL>
+__device__ __forceinline__ void bin_cells(const PGridParams& g, const Footprint& fp, uint32_t base, uint32_t slot, uint32_t first, uint32_t step) {
+    const uint32_t w = (uint32_t)(fp.x1 - fp.x0 + 1), n = w * (uint32_t)(fp.y1 - fp.y0 + 1);
+    // conservative rasterisation: a cell (grown by the margin of one unit and by the rounding of the f32 coordinates) that lies
+    // entirely beyond one edge of the projected triangle cannot be reached by it
+    const float area2 = (fp.pu[1] - fp.pu[0]) * (fp.pv[2] - fp.pv[0]) - (fp.pu[2] - fp.pu[0]) * (fp.pv[1] - fp.pv[0]);
+    const bool edges = fp.tight && n > 1u && fabsf(area2) > 1e-3f;
+    const float sgn = area2 < 0.f ? -1.f : 1.f, cs = (float)g.cell;
+    for (uint32_t k = first; k < n; k += step) {
+        const uint32_t cy = (uint32_t)fp.y0 + k / w, cx = (uint32_t)fp.x0 + k % w;
+        if (edges) {
+            const float grow = 1.0f + 2e-3f * cs + 1e-6f * ((float)(cx + cy + 2u) * cs);
+            const float xl = (float)cx * cs - grow, xh = (float)(cx + 1u) * cs + grow, yl = (float)cy * cs - grow, yh = (float)(cy + 1u) * cs + grow;
+            bool reach = true;
+            for (int i = 0; i < 3; ++i) {
+                const int j = i == 2 ? 0 : i + 1;
+                const float a = sgn * (fp.pu[j] - fp.pu[i]), b = sgn * (fp.pv[j] - fp.pv[i]);  // inside: a (y - v_i) - b (x - u_i) >= 0
+                const float best = a * ((a > 0.f ? yh : yl) - fp.pv[i]) - b * ((b > 0.f ? xl : xh) - fp.pu[i]);
+                // (the products round: keep a cell unless it is beyond the edge by more than that)
+                reach = reach && best >= -1e-4f * (fabsf(a) + fabsf(b)) * (fabsf(xh) + fabsf(yh) + fabsf(fp.pu[i]) + fabsf(fp.pv[i]));
+            }
+            if (!reach) continue;
+        }
+        const uint32_t cell = base + cy * g.nx + cx;
+        if (FILL) g.entries[atomicAdd(&g.cursor[cell], 1u)] = make_uint2(slot, __float_as_uint(fp.key));
+        else atomicAdd(&g.count[cell], 1u);
+    }
+}
+// distance from the origin to the triangle's bounding box, squared: a lower bound of the distance to the triangle
+__device__ __forceinline__ double box_distance2(const PGridParams& g, const float4* tri) {
+    const float4 t0 = tri[0], t1 = tri[1], t2 = tri[2];
+    const double v0[3] = {t0.x, t0.y, t0.z}, e1[3] = {t0.w, t1.x, t1.y}, e2[3] = {t1.z, t1.w, t2.x};
+    double d2 = 0.0;
+    for (int a = 0; a < 3; ++a) {
+        const double lo = v0[a] + fmin(0.0, fmin(e1[a], e2[a])), hi = v0[a] + fmax(0.0, fmax(e1[a], e2[a]));
+        const double d = fmax(0.0, fmax(lo - g.origin[a], g.origin[a] - hi));
+        d2 += d * d;
+    }
+    return d2;
+}
+__device__ __forceinline__ Footprint footprint_of(const PGridParams& g, uint32_t f, const float4* tri) {
+    Footprint fp;
+    double z_min;
+    float uv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const CellBox c = triangle_cells(g, g.A[f], tri, &z_min, uv, &fp.tight);
+    fp.x0 = c.x0, fp.x1 = c.x1, fp.y0 = c.y0, fp.y1 = c.y1;
+    fp.key = g.key_mode == 1u ? __double2float_rd(sqrt(box_distance2(g, tri)) * (1.0 - 1e-12)) : __double2float_rd(z_min);
+    for (int k = 0; k < 3; ++k) fp.pu[k] = uv[2 * k], fp.pv[k] = uv[2 * k + 1];
+    return fp;
+}
+
+constexpr uint32_t kBigCells = 256;  // a footprint of more cells than this is left to pgrid_big_kernel (all blocks share its cells)
+
+// One warp per triangle. Lane f works out the footprint in frustum f (binary64 clipping and projection: once per frustum, not once per
+// lane), the warp then walks each frustum's cells together. FILL = false counts and queues the big footprints, FILL = true writes the
+// entries (cursor[] starts as a copy of start[]).
 template <bool FILL>
 __global__ void __launch_bounds__(256) pgrid_bin_kernel(const PGridParams g) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < g.n_slots; slot += warps) {
         const float4* tri = g.tris + 3 * (size_t)slot;
-        CellBox c = {1, 0, 1, 0};
-        float key = 0.f, uv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        int tight = 0;
-        if (lane < g.n_frusta) {
-            double z_min;
-            c = triangle_cells(g, g.A[lane], tri, &z_min, uv, &tight);
-            key = __double2float_rd(z_min);
-        }
-        if (lane == 0u && (g.dmin2 || g.key_mode == 1u)) {  // distance from the origin to the triangle's bounding box, rounded down: a lower bound
-            const float4 t0 = tri[0], t1 = tri[1], t2 = tri[2];
-            const double v0[3] = {t0.x, t0.y, t0.z}, e1[3] = {t0.w, t1.x, t1.y}, e2[3] = {t1.z, t1.w, t2.x};
-            double d2 = 0.0;
-            for (int a = 0; a < 3; ++a) {
-                const double lo = v0[a] + fmin(0.0, fmin(e1[a], e2[a])), hi = v0[a] + fmax(0.0, fmax(e1[a], e2[a]));
-                const double d = fmax(0.0, fmax(lo - g.origin[a], g.origin[a] - hi));
-                d2 += d * d;
-            }
-            if (g.key_mode == 1u) key = __double2float_rd(sqrt(d2) * (1.0 - 1e-12));
-            // (non-negative floats order like their bit patterns)
-            if (!FILL && g.dmin2) atomicMin(reinterpret_cast<unsigned int*>(g.dmin2), __float_as_uint(__double2float_rd(d2 * (1.0 - 1e-12))));
-        }
-        if (g.key_mode == 1u) key = __shfl_sync(0xffffffffu, key, 0);  // one distance for all six faces
+        Footprint mine;
+        mine.x0 = 1, mine.x1 = 0, mine.y0 = 1, mine.y1 = 0, mine.tight = 0, mine.key = 0.f;
+        for (int k = 0; k < 3; ++k) mine.pu[k] = mine.pv[k] = 0.f;
+        if (lane < g.n_frusta) mine = footprint_of(g, lane, tri);
+        if (!FILL && g.dmin2 && lane == 0u)  // (rounded down; non-negative floats order like their bit patterns)
+            atomicMin(reinterpret_cast<unsigned int*>(g.dmin2), __float_as_uint(__double2float_rd(box_distance2(g, tri) * (1.0 - 1e-12))));
         for (uint32_t f = 0; f < g.n_frusta; ++f) {
-            const int x0 = __shfl_sync(0xffffffffu, c.x0, f), x1 = __shfl_sync(0xffffffffu, c.x1, f);
-            const int y0 = __shfl_sync(0xffffffffu, c.y0, f), y1 = __shfl_sync(0xffffffffu, c.y1, f);
-            const float kf = __shfl_sync(0xffffffffu, key, f);
-            const int tf = __shfl_sync(0xffffffffu, tight, f);
-            float pu[3], pv[3];
-            for (int k = 0; k < 3; ++k) pu[k] = __shfl_sync(0xffffffffu, uv[2 * k], f), pv[k] = __shfl_sync(0xffffffffu, uv[2 * k + 1], f);
-            if (x0 > x1 || y0 > y1) continue;
-            const uint32_t base = g.cell_base + f * g.nx * g.ny;
-            const uint32_t w = (uint32_t)(x1 - x0 + 1), n = w * (uint32_t)(y1 - y0 + 1);
-            // conservative rasterisation: a cell (grown by the margin of one unit and by the rounding of the f32 coordinates) that lies
-            // entirely beyond one edge of the projected triangle cannot be reached by it
-            const float area2 = (pu[1] - pu[0]) * (pv[2] - pv[0]) - (pu[2] - pu[0]) * (pv[1] - pv[0]);
-            const bool edges = tf && n > 1u && fabsf(area2) > 1e-3f;
-            const float sgn = area2 < 0.f ? -1.f : 1.f, cs = (float)g.cell;
-            for (uint32_t k = lane; k < n; k += 32u) {
-                const uint32_t cy = (uint32_t)y0 + k / w, cx = (uint32_t)x0 + k % w;
-                if (edges) {
-                    const float grow = 1.0f + 2e-3f * cs + 1e-6f * ((float)(cx + cy + 2u) * cs);
-                    const float xl = (float)cx * cs - grow, xh = (float)(cx + 1u) * cs + grow, yl = (float)cy * cs - grow, yh = (float)(cy + 1u) * cs + grow;
-                    bool reach = true;
-                    for (int i = 0; i < 3; ++i) {
-                        const int j = i == 2 ? 0 : i + 1;
-                        const float a = sgn * (pu[j] - pu[i]), b = sgn * (pv[j] - pv[i]);  // inside: a (y - v_i) - b (x - u_i) >= 0
-                        const float best = a * ((a > 0.f ? yh : yl) - pv[i]) - b * ((b > 0.f ? xl : xh) - pu[i]);
-                        // (the products round: keep a cell unless it is beyond the edge by more than that)
-                        reach = reach && best >= -1e-4f * (fabsf(a) + fabsf(b)) * (fabsf(xh) + fabsf(yh) + fabsf(pu[i]) + fabsf(pv[i]));
-                    }
-                    if (!reach) continue;
-                }
-                const uint32_t cell = base + cy * g.nx + cx;
-                if (FILL) g.entries[atomicAdd(&g.cursor[cell], 1u)] = make_uint2(slot, __float_as_uint(kf));
-                else atomicAdd(&g.count[cell], 1u);
+            Footprint fp;
+            fp.x0 = __shfl_sync(0xffffffffu, mine.x0, f), fp.x1 = __shfl_sync(0xffffffffu, mine.x1, f);
+            fp.y0 = __shfl_sync(0xffffffffu, mine.y0, f), fp.y1 = __shfl_sync(0xffffffffu, mine.y1, f);
+            fp.key = __shfl_sync(0xffffffffu, mine.key, f);
+            fp.tight = __shfl_sync(0xffffffffu, mine.tight, f);
+            for (int k = 0; k < 3; ++k) fp.pu[k] = __shfl_sync(0xffffffffu, mine.pu[k], f), fp.pv[k] = __shfl_sync(0xffffffffu, mine.pv[k], f);
+            if (fp.x0 > fp.x1 || fp.y0 > fp.y1) continue;
+            const uint32_t n = (uint32_t)(fp.x1 - fp.x0 + 1) * (uint32_t)(fp.y1 - fp.y0 + 1);
+            if (n > kBigCells) {  // one warp would walk thousands of cells while the rest of the GPU has finished
+                if (!FILL && lane == 0u) g.big_queue[atomicAdd(g.big_count, 1u)] = slot * 8u + f;
+                continue;
             }
+            bin_cells<FILL>(g, fp, g.cell_base + f * g.nx * g.ny, slot, lane, 32u);
         }
+    }
+}
+// the big footprints queued by the counting pass: every block takes a share of every footprint's cells
+template <bool FILL>
+__global__ void __launch_bounds__(256) pgrid_big_kernel(const PGridParams g) {
+    __shared__ Footprint fp;
+    const uint32_t nq = *g.big_count;
+    for (uint32_t q = 0; q < nq; ++q) {
+        const uint32_t item = g.big_queue[q], slot = item >> 3, f = item & 7u;
+        if (threadIdx.x == 0u) fp = footprint_of(g, f, g.tris + 3 * (size_t)slot);
+        __syncthreads();
+        const Footprint local = fp;
+        bin_cells<FILL>(g, local, g.cell_base + f * g.nx * g.ny, slot, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+        __syncthreads();
     }
 }
 
@@ -283,8 +322,11 @@ __global__ void __launch_bounds__(1024) pgrid_scan_apply_kernel(const uint32_t* 
 }  // namespace
 
 cudaError_t pgrid_bin_count(const PGridParams& g, int num_sms, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(g.big_count, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
     const uint32_t blocks = (uint32_t)max(1, min(num_sms * 8, (int)((g.n_slots + 7u) / 8u)));
     pgrid_bin_kernel<false><<<blocks, 256, 0, stream>>>(g);
+    pgrid_big_kernel<false><<<num_sms * 2, 256, 0, stream>>>(g);
     return cudaGetLastError();
 }
 cudaError_t pgrid_scan(const uint32_t* count, uint32_t* start, uint32_t* cursor, uint32_t n, uint32_t* total, uint32_t* block_sums, cudaStream_t stream) {
@@ -298,6 +340,7 @@ cudaError_t pgrid_scan(const uint32_t* count, uint32_t* start, uint32_t* cursor,
 cudaError_t pgrid_bin_fill(const PGridParams& g, int num_sms, cudaStream_t stream) {
     const uint32_t blocks = (uint32_t)max(1, min(num_sms * 8, (int)((g.n_slots + 7u) / 8u)));
     pgrid_bin_kernel<true><<<blocks, 256, 0, stream>>>(g);
+    pgrid_big_kernel<true><<<num_sms * 2, 256, 0, stream>>>(g);  // the queue the counting pass of the same g left behind
     return cudaGetLastError();
 }
 

@@ -198,7 +198,7 @@ struct rt_raytracer {
     int blocks_per_sm[5][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [kernel accel][bounce]; 4 = binary BVH + camera grid
     // perspective grid of the camera rays (pgrid_build.cu): rebuilt when the camera, the resolution or the triangle array changes
     int camera_grid_log2 = 3;  // RT_TUNE_CAMERA_GRID: 0 = camera rays walk the BVH, 2..5 = grid cells of 4..32 pixels
-    DevBuf<uint32_t> d_pg_count, d_pg_start, d_pg_cursor, d_pg_total;
+    DevBuf<uint32_t> d_pg_count, d_pg_start, d_pg_cursor, d_pg_total, d_pg_big;
     DevBuf<uint2> d_pg_entries;
     struct PGridKey {
         float cam[21];  // rotation[16], ray origin[3], max_x, max_y
@@ -209,7 +209,7 @@ struct rt_raytracer {
     // cube of grids around every point light, for the shadow rays of ACCEL = 4 kernels: built once per (triangle array, lights)
     int light_grid_min_tris = 256;
     int light_grid_log2 = 8;  // RT_TUNE_LIGHT_GRID: 0 = shadow rays walk the BVH, 6..9 = 64..512 cells per cube-face edge (8 grid units each)
-    DevBuf<uint32_t> d_lg_count, d_lg_start, d_lg_cursor, d_lg_total;
+    DevBuf<uint32_t> d_lg_count, d_lg_start, d_lg_cursor, d_lg_total, d_lg_big;
     DevBuf<uint2> d_lg_entries;
     DevBuf<float> d_lg_dmin2;
     const float4* lg_tris_key = nullptr;
@@ -768,6 +768,7 @@ struct rt_raytracer {
                 d_pg_cursor.alloc(n_cells);
             }
             if (!d_pg_total.p) d_pg_total.alloc(1 + 1024);  // entry count, then the scan's block sums
+            if (d_pg_big.n < (size_t)key.n_slots + 1) d_pg_big.alloc((size_t)key.n_slots + 1);  // count, then the queue of big footprints
             g.tris = key.tris;
             g.n_slots = key.n_slots;
             g.count = d_pg_count.p;
@@ -775,6 +776,8 @@ struct rt_raytracer {
             g.entries = d_pg_entries.p;
             g.n_frusta = 1;
             g.cell_base = 0;
+            g.big_count = d_pg_big.p;
+            g.big_queue = d_pg_big.p + 1;
             g.key_mode = 0;
             g.dmin2 = nullptr;
             RT_CUDA(cudaMemsetAsync(d_pg_count.p, 0, (size_t)n_cells * 4, stream));
@@ -787,8 +790,8 @@ struct rt_raytracer {
             g.entries = d_pg_entries.p;
             RT_CUDA(pgrid_bin_fill(g, num_sms, stream));
             RT_CUDA(pgrid_sort_lists(d_pg_start.p, d_pg_entries.p, n_cells, stream));
-            total_kernels += 6;
-            last.kernels_launched += 6;
+            total_kernels += 8;
+            last.kernels_launched += 8;
             pg_key = key;
             pg_nx = g.nx;
             pg_cells = n_cells;
@@ -823,6 +826,8 @@ struct rt_raytracer {
             d_lg_cursor.alloc(n_cells);
             if (!d_lg_total.p) d_lg_total.alloc(1 + 1024);
             if (!d_lg_dmin2.p) d_lg_dmin2.alloc(kGridLights);
+            const size_t big_words = (size_t)n_slots * 6 + 1;  // per light: count, then the queue
+            d_lg_big.alloc(big_words * n_lights);
             RT_CUDA(cudaMemsetAsync(d_lg_count.p, 0, (size_t)n_cells * 4, stream));
             RT_CUDA(cudaMemsetAsync(d_lg_dmin2.p, 0x7f, kGridLights * sizeof(float), stream));  // 3.39e38
             double extent = 0.0;
@@ -853,6 +858,8 @@ struct rt_raytracer {
                 q.cursor = d_lg_cursor.p;
                 q.entries = nullptr;
                 q.dmin2 = d_lg_dmin2.p + li;
+                q.big_count = d_lg_big.p + big_words * li;
+                q.big_queue = q.big_count + 1;
                 q.key_mode = 1;
                 RT_CUDA(pgrid_bin_count(q, num_sms, stream));
             }
@@ -871,8 +878,8 @@ struct rt_raytracer {
                 lg_far2[li] = dmin2[li] * 1e4f * 0.98f;
             }
             RT_CUDA(pgrid_sort_lists(d_lg_start.p, d_lg_entries.p, n_cells, stream));
-            total_kernels += 2 * n_lights + 4;
-            last.kernels_launched += 2 * n_lights + 4;
+            total_kernels += 4 * n_lights + 4;
+            last.kernels_launched += 4 * n_lights + 4;
             lg_tris_key = p->bvh_tris;
             lg_slots_key = n_slots;
             lg_log2_key = light_grid_log2;
