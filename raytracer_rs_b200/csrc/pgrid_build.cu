@@ -201,17 +201,23 @@ __global__ void __launch_bounds__(256) pgrid_bin_kernel(const PGridParams g) {
         }
     }
 }
-// the big footprints queued by the counting pass: every block takes a share of every footprint's cells
+// the big footprints queued by the counting pass: the blocks split into one team per footprint (when there are more footprints than
+// blocks a block takes several in turn), and a team shares its footprint's cells — no block waits for a footprint it does not work on
 template <bool FILL>
 __global__ void __launch_bounds__(256) pgrid_big_kernel(const PGridParams g) {
     __shared__ Footprint fp;
     const uint32_t nq = *g.big_count;
-    for (uint32_t q = 0; q < nq; ++q) {
+    if (nq == 0u) return;
+    const uint32_t team_size = max(1u, gridDim.x / nq);      // blocks per footprint
+    const uint32_t teams = min(nq, gridDim.x);                // footprints in flight at once
+    const uint32_t team = blockIdx.x % teams, member = blockIdx.x / teams;
+    if (member >= team_size) return;
+    for (uint32_t q = team; q < nq; q += teams) {
         const uint32_t item = g.big_queue[q], slot = item >> 3, f = item & 7u;
         if (threadIdx.x == 0u) fp = footprint_of(g, f, g.tris + 3 * (size_t)slot);
         __syncthreads();
         const Footprint local = fp;
-        bin_cells<FILL>(g, local, g.cell_base + f * g.nx * g.ny, slot, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+        bin_cells<FILL>(g, local, g.cell_base + f * g.nx * g.ny, slot, member * blockDim.x + threadIdx.x, team_size * blockDim.x);
         __syncthreads();
     }
 }
