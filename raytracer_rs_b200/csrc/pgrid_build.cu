@@ -8,10 +8,13 @@
 // plane at (U, V) = (X / Z, Y / Z) with (X, Y, Z) = A (p - origin); the host folds the 3x3 inverse, max_x, max_y, W and H into A
 // (raytracer.cu, ensure_pgrid). Pixel (u, v) owns [u, u + 1) x [v, v + 1) of that plane whatever its offsets are.
 //
-// Per triangle (one warp each): the three vertices go through A in binary64, the triangle is clipped against the frustum, the rest is
-// projected, and every cell the bounding box of the projection touches — widened by a margin of one grid unit, orders of magnitude
-// more than the rounding of the f32 Moller-Trumbore test can move a hit — lists the triangle.
-// count -> exclusive scan -> fill; the lists are unordered (the closest-hit rule does not depend on the order of the tests).
+// Per triangle (one warp each): the three vertices go through A in binary64, the triangle is clipped against the frustum (almost always
+// a trivial accept or reject), the rest is projected, and every cell the bounding box of the projection touches — widened by a margin
+// of one grid unit, orders of magnitude more than the rounding of the f32 Moller-Trumbore test can move a hit — lists the triangle,
+// unless the cell lies entirely beyond one edge of the projected triangle (conservative rasterisation, same margin). A footprint of
+// more than 256 cells is queued and shared by a team of blocks in a second launch.
+// count -> exclusive scan -> fill -> every list sorted by a key (the triangle's smallest Z for the camera, a lower bound of its distance
+// for a light): the closest-hit rule does not depend on the order of the tests, and a walk can stop at the first key beyond its reach.
 #include <cuda_runtime.h>
 
 #include <cstdint>
