@@ -216,6 +216,7 @@ struct rt_raytracer {
     uint32_t lg_slots_key = 0, lg_n = 0, lg_entries = 0, lg_cells = 0;
     int lg_log2_key = -1;
     bool lg_valid = false, lg_off = false;
+    static constexpr uint32_t kGridMaxEntries = 1u << 26;  // 512 MB of (slot, key) pairs
     float lg_far2[kGridLights] = {0.f, 0.f, 0.f, 0.f};
     PGridKey pg_seen;                 // the view of the last launch that had no grid
     uint32_t pg_seen_launches = 0;
@@ -786,6 +787,10 @@ struct rt_raytracer {
             uint32_t total = 0;
             RT_CUDA(cudaMemcpyAsync(&total, d_pg_total.p, 4, cudaMemcpyDeviceToHost, stream));
             RT_CUDA(cudaStreamSynchronize(stream));  // (also: no launch still reads the old lists)
+            if (total > kGridMaxEntries) {  // a view from inside a dense mesh can list every triangle in most cells: the tree then serves better
+                pg_seen_launches = 0;       // (asked again after `camera_grid_after` more launches of this view; a new view asks at once)
+                return false;
+            }
             if (d_pg_entries.n < total) d_pg_entries.alloc((size_t)total + total / 2 + 1024);
             g.entries = d_pg_entries.p;
             RT_CUDA(pgrid_bin_fill(g, num_sms, stream));
@@ -813,10 +818,12 @@ struct rt_raytracer {
     void ensure_lgrid(TraceParams* p) {
         const uint32_t n_lights = (uint32_t)std::min<size_t>(scene.lights.size(), (size_t)kGridLights);
         if (light_grid_log2 <= 0 || n_lights == 0 || !p->bvh_tris) return;
+        if (lg_off && lg_tris_key == p->bvh_tris && lg_log2_key == light_grid_log2) return;  // measured too large for this tree and resolution
         const uint32_t n_slots = (uint32_t)((cfg.accel == RT_ACCEL_LBVH ? d_lbvh_tris.n : d_bvh_tris.n) / 3);
         if (n_slots < (uint32_t)light_grid_min_tris) return;  // a tree of a few dozen nodes is walked faster than a list is read (4boxes: 0.057 against 0.061 ms)
         if (!lg_valid || lg_tris_key != p->bvh_tris || lg_slots_key != n_slots || lg_log2_key != light_grid_log2) {
             lg_valid = false;
+            lg_off = false;
             uint32_t n = 1u << light_grid_log2;
             while (n > 32u && (uint64_t)n_lights * 6u * n * n >= (1u << 20)) n >>= 1;  // (the scan handles < 2^20 cells)
             const uint32_t shift = 3u, face_cells = n * n, n_cells = n_lights * 6u * face_cells;
@@ -869,6 +876,12 @@ struct rt_raytracer {
             RT_CUDA(cudaMemcpyAsync(&total, d_lg_total.p, 4, cudaMemcpyDeviceToHost, stream));
             RT_CUDA(cudaMemcpyAsync(dmin2, d_lg_dmin2.p, sizeof(dmin2), cudaMemcpyDeviceToHost, stream));
             RT_CUDA(cudaStreamSynchronize(stream));
+            if (total > kGridMaxEntries) {  // a light buried in a dense mesh: shadow rays keep walking the tree
+                lg_off = true;
+                lg_tris_key = p->bvh_tris;
+                lg_log2_key = light_grid_log2;
+                return;
+            }
             if (d_lg_entries.n < total) d_lg_entries.alloc((size_t)total + 1024);
             for (uint32_t li = 0; li < n_lights; ++li) {
                 g[li].entries = d_lg_entries.p;
