@@ -664,7 +664,7 @@ def main():
         tracer.film.clear()
 
     # ---- the other BASELINE configurations and the reference's default mode, in the same run ----
-    configs, rec2 = None, None
+    configs, rec2, tree_walk = None, None, None
     if extras and args.workload == "thai2_1080p":
         configs = {}
         names = ["ico2_1024x768", "4boxes_1080p", "ico3_tex_1080p", "thai2_4k_16spp"] if world == 1 else ["thai2_4k_16spp"]
@@ -718,6 +718,43 @@ def main():
                     "value_primary_shadow": (rays3["primary"] + rays3["shadow"]) / ms3 / 1e3, "unit": UNIT,
                     "note": "thai2 1080p, recursions 2, sub_spread 1, hashed jitter, 1 spp per step; primary + shadow + bounce rays"}
             t3.close()
+            # the headline workload with every ray walking the tree (RT_TUNE_CAMERA_GRID = 0): what the perspective grids replace
+            if accel in (rt.ACCEL_BVH, rt.ACCEL_LBVH) and not grids_off:
+                t4 = rt.RayTracer.from_scene(scene, rt.Config(W, H, recursions=0, jitter_mode=rt.JITTER_FIXED_HALF, seed=0, accel=accel, device=local_rank))
+                t4.set_stream(stream.cuda_stream)
+                t4.set_tuning(22, 0)
+                t4.set_tuning(10, 0)
+                for _ in range(4):
+                    t4.trace_rows(0, H, 1, want_shadow=False)
+                tot0 = t4.ray_totals()
+                ev = []
+                with torch.cuda.stream(stream):
+                    for _ in range(n3):
+                        flush.zero_()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(stream)
+                        t4.trace_rows(0, H, 1, want_shadow=False)
+                        e1.record(stream)
+                        ev.append((e0, e1))
+                torch.cuda.synchronize(dev)
+                tot1 = t4.ray_totals()
+                ms4 = sum(a.elapsed_time(b) for a, b in ev) / n3
+                # and the two paths render the same thing: one fresh sample each, frame and film compared bit for bit
+                t4.film.clear()
+                t4.trace_rows(0, H, 1)
+                t5 = rt.RayTracer.from_scene(scene, rt.Config(W, H, recursions=0, jitter_mode=rt.JITTER_FIXED_HALF, seed=0, accel=accel, device=local_rank))
+                t5.set_stream(stream.cuda_stream)
+                for _ in range(3):  # (a view gets its grid on its second launch)
+                    t5.trace_rows(0, H, 1)
+                t5.film.clear()
+                t5.trace_rows(0, H, 1)
+                same = bool(np.array_equal(t4.get_tonemapped_pixels(), t5.get_tonemapped_pixels()) and
+                            t4.film.pixel_datas().tobytes() == t5.film.pixel_datas().tobytes())
+                tree_walk = {"value": (tot1["primary"] - tot0["primary"] + tot1["shadow"] - tot0["shadow"]) / n3 / ms4 / 1e3, "unit": UNIT, "ms_per_step": ms4,
+                             "frame_and_film_equal_the_grid_path": same,
+                             "note": "same workload and timing as `value`, camera and shadow rays through the BVH instead of the perspective grids"}
+                t4.close()
+                t5.close()
 
     sampler.stop()
     if rank != 0:
@@ -832,6 +869,8 @@ def main():
         line["configs"] = configs
     if rec2:
         line["recursions2"] = rec2
+    if tree_walk is not None:
+        line["value_tree_walk"] = tree_walk
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.workload, rt, scene)
     print(json.dumps(line), flush=True)

@@ -101,7 +101,7 @@ class FakeTracer:
         self.primary = self.shadow = self.bounce = self.kernels = 0
         self.tuning, self.calls = {}, []
         self.camera = types.SimpleNamespace(set_state=lambda *a: self.calls.append("camera"), move_rel=lambda *a: self.calls.append("move"))
-        self.film = types.SimpleNamespace(clear=lambda: self.calls.append("clear"))
+        self.film = types.SimpleNamespace(clear=lambda: self.calls.append("clear"), pixel_datas=lambda: np.zeros((w * h, 7), np.float32))
 
     def _trace(self, rows, spp):
         time.sleep(0.002)  # the clock sampler takes a sample every 2 ms: the timed region must see a few
@@ -302,7 +302,7 @@ def test_bench_line_carries_the_whole_contract(monkeypatch):
     pipe = [c for c in tracer.calls if c in ("async", "wait1", "wait0")]  # frame i is queued before the host waits for frame i-1
     assert pipe == ["async", "wait1"] * 3 + ["wait0"] + ["async", "wait1"] * 6 + ["wait0"]
     assert tracer.tuning.get(10) == 0  # launch timing is off outside the roofline leg
-    for key in ("value_long", "configs", "recursions2", "e2e_reference_call_pattern", "first_frame_after_move", "strong"):
+    for key in ("value_long", "configs", "recursions2", "value_tree_walk", "e2e_reference_call_pattern", "first_frame_after_move", "strong"):
         assert key not in line
 
 
@@ -329,6 +329,7 @@ def test_bench_extras_on_one_gpu(monkeypatch):
         assert set(chk) == {"band_rows", "ids_agree", "max_lsb_diff", "pixels_within_1_lsb"} and 0.0 <= chk["ids_agree"] <= 1.0
     assert cfgs["thai2_4k_16spp"]["spp"] == 16 and cfgs["thai2_4k_16spp"]["oracle_check"]["band_rows"] == [540, 556]
     rec = line["recursions2"]
+    assert line["value_tree_walk"]["frame_and_film_equal_the_grid_path"] is True and line["value_tree_walk"]["value"] > 0
     assert rec["frame_ms"] > 0 and rec["rays_per_frame"]["bounce"] > 0 and rec["grays_per_s_all_rays"] > 0
     assert any(t.recursions == 2 for t in tracers)
 
