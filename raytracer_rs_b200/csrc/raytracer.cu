@@ -922,13 +922,26 @@ struct rt_raytracer {
         // kernel instantiation: the binary-BVH kernels exist a second time with the camera rays sent through the perspective grid
         int ka = a;
         if (a == 1 && variant == 1 && !use_pool) {
+            // the grids are an accelerator of the accelerator: a build that fails (device memory) switches them off, the launch walks the tree
             try {
-                if (ensure_pgrid(&p)) {
-                    ka = 4;
-                    ensure_lgrid(&p);
-                }
+                if (ensure_pgrid(&p)) ka = 4;
             } catch (CudaFail&) {
-                return cudaErrorMemoryAllocation;
+                cudaGetLastError();
+                camera_grid_log2 = 0;
+                pg_valid = false;
+                ka = a;
+            }
+            if (ka == 4) {
+                try {
+                    ensure_lgrid(&p);
+                } catch (CudaFail&) {
+                    cudaGetLastError();
+                    light_grid_log2 = 0;
+                    lg_valid = false;
+                    p.lg_start = nullptr;
+                    p.lg_tris = nullptr;
+                    p.grid_lines[2] = p.grid_lines[3] = 0u;
+                }
             }
         }
         if (!use_pool && variant != 0 && blocks_per_sm[ka][b] == 0) blocks_per_sm[ka][b] = persistent_blocks_per_sm(ka, b);
