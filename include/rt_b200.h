@@ -197,6 +197,12 @@ int rt_camera_get(const rt_raytracer* rt, float* out34);
    update_matrices() (camera.rs:92-98). Uploads 128 bytes to the device on the next trace call. */
 int rt_camera_set_state(rt_raytracer* rt, float x_angle, float y_angle, const float pos[3]);
 
+/* The map behind the perspective grid of the camera rays (RT_TUNE_CAMERA_GRID), i.e. the inverse of Camera::get_ray
+   (camera.rs:80-90) for the handle's current view: out12[0..9) = A row major, out12[9..12) = the ray origin. A point p = origin + t * dir
+   of the camera ray of pixel (u, v) with sub-pixel offsets (xi1, xi2) has (X, Y, Z) = A (p - origin) with X / Z = u + xi1, Y / Z = v + xi2
+   and Z = t. Needs no device. */
+int rt_get_camera_plane_matrix(rt_raytracer* rt, double* out12);
+
 /* ---- device-side access for multi-GPU gather and for timing on a caller-owned stream ------------------- */
 
 /* All later launches / copies of this handle are issued on `cuda_stream` (a cudaStream_t; NULL = default stream). */

@@ -96,7 +96,7 @@ ABI_SYMBOLS = [
     "rt_configure", "rt_set_rows_per_call", "rt_trace_frame_additive", "rt_trace_rows",
     "rt_get_tonemapped_pixels", "rt_get_tonemapped_pixels_delta", "rt_get_tonemapped_pixels_async", "rt_wait_pixels", "rt_wait_pixels_keep", "rt_film_clear", "rt_get_film",
     "rt_set_film", "rt_get_estimated_variances", "rt_get_primary_ids", "rt_camera_move_rel",
-    "rt_camera_add_x_angle", "rt_camera_add_y_angle", "rt_camera_get", "rt_camera_set_state", "rt_set_stream",
+    "rt_camera_add_x_angle", "rt_camera_add_y_angle", "rt_camera_get", "rt_camera_set_state", "rt_get_camera_plane_matrix", "rt_set_stream",
     "rt_get_ldr_device_ptr", "rt_set_ldr_target", "rt_get_owned_ldr_rows_device", "rt_get_launch_stats",
     "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_get_counters_device_ptr",
     "rt_stream_signal_flag", "rt_stream_signal_then_wait", "rt_stream_wait_flags", "rt_sync_timeouts", "rt_set_done_signal", "rt_stream_write_value", "rt_stream_wait_value",
@@ -159,6 +159,7 @@ def lib() -> C.CDLL:
         "rt_camera_add_x_angle": (C.c_int, [vp, f32]),
         "rt_camera_add_y_angle": (C.c_int, [vp, f32]),
         "rt_camera_get": (C.c_int, [vp, vp]),
+        "rt_get_camera_plane_matrix": (C.c_int, [vp, vp]),
         "rt_camera_set_state": (C.c_int, [vp, f32, f32, P(f32)]),
         "rt_set_stream": (C.c_int, [vp, vp]),
         "rt_get_ldr_device_ptr": (C.c_int, [vp, P(vp)]),
@@ -327,6 +328,13 @@ class _Camera:
     def set_state(self, x_angle: float, y_angle: float, pos) -> None:
         p = (C.c_float * 3)(*[float(v) for v in pos])
         self._rt._check(lib().rt_camera_set_state(self._rt._h, x_angle, y_angle, p))
+
+    def plane_matrix(self):
+        """(A, origin) of rt_get_camera_plane_matrix: (X, Y, Z) = A (p - origin) puts a point of the camera ray of pixel (u, v) at
+        X / Z = u + xi1, Y / Z = v + xi2, Z = t"""
+        out = np.zeros(12, np.float64)
+        self._rt._check(lib().rt_get_camera_plane_matrix(self._rt._h, _ptr(out)))
+        return out[:9].reshape(3, 3), out[9:]
 
     def matrices(self) -> np.ndarray:
         """rotation_matrix[16], orientation_matrix[16], max_x, max_y"""

@@ -711,6 +711,31 @@ struct rt_raytracer {
         return schedules.back().get();
     }
 
+    // The inverse of Camera::get_ray (camera.rs:80-90) as a matrix: dir = a e0 + b e1 + e2 with a = dir_x, b = -dir_y and e0, e1, e2 = rows 0, 1,
+    // 2 + 3 of the rotation matrix, so a point p = origin + t dir has (a t, b t, t) = B^-1 (p - origin), B = [e0 e1 e2] as columns (inverted in
+    // binary64). Folded with U = W/2 + a W / (2 max_x), V = H/2 - b H / (2 max_y): (X, Y, Z) = A (p - origin), sample-plane position
+    // (U, V) = (X / Z, Y / Z) in pixels, and Z = t. False when the camera matrix cannot be inverted.
+    bool camera_plane_matrix(double A[9]) const {
+        const float* R = camera.rotation.data();
+        const double e[3][3] = {{R[0], R[1], R[2]}, {R[4], R[5], R[6]}, {(double)R[8] + R[12], (double)R[9] + R[13], (double)R[10] + R[14]}};
+        // rows of the inverse are cross products / det
+        const double c0[3] = {e[1][1] * e[2][2] - e[1][2] * e[2][1], e[1][2] * e[2][0] - e[1][0] * e[2][2], e[1][0] * e[2][1] - e[1][1] * e[2][0]};
+        const double c1[3] = {e[2][1] * e[0][2] - e[2][2] * e[0][1], e[2][2] * e[0][0] - e[2][0] * e[0][2], e[2][0] * e[0][1] - e[2][1] * e[0][0]};
+        const double c2[3] = {e[0][1] * e[1][2] - e[0][2] * e[1][1], e[0][2] * e[1][0] - e[0][0] * e[1][2], e[0][0] * e[1][1] - e[0][1] * e[1][0]};
+        const double det = e[0][0] * c0[0] + e[0][1] * c0[1] + e[0][2] * c0[2];
+        const double scale = std::fabs(e[0][0]) + std::fabs(e[0][1]) + std::fabs(e[0][2]) + std::fabs(e[1][0]) + std::fabs(e[1][1]) + std::fabs(e[1][2]) +
+                             std::fabs(e[2][0]) + std::fabs(e[2][1]) + std::fabs(e[2][2]);
+        if (!(std::fabs(det) > 1e-9 * scale * scale * scale) || !(camera.max_x > 0.f) || !(camera.max_y > 0.f)) return false;
+        const double W = cfg.width, H = cfg.height, sx = W / (2.0 * camera.max_x), sy = H / (2.0 * camera.max_y);
+        for (int k = 0; k < 3; ++k) {
+            const double i0 = c0[k] / det, i1 = c1[k] / det, i2 = c2[k] / det;
+            A[k] = sx * i0 + 0.5 * W * i2;
+            A[3 + k] = -sy * i1 + 0.5 * H * i2;  // (dir_y = -b)
+            A[6 + k] = i2;
+        }
+        return true;
+    }
+
     // (Re)builds the camera grid for the current view over `tris` and fills p's grid fields; false = no grid for this launch (switched off,
     // or the camera matrix cannot be inverted): the camera rays walk the BVH.
     bool ensure_pgrid(TraceParams* p) {
@@ -732,25 +757,8 @@ struct rt_raytracer {
                 pg_seen_launches = 0;
             }
             if (pg_seen_launches++ < (uint32_t)camera_grid_after) return false;
-            // dir = a e0 + b e1 + e2 with a = dir_x, b = -dir_y (camera.rs:85-89): invert [e0 e1 e2] in binary64
-            const float* R = camera.rotation.data();
-            const double e[3][3] = {{R[0], R[1], R[2]}, {R[4], R[5], R[6]}, {(double)R[8] + R[12], (double)R[9] + R[13], (double)R[10] + R[14]}};
-            // columns of B are e0, e1, e2; rows of its inverse are cross products / det
-            const double c0[3] = {e[1][1] * e[2][2] - e[1][2] * e[2][1], e[1][2] * e[2][0] - e[1][0] * e[2][2], e[1][0] * e[2][1] - e[1][1] * e[2][0]};
-            const double c1[3] = {e[2][1] * e[0][2] - e[2][2] * e[0][1], e[2][2] * e[0][0] - e[2][0] * e[0][2], e[2][0] * e[0][1] - e[2][1] * e[0][0]};
-            const double c2[3] = {e[0][1] * e[1][2] - e[0][2] * e[1][1], e[0][2] * e[1][0] - e[0][0] * e[1][2], e[0][0] * e[1][1] - e[0][1] * e[1][0]};
-            const double det = e[0][0] * c0[0] + e[0][1] * c0[1] + e[0][2] * c0[2];
-            const double scale = std::fabs(e[0][0]) + std::fabs(e[0][1]) + std::fabs(e[0][2]) + std::fabs(e[1][0]) + std::fabs(e[1][1]) + std::fabs(e[1][2]) +
-                                 std::fabs(e[2][0]) + std::fabs(e[2][1]) + std::fabs(e[2][2]);
-            if (!(std::fabs(det) > 1e-9 * scale * scale * scale) || !(camera.max_x > 0.f) || !(camera.max_y > 0.f)) return false;
             PGridParams g{};
-            const double W = cfg.width, H = cfg.height, sx = W / (2.0 * camera.max_x), sy = H / (2.0 * camera.max_y);
-            for (int k = 0; k < 3; ++k) {
-                const double i0 = c0[k] / det, i1 = c1[k] / det, i2 = c2[k] / det;  // (a c, b c, c) = (i0, i1, i2) . w
-                g.A[0][k] = sx * i0 + 0.5 * W * i2;       // U = W/2 + a W / (2 max_x)
-                g.A[0][3 + k] = -sy * i1 + 0.5 * H * i2;  // V = H/2 - b H / (2 max_y)   (dir_y = -b)
-                g.A[0][6 + k] = i2;
-            }
+            if (!camera_plane_matrix(g.A[0])) return false;
             g.origin[0] = o.x, g.origin[1] = o.y, g.origin[2] = o.z;
             double extent = 0.0;
             for (int a = 0; a < 3; ++a) extent = std::max(extent, (double)root_hi[a] - (double)root_lo[a]);
@@ -1945,6 +1953,14 @@ int rt_get_counters_device_ptr(rt_raytracer* rt, void** dev_ptr) {
 }
 uint32_t rt_launch_param_bytes(void) { return (uint32_t)sizeof(TraceParams); }
 
+int rt_get_camera_plane_matrix(rt_raytracer* rt, double* out12) {
+    if (!out12) return RT_ERR_INVALID;
+    RT_GUARD_HOST(rt, {
+        if (!rt->camera_plane_matrix(out12)) throw std::invalid_argument("the camera matrix cannot be inverted");
+        const f3 o = rt->camera.ray_origin();
+        out12[9] = o.x, out12[10] = o.y, out12[11] = o.z;
+    });
+}
 int rt_set_tuning(rt_raytracer* rt, int32_t key, int32_t value) {
     if (!rt) return RT_ERR_INVALID;
     if (key == RT_TUNE_KERNEL_VARIANT && value >= 0 && value <= 2) {

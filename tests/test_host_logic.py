@@ -335,6 +335,35 @@ def test_camera_matches_oracle_through_interactive_moves(scenes):
     assert np.array_equal(r.camera.matrices(), o2.camera())
 
 
+@pytest.mark.parametrize("w,h", [(1920, 1080), (1024, 768), (300, 500)])
+def test_camera_plane_matrix_inverts_get_ray(scenes, w, h):
+    """The map behind the perspective grid of the camera rays (rt_get_camera_plane_matrix; csrc/pgrid_build.cu bins triangles with it): a point
+    origin + t * dir of the ORACLE's camera ray (camera.rs:80-90 restated in oracle/rt_oracle.cpp) of pixel idx, with u = idx % W and
+    v = idx / H (mod.rs:96) and any sub-pixel offsets, lands inside the pixel's unit square of the sample plane, and its Z is t. Checked
+    for the start view and through moves and turns."""
+    s = scenes("thai2")
+    r, o = host_tracer(s, w, h), Oracle(s, w, h)
+    rng = np.random.default_rng(5)
+    moves = [None, ("move_rel", (0.3, -0.2, 1.5)), ("add_y_angle", (0.7,)), ("add_x_angle", (-0.4,)), ("move_rel", (-2.0, 0.5, 0.1)), ("add_y_angle", (2.9,))]
+    for mv in moves:
+        if mv:
+            getattr(r.camera, mv[0])(*mv[1])
+            getattr(o, mv[0])(*mv[1])
+        A, origin = r.camera.plane_matrix()
+        for idx in np.concatenate([[0, w * h - 1, w - 1, w * (h - 1)], rng.integers(0, w * h, 60)]):
+            u, v = int(idx) % w, int(idx) // h
+            xi1, xi2 = (0.5, 0.5) if idx % 3 == 0 else rng.random(2) * 0.998 + 0.001
+            ray = o.get_ray(u, v, float(xi1), float(xi2)).astype(np.float64)
+            pos, d = ray[:3], ray[3:]
+            assert np.allclose(pos, origin, rtol=0, atol=1e-6 * (1 + np.abs(origin).max()))
+            for t in (0.25, 3.0, 400.0):
+                X, Y, Z = A @ (pos + t * d - origin)
+                assert abs(Z - t) <= 2e-5 * t, (mv, idx, t, Z)
+                # the f32 ray against the binary64 map: within a few thousandths of a pixel of the sample position
+                assert abs(X / Z - (u + xi1)) < 5e-3 and abs(Y / Z - (v + xi2)) < 5e-3, (mv, idx, X / Z - u, Y / Z - v)
+    r.close()
+
+
 def test_render_calls_fail_loudly_without_a_device(scenes):
     """No CPU fallback: a host-side handle refuses to render."""
     r = host_tracer(scenes("4boxes"))
