@@ -929,6 +929,7 @@ struct rt_raytracer {
         if (use_pool && pool_blocks == 0) pool_blocks = pool_blocks_per_sm();
         // kernel instantiation: the binary-BVH kernels exist a second time with the camera rays sent through the perspective grid
         int ka = a;
+        const uint64_t pg_builds_before = pg_builds;
         if (a == 1 && variant == 1 && !use_pool) {
             // the grids are an accelerator of the accelerator: a build that fails (device memory) switches them off, the launch walks the tree
             try {
@@ -1014,6 +1015,24 @@ struct rt_raytracer {
             p.queue_items = sc->order.p + (sc->order.n - 1);
             ++sc->launches;
             ++sc->recorded;
+            // The view just got its grid, so it stays: its first frame walked the tree and left that kernel's schedule one recorded launch that
+            // nothing would ever sort (the tree-walking kernel runs again only after the next camera move, which restarts the record). Sort it
+            // now, on this frame, which pays for the build anyway: the first frame after the NEXT key press then runs with an order that is one
+            // view old — what it had before the grids existed — instead of the order of the handle's very first view.
+            if (ka == 4 && pg_builds != pg_builds_before && blocks_per_sm[1][b] > 0) {
+                for (auto& s1 : schedules)
+                    if (s1->kernel == 1 && s1->first == sc->first && s1->rows == sc->rows && s1->tiles == tiles && s1->samples_log2 == sc->samples_log2 &&
+                        s1->launches >= 1 && !s1->restart_costs) {
+                        const uint32_t warps1 = (uint32_t)(blocks_per_sm[1][b] * num_sms * 8);
+                        const uint32_t level1 = split_quarters > 0 ? s1->max_level : 0u;
+                        cudaError_t e1 = launch_tile_sort(s1->cost.p, s1->order.p, tiles, warps1, (uint32_t)split_quarters, level1, tiles < warps1 ? 10000u : 40000u,
+                                                          s1->order.p + (s1->order.n - 1), stream);
+                        if (e1 != cudaSuccess) return e1;
+                        ++total_kernels;
+                        ++last.kernels_launched;
+                        s1->have_order = true;
+                    }
+            }
         }
         cudaError_t e;
         if (use_pool) e = launch_trace(p, a, 2, pool_blocks * num_sms, stream);
